@@ -1,0 +1,791 @@
+// clb_api.cu -- C-ABI of libcareless_b200.so (see include/careless_b200.h).
+//
+// Host side of the B200-native ELBO gradient + Adam step: device memory, the host prep that
+// turns the reference's input tuple (careless/models/base.py:22-31) into the sorted / padded
+// SoA device layout, kernel launches, and the parameter / optimiser state.
+#include "../../include/careless_b200.h"
+#include "clb_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace clb;
+
+namespace {
+
+std::string g_create_error;
+
+struct DevBuf {
+  void* p = nullptr; size_t bytes = 0;
+  ~DevBuf() { if (p) cudaFree(p); }
+  cudaError_t alloc(size_t n) {
+    if (p && n <= bytes) return cudaSuccess;
+    if (p) { cudaFree(p); p = nullptr; bytes = 0; }
+    if (n == 0) return cudaSuccess;
+    cudaError_t e = cudaMalloc(&p, n);
+    if (e == cudaSuccess) bytes = n;
+    return e;
+  }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct PinBuf {
+  void* p = nullptr; size_t bytes = 0;
+  ~PinBuf() { if (p) cudaFreeHost(p); }
+  cudaError_t alloc(size_t n) {
+    if (p && n <= bytes) return cudaSuccess;
+    if (p) { cudaFreeHost(p); p = nullptr; bytes = 0; }
+    if (n == 0) return cudaSuccess;
+    cudaError_t e = cudaMallocHost(&p, n);
+    if (e == cudaSuccess) bytes = n;
+    return e;
+  }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+}  // namespace
+
+struct clb_handle {
+  clb_config cfg{};
+  std::string err;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int n_sms = 0;
+
+  // sizes
+  int64_t R = 0; int S = 1;
+  int64_t n_rows_raw = 0, n_rows = 0 /*padded*/, n_rows_total = 0;
+  int WP = 0, NL = 0, KS = 1, grid_obs = 0;
+  size_t smem_obs = 0;
+  MlpLayout lay{};
+  VarTable vt{};
+  int var_group[kMaxVars]{};
+  int64_t goff[CLB_N_GROUPS]{}, gsize[CLB_N_GROUPS]{};
+  int gtrain[CLB_N_GROUPS]{};
+  int64_t P = 0;           // total parameters
+  int64_t adam_t = 0;
+  uint32_t step_counter = 0;   // RNG step index
+  bool have_obs = false, have_prior = false, in_step = false;
+  int order = CLB_ORDER_REFL;
+  double ll_const = 0.0;   // per-sample constant log-likelihood of empty Laue slots
+
+  // device state
+  DevBuf theta, m, v, grad;
+  DevBuf centric, eps_sigma, dw_parent, asu_id, r_const, refl_index;
+  DevBuf z, gz;
+  DevBuf rows;             // one allocation holding all row arrays
+  PinBuf rows_host;        // pinned mirror (for re-upload)
+  size_t rows_bytes = 0;
+  int32_t *d_refl = nullptr, *d_image = nullptr, *d_spot = nullptr; uint32_t* d_oidx = nullptr;
+  float *d_meta = nullptr, *d_iobs = nullptr, *d_sig = nullptr;
+  DevBuf partials, scratch;
+  DevBuf acc, var_sums, red, metrics, var_scale, adam_alpha, stop_step;
+  DevBuf inj_u, inj_eps, ipred;
+  bool want_ipred = false;
+  int metrics_cap = 0;
+
+  // timing
+  bool timing = false;
+  std::vector<cudaEvent_t> ev;   // pairs
+  size_t ev_used = 0;
+  double obs_ms = 0.0; int64_t obs_launches = 0, total_launches = 0;
+
+  ~clb_handle() {
+    for (auto e : ev) cudaEventDestroy(e);
+    if (own_stream && stream) cudaStreamDestroy(stream);
+  }
+};
+
+namespace {
+
+int fail(clb_handle* h, int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+  if (h) h->err = buf; else g_create_error = buf;
+  return code;
+}
+
+#define CLB_CUDA(h, expr)                                                                      \
+  do { cudaError_t e_ = (expr);                                                                \
+       if (e_ != cudaSuccess) return fail(h, CLB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,     \
+                                          cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+int round_width(int w) { return w <= 8 ? 8 : w <= 16 ? 16 : w <= 32 ? 32 : -1; }
+
+template <int WP, int LIK> cudaError_t launch_obs(clb_handle* h, const ObsArgs& a) {
+  cudaError_t e = cudaFuncSetAttribute(k_obs<WP, LIK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_obs);
+  if (e != cudaSuccess) return e;
+  k_obs<WP, LIK><<<h->grid_obs, kObsThreads, h->smem_obs, h->stream>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t dispatch_obs(clb_handle* h, const ObsArgs& a) {
+  const int lik = h->cfg.likelihood;
+  switch (h->WP) {
+    case 8:  return lik ? launch_obs<8, 1>(h, a) : launch_obs<8, 0>(h, a);
+    case 16: return lik ? launch_obs<16, 1>(h, a) : launch_obs<16, 0>(h, a);
+    case 32: return lik ? launch_obs<32, 1>(h, a) : launch_obs<32, 0>(h, a);
+  }
+  return cudaErrorInvalidValue;
+}
+
+int ks_for(int WP) { return std::max(1, kObsThreads / (WP * (WP / 4))); }
+
+void build_layout(clb_handle* h) {
+  const clb_config& c = h->cfg;
+  MlpLayout& l = h->lay;
+  int off = 0, fan_in = c.n_meta;
+  l.n_layers = c.mlp_layers + 1;
+  for (int k = 0; k < c.mlp_layers; ++k) {
+    l.in_dim[k] = fan_in; l.out_dim[k] = c.mlp_width;
+    l.koff[k] = off; off += fan_in * c.mlp_width;
+    l.boff[k] = off; off += c.mlp_width;
+    fan_in = c.mlp_width;
+  }
+  const int k = c.mlp_layers;
+  l.in_dim[k] = fan_in; l.out_dim[k] = 2;
+  l.koff[k] = off; off += fan_in * 2;
+  l.boff[k] = off; off += 2;
+  l.n_params = off;
+}
+
+void build_vars(clb_handle* h) {
+  const clb_config& c = h->cfg;
+  h->gsize[CLB_GROUP_SF_LOC] = h->R;
+  h->gsize[CLB_GROUP_SF_SCALE] = h->R;
+  h->gsize[CLB_GROUP_MLP] = h->lay.n_params;
+  h->gsize[CLB_GROUP_IMAGE_SCALES] = c.image_scales ? std::max(0, c.n_images - 1) : 0;
+  h->gsize[CLB_GROUP_DW_R] = (c.prior == CLB_PRIOR_DOUBLE_WILSON && c.optimize_dw_r) ? c.n_asu : 0;
+  int64_t off = 0;
+  for (int g = 0; g < CLB_N_GROUPS; ++g) { h->goff[g] = off; off += h->gsize[g]; h->gtrain[g] = 1; }
+  h->P = off;
+  VarTable& vt = h->vt;
+  int n = 0;
+  auto add = [&](int group, int64_t o, int64_t sz, int repl) {
+    vt.off[n] = o; vt.size[n] = sz; vt.trainable[n] = 1; vt.replicated[n] = repl; h->var_group[n] = group; ++n;
+  };
+  add(CLB_GROUP_SF_LOC, h->goff[CLB_GROUP_SF_LOC], h->R, 0);
+  add(CLB_GROUP_SF_SCALE, h->goff[CLB_GROUP_SF_SCALE], h->R, 0);
+  for (int k = 0; k < h->lay.n_layers; ++k) {
+    add(CLB_GROUP_MLP, h->goff[CLB_GROUP_MLP] + h->lay.koff[k], (int64_t)h->lay.in_dim[k] * h->lay.out_dim[k], 1);
+    add(CLB_GROUP_MLP, h->goff[CLB_GROUP_MLP] + h->lay.boff[k], h->lay.out_dim[k], 1);
+  }
+  if (h->gsize[CLB_GROUP_IMAGE_SCALES] > 0) add(CLB_GROUP_IMAGE_SCALES, h->goff[CLB_GROUP_IMAGE_SCALES], h->gsize[CLB_GROUP_IMAGE_SCALES], 1);
+  if (h->gsize[CLB_GROUP_DW_R] > 0) add(CLB_GROUP_DW_R, h->goff[CLB_GROUP_DW_R], h->gsize[CLB_GROUP_DW_R], 1);
+  vt.n_vars = n;
+}
+
+void refresh_trainable(clb_handle* h) {
+  for (int v = 0; v < h->vt.n_vars; ++v) h->vt.trainable[v] = h->gtrain[h->var_group[v]];
+}
+
+double lgamma_d(double x) { return std::lgamma(x); }
+
+// log-density of x=0 under the likelihood with (loc, scale): the empty Laue slots (laue.py:23-25)
+double lik_logpdf_zero(const clb_config& c, double loc, double scale) {
+  const double t = (0.0 - loc) / scale;
+  if (c.likelihood == CLB_LIK_NORMAL) return -0.5 * t * t - std::log(scale) - 0.5 * std::log(2.0 * M_PI);
+  const double v = c.dof;
+  return lgamma_d(0.5 * (v + 1.0)) - lgamma_d(0.5 * v) - 0.5 * std::log(v * M_PI) - std::log(scale)
+         - 0.5 * (v + 1.0) * std::log1p(t * t / v);
+}
+
+}  // namespace
+
+extern "C" {
+
+int clb_abi_version(void) { return CLB_ABI_VERSION; }
+
+const char* clb_last_error(const clb_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int clb_create(const clb_config* cfg, clb_handle** out) {
+  if (!cfg || !out) return fail(nullptr, CLB_ERR_INVALID, "clb_create: null argument");
+  *out = nullptr;
+  if (cfg->abi_version != CLB_ABI_VERSION) return fail(nullptr, CLB_ERR_INVALID, "ABI version mismatch: got %d, library is %d", cfg->abi_version, CLB_ABI_VERSION);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || cfg->device >= ndev)
+    return fail(nullptr, CLB_ERR_NO_DEVICE, "no CUDA device %d (found %d); careless_b200 has no CPU fallback", cfg->device, ndev);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) return fail(nullptr, CLB_ERR_CUDA, "cudaGetDeviceProperties failed");
+  if (prop.major != 10) return fail(nullptr, CLB_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", cfg->device, prop.major, prop.minor);
+  if (cfg->n_refl <= 0 || cfg->n_meta <= 0 || cfg->mlp_layers < 0 || cfg->mlp_width <= 0 || cfg->mc_samples <= 0)
+    return fail(nullptr, CLB_ERR_INVALID, "invalid sizes: n_refl=%lld n_meta=%d mlp_layers=%d mlp_width=%d mc_samples=%d",
+                (long long)cfg->n_refl, cfg->n_meta, cfg->mlp_layers, cfg->mlp_width, cfg->mc_samples);
+  if (cfg->mlp_layers + 1 > kMaxLayers) return fail(nullptr, CLB_ERR_INVALID, "mlp_layers %d exceeds the supported maximum %d", cfg->mlp_layers, kMaxLayers - 1);
+  if (cfg->likelihood == CLB_LIK_STUDENTT && !(cfg->dof > 0.f)) return fail(nullptr, CLB_ERR_INVALID, "student-t likelihood needs dof > 0");
+  if (cfg->image_scales && cfg->n_images <= 0) return fail(nullptr, CLB_ERR_INVALID, "image scales need n_images > 0");
+  if (cfg->prior == CLB_PRIOR_DOUBLE_WILSON && cfg->n_asu <= 0) return fail(nullptr, CLB_ERR_INVALID, "DoubleWilson needs n_asu > 0");
+  const int wmax = std::max(std::max(cfg->n_meta, cfg->mlp_width), 2);
+  const int WP = round_width(wmax);
+  if (WP < 0) return fail(nullptr, CLB_ERR_INVALID, "max(n_meta, mlp_width) = %d exceeds the supported width 32", wmax);
+
+  clb_handle* h = new clb_handle();
+  h->cfg = *cfg;
+  if (h->cfg.n_refl_total <= 0) h->cfg.n_refl_total = h->cfg.n_refl;
+  if (h->cfg.world_size <= 0) { h->cfg.world_size = 1; h->cfg.rank = 0; }
+  h->R = cfg->n_refl; h->S = cfg->mc_samples; h->WP = WP; h->KS = ks_for(WP);
+  auto bail = [&](int code) { g_create_error = h->err; delete h; return code; };
+#define CREATE_CUDA(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { fail(h, CLB_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); return bail(CLB_ERR_CUDA); } } while (0)
+  CREATE_CUDA(cudaSetDevice(cfg->device));
+  h->n_sms = prop.multiProcessorCount;
+  if (cfg->stream) h->stream = (cudaStream_t)cfg->stream;
+  else { CREATE_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)); h->own_stream = true; }
+  build_layout(h);
+  build_vars(h);
+  h->NL = h->lay.n_layers;
+  switch (WP) {
+    case 8: h->smem_obs = ObsSmem<8>::bytes(h->NL); break;
+    case 16: h->smem_obs = ObsSmem<16>::bytes(h->NL); break;
+    default: h->smem_obs = ObsSmem<32>::bytes(h->NL); break;
+  }
+  if (h->smem_obs > (size_t)prop.sharedMemPerBlockOptin) {
+    fail(h, CLB_ERR_INVALID, "scale MLP (%d layers x padded width %d) needs %zu B of shared memory; the device offers %zu",
+         cfg->mlp_layers, WP, h->smem_obs, (size_t)prop.sharedMemPerBlockOptin);
+    return bail(CLB_ERR_INVALID);
+  }
+  const size_t pb = sizeof(float) * (size_t)h->P;
+  CREATE_CUDA(h->theta.alloc(pb)); CREATE_CUDA(h->m.alloc(pb)); CREATE_CUDA(h->v.alloc(pb)); CREATE_CUDA(h->grad.alloc(pb));
+  CREATE_CUDA(cudaMemsetAsync(h->m.p, 0, pb, h->stream));
+  CREATE_CUDA(cudaMemsetAsync(h->v.p, 0, pb, h->stream));
+  CREATE_CUDA(cudaMemsetAsync(h->grad.p, 0, pb, h->stream));
+  CREATE_CUDA(h->z.alloc(sizeof(float) * h->R * h->S));
+  CREATE_CUDA(h->gz.alloc(sizeof(float) * h->R * h->S));
+  CREATE_CUDA(h->acc.alloc(sizeof(double) * ACC_COUNT));
+  CREATE_CUDA(h->var_sums.alloc(sizeof(double) * 2 * kMaxVars));
+  CREATE_CUDA(h->red.alloc(sizeof(double) * (2 + 2 * kMaxVars)));
+  CREATE_CUDA(h->var_scale.alloc(sizeof(float) * kMaxVars));
+  CREATE_CUDA(h->adam_alpha.alloc(sizeof(float) * 4));
+  CREATE_CUDA(h->stop_step.alloc(sizeof(int) * 4));
+  // reference initial values: identity kernels, zero biases (nn.py:55-79), image scales 1 (image.py:21)
+  std::vector<float> init((size_t)h->P, 0.f);
+  float* mlp = init.data() + h->goff[CLB_GROUP_MLP];
+  for (int k = 0; k < h->lay.n_layers; ++k)
+    for (int i = 0; i < std::min(h->lay.in_dim[k], h->lay.out_dim[k]); ++i) mlp[h->lay.koff[k] + i * h->lay.out_dim[k] + i] = 1.f;
+  for (int64_t i = 0; i < h->gsize[CLB_GROUP_IMAGE_SCALES]; ++i) init[h->goff[CLB_GROUP_IMAGE_SCALES] + i] = 1.f;
+  CREATE_CUDA(cudaMemcpyAsync(h->theta.p, init.data(), pb, cudaMemcpyHostToDevice, h->stream));
+  const int big = 0x7fffffff;
+  CREATE_CUDA(cudaMemcpyAsync(h->stop_step.p, &big, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  CREATE_CUDA(cudaStreamSynchronize(h->stream));
+#undef CREATE_CUDA
+  *out = h;
+  return CLB_OK;
+}
+
+void clb_destroy(clb_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->cfg.device);
+  cudaStreamSynchronize(h->stream);
+  delete h;
+}
+
+int clb_synchronize(clb_handle* h) {
+  if (!h) return CLB_ERR_INVALID;
+  CLB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return CLB_OK;
+}
+
+int clb_set_observations(clb_handle* h, int64_t n, int64_t n_total, const int64_t* refl_id, const int64_t* image_id,
+                         const float* metadata, const float* iobs, const float* sig,
+                         const int64_t* harmonic_id, const int64_t* obs_index, int32_t order) {
+  if (!h) return CLB_ERR_INVALID;
+  const clb_config& c = h->cfg;
+  if (n <= 0 || !refl_id || !metadata || !iobs || !sig) return fail(h, CLB_ERR_INVALID, "clb_set_observations: null/empty input");
+  if (c.laue && !harmonic_id) return fail(h, CLB_ERR_INVALID, "Laue model needs harmonic_id");
+  if (c.image_scales && !image_id) return fail(h, CLB_ERR_INVALID, "image scales need image_id");
+  if (n >= (int64_t)1 << 31) return fail(h, CLB_ERR_INVALID, "n_rows %lld exceeds 2^31-1 per handle", (long long)n);
+  if (n_total <= 0) n_total = n;
+  CLB_CUDA(h, cudaSetDevice(c.device));
+  if (order == CLB_ORDER_AUTO) order = c.laue ? CLB_ORDER_SPOT : CLB_ORDER_REFL;
+  if (c.laue && order != CLB_ORDER_SPOT) return fail(h, CLB_ERR_INVALID, "Laue rows must use CLB_ORDER_SPOT");
+  const int d = c.n_meta;
+
+  // ---- validate ids and build the sort key ----
+  std::vector<int32_t> key((size_t)n);
+  int64_t n_keys = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    if (refl_id[i] < 0 || refl_id[i] >= h->R) return fail(h, CLB_ERR_INVALID, "refl_id[%lld]=%lld outside [0,%lld)", (long long)i, (long long)refl_id[i], (long long)h->R);
+    if (c.image_scales && (image_id[i] < 0 || image_id[i] >= c.n_images)) return fail(h, CLB_ERR_INVALID, "image_id[%lld]=%lld outside [0,%d)", (long long)i, (long long)image_id[i], c.n_images);
+    if (obs_index && (obs_index[i] < 0 || obs_index[i] >= n_total)) return fail(h, CLB_ERR_INVALID, "obs_index[%lld] outside [0,n_rows_total)", (long long)i);
+  }
+  if (order == CLB_ORDER_REFL) { for (int64_t i = 0; i < n; ++i) key[i] = (int32_t)refl_id[i]; n_keys = h->R; }
+  else if (order == CLB_ORDER_SPOT) {
+    for (int64_t i = 0; i < n; ++i) {
+      if (harmonic_id[i] < 0 || harmonic_id[i] >= n) return fail(h, CLB_ERR_INVALID, "harmonic_id[%lld] outside [0,n_rows)", (long long)i);
+      key[i] = (int32_t)harmonic_id[i];
+    }
+    n_keys = n;
+  } else if (order == CLB_ORDER_IMAGE) {
+    if (!image_id) return fail(h, CLB_ERR_INVALID, "CLB_ORDER_IMAGE needs image_id");
+    int64_t mx = 0; for (int64_t i = 0; i < n; ++i) mx = std::max(mx, image_id[i]);
+    for (int64_t i = 0; i < n; ++i) key[i] = (int32_t)image_id[i]; n_keys = mx + 1;
+  } else { n_keys = 0; }
+
+  // ---- stable counting sort -> perm[sorted position] = original row ----
+  std::vector<int32_t> perm((size_t)n);
+  std::vector<int64_t> count;
+  if (n_keys > 0) {
+    count.assign((size_t)n_keys + 1, 0);
+    for (int64_t i = 0; i < n; ++i) count[key[i] + 1]++;
+    for (int64_t k = 0; k < n_keys; ++k) count[k + 1] += count[k];
+    std::vector<int64_t> cur(count.begin(), count.end() - 1);
+    for (int64_t i = 0; i < n; ++i) perm[cur[key[i]]++] = (int32_t)i;
+  } else {
+    for (int64_t i = 0; i < n; ++i) perm[i] = (int32_t)i;
+  }
+
+  // ---- padded positions (Laue: no spot may straddle a 32-row warp chunk) ----
+  std::vector<int64_t> pos((size_t)n);
+  int64_t npad = 0;
+  h->ll_const = 0.0;
+  if (order == CLB_ORDER_SPOT) {
+    int64_t p = 0;
+    for (int64_t k = 0; k < n_keys; ++k) {
+      const int64_t len = count[k + 1] - count[k];
+      if (len == 0) { h->ll_const += lik_logpdf_zero(c, iobs[k], sig[k]); continue; }
+      if (len > 32) return fail(h, CLB_ERR_INVALID, "spot %lld has %lld harmonics; at most 32 are supported", (long long)k, (long long)len);
+      if ((p & 31) + len > 32) p = (p + 31) & ~(int64_t)31;
+      for (int64_t j = 0; j < len; ++j) pos[count[k] + j] = p + j;
+      p += len;
+    }
+    npad = p;
+  } else {
+    for (int64_t i = 0; i < n; ++i) pos[i] = i;
+    npad = n;
+  }
+  npad = (npad + 31) & ~(int64_t)31;
+
+  // ---- build the SoA device layout in pinned memory ----
+  const bool has_img = image_id != nullptr;
+  const bool has_spot = c.laue != 0;
+  size_t bytes = 0;
+  auto carve = [&](size_t nbytes) { size_t o = bytes; bytes += (nbytes + 255) & ~(size_t)255; return o; };
+  const size_t o_refl = carve(sizeof(int32_t) * npad);
+  const size_t o_img = has_img ? carve(sizeof(int32_t) * npad) : 0;
+  const size_t o_spot = has_spot ? carve(sizeof(int32_t) * npad) : 0;
+  const size_t o_oidx = carve(sizeof(uint32_t) * npad);
+  const size_t o_meta = carve(sizeof(float) * npad * d);
+  const size_t o_iobs = carve(sizeof(float) * npad);
+  const size_t o_sig = carve(sizeof(float) * npad);
+  CLB_CUDA(h, h->rows_host.alloc(bytes));
+  CLB_CUDA(h, h->rows.alloc(bytes));
+  char* hb = h->rows_host.as<char>();
+  int32_t* p_refl = reinterpret_cast<int32_t*>(hb + o_refl);
+  int32_t* p_img = has_img ? reinterpret_cast<int32_t*>(hb + o_img) : nullptr;
+  int32_t* p_spot = has_spot ? reinterpret_cast<int32_t*>(hb + o_spot) : nullptr;
+  uint32_t* p_oidx = reinterpret_cast<uint32_t*>(hb + o_oidx);
+  float* p_meta = reinterpret_cast<float*>(hb + o_meta);
+  float* p_iobs = reinterpret_cast<float*>(hb + o_iobs);
+  float* p_sig = reinterpret_cast<float*>(hb + o_sig);
+  for (int64_t i = 0; i < npad; ++i) { p_refl[i] = -1; p_oidx[i] = 0; p_iobs[i] = 0.f; p_sig[i] = 1.f; }
+  if (p_img) std::fill(p_img, p_img + npad, 0);
+  if (p_spot) std::fill(p_spot, p_spot + npad, -1);
+  std::fill(p_meta, p_meta + (size_t)npad * d, 0.f);
+  for (int64_t sidx = 0; sidx < n; ++sidx) {
+    const int64_t i = perm[sidx], p = pos[sidx];
+    p_refl[p] = (int32_t)refl_id[i];
+    if (p_img) p_img[p] = (int32_t)image_id[i];
+    p_oidx[p] = (uint32_t)(obs_index ? obs_index[i] : i);
+    for (int j = 0; j < d; ++j) p_meta[(size_t)j * npad + p] = metadata[(size_t)i * d + j];
+    if (has_spot) {
+      const int64_t k = harmonic_id[i];
+      p_spot[p] = (int32_t)k; p_iobs[p] = iobs[k]; p_sig[p] = sig[k];     // formatter.py:637-640: spot k's value sits at index k
+    } else { p_iobs[p] = iobs[i]; p_sig[p] = sig[i]; }
+  }
+  h->rows_bytes = bytes;
+  char* db = h->rows.as<char>();
+  h->d_refl = reinterpret_cast<int32_t*>(db + o_refl);
+  h->d_image = has_img ? reinterpret_cast<int32_t*>(db + o_img) : nullptr;
+  h->d_spot = has_spot ? reinterpret_cast<int32_t*>(db + o_spot) : nullptr;
+  h->d_oidx = reinterpret_cast<uint32_t*>(db + o_oidx);
+  h->d_meta = reinterpret_cast<float*>(db + o_meta);
+  h->d_iobs = reinterpret_cast<float*>(db + o_iobs);
+  h->d_sig = reinterpret_cast<float*>(db + o_sig);
+  h->n_rows_raw = n; h->n_rows = npad; h->n_rows_total = n_total; h->order = order;
+
+  // ---- launch geometry + per-CTA buffers of the observation kernel ----
+  const int64_t n_tiles = (npad + kObsThreads - 1) / kObsThreads;
+  h->grid_obs = (int)std::min<int64_t>(n_tiles, h->n_sms);
+  CLB_CUDA(h, h->partials.alloc(sizeof(float) * (size_t)h->grid_obs * h->KS * h->lay.n_params));
+  CLB_CUDA(h, h->scratch.alloc(sizeof(float4) * (size_t)h->grid_obs * std::max(1, c.mlp_layers) * (h->WP / 4) * kObsThreads));
+  h->have_obs = true;
+  return clb_upload_observations(h);
+}
+
+int clb_upload_observations(clb_handle* h) {
+  if (!h || !h->have_obs) return fail(h, CLB_ERR_STATE, "clb_upload_observations before clb_set_observations");
+  CLB_CUDA(h, cudaSetDevice(h->cfg.device));
+  CLB_CUDA(h, cudaMemcpyAsync(h->rows.p, h->rows_host.p, h->rows_bytes, cudaMemcpyHostToDevice, h->stream));
+  return CLB_OK;
+}
+
+int clb_set_prior(clb_handle* h, const uint8_t* centric, const float* mult, const float* sigma,
+                  const int32_t* dw_parent, const int32_t* asu_id, const float* r,
+                  const int64_t* refl_index, float init_scale) {
+  if (!h || !centric || !mult) return fail(h, CLB_ERR_INVALID, "clb_set_prior: null input");
+  const clb_config& c = h->cfg;
+  const bool dw = c.prior == CLB_PRIOR_DOUBLE_WILSON;
+  if (dw && (!dw_parent || !asu_id || !r)) return fail(h, CLB_ERR_INVALID, "DoubleWilson needs dw_parent, asu_id and r");
+  CLB_CUDA(h, cudaSetDevice(c.device));
+  const int64_t R = h->R;
+  std::vector<float> es((size_t)R);
+  std::vector<uint32_t> ridx((size_t)R);
+  for (int64_t i = 0; i < R; ++i) {
+    es[i] = mult[i] * (sigma ? sigma[i] : 1.0f);
+    if (!(es[i] > 0.f)) return fail(h, CLB_ERR_INVALID, "multiplicity*sigma must be positive (entry %lld)", (long long)i);
+    ridx[i] = (uint32_t)(refl_index ? refl_index[i] : i);
+  }
+  if (dw) {
+    for (int i = 0; i < c.n_asu; ++i)
+      if (r[i] >= 1.f || r[i] <= -1.f) return fail(h, CLB_ERR_INVALID, "double-wilson r value %g outside of allowed range (-1, 1)", r[i]);   // manager.py:415-419
+    for (int64_t i = 0; i < R; ++i) {
+      if (dw_parent[i] < -2 || dw_parent[i] >= R) return fail(h, CLB_ERR_INVALID, "dw_parent[%lld] out of range", (long long)i);
+      if (asu_id[i] < 0 || asu_id[i] >= c.n_asu) return fail(h, CLB_ERR_INVALID, "asu_id[%lld] out of range", (long long)i);
+    }
+  }
+  CLB_CUDA(h, h->centric.alloc(R)); CLB_CUDA(h, h->eps_sigma.alloc(sizeof(float) * R)); CLB_CUDA(h, h->refl_index.alloc(sizeof(uint32_t) * R));
+  CLB_CUDA(h, cudaMemcpyAsync(h->centric.p, centric, R, cudaMemcpyHostToDevice, h->stream));
+  CLB_CUDA(h, cudaMemcpyAsync(h->eps_sigma.p, es.data(), sizeof(float) * R, cudaMemcpyHostToDevice, h->stream));
+  CLB_CUDA(h, cudaMemcpyAsync(h->refl_index.p, ridx.data(), sizeof(uint32_t) * R, cudaMemcpyHostToDevice, h->stream));
+  if (dw) {
+    CLB_CUDA(h, h->dw_parent.alloc(sizeof(int32_t) * R)); CLB_CUDA(h, h->asu_id.alloc(sizeof(int32_t) * R)); CLB_CUDA(h, h->r_const.alloc(sizeof(float) * c.n_asu));
+    CLB_CUDA(h, cudaMemcpyAsync(h->dw_parent.p, dw_parent, sizeof(int32_t) * R, cudaMemcpyHostToDevice, h->stream));
+    CLB_CUDA(h, cudaMemcpyAsync(h->asu_id.p, asu_id, sizeof(int32_t) * R, cudaMemcpyHostToDevice, h->stream));
+    CLB_CUDA(h, cudaMemcpyAsync(h->r_const.p, r, sizeof(float) * c.n_asu, cudaMemcpyHostToDevice, h->stream));
+    if (c.optimize_dw_r) {
+      std::vector<float> logit((size_t)c.n_asu);
+      for (int i = 0; i < c.n_asu; ++i) logit[i] = std::log(r[i]) - std::log1p(-r[i]);     // tfb.Sigmoid inverse, wilson.py:105-110
+      CLB_CUDA(h, cudaMemcpyAsync(h->theta.as<float>() + h->goff[CLB_GROUP_DW_R], logit.data(), sizeof(float) * c.n_asu, cudaMemcpyHostToDevice, h->stream));
+    }
+  }
+  if (init_scale >= 0.f) {   // manager.py:432-436: loc = prior.mean(), scale = prior.stddev() * init_scale
+    std::vector<float> vl((size_t)R), vs((size_t)R);
+    for (int64_t i = 0; i < R; ++i) {
+      const double s = std::sqrt((double)es[i]);
+      double mean, sd;
+      if (centric[i]) { mean = s * std::sqrt(2.0 / M_PI); sd = s * std::sqrt(1.0 - 2.0 / M_PI); }
+      else { mean = s * std::sqrt(M_PI) / 2.0; sd = s * std::sqrt(1.0 - M_PI / 4.0); }
+      const float loc = (float)mean, scale = (float)(sd * init_scale);
+      vl[i] = std::log(loc);
+      vs[i] = std::log(scale - c.epsilon);
+    }
+    CLB_CUDA(h, cudaMemcpyAsync(h->theta.as<float>() + h->goff[CLB_GROUP_SF_LOC], vl.data(), sizeof(float) * R, cudaMemcpyHostToDevice, h->stream));
+    CLB_CUDA(h, cudaMemcpyAsync(h->theta.as<float>() + h->goff[CLB_GROUP_SF_SCALE], vs.data(), sizeof(float) * R, cudaMemcpyHostToDevice, h->stream));
+  }
+  CLB_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->have_prior = true;
+  return CLB_OK;
+}
+
+int64_t clb_group_size(const clb_handle* h, int32_t group) {
+  if (!h || group < 0 || group >= CLB_N_GROUPS) return -1;
+  return h->gsize[group];
+}
+
+static int copy_group(clb_handle* h, DevBuf& buf, int32_t group, float* host, int64_t n, bool to_host) {
+  if (!h || group < 0 || group >= CLB_N_GROUPS || (!host && n > 0)) return fail(h, CLB_ERR_INVALID, "bad group/pointer");
+  if (n != h->gsize[group]) return fail(h, CLB_ERR_INVALID, "group %d has %lld values, caller passed %lld", group, (long long)h->gsize[group], (long long)n);
+  if (n == 0) return CLB_OK;
+  CLB_CUDA(h, cudaSetDevice(h->cfg.device));
+  float* dev = buf.as<float>() + h->goff[group];
+  if (to_host) CLB_CUDA(h, cudaMemcpyAsync(host, dev, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
+  else CLB_CUDA(h, cudaMemcpyAsync(dev, host, sizeof(float) * n, cudaMemcpyHostToDevice, h->stream));
+  CLB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return CLB_OK;
+}
+
+int clb_get_params(clb_handle* h, int32_t group, float* out, int64_t n) { return copy_group(h, h->theta, group, out, n, true); }
+int clb_set_params(clb_handle* h, int32_t group, const float* in, int64_t n) { return copy_group(h, h->theta, group, const_cast<float*>(in), n, false); }
+int clb_get_grads(clb_handle* h, int32_t group, float* out, int64_t n) { return copy_group(h, h->grad, group, out, n, true); }
+
+int clb_get_adam_state(clb_handle* h, int32_t group, float* m, float* v, int64_t n, int64_t* t) {
+  if (!h) return CLB_ERR_INVALID;
+  if (m) { int rc = copy_group(h, h->m, group, m, n, true); if (rc) return rc; }
+  if (v) { int rc = copy_group(h, h->v, group, v, n, true); if (rc) return rc; }
+  if (t) *t = h->adam_t;
+  return CLB_OK;
+}
+
+int clb_set_trainable(clb_handle* h, int32_t group, int32_t trainable) {
+  if (!h || group < 0 || group >= CLB_N_GROUPS) return fail(h, CLB_ERR_INVALID, "bad group");
+  h->gtrain[group] = trainable ? 1 : 0;
+  refresh_trainable(h);
+  return CLB_OK;
+}
+
+int clb_enable_ipred(clb_handle* h, int32_t enable) {
+  if (!h) return CLB_ERR_INVALID;
+  h->want_ipred = enable != 0;
+  return CLB_OK;
+}
+
+int clb_get_samples(clb_handle* h, float* z_f, int64_t n) {
+  if (!h || !z_f || n != h->R * h->S) return fail(h, CLB_ERR_INVALID, "clb_get_samples: expected %lld values", h ? (long long)(h->R * h->S) : 0LL);
+  CLB_CUDA(h, cudaSetDevice(h->cfg.device));
+  CLB_CUDA(h, cudaMemcpyAsync(z_f, h->z.p, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
+  CLB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return CLB_OK;
+}
+
+int clb_get_ipred(clb_handle* h, float* ipred, int64_t n) {
+  if (!h || !ipred || !h->ipred.p || n != h->n_rows_total * h->S) return fail(h, CLB_ERR_INVALID, "clb_get_ipred: call clb_enable_ipred(1) and a step first; expected %lld values", h ? (long long)(h->n_rows_total * h->S) : 0LL);
+  CLB_CUDA(h, cudaSetDevice(h->cfg.device));
+  CLB_CUDA(h, cudaMemcpyAsync(ipred, h->ipred.p, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
+  CLB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return CLB_OK;
+}
+
+int clb_reset_timers(clb_handle* h, int32_t enable) {
+  if (!h) return CLB_ERR_INVALID;
+  h->timing = enable != 0; h->ev_used = 0; h->obs_ms = 0.0; h->obs_launches = 0; h->total_launches = 0;
+  return CLB_OK;
+}
+
+int clb_kernel_time_ms(clb_handle* h, double* ms, int64_t* launches, int64_t* total) {
+  if (!h) return CLB_ERR_INVALID;
+  CLB_CUDA(h, cudaSetDevice(h->cfg.device));
+  CLB_CUDA(h, cudaStreamSynchronize(h->stream));
+  for (size_t i = 0; i + 1 < h->ev_used; i += 2) {
+    float t = 0.f;
+    CLB_CUDA(h, cudaEventElapsedTime(&t, h->ev[i], h->ev[i + 1]));
+    h->obs_ms += t;
+  }
+  h->ev_used = 0;
+  if (ms) *ms = h->obs_ms;
+  if (launches) *launches = h->obs_launches;
+  if (total) *total = h->total_launches;
+  return CLB_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// the step
+// ---------------------------------------------------------------------------------------
+static int ensure_metrics(clb_handle* h, int n) {
+  if (n <= h->metrics_cap) return CLB_OK;
+  CLB_CUDA(h, h->metrics.alloc(sizeof(double) * 4 * n));
+  h->metrics_cap = n;
+  return CLB_OK;
+}
+
+static int step_begin_impl(clb_handle* h, const float* inj_u, const float* inj_eps) {
+  const clb_config& c = h->cfg;
+  if (!h->have_obs || !h->have_prior) return fail(h, CLB_ERR_STATE, "clb_step before clb_set_observations / clb_set_prior");
+  CLB_CUDA(h, cudaSetDevice(c.device));
+  cudaStream_t st = h->stream;
+  const int64_t R = h->R; const int S = h->S;
+  float* theta = h->theta.as<float>();
+  float* grad = h->grad.as<float>();
+  const double kl_div = c.use_kl_weight ? (double)S * (double)c.n_refl_total : (double)S;
+  const double kl_coef = c.use_kl_weight ? (double)c.kl_weight : 1.0;
+  const double ll_div = c.use_kl_weight ? (double)S * (double)h->n_rows_total : (double)S;
+  const float cq = (float)(kl_coef / kl_div), cl = (float)(1.0 / ll_div);
+
+  const float* d_inj_u = nullptr; const float* d_inj_eps = nullptr;
+  if (inj_u) {
+    CLB_CUDA(h, h->inj_u.alloc(sizeof(float) * R * S));
+    CLB_CUDA(h, cudaMemcpyAsync(h->inj_u.p, inj_u, sizeof(float) * R * S, cudaMemcpyHostToDevice, st));
+    d_inj_u = h->inj_u.as<float>();
+  }
+  if (inj_eps) {
+    CLB_CUDA(h, h->inj_eps.alloc(sizeof(float) * h->n_rows_total * S));
+    CLB_CUDA(h, cudaMemcpyAsync(h->inj_eps.p, inj_eps, sizeof(float) * h->n_rows_total * S, cudaMemcpyHostToDevice, st));
+    d_inj_eps = h->inj_eps.as<float>();
+  }
+  if (h->want_ipred) {
+    CLB_CUDA(h, h->ipred.alloc(sizeof(float) * h->n_rows_total * S));
+    CLB_CUDA(h, cudaMemsetAsync(h->ipred.p, 0, sizeof(float) * h->n_rows_total * S, st));
+  }
+  CLB_CUDA(h, cudaMemsetAsync(h->acc.p, 0, sizeof(double) * ACC_COUNT, st));
+  CLB_CUDA(h, cudaMemsetAsync(h->var_sums.p, 0, sizeof(double) * 2 * kMaxVars, st));
+  // gradients of the replicated groups are accumulated with atomics / overwritten by the reduction
+  if (h->P > 2 * R) CLB_CUDA(h, cudaMemsetAsync(grad + 2 * R, 0, sizeof(float) * (h->P - 2 * R), st));
+  const bool train_mlp = h->gtrain[CLB_GROUP_MLP] != 0;
+  if (train_mlp) CLB_CUDA(h, cudaMemsetAsync(h->partials.p, 0, sizeof(float) * (size_t)h->grid_obs * h->KS * h->lay.n_params, st));
+
+  const bool dw = c.prior == CLB_PRIOR_DOUBLE_WILSON;
+  {
+    ReflArgs a{};
+    a.v_loc = theta + h->goff[CLB_GROUP_SF_LOC]; a.v_scale = theta + h->goff[CLB_GROUP_SF_SCALE];
+    a.centric = h->centric.as<uint8_t>(); a.eps_sigma = h->eps_sigma.as<float>();
+    a.dw_parent = dw ? h->dw_parent.as<int32_t>() : nullptr;
+    a.refl_index = h->refl_index.as<uint32_t>(); a.inj_u = d_inj_u;
+    a.z = h->z.as<float>(); a.gz = h->gz.as<float>(); a.acc = h->acc.as<double>();
+    a.R = R; a.S = S; a.eps = c.epsilon; a.cq = cq; a.seed = c.seed; a.step = h->step_counter;
+    const int64_t nthr = R * S;
+    k_refl_sample<<<(unsigned)((nthr + 255) / 256), 256, 0, st>>>(a);
+    CLB_CUDA(h, cudaGetLastError()); h->total_launches++;
+  }
+  if (dw) {
+    DwArgs a{};
+    a.z = h->z.as<float>(); a.gz = h->gz.as<float>();
+    a.centric = h->centric.as<uint8_t>(); a.eps_sigma = h->eps_sigma.as<float>();
+    a.dw_parent = h->dw_parent.as<int32_t>(); a.asu_id = h->asu_id.as<int32_t>();
+    a.r_const = h->r_const.as<float>();
+    a.r_logit = c.optimize_dw_r ? theta + h->goff[CLB_GROUP_DW_R] : nullptr;
+    a.g_r_logit = c.optimize_dw_r ? grad + h->goff[CLB_GROUP_DW_R] : nullptr;
+    a.acc = h->acc.as<double>(); a.R = R; a.S = S; a.cq = cq;
+    const int64_t nthr = R * S;
+    k_dw_prior<<<(unsigned)((nthr + 255) / 256), 256, 0, st>>>(a);
+    CLB_CUDA(h, cudaGetLastError()); h->total_launches++;
+  }
+  {
+    ObsArgs a{};
+    a.refl = h->d_refl; a.image = h->d_image; a.spot = h->d_spot; a.oidx = h->d_oidx;
+    a.meta = h->d_meta; a.iobs = h->d_iobs; a.sig = h->d_sig;
+    a.n_rows = h->n_rows; a.n_rows_total = h->n_rows_total; a.d = c.n_meta;
+    a.theta_mlp = theta + h->goff[CLB_GROUP_MLP];
+    a.theta_img = c.image_scales ? theta + h->goff[CLB_GROUP_IMAGE_SCALES] : nullptr;
+    a.lay = h->lay;
+    a.z = h->z.as<float>(); a.gz = h->gz.as<float>(); a.R = R; a.S = S;
+    a.inj_eps = d_inj_eps;
+    a.g_img = (c.image_scales && h->gtrain[CLB_GROUP_IMAGE_SCALES]) ? grad + h->goff[CLB_GROUP_IMAGE_SCALES] : nullptr;
+    a.partials = h->partials.as<float>(); a.scratch = h->scratch.as<float4>();
+    a.ipred_out = h->want_ipred ? h->ipred.as<float>() : nullptr;
+    a.acc = h->acc.as<double>();
+    a.lik.dof = c.dof; a.lik.half_dofp1 = 0.5f * (c.dof + 1.0f);
+    a.lik.lnorm = (c.likelihood == CLB_LIK_STUDENTT)
+                      ? (float)(lgamma_d(0.5 * (c.dof + 1.0)) - lgamma_d(0.5 * c.dof) - 0.5 * std::log((double)c.dof * M_PI)) : 0.f;
+    a.cl = cl; a.bijector = c.scale_bijector; a.shift = c.scale_shift; a.eps = c.epsilon;
+    a.seed = c.seed; a.step = h->step_counter; a.laue = c.laue; a.train_mlp = train_mlp ? 1 : 0;
+    if (h->timing) {
+      while (h->ev.size() < h->ev_used + 2) { cudaEvent_t e; CLB_CUDA(h, cudaEventCreate(&e)); h->ev.push_back(e); }
+      CLB_CUDA(h, cudaEventRecord(h->ev[h->ev_used], st));
+    }
+    CLB_CUDA(h, dispatch_obs(h, a)); h->total_launches++; h->obs_launches++;
+    if (h->timing) { CLB_CUDA(h, cudaEventRecord(h->ev[h->ev_used + 1], st)); h->ev_used += 2; }
+  }
+  if (train_mlp) {
+    const int np = h->lay.n_params;
+    k_reduce_partials<<<(np + 255) / 256, 256, 0, st>>>(h->partials.as<float>(), h->grid_obs * h->KS, np, grad + h->goff[CLB_GROUP_MLP]);
+    CLB_CUDA(h, cudaGetLastError()); h->total_launches++;
+  }
+  {
+    ReflBwdArgs a{};
+    a.v_loc = theta + h->goff[CLB_GROUP_SF_LOC]; a.v_scale = theta + h->goff[CLB_GROUP_SF_SCALE];
+    a.centric = h->centric.as<uint8_t>(); a.refl_index = h->refl_index.as<uint32_t>();
+    a.inj_u = d_inj_u; a.gz = h->gz.as<float>();
+    a.g_loc = grad + h->goff[CLB_GROUP_SF_LOC]; a.g_scale = grad + h->goff[CLB_GROUP_SF_SCALE];
+    a.R = R; a.S = S; a.eps = c.epsilon; a.cq = cq; a.seed = c.seed; a.step = h->step_counter;
+    k_refl_backward<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(a);
+    CLB_CUDA(h, cudaGetLastError()); h->total_launches++;
+  }
+  h->in_step = true;
+  return CLB_OK;
+}
+
+// after the all-reduce of the replicated gradients: per-variable norms + scalar packing
+static int step_norms_impl(clb_handle* h) {
+  if (!h->in_step) return fail(h, CLB_ERR_STATE, "clb_step_norms without clb_step_begin");
+  cudaStream_t st = h->stream;
+  refresh_trainable(h);
+  int64_t maxsz = 1;
+  for (int v = 0; v < h->vt.n_vars; ++v) maxsz = std::max(maxsz, h->vt.size[v]);
+  const int chunks = (int)std::min<int64_t>((maxsz + 256 * 8 - 1) / (256 * 8), 4 * h->n_sms);
+  k_var_sumsq<<<dim3(std::max(chunks, 1), h->vt.n_vars), 256, 0, st>>>(h->grad.as<float>(), h->vt, h->var_sums.as<double>());
+  CLB_CUDA(h, cudaGetLastError()); h->total_launches++;
+  k_pack_scalars<<<1, 128, 0, st>>>(h->acc.as<double>(), h->var_sums.as<double>(), h->vt, h->red.as<double>(), h->cfg.rank,
+                                  (double)h->S * h->ll_const);
+  CLB_CUDA(h, cudaGetLastError()); h->total_launches++;
+  return CLB_OK;
+}
+
+static int step_end_impl(clb_handle* h, double* d_metrics) {
+  const clb_config& c = h->cfg;
+  if (!h->in_step) return fail(h, CLB_ERR_STATE, "clb_step_end without clb_step_begin");
+  cudaStream_t st = h->stream;
+  const int S = h->S;
+  FinalizeArgs f{};
+  f.acc = h->acc.as<double>(); f.red = h->red.as<double>(); f.vt = h->vt;
+  f.metrics = d_metrics; f.var_scale = h->var_scale.as<float>(); f.adam_alpha = h->adam_alpha.as<float>();
+  f.stop_step = h->stop_step.as<int>(); f.step = (int)h->step_counter;
+  f.kl_div = c.use_kl_weight ? (double)S * (double)c.n_refl_total : (double)S;
+  f.kl_coef = c.use_kl_weight ? (double)c.kl_weight : 1.0;
+  f.ll_div = c.use_kl_weight ? (double)S * (double)h->n_rows_total : (double)S;
+  f.clipnorm = c.clipnorm; f.global_clipnorm = c.global_clipnorm;
+  f.lr = c.learning_rate; f.beta1 = c.beta_1; f.beta2 = c.beta_2; f.t = h->adam_t + 1;
+  k_finalize<<<1, 32, 0, st>>>(f);
+  CLB_CUDA(h, cudaGetLastError()); h->total_launches++;
+  int64_t maxsz = 1;
+  for (int v = 0; v < h->vt.n_vars; ++v) if (h->vt.trainable[v]) maxsz = std::max(maxsz, h->vt.size[v]);
+  const int chunks = (int)std::min<int64_t>((maxsz + 256 * 4 - 1) / (256 * 4), 8 * h->n_sms);
+  k_adam<<<dim3(std::max(chunks, 1), h->vt.n_vars), 256, 0, st>>>(h->theta.as<float>(), h->m.as<float>(), h->v.as<float>(), h->grad.as<float>(),
+                                                                   h->vt, h->var_scale.as<float>(), h->adam_alpha.as<float>(),
+                                                                   c.clipvalue, c.beta_1, c.beta_2, c.adam_epsilon, h->stop_step.as<int>(), (int)h->step_counter);
+  CLB_CUDA(h, cudaGetLastError()); h->total_launches++;
+  h->adam_t += 1;
+  h->step_counter += 1;
+  h->in_step = false;
+  return CLB_OK;
+}
+
+int clb_step_begin(clb_handle* h, const float* inj_u_f, const float* inj_eps_s) {
+  if (!h) return CLB_ERR_INVALID;
+  return step_begin_impl(h, inj_u_f, inj_eps_s);
+}
+
+int clb_step_norms(clb_handle* h) {
+  if (!h) return CLB_ERR_INVALID;
+  return step_norms_impl(h);
+}
+
+int clb_step_end(clb_handle* h, clb_metrics* out) {
+  if (!h) return CLB_ERR_INVALID;
+  int rc = ensure_metrics(h, 1); if (rc) return rc;
+  rc = step_end_impl(h, h->metrics.as<double>()); if (rc) return rc;
+  if (out) {
+    double m[4];
+    CLB_CUDA(h, cudaMemcpyAsync(m, h->metrics.p, sizeof m, cudaMemcpyDeviceToHost, h->stream));
+    CLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    out->loss = m[0]; out->nll = m[1]; out->kl = m[2]; out->grad_norm = m[3];
+  }
+  return CLB_OK;
+}
+
+int clb_reduce_buffers(clb_handle* h, void** gf, int64_t* nf, void** sd, int64_t* nd) {
+  if (!h) return CLB_ERR_INVALID;
+  if (gf) *gf = h->grad.as<float>() + 2 * h->R;
+  if (nf) *nf = h->P - 2 * h->R;
+  if (sd) *sd = h->red.p;
+  if (nd) *nd = 2 + 2 * h->vt.n_vars;
+  return CLB_OK;
+}
+
+int clb_step(clb_handle* h, int32_t n_steps, const float* inj_u_f, const float* inj_eps_s,
+             clb_metrics* out, int32_t* steps_done) {
+  if (!h || n_steps <= 0) return fail(h, CLB_ERR_INVALID, "clb_step: n_steps must be positive");
+  if (h->cfg.world_size > 1) return fail(h, CLB_ERR_STATE, "clb_step is single-GPU; with world_size > 1 drive clb_step_begin/_norms/_end around the all-reduces");
+  int rc = ensure_metrics(h, n_steps); if (rc) return rc;
+  {
+    const int big = 0x7fffffff;   // a new train_model call starts with a clean early-stop state
+    CLB_CUDA(h, cudaSetDevice(h->cfg.device));
+    CLB_CUDA(h, cudaMemcpyAsync(h->stop_step.p, &big, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  }
+  const int first_step = (int)h->step_counter;
+  const int64_t t0 = h->adam_t;
+  for (int i = 0; i < n_steps; ++i) {
+    const float* u = inj_u_f ? inj_u_f + (size_t)i * h->R * h->S : nullptr;
+    const float* e = inj_eps_s ? inj_eps_s + (size_t)i * h->n_rows_total * h->S : nullptr;
+    rc = step_begin_impl(h, u, e); if (rc) return rc;
+    rc = step_norms_impl(h); if (rc) return rc;
+    rc = step_end_impl(h, h->metrics.as<double>() + 4 * i); if (rc) return rc;
+  }
+  std::vector<double> m((size_t)4 * n_steps);
+  int stop = 0;
+  CLB_CUDA(h, cudaMemcpyAsync(m.data(), h->metrics.p, sizeof(double) * 4 * n_steps, cudaMemcpyDeviceToHost, h->stream));
+  CLB_CUDA(h, cudaMemcpyAsync(&stop, h->stop_step.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CLB_CUDA(h, cudaStreamSynchronize(h->stream));
+  int done = n_steps;
+  if (stop != 0x7fffffff && stop >= first_step) {      // variational.py:271-274
+    done = std::min(n_steps, stop - first_step + 1);
+    h->adam_t = t0 + done;
+  }
+  if (out) for (int i = 0; i < done; ++i) { out[i].loss = m[4 * i]; out[i].nll = m[4 * i + 1]; out[i].kl = m[4 * i + 2]; out[i].grad_norm = m[4 * i + 3]; }
+  if (steps_done) *steps_done = done;
+  return CLB_OK;
+}
+
+}  // extern "C"

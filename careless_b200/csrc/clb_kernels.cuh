@@ -1,0 +1,566 @@
+// clb_kernels.cuh -- CUDA kernels of the ELBO gradient + Adam step (sm_100a).
+//
+// Step = k_refl_sample -> [k_dw_prior] -> k_obs -> k_reduce_partials -> k_refl_backward
+//        -> k_var_sumsq -> (all-reduce) -> k_finalize -> k_adam
+// See DESIGN.md for the data layout and the roofline of each kernel.
+#pragma once
+#include "clb_math.cuh"
+
+namespace clb {
+
+constexpr int kMaxLayers = 48;       // MLP layers incl. the Dense(2) head
+constexpr int kObsThreads = 256;     // observations per CTA tile (one per thread)
+constexpr int kMaxVars = 2 * kMaxLayers + 8;
+
+// scalar accumulators (double) of one step
+enum { ACC_LOGQ_MINUS_LOGP = 0, ACC_LL = 1, ACC_SUMSQ_RAW = 2, ACC_SUMSQ_FILT = 3, ACC_NONFINITE = 4, ACC_COUNT = 8 };
+
+// ---------------------------------------------------------------------------------------
+// Per-reflection forward: reparameterised truncated-normal draw, log q, Wilson log p.
+// One thread per (sample, reflection).  Initialises gz with the KL part of dL/dz.
+// (variational.py:154, :123-139; surrogate_posteriors.py:50-53; wilson.py:50-57)
+// ---------------------------------------------------------------------------------------
+struct ReflArgs {
+  const float* v_loc; const float* v_scale;       // (R)
+  const uint8_t* centric; const float* eps_sigma; // (R): centric flag, epsilon*Sigma
+  const int32_t* dw_parent;                       // (R) or null; -2 root, -1 absent, >=0 parent
+  const uint32_t* refl_index;                     // (R) global index for the RNG
+  const float* inj_u;                             // (S,R) or null
+  float* z; float* gz;                            // (S,R)
+  double* acc;
+  int64_t R; int S; float eps; float cq;          // cq: KL coefficient per element
+  uint64_t seed; uint32_t step;
+};
+
+__global__ void __launch_bounds__(256) k_refl_sample(ReflArgs a) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double kl = 0.0;
+  if (idx < a.R * a.S) {
+    const int64_t r = idx % a.R;
+    const int s = (int)(idx / a.R);
+    const bool centric = a.centric[r] != 0;
+    const float low = centric ? 0.0f : 1e-32f;     // manager.py:434
+    const float u = a.inj_u ? a.inj_u[idx] : refl_uniform(a.seed, a.step, (uint32_t)s, a.refl_index[r]);
+    const TnSample t = tn_forward(a.v_loc[r], a.v_scale[r], low, a.eps, u);
+    a.z[idx] = t.z;
+    float g = t.dlogq_dz;
+    float term = t.logq;
+    const bool wilson = (a.dw_parent == nullptr) || (a.dw_parent[r] == -2);
+    if (wilson) {
+      float lp, dlp;
+      wilson_logp(t.z, centric, a.eps_sigma[r], lp, dlp);
+      term -= lp;
+      g -= dlp;
+    }
+    a.gz[idx] = a.cq * g;
+    kl = (double)term;
+  }
+  kl = warp_sum(kl);
+  __shared__ double sm[8];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = kl;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += sm[i];
+    atomicAdd(&a.acc[ACC_LOGQ_MINUS_LOGP], t);
+  }
+}
+
+// DoubleWilson conditional prior for non-root entries (wilson.py:146-175): needs every z.
+struct DwArgs {
+  const float* z; float* gz;                      // (S,R)
+  const uint8_t* centric; const float* eps_sigma; const int32_t* dw_parent; const int32_t* asu_id;
+  const float* r_const;                           // (n_asu) fixed r, or
+  const float* r_logit; float* g_r_logit;         // trainable logits + their gradient (optimize_r)
+  double* acc;
+  int64_t R; int S; float cq;
+};
+
+__global__ void __launch_bounds__(256) k_dw_prior(DwArgs a) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double kl = 0.0;
+  if (idx < a.R * a.S) {
+    const int64_t r = idx % a.R;
+    const int64_t s = idx / a.R;
+    const int parent = a.dw_parent[r];
+    if (parent != -2) {
+      const bool centric = a.centric[r] != 0;
+      const int asu = a.asu_id[r];
+      const float rr = a.r_logit ? sigmoidf(a.r_logit[asu]) : a.r_const[asu];
+      const float zp = parent >= 0 ? a.z[s * a.R + parent] : 0.0f;
+      const float loc = zp * rr;
+      const float es = a.eps_sigma[r];
+      const float s2 = (centric ? 1.0f : 0.5f) * es * (1.0f - rr * rr);
+      float lp, dz, dloc, ds2;
+      dw_child_logp(a.z[idx], loc, s2, centric, lp, dz, dloc, ds2);
+      kl = -(double)lp;
+      atomicAdd(&a.gz[idx], -a.cq * dz);
+      if (parent >= 0) atomicAdd(&a.gz[s * a.R + parent], -a.cq * dloc * rr);
+      if (a.r_logit) {
+        const float ds2_dr = -(centric ? 2.0f : 1.0f) * es * rr;
+        const float dlp_dr = dloc * zp + ds2 * ds2_dr;
+        atomicAdd(&a.g_r_logit[asu], -a.cq * dlp_dr * rr * (1.0f - rr));
+      }
+    }
+  }
+  kl = warp_sum(kl);
+  __shared__ double sm[8];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = kl;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += sm[i];
+    atomicAdd(&a.acc[ACC_LOGQ_MINUS_LOGP], t);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Observation kernel: scale MLP forward, scale sample, gather of z_f, likelihood, backward
+// through everything, segmented reduction of dL/dz_f, per-CTA weight-gradient partials.
+// (variational.py:156-171; scaling/nn.py:92-120; scaling/image.py:40-63; likelihoods/*.py)
+// ---------------------------------------------------------------------------------------
+struct MlpLayout {                 // flat (keras-order) parameter layout of the scale MLP
+  int n_layers;                    // L + 1 (last = Dense(2) head)
+  int in_dim[kMaxLayers], out_dim[kMaxLayers];
+  int koff[kMaxLayers], boff[kMaxLayers];   // offsets of kernel / bias inside the MLP group
+  int n_params;
+};
+
+struct ObsArgs {
+  // rows (device layout: sorted + padded, SoA)
+  const int32_t* refl; const int32_t* image; const int32_t* spot; const uint32_t* oidx;
+  const float* meta;               // [d][Npad]
+  const float* iobs; const float* sig;
+  int64_t n_rows;                  // Npad
+  int64_t n_rows_total;            // stride of injected eps (global N)
+  int d;
+  // model
+  const float* theta_mlp; const float* theta_img;   // image scales (n_img-1) or null
+  MlpLayout lay;
+  const float* z; float* gz; int64_t R; int S;
+  const float* inj_eps;            // (S, N_total) or null
+  float* g_img;                    // gradient of image scales or null
+  float* partials;                 // [grid*KS][n_params]
+  float4* scratch;                 // [grid][L][WP/4][T]
+  float* ipred_out;                // (S, N_total) original order, or null
+  double* acc;
+  LikConst lik; float cl;          // likelihood coefficient (1/S or 1/(S*N))
+  int bijector; float shift; float eps;
+  uint64_t seed; uint32_t step;
+  int laue; int train_mlp;
+};
+
+template <int WP> struct ObsSmem {
+  static constexpr int T = kObsThreads;
+  static constexpr int HS = T + 4;                    // padded stride of the transposed activation tile
+  static size_t bytes(int n_layers) {
+    return sizeof(float) * ((size_t)n_layers * WP * WP + (size_t)n_layers * WP   // W, b
+                            + (size_t)n_layers * WP                                // bias-grad accumulators
+                            + (size_t)WP * HS + (size_t)T * WP) + 64 * sizeof(double);
+  }
+};
+
+// One layer's weight gradient over the CTA tile: dW[i][j] = sum_obs a[obs][i] * dp[obs][j].
+// a is staged transposed (S_h[i][obs]), dp row-major with XOR-swizzled float4 chunks.
+template <int WP>
+__device__ __forceinline__ void stage_and_accumulate(const float (&ain)[WP], const float (&dp)[WP],
+                                                     float* S_h, float4* S_d, float* dbacc_k,
+                                                     float* part_rows, int koff, int boff, int in_dim, int out_dim,
+                                                     int tid) {
+  constexpr int T = kObsThreads, HS = T + 4, NC = WP / 4;
+  constexpr int TPL = WP * NC;            // threads covering one WPxWP matrix with 1x4 patches
+  constexpr int KS = T / TPL;             // K (observation) split
+  static_assert(KS >= 1, "WP too large for the tile");
+  __syncthreads();                        // previous consumer of the staging buffers is done
+#pragma unroll
+  for (int i = 0; i < WP; ++i) S_h[i * HS + tid] = ain[i];
+#pragma unroll
+  for (int c = 0; c < NC; ++c)
+    S_d[tid * NC + (c ^ (tid & (NC - 1)))] = make_float4(dp[4 * c], dp[4 * c + 1], dp[4 * c + 2], dp[4 * c + 3]);
+  __syncthreads();
+  const int pi = tid % WP, pjq = (tid / WP) % NC, ks = tid / TPL;   // part_rows already points at row ks
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int o0 = ks * (T / KS);
+#pragma unroll 4
+  for (int o = o0; o < o0 + T / KS; o += 4) {
+    const float4 h4 = *reinterpret_cast<const float4*>(&S_h[pi * HS + o]);
+    const float hv[4] = {h4.x, h4.y, h4.z, h4.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 d4 = S_d[(o + q) * NC + (pjq ^ ((o + q) & (NC - 1)))];
+      acc.x = fmaf(hv[q], d4.x, acc.x); acc.y = fmaf(hv[q], d4.y, acc.y);
+      acc.z = fmaf(hv[q], d4.z, acc.z); acc.w = fmaf(hv[q], d4.w, acc.w);
+    }
+  }
+  // read-modify-write of this CTA's private partial (exclusive ownership: no atomics)
+  if (pi < in_dim) {
+    const float av[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int j = 4 * pjq + c;
+      if (j < out_dim) part_rows[koff + pi * out_dim + j] += av[c];
+    }
+  }
+  // bias gradient: column sums of dp
+  {
+    constexpr int G = T / WP;
+    const int j = tid % WP, g = tid / WP;
+    float s = 0.f;
+    for (int o = g * (T / G); o < (g + 1) * (T / G); ++o) {
+      const float4 d4 = S_d[o * NC + ((j >> 2) ^ (o & (NC - 1)))];
+      s += (j & 3) == 0 ? d4.x : (j & 3) == 1 ? d4.y : (j & 3) == 2 ? d4.z : d4.w;
+    }
+    if (j < out_dim) atomicAdd(&dbacc_k[j], s);
+  }
+  (void)boff;
+}
+
+template <int WP, int LIK>
+__global__ void __launch_bounds__(kObsThreads, 1) k_obs(ObsArgs a) {
+  constexpr int T = kObsThreads, HS = T + 4, NC = WP / 4;
+  constexpr int TPL = WP * NC, KS = T / TPL;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int NL = a.lay.n_layers;          // incl. head
+  const int L = NL - 1;                   // hidden layers
+  float* Wsm = reinterpret_cast<float*>(smem_raw);          // [NL][WP][WP]
+  float* bsm = Wsm + (size_t)NL * WP * WP;                  // [NL][WP]
+  float* dbacc = bsm + (size_t)NL * WP;                     // [NL][WP]
+  float* S_h = dbacc + (size_t)NL * WP;                     // [WP][HS]
+  float4* S_d = reinterpret_cast<float4*>(S_h + (size_t)WP * HS);   // [T][NC]
+  double* red = reinterpret_cast<double*>(reinterpret_cast<float*>(S_d) + (size_t)T * WP);
+
+  const int tid = threadIdx.x, lane = tid & 31;
+  // ---- stage the weights (zero padded to WP x WP) ----
+  for (int idx = tid; idx < NL * WP * WP; idx += T) {
+    const int k = idx / (WP * WP), i = (idx / WP) % WP, j = idx % WP;
+    float w = 0.f;
+    if (i < a.lay.in_dim[k] && j < a.lay.out_dim[k]) w = a.theta_mlp[a.lay.koff[k] + i * a.lay.out_dim[k] + j];
+    Wsm[idx] = w;
+  }
+  for (int idx = tid; idx < NL * WP; idx += T) {
+    const int k = idx / WP, j = idx % WP;
+    bsm[idx] = (j < a.lay.out_dim[k]) ? a.theta_mlp[a.lay.boff[k] + j] : 0.f;
+    dbacc[idx] = 0.f;
+  }
+  __syncthreads();
+
+  float* part_rows = a.partials + ((size_t)blockIdx.x * KS + (tid / TPL)) * a.lay.n_params;
+  float4* scr = a.scratch + (size_t)blockIdx.x * L * NC * T;
+  double ll_sum = 0.0;
+  const int64_t n_tiles = (a.n_rows + T - 1) / T;
+
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t row = tile * T + tid;
+    const bool inb = row < a.n_rows;
+    const int refl = inb ? a.refl[row] : -1;
+    const bool active = refl >= 0;
+    // ---------------- forward ----------------
+    float h[WP];
+#pragma unroll
+    for (int i = 0; i < WP; ++i) h[i] = (inb && i < a.d) ? a.meta[(size_t)i * a.n_rows + row] : 0.f;
+    for (int k = 0; k < L; ++k) {
+      const float* Wk = Wsm + (size_t)k * WP * WP;
+      float o[WP];
+#pragma unroll
+      for (int j = 0; j < WP; ++j) o[j] = bsm[k * WP + j];
+#pragma unroll
+      for (int i = 0; i < WP; ++i) {
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          const float4 w = *reinterpret_cast<const float4*>(&Wk[i * WP + 4 * c]);
+          o[4 * c] = fmaf(h[i], w.x, o[4 * c]); o[4 * c + 1] = fmaf(h[i], w.y, o[4 * c + 1]);
+          o[4 * c + 2] = fmaf(h[i], w.z, o[4 * c + 2]); o[4 * c + 3] = fmaf(h[i], w.w, o[4 * c + 3]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < WP; ++j) h[j] = o[j] > 0.f ? o[j] : kLeak * o[j];
+      if (a.train_mlp) {
+#pragma unroll
+        for (int c = 0; c < NC; ++c) scr[((size_t)k * NC + c) * T + tid] = make_float4(h[4 * c], h[4 * c + 1], h[4 * c + 2], h[4 * c + 3]);
+      }
+    }
+    float out0, out1;
+    {
+      const float* Wk = Wsm + (size_t)L * WP * WP;
+      out0 = bsm[L * WP]; out1 = bsm[L * WP + 1];
+#pragma unroll
+      for (int i = 0; i < WP; ++i) {
+        const float2 w = *reinterpret_cast<const float2*>(&Wk[i * WP]);
+        out0 = fmaf(h[i], w.x, out0); out1 = fmaf(h[i], w.y, out1);
+      }
+    }
+    // ---------------- scale sample, gather, likelihood ----------------
+    float sig_s, dsig;
+    if (a.bijector == 0) { dsig = expf(out1); sig_s = dsig + a.eps; }
+    else { sig_s = softplusf(out1) + a.eps; dsig = sigmoidf(out1); }
+    const int img = (a.image != nullptr && inb) ? a.image[row] : 0;
+    const float aimg = (a.theta_img != nullptr && img > 0) ? a.theta_img[img - 1] : 1.0f;
+    const uint32_t oi = inb ? a.oidx[row] : 0u;
+    const float iobs = inb ? a.iobs[row] : 0.f;
+    const float sg = inb ? a.sig[row] : 1.f;
+    const int spot = (a.laue && inb) ? a.spot[row] : -1 - lane;   // unique keys when not Laue
+    float dmu = 0.f, drho = 0.f, d_aimg = 0.f;
+    for (int s = 0; s < a.S; ++s) {
+      float e = 0.f;
+      if (active) e = a.inj_eps ? a.inj_eps[(size_t)s * a.n_rows_total + oi] : obs_normal(a.seed, a.step, (uint32_t)s, oi);
+      const float base = fmaf(sig_s, e, out0) + a.shift;
+      const float zs = aimg * base;
+      const float zf = active ? __ldg(&a.z[(size_t)s * a.R + refl]) : 0.f;
+      const float ip = zs * zf * zf;
+      if (a.ipred_out != nullptr && active) a.ipred_out[(size_t)s * a.n_rows_total + oi] = ip;
+      float x = ip;
+      bool eval = active;
+      if (a.laue) {           // harmonic segment-sum within the warp (spots never straddle a warp)
+        const float tot = warp_segsum(active ? ip : 0.f, spot, lane);
+        const bool tail = warp_run_tail(spot, lane);
+        const unsigned tails = __ballot_sync(0xffffffffu, tail);
+        const int my_tail = __ffs(tails >> lane) - 1 + lane;
+        x = __shfl_sync(0xffffffffu, tot, my_tail);
+        eval = active && tail;   // count each spot once
+      }
+      float ll = 0.f, g = 0.f;
+      if (active) lik_eval<LIK>(x, iobs, sg, a.lik, ll, g);
+      if (eval) ll_sum += (double)ll;
+      const float G = active ? a.cl * g : 0.f;
+      const float d_zs = G * zf * zf;
+      const float d_zf = G * zs * 2.0f * zf;
+      // segmented reduction of dL/dz_f over runs of equal refl_id, one atomic per run
+      {
+        const int key = active ? refl : -1 - lane;
+        const float tot = warp_segsum(d_zf, key, lane);
+        if (active && warp_run_tail(key, lane)) atomicAdd(&a.gz[(size_t)s * a.R + refl], tot);
+      }
+      const float d_base = aimg * d_zs;
+      d_aimg += base * d_zs;
+      dmu += d_base;
+      drho += d_base * e * dsig;
+    }
+    if (a.g_img != nullptr) {
+      const int key = (active && img > 0) ? img : -1 - lane;
+      const float tot = warp_segsum(d_aimg, key, lane);
+      if (key > 0 && warp_run_tail(key, lane)) atomicAdd(&a.g_img[img - 1], tot);
+    }
+    if (!a.train_mlp) continue;
+    // ---------------- backward through the MLP ----------------
+    float dp[WP], ain[WP];
+#pragma unroll
+    for (int j = 0; j < WP; ++j) dp[j] = 0.f;
+    dp[0] = dmu; dp[1] = drho;
+    // head: dW_out = a_L^T [dmu, drho]
+    stage_and_accumulate<WP>(h, dp, S_h, S_d, dbacc + L * WP, part_rows, a.lay.koff[L], a.lay.boff[L],
+                             a.lay.in_dim[L], a.lay.out_dim[L], tid);
+    {
+      const float* Wk = Wsm + (size_t)L * WP * WP;
+#pragma unroll
+      for (int i = 0; i < WP; ++i) {
+        const float2 w = *reinterpret_cast<const float2*>(&Wk[i * WP]);
+        dp[i] = w.x * dmu + w.y * drho;          // delta a_L
+      }
+    }
+    // h currently holds a_L (output of hidden layer L-1)
+    for (int k = L - 1; k >= 0; --k) {
+      // delta p_k = delta a_{k+1} * leaky'(a_{k+1});  sign(a) == sign(pre-activation)
+#pragma unroll
+      for (int j = 0; j < WP; ++j) dp[j] = h[j] > 0.f ? dp[j] : kLeak * dp[j];
+      if (k > 0) {
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          const float4 v = scr[((size_t)(k - 1) * NC + c) * T + tid];
+          ain[4 * c] = v.x; ain[4 * c + 1] = v.y; ain[4 * c + 2] = v.z; ain[4 * c + 3] = v.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < WP; ++i) ain[i] = (inb && i < a.d) ? a.meta[(size_t)i * a.n_rows + row] : 0.f;
+      }
+      stage_and_accumulate<WP>(ain, dp, S_h, S_d, dbacc + k * WP, part_rows, a.lay.koff[k], a.lay.boff[k],
+                               a.lay.in_dim[k], a.lay.out_dim[k], tid);
+      if (k > 0) {
+        const float* Wk = Wsm + (size_t)k * WP * WP;
+        float da[WP];
+#pragma unroll
+        for (int i = 0; i < WP; ++i) {
+          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+          for (int c = 0; c < NC; ++c) {
+            const float4 w = *reinterpret_cast<const float4*>(&Wk[i * WP + 4 * c]);
+            s0 = fmaf(w.x, dp[4 * c], s0); s1 = fmaf(w.y, dp[4 * c + 1], s1);
+            s2 = fmaf(w.z, dp[4 * c + 2], s2); s3 = fmaf(w.w, dp[4 * c + 3], s3);
+          }
+          da[i] = (s0 + s1) + (s2 + s3);
+        }
+#pragma unroll
+        for (int i = 0; i < WP; ++i) { dp[i] = da[i]; h[i] = ain[i]; }
+      }
+    }
+  }
+  // ---- flush: bias gradients and the log-likelihood sum ----
+  __syncthreads();
+  if (a.train_mlp) {
+    for (int idx = tid; idx < NL * WP; idx += T) {
+      const int k = idx / WP, j = idx % WP;
+      if (j < a.lay.out_dim[k]) a.partials[(size_t)blockIdx.x * KS * a.lay.n_params + a.lay.boff[k] + j] += dbacc[idx];
+    }
+  }
+  ll_sum = warp_sum(ll_sum);
+  if (lane == 0) red[tid >> 5] = ll_sum;
+  __syncthreads();
+  if (tid == 0) {
+    double t = 0.0;
+    for (int i = 0; i < T / 32; ++i) t += red[i];
+    atomicAdd(&a.acc[ACC_LL], t);
+  }
+}
+
+// Sum the per-CTA partial weight gradients: grad[p] = sum_rows partials[row][p]  (deterministic order).
+__global__ void __launch_bounds__(256) k_reduce_partials(const float* partials, int rows, int n_params, float* grad) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_params) return;
+  float s = 0.f;
+  for (int r = 0; r < rows; ++r) s += partials[(size_t)r * n_params + p];
+  grad[p] = s;
+}
+
+// ---------------------------------------------------------------------------------------
+// Per-reflection backward: chain dL/dz to (v_loc, v_scale).  One thread per reflection.
+// ---------------------------------------------------------------------------------------
+struct ReflBwdArgs {
+  const float* v_loc; const float* v_scale; const uint8_t* centric; const uint32_t* refl_index;
+  const float* inj_u; const float* gz;
+  float* g_loc; float* g_scale;
+  int64_t R; int S; float eps; float cq; uint64_t seed; uint32_t step;
+};
+
+__global__ void __launch_bounds__(256) k_refl_backward(ReflBwdArgs a) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= a.R) return;
+  const bool centric = a.centric[r] != 0;
+  const float low = centric ? 0.0f : 1e-32f;
+  const float vl = a.v_loc[r], vs = a.v_scale[r];
+  float gmu = 0.f, gsig = 0.f, mu = 0.f, sigma = 0.f;
+  for (int s = 0; s < a.S; ++s) {
+    const int64_t idx = (int64_t)s * a.R + r;
+    const float u = a.inj_u ? a.inj_u[idx] : refl_uniform(a.seed, a.step, (uint32_t)s, a.refl_index[r]);
+    const TnSample t = tn_forward(vl, vs, low, a.eps, u);
+    const float g = a.gz[idx];
+    gmu += g * t.dz_dmu + a.cq * t.dlogq_dmu;
+    gsig += g * t.dz_dsigma + a.cq * t.dlogq_dsigma;
+    mu = t.mu; sigma = t.sigma;
+  }
+  a.g_loc[r] = gmu * mu;                 // d mu / d v_loc = mu
+  a.g_scale[r] = gsig * (sigma - a.eps); // d sigma / d v_scale = exp(v_scale)
+}
+
+// ---------------------------------------------------------------------------------------
+// Optimiser: per-variable sums of squares, finalize (norms, clip factors, metrics), Adam.
+// ---------------------------------------------------------------------------------------
+struct VarTable {
+  int n_vars;
+  int64_t off[kMaxVars], size[kMaxVars];
+  int trainable[kMaxVars];
+  int replicated[kMaxVars];     // 1: gradient is all-reduced across ranks (count its norm once)
+};
+
+// grid = (chunks, n_vars).  sums[2*v] = raw sum of squares (NaN/inf propagate), sums[2*v+1] = filtered.
+__global__ void __launch_bounds__(256) k_var_sumsq(const float* grad, VarTable vt, double* sums) {
+  const int v = blockIdx.y;
+  if (!vt.trainable[v]) return;
+  const int64_t n = vt.size[v];
+  const float* g = grad + vt.off[v];
+  double raw = 0.0, filt = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float x = g[i];
+    const double x2 = (double)x * (double)x;
+    raw += x2;
+    if (isfinite(x)) filt += x2;
+  }
+  raw = warp_sum(raw); filt = warp_sum(filt);
+  __shared__ double sm[2][8];
+  if ((threadIdx.x & 31) == 0) { sm[0][threadIdx.x >> 5] = raw; sm[1][threadIdx.x >> 5] = filt; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    for (int i = 0; i < 8; ++i) { a += sm[0][i]; b += sm[1][i]; }
+    if (a != 0.0) atomicAdd(&sums[2 * v], a);      // NaN != 0 is true, so NaN propagates
+    if (b != 0.0) atomicAdd(&sums[2 * v + 1], b);
+  }
+}
+
+struct FinalizeArgs {
+  const double* acc;            // local accumulators
+  double* red;                  // reduce scalars: [0]=logq-logp sum, [1]=ll sum, [2..]=per-var sums (2 each)
+  VarTable vt;
+  double* metrics;              // [4] loss nll kl gradnorm for this step
+  float* var_scale;             // per-variable gradient scale from clipping
+  float* adam_alpha;            // [1]
+  int* stop_step; int step;
+  double kl_div, kl_coef, ll_div;   // kl = sum/kl_div ; loss = kl_coef*kl - ll/ll_div
+  float clipnorm, global_clipnorm;
+  float lr, beta1, beta2; int64_t t;   // t = step index (1-based) for bias correction
+};
+
+// Packs the local scalars into the reduce buffer (so one all-reduce covers them).
+__global__ void k_pack_scalars(const double* acc, const double* var_sums, VarTable vt, double* red, int rank,
+                               double ll_const) {
+  const int i = threadIdx.x;
+  if (i == 0) red[0] = acc[ACC_LOGQ_MINUS_LOGP];
+  if (i == 1) red[1] = acc[ACC_LL] + ll_const;   // + constant log-density of this rank's empty Laue slots
+  if (i < vt.n_vars) {
+    // replicated variables hold the same (all-reduced) gradient on every rank: count them once
+    const bool mine = !vt.replicated[i] || rank == 0;
+    red[2 + 2 * i] = mine ? var_sums[2 * i] : 0.0;
+    red[3 + 2 * i] = mine ? var_sums[2 * i + 1] : 0.0;
+  }
+}
+
+__global__ void k_finalize(FinalizeArgs a) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const double kl = a.red[0] / a.kl_div;
+  const double ll = a.red[1] / a.ll_div;
+  double raw = 0.0, filt = 0.0;
+  for (int v = 0; v < a.vt.n_vars; ++v) {
+    if (!a.vt.trainable[v]) continue;
+    raw += a.red[2 + 2 * v];
+    filt += a.red[3 + 2 * v];
+  }
+  const double gn = sqrt(raw);
+  a.metrics[0] = a.kl_coef * kl - ll;
+  a.metrics[1] = -ll;
+  a.metrics[2] = kl;
+  a.metrics[3] = gn;
+  const float gscale = (a.global_clipnorm > 0.f) ? (float)(a.global_clipnorm / fmax(sqrt(filt), (double)a.global_clipnorm)) : 1.0f;
+  for (int v = 0; v < a.vt.n_vars; ++v) {
+    float sc = 1.0f;
+    if (a.clipnorm > 0.f) sc = (float)(a.clipnorm / fmax(sqrt(a.red[3 + 2 * v]), (double)a.clipnorm));
+    a.var_scale[v] = sc * gscale;
+  }
+  const double t = (double)a.t;
+  a.adam_alpha[0] = (float)(a.lr * sqrt(1.0 - pow((double)a.beta2, t)) / (1.0 - pow((double)a.beta1, t)));
+  if (!isfinite(gn) && a.step < *a.stop_step) *a.stop_step = a.step;
+}
+
+// grid = (chunks, n_vars).  [3P] tf_keras Adam.update_step; non-finite gradient elements -> 0 (variational.py:208).
+__global__ void __launch_bounds__(256) k_adam(float* theta, float* m, float* v, const float* grad, VarTable vt,
+                                              const float* var_scale, const float* adam_alpha,
+                                              float clipvalue, float beta1, float beta2, float adam_eps,
+                                              const int* stop_step, int step) {
+  const int var = blockIdx.y;
+  if (!vt.trainable[var]) return;
+  // variational.py:271-274: the loop breaks AFTER the step whose norm was non-finite has been
+  // applied (with the filtered gradient); later enqueued steps must not touch the state.
+  if (step > *stop_step) return;
+  const float sc = var_scale[var];
+  const float alpha = adam_alpha[0];
+  const int64_t n = vt.size[var], off = vt.off[var];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float g = grad[off + i];
+    g = isfinite(g) ? g * sc : 0.f;
+    if (clipvalue > 0.f) g = fminf(fmaxf(g, -clipvalue), clipvalue);
+    float mi = m[off + i], vi = v[off + i];
+    mi += (g - mi) * (1.0f - beta1);
+    vi += (g * g - vi) * (1.0f - beta2);
+    m[off + i] = mi; v[off + i] = vi;
+    theta[off + i] -= alpha * mi / (sqrtf(vi) + adam_eps);
+  }
+}
+
+}  // namespace clb

@@ -1,0 +1,215 @@
+// clb_math.cuh -- scalar device math shared by the kernels of libcareless_b200.
+//
+// FP32 restatement of the per-element formulas of the reference hot path
+// (/root/reference: careless/models/merging/surrogate_posteriors.py:45-131,
+//  careless/models/priors/wilson.py:13-175, careless/utils/distributions.py:228-348,
+//  careless/models/likelihoods/mono.py:10-37), with closed-form backward passes
+// (SURVEY.md appendix B).  Everything here is pure (no memory access).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <float.h>
+#include <math.h>
+
+#define CLB_DEV __device__ __forceinline__
+
+namespace clb {
+
+constexpr float kLog2Pi = 1.8378770664093453f;
+constexpr float kInvSqrt2Pi = 0.3989422804014327f;
+constexpr float kHigh = 1e10f;           // surrogate_posteriors.py:105
+constexpr float kLeak = 0.01f;           // scaling/nn.py:32
+
+// ---------------------------------------------------------------------------------------
+// Philox4x32-10 (same stream as oracle/philox.py)
+// ---------------------------------------------------------------------------------------
+constexpr uint32_t kPhiloxM0 = 0xD2511F53u, kPhiloxM1 = 0xCD9E8D57u;
+constexpr uint32_t kPhiloxW0 = 0x9E3779B9u, kPhiloxW1 = 0xBB67AE85u;
+constexpr uint32_t kStreamRefl = 0u, kStreamObs = 1u;
+
+CLB_DEV uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(kPhiloxM0, c0), lo0 = kPhiloxM0 * c0;
+    uint32_t hi1 = __umulhi(kPhiloxM1, c2), lo1 = kPhiloxM1 * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += kPhiloxW0; k1 += kPhiloxW1;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+
+// uint32 -> (0,1) on the 24-bit grid; exact in float32, never 0 or 1.
+CLB_DEV float u01(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+
+CLB_DEV float refl_uniform(uint64_t seed, uint32_t step, uint32_t s, uint32_t refl_index) {
+  uint4 x = philox4x32_10(refl_index, s, step, kStreamRefl, (uint32_t)seed, (uint32_t)(seed >> 32));
+  return u01(x.x);
+}
+
+CLB_DEV float obs_normal(uint64_t seed, uint32_t step, uint32_t s, uint32_t obs_index) {
+  uint4 x = philox4x32_10(obs_index, s, step, kStreamObs, (uint32_t)seed, (uint32_t)(seed >> 32));
+  float u1 = u01(x.x), u2 = u01(x.y);
+  return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+}
+
+// ---------------------------------------------------------------------------------------
+// Truncated-normal surrogate: reparameterised draw, log-density and their derivatives
+// ---------------------------------------------------------------------------------------
+struct TnSample {
+  float mu, sigma;     // loc = exp(v_loc), scale = exp(v_scale) + eps
+  float z;             // max(low, mu + sigma e)
+  float ez;            // standardised value of z
+  float dz_dmu, dz_dsigma;       // reparameterisation gradient (0 where the max clamps)
+  float logq;                    // log q(z)
+  float dlogq_dz;                // d log q / d z
+  float dlogq_dmu, dlogq_dsigma; // explicit partials at fixed z
+};
+
+// u in (0,1).  [3P] tfd.TruncatedNormal sampler gradient: de/dalpha = exp((e^2-a^2)/2)(1-u'),
+// de/dbeta = exp((e^2-b^2)/2) u', u' = clip(u, FLT_MIN, 1-FLT_EPS).
+CLB_DEV TnSample tn_forward(float v_loc, float v_scale, float low, float eps, float u) {
+  TnSample t;
+  t.mu = expf(v_loc);
+  t.sigma = expf(v_scale) + eps;
+  const float inv_s = 1.0f / t.sigma;
+  const float alpha = (low - t.mu) * inv_s;
+  const float beta = (kHigh - t.mu) * inv_s;
+  const float Pa = normcdff(alpha);
+  const float Qb = normcdff(-beta);                 // upper tail mass beyond high
+  const float Z = normcdff(-alpha) - Qb;            // Phi(beta) - Phi(alpha)
+  const float p = fmaf(u, Z, Pa);
+  const float q = fmaf(1.0f - u, Z, Qb);            // 1 - p without cancellation
+  const float e = (p < 0.5f) ? normcdfinvf(p) : -normcdfinvf(q);
+  const float x = fmaf(t.sigma, e, t.mu);
+  const bool free_ = x > low;                       // tf.maximum(low, s): grad only where s > low
+  t.z = free_ ? x : low;
+  t.ez = free_ ? e : alpha;
+  const float uc = fminf(fmaxf(u, FLT_MIN), 1.0f - FLT_EPSILON);
+  const float dl = expf(0.5f * (e * e - alpha * alpha)) * (1.0f - uc);
+  const float du = expf(0.5f * (e * e - beta * beta)) * uc;
+  t.dz_dmu = free_ ? (1.0f - dl - du) : 0.0f;
+  const float bdu = (du == 0.0f) ? 0.0f : beta * du;
+  t.dz_dsigma = free_ ? (e - alpha * dl - bdu) : 0.0f;
+  const float phi_a = kInvSqrt2Pi * expf(-0.5f * alpha * alpha);
+  const float phi_b = kInvSqrt2Pi * expf(-0.5f * beta * beta);
+  const float b_phi_b = (phi_b == 0.0f) ? 0.0f : beta * phi_b;
+  const float invZ = 1.0f / Z;
+  t.logq = -0.5f * t.ez * t.ez - 0.5f * kLog2Pi - logf(t.sigma) - logf(Z);
+  t.dlogq_dz = -t.ez * inv_s;
+  t.dlogq_dmu = t.ez * inv_s - (phi_a - phi_b) * inv_s * invZ;
+  t.dlogq_dsigma = (t.ez * t.ez - 1.0f) * inv_s - (alpha * phi_a - b_phi_b) * inv_s * invZ;
+  return t;
+}
+
+// ---------------------------------------------------------------------------------------
+// Wilson prior (wilson.py:13-57): value and d/dz.  es = epsilon * Sigma.
+// ---------------------------------------------------------------------------------------
+CLB_DEV void wilson_logp(float z, bool centric, float es, float& lp, float& dlp_dz) {
+  if (centric) {   // HalfNormal(sqrt(es))
+    lp = 0.5f * logf(2.0f / 3.14159265358979f) - 0.5f * logf(es) - 0.5f * z * z / es;
+    dlp_dz = -z / es;
+  } else {         // Weibull(k=2, lambda=sqrt(es))
+    lp = logf(2.0f) + logf(z) - logf(es) - z * z / es;
+    dlp_dz = 1.0f / z - 2.0f * z / es;
+  }
+}
+
+// log I0(x) - |x| = log(i0e(x)) and rho(x) = I1(x)/I0(x), x >= 0.
+// Small x: CUDA cyl_bessel_i{0,1}f; large x: Hankel asymptotic series (error < 1e-7 for x >= 15).
+CLB_DEV void log_i0e_and_ratio(float x, float& log_i0e, float& rho) {
+  x = fabsf(x);
+  if (x < 15.0f) {
+    const float i0 = cyl_bessel_i0f(x), i1 = cyl_bessel_i1f(x);
+    log_i0e = logf(i0) - x;
+    rho = i1 / i0;
+  } else {
+    const float y = 1.0f / x;
+    // I0e ~ (2 pi x)^-1/2 * P0(y),  I1e ~ (2 pi x)^-1/2 * P1(y)
+    const float p0 = 1.0f + y * (0.125f + y * (0.0703125f + y * (0.0732421875f + y * (0.112152099609375f
+                     + y * (0.22710800170898438f + y * 0.5725014209747314f)))));
+    const float p1 = 1.0f - y * (0.375f + y * (0.1171875f + y * (0.1025390625f + y * (0.144195556640625f
+                     + y * (0.2775764465332031f + y * 0.6765925884246826f)))));
+    log_i0e = logf(p0) - 0.5f * logf(6.283185307179586f * x);
+    rho = p1 / p0;
+  }
+}
+
+// DoubleWilson child density (wilson.py:146-175; distributions.py:278-283, 300-335).
+// s2 = scale^2.  Returns log p and its partials wrt z, loc and s2.
+CLB_DEV void dw_child_logp(float z, float loc, float s2, bool centric,
+                           float& lp, float& d_z, float& d_loc, float& d_s2) {
+  const float inv = 1.0f / s2;
+  const float x = z * loc * inv;
+  const float quad = (z * z + loc * loc) * inv;
+  if (centric) {   // folded normal: log[N(z;loc,s)+N(-z;loc,s)]
+    const float ax = fabsf(x);
+    const float t = tanhf(x);
+    lp = -0.5f * kLog2Pi - 0.5f * logf(s2) - 0.5f * quad + ax + log1pf(expf(-2.0f * ax));
+    d_z = (-z + t * loc) * inv;
+    d_loc = (-loc + t * z) * inv;
+    d_s2 = (-0.5f + 0.5f * quad - t * x) * inv;
+  } else {         // Rice(nu=loc, sigma^2=s2)
+    float li0e, rho;
+    log_i0e_and_ratio(x, li0e, rho);
+    if (x < 0.0f) rho = -rho;
+    lp = logf(z) - logf(s2) - 0.5f * quad + li0e + fabsf(x);
+    d_z = 1.0f / z + (-z + rho * loc) * inv;
+    d_loc = (-loc + rho * z) * inv;
+    d_s2 = (-1.0f + 0.5f * quad - rho * x) * inv;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Likelihoods (mono.py:16-37): log-density of x under loc/scale, and d(-ll)/dx.
+// ---------------------------------------------------------------------------------------
+struct LikConst { float dof, half_dofp1, lnorm; };   // lnorm = lgamma((v+1)/2)-lgamma(v/2)-0.5 log(v pi)
+
+template <int LIK>
+CLB_DEV void lik_eval(float x, float loc, float scale, const LikConst& c, float& ll, float& dnll_dx) {
+  const float inv = 1.0f / scale;
+  const float t = (x - loc) * inv;
+  if (LIK == 0) {
+    ll = -0.5f * t * t - logf(scale) - 0.5f * kLog2Pi;
+    dnll_dx = t * inv;
+  } else {
+    ll = c.lnorm - logf(scale) - c.half_dofp1 * log1pf(t * t / c.dof);
+    dnll_dx = 2.0f * c.half_dofp1 * t / (c.dof + t * t) * inv;
+  }
+}
+
+CLB_DEV float softplusf(float x) { return (x > 15.0f) ? x + log1pf(expf(-x)) : log1pf(expf(x)); }
+CLB_DEV float sigmoidf(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// ---------------------------------------------------------------------------------------
+// warp helpers
+// ---------------------------------------------------------------------------------------
+CLB_DEV double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+CLB_DEV float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Inclusive segmented sum over runs of equal keys in consecutive lanes.  After the call the
+// LAST lane of every run holds the run total.  All 32 lanes must participate.
+CLB_DEV float warp_segsum(float v, int key, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float ov = __shfl_up_sync(0xffffffffu, v, o);
+    const int ok = __shfl_up_sync(0xffffffffu, key, o);
+    if (lane >= o && ok == key) v += ov;
+  }
+  return v;
+}
+// true for the last lane of each run of equal keys
+CLB_DEV bool warp_run_tail(int key, int lane) {
+  const int nk = __shfl_down_sync(0xffffffffu, key, 1);
+  return (lane == 31) || (nk != key);
+}
+
+}  // namespace clb

@@ -1,0 +1,181 @@
+/*
+ * careless_b200.h -- C-ABI of libcareless_b200.so: the B200-native ELBO-gradient + Adam step
+ * of careless's VariationalMergingModel.
+ *
+ * The reference (rs-station/careless v0.5.4) is pure Python over TensorFlow and defines NO
+ * FFI of its own; the boundary it exposes for this path is the Python object protocol of
+ *   careless/models/merging/variational.py:15      VariationalMergingModel(...)
+ *   careless/models/merging/variational.py:226     train_model(data, steps, ...)
+ *   careless/models/merging/variational.py:185     train_step_with_gradient_norm(...)
+ *   careless/io/manager.py:380                     DataManager.build_model(...)
+ * Each entry point below names the reference interface it replaces.  All functions return
+ * 0 on success and a negative clb_status on failure; clb_last_error() gives the message.
+ * Host arrays are borrowed for the duration of the call and copied; device memory is
+ * owned by the handle.  A handle is bound to one CUDA device and one stream and is not
+ * thread-safe.  There is no CPU fallback: clb_create() fails without an sm_100 device.
+ */
+#ifndef CARELESS_B200_H
+#define CARELESS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CLB_ABI_VERSION 1
+
+typedef struct clb_handle clb_handle;
+
+typedef enum {
+  CLB_OK = 0,
+  CLB_ERR_INVALID = -1,     /* bad argument / unsupported configuration */
+  CLB_ERR_CUDA = -2,        /* CUDA runtime error (message has the cudaError string) */
+  CLB_ERR_NO_DEVICE = -3,   /* no sm_100 device: the library never falls back to the CPU */
+  CLB_ERR_STATE = -4        /* call order violated (e.g. step before set_observations) */
+} clb_status;
+
+/* likelihood kinds: careless/models/likelihoods/mono.py:16-37, laue.py:68-100 */
+enum { CLB_LIK_NORMAL = 0, CLB_LIK_STUDENTT = 1 };
+/* prior kinds: careless/models/priors/wilson.py:29-80 (Wilson), :82-175 (DoubleWilson) */
+enum { CLB_PRIOR_WILSON = 0, CLB_PRIOR_DOUBLE_WILSON = 1 };
+/* scale bijector: careless/io/manager.py:450-463 (--scale-bijector exp|softplus) */
+enum { CLB_BIJ_EXP = 0, CLB_BIJ_SOFTPLUS = 1 };
+/* row order chosen by the host prep inside clb_set_observations */
+enum { CLB_ORDER_AUTO = 0, CLB_ORDER_REFL = 1, CLB_ORDER_SPOT = 2, CLB_ORDER_IMAGE = 3, CLB_ORDER_NONE = 4 };
+
+/* parameter groups for clb_get_params / clb_set_params / clb_get_grads / clb_set_trainable.
+ * They are the reference's trainable variables:
+ *   SF_LOC, SF_SCALE  surrogate_posteriors.py:104-131 (raw, i.e. inverse-bijected values)
+ *   MLP               scaling/nn.py:55-79, keras order [kernel_0, bias_0, ..., kernel_out, bias_out]
+ *   IMAGE_SCALES      scaling/image.py:21   (n_images-1 values; image 0 is pinned to 1)
+ *   DW_R              priors/wilson.py:105-110 (logits of r, one per ASU; --optimize-double-wilson-r)
+ */
+enum { CLB_GROUP_SF_LOC = 0, CLB_GROUP_SF_SCALE = 1, CLB_GROUP_MLP = 2, CLB_GROUP_IMAGE_SCALES = 3,
+       CLB_GROUP_DW_R = 4, CLB_N_GROUPS = 5 };
+
+/* Everything DataManager.build_model (careless/io/manager.py:380-507) decides, flattened. */
+typedef struct {
+  int32_t abi_version;        /* = CLB_ABI_VERSION */
+  int32_t device;             /* CUDA device ordinal */
+  void*   stream;             /* cudaStream_t to run on; NULL = library-owned stream */
+
+  int64_t n_refl;             /* R: surrogate entries held by this handle (all ASU reflections) */
+  int64_t n_refl_total;       /* R over all ranks (= n_refl on one GPU); used by --kl-weight mean */
+  int32_t n_meta;             /* d: metadata columns */
+  int32_t mlp_width;          /* W   (--mlp-width, args/scaling.py:27-31) */
+  int32_t mlp_layers;         /* L   (--mlp-layers, args/scaling.py:21-25) */
+  int32_t n_images;           /* max(image_id)+1 when image scales are on, else 0 */
+  int32_t image_scales;       /* HybridImageScaler(MLPScaler, ImageScaler): manager.py:484-487 */
+  int32_t mc_samples;         /* S   (--mc-samples, args/common.py:11-15) */
+  int32_t likelihood;         /* CLB_LIK_* */
+  float   dof;                /* --studentt-likelihood-dof */
+  int32_t laue;               /* careless poly: harmonic segment-sum before the likelihood */
+  int32_t prior;              /* CLB_PRIOR_* */
+  int32_t n_asu;              /* DoubleWilson: number of ASUs (length of r) */
+  int32_t optimize_dw_r;      /* --optimize-double-wilson-r */
+  int32_t scale_bijector;     /* CLB_BIJ_* */
+  float   scale_shift;        /* additive tfb.Shift(scale_multiplier), scaling/nn.py:84-87; 0 = none */
+  float   epsilon;            /* --epsilon (args/common.py:38-42) */
+  int32_t use_kl_weight;      /* 0: 'sum' reduction (default); 1: kl_weight * mean, variational.py:172-177 */
+  float   kl_weight;
+
+  /* tf_keras Adam built at manager.py:494-501; defaults args/optimizer.py:5-45 */
+  float   learning_rate, beta_1, beta_2, adam_epsilon;
+  float   clipnorm, clipvalue, global_clipnorm;   /* <= 0 means "not set" */
+
+  uint64_t seed;              /* Philox key for in-kernel draws (--seed, args/tf_options.py:50-54) */
+  int32_t rank, world_size;   /* reflection-partitioned data parallelism; 0,1 on one GPU */
+} clb_config;
+
+/* Per-step metrics: the keys of the history dict returned by train_model (variational.py:214-224, 262-268). */
+typedef struct {
+  double loss;        /* "loss"      = kl_term - log-likelihood term */
+  double nll;         /* "NLL"       */
+  double kl;          /* "F KLDiv"   */
+  double grad_norm;   /* "Grad Norm" (global norm BEFORE the non-finite filter, :205) */
+} clb_metrics;
+
+int clb_abi_version(void);
+const char* clb_last_error(const clb_handle* h);   /* h may be NULL: error of the last failed clb_create */
+
+/* Replaces: VariationalMergingModel.__init__ + DataManager.build_model + model.compile
+ * (variational.py:15-45, manager.py:380-507).  Parameters start at the reference's
+ * initial values (identity MLP, image scales 1); the surrogate is initialised by
+ * clb_set_prior (prior mean / stddev, manager.py:432-436). */
+int clb_create(const clb_config* cfg, clb_handle** out);
+void clb_destroy(clb_handle* h);
+
+/* Replaces: tf.convert_to_tensor of the input tuple at careless/careless.py:62 and the
+ * accessors of careless/models/base.py:22-121.  Arrays are in the REFERENCE layout
+ * (formatter.py:382-400 / :631-653): int64 ids of shape (N,[1]), metadata (N,d) row-major
+ * float32, intensities/uncertainties float32 (Laue: the n_spots per-spot values first, then
+ * 1.0 padding).  harmonic_id == NULL for mono.  obs_index (optional, NULL = 0..N-1) is the
+ * GLOBAL row index of each observation (used as RNG counter and to look up injected draws);
+ * refl_id indexes this handle's n_refl surrogate entries.
+ * The call sorts/pads the rows into the device layout and uploads them. */
+int clb_set_observations(clb_handle* h, int64_t n_rows, int64_t n_rows_total,
+                         const int64_t* refl_id, const int64_t* image_id,
+                         const float* metadata, const float* intensities, const float* uncertainties,
+                         const int64_t* harmonic_id, const int64_t* obs_index, int32_t order);
+/* Re-upload of the already prepared (pinned) device-layout rows: the host->device copy of
+ * one step's inputs, used by the end-to-end measurement. */
+int clb_upload_observations(clb_handle* h);
+
+/* Replaces: WilsonPrior / DoubleWilsonPrior construction (priors/wilson.py:29-49, 82-138) and
+ * the surrogate initialisation of manager.py:432-436.  centric (R) uint8, multiplicity (R),
+ * sigma (R) Wilson Sigma.  DoubleWilson only (else NULL): dw_parent (R) int32 = surrogate index
+ * of the parent reflection, -1 = parent absent, -2 = root entry; asu_id (R) int32; r (n_asu).
+ * refl_index (optional) = global reflection index per entry (RNG counter).  init_scale is
+ * --structure-factor-init-scale; pass a negative value to leave the surrogate untouched. */
+int clb_set_prior(clb_handle* h, const uint8_t* centric, const float* multiplicity, const float* sigma,
+                  const int32_t* dw_parent, const int32_t* asu_id, const float* r,
+                  const int64_t* refl_index, float init_scale);
+
+/* Replaces: keras get_weights/set_weights, save_weights/load_weights (careless.py:48-56,79-80)
+ * and `.trainable = False` (careless.py:50-56,104). */
+int64_t clb_group_size(const clb_handle* h, int32_t group);
+int clb_get_params(clb_handle* h, int32_t group, float* out, int64_t n);
+int clb_set_params(clb_handle* h, int32_t group, const float* in, int64_t n);
+int clb_get_grads(clb_handle* h, int32_t group, float* out, int64_t n);      /* of the last step (pre-filter) */
+int clb_get_adam_state(clb_handle* h, int32_t group, float* m, float* v, int64_t n, int64_t* t);
+int clb_set_trainable(clb_handle* h, int32_t group, int32_t trainable);
+
+/* Replaces: the hot loop train_model -> train_step_with_gradient_norm
+ * (variational.py:255-256, :185-224): n_steps full-batch ELBO gradient + Adam steps.
+ * inj_u_f  (n_steps, S, R)        uniforms in (0,1) for the truncated-normal surrogate, or NULL
+ * inj_eps_s(n_steps, S, N_total)  standard normals for the scale sample, indexed by obs_index, or NULL
+ * (NULL => in-kernel Philox4x32-10 keyed by seed/step/index).  metrics_out (n_steps) may be NULL.
+ * Stops early after a step whose gradient norm is non-finite (:271-274); returns the number
+ * of steps taken in *steps_done (may be NULL). */
+int clb_step(clb_handle* h, int32_t n_steps, const float* inj_u_f, const float* inj_eps_s,
+             clb_metrics* metrics_out, int32_t* steps_done);
+
+/* Multi-GPU form of one step, split around the two all-reduces (sum) over NCCL:
+ *   clb_step_begin  -> kernels up to the local gradients
+ *   (caller all-reduces the float32 buffer: gradients of the replicated groups MLP / image scales / r)
+ *   clb_step_norms  -> per-variable gradient norms; packs {sum(log q - log p), sum(ll), norms} as float64
+ *   (caller all-reduces the float64 scalar buffer)
+ *   clb_step_end    -> global grad norm, non-finite filter, clipping, Adam; metrics
+ * Both buffers (device pointers, owned by the handle) come from clb_reduce_buffers.
+ * With world_size == 1, clb_step() is exactly begin + norms + end without the all-reduces. */
+int clb_step_begin(clb_handle* h, const float* inj_u_f, const float* inj_eps_s);
+int clb_step_norms(clb_handle* h);
+int clb_step_end(clb_handle* h, clb_metrics* metrics_out);
+int clb_reduce_buffers(clb_handle* h, void** grads_f32, int64_t* n_f32, void** scalars_f64, int64_t* n_f64);
+
+/* Debug / parity hooks (variational.py:154,167): sampled structure factors z_f (S,R) and
+ * predicted intensities ipred (S,N) in the caller's original row order, from the last step. */
+int clb_get_samples(clb_handle* h, float* z_f, int64_t n);
+int clb_enable_ipred(clb_handle* h, int32_t enable);
+int clb_get_ipred(clb_handle* h, float* ipred, int64_t n);
+int clb_synchronize(clb_handle* h);
+
+/* Device timing of the dominant kernel (CUDA events on the handle's stream), for bench.py's roofline. */
+int clb_kernel_time_ms(clb_handle* h, double* obs_kernel_ms_sum, int64_t* obs_kernel_launches, int64_t* total_launches);
+int clb_reset_timers(clb_handle* h, int32_t enable_event_timing);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CARELESS_B200_H */

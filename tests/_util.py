@@ -1,0 +1,116 @@
+"""Shared helpers of the test-suite: oracle <-> engine parameter plumbing and comparison."""
+import numpy as np
+import torch
+
+from oracle import model as om
+from careless_b200.engine import Engine, EngineConfig
+
+
+def mlp_names(cfg):
+    names = []
+    for k in range(cfg.mlp_layers):
+        names += [f"mlp.{k}.kernel", f"mlp.{k}.bias"]
+    names += ["mlp.out.kernel", "mlp.out.bias"]
+    return names
+
+
+def mlp_flat(params, cfg):
+    return np.concatenate([np.asarray(params[n].detach().cpu().numpy(), dtype=np.float64).reshape(-1) for n in mlp_names(cfg)])
+
+
+def mlp_unflat(flat, like, cfg):
+    out, off = {}, 0
+    for n in mlp_names(cfg):
+        sz = like[n].numel()
+        out[n] = torch.as_tensor(np.asarray(flat[off:off + sz], dtype=np.float64).reshape(tuple(like[n].shape)))
+        off += sz
+    return out
+
+
+def build(problem, *, mlp_width, mlp_layers, likelihood="normal", dof=None, laue=False, prior="wilson",
+          mc_samples=1, kl_weight=None, scale_bijector="exp", scale_shift=None, image_scales=False,
+          optimize_dw_r=False, sigma=1.0, opt=None, seed=1234, eps=1e-7):
+    """(oracle cfg, oracle prior, engine) for a synthetic problem dict from careless_b200.synth."""
+    R = len(problem["centric"])
+    d = problem["metadata"].shape[1]
+    n_images = int(problem["n_images"])
+    ocfg = om.ModelConfig(n_refl=R, n_meta=d, mlp_width=mlp_width, mlp_layers=mlp_layers, likelihood=likelihood,
+                          dof=dof, laue=laue, prior=prior, mc_samples=mc_samples, kl_weight=kl_weight,
+                          scale_bijector=scale_bijector, scale_shift=scale_shift, eps=eps,
+                          image_scales=image_scales, n_images=n_images, optimize_dw_r=optimize_dw_r)
+    oprior = om.PriorData(centric=problem["centric"], multiplicity=problem["multiplicity"], sigma=sigma,
+                          reflids=problem.get("reflids"), root=problem.get("root"), asu_ids=problem.get("asu_id"),
+                          r=problem.get("r"))
+    opt = opt or om.AdamConfig()
+    ecfg = EngineConfig(n_refl=R, n_meta=d, mlp_width=mlp_width, mlp_layers=mlp_layers, n_images=n_images,
+                        image_scales=image_scales, mc_samples=mc_samples, likelihood=likelihood, dof=dof, laue=laue,
+                        prior=prior, n_asu=int(problem.get("n_asu", 0)), optimize_dw_r=optimize_dw_r,
+                        scale_bijector=scale_bijector, scale_shift=scale_shift, epsilon=eps, kl_weight=kl_weight,
+                        learning_rate=opt.lr, beta_1=opt.beta1, beta_2=opt.beta2, adam_epsilon=opt.eps,
+                        clipnorm=opt.clipnorm, clipvalue=opt.clipvalue, global_clipnorm=opt.global_clipnorm, seed=seed)
+    eng = Engine(ecfg)
+    eng.set_observations(problem["refl_id"], problem["image_id"], problem["metadata"], problem["intensities"],
+                         problem["uncertainties"], harmonic_id=problem.get("harmonic_id") if laue else None)
+    sig = None if np.isscalar(sigma) and sigma == 1.0 else np.broadcast_to(np.asarray(sigma, dtype=np.float32), (R,))
+    eng.set_prior(problem["centric"], problem["multiplicity"], sig, dw_parent=problem.get("dw_parent") if prior == "double_wilson" else None,
+                  asu_id=problem.get("asu_id") if prior == "double_wilson" else None,
+                  r=problem.get("r") if prior == "double_wilson" else None)
+    return ocfg, oprior, eng
+
+
+def perturbed_params(ocfg, oprior, rng, amount=0.1):
+    """Reference initial parameters plus noise, rounded to float32 so both sides start identical."""
+    p = om.init_params(ocfg, oprior)
+    for k in p:
+        noise = amount * rng.standard_normal(tuple(p[k].shape))
+        p[k] = torch.as_tensor((p[k].numpy() + noise).astype(np.float32).astype(np.float64))
+    return p
+
+
+def push_params(eng, params, ocfg):
+    eng.set_params("sf_loc_raw", params["sf_loc_raw"].numpy())
+    eng.set_params("sf_scale_raw", params["sf_scale_raw"].numpy())
+    eng.set_params("mlp", mlp_flat(params, ocfg))
+    if "image_scales" in params:
+        eng.set_params("image_scales", params["image_scales"].numpy())
+    if "dw_r_logit" in params:
+        eng.set_params("dw_r_logit", params["dw_r_logit"].numpy())
+
+
+def pull_params(eng, like, ocfg):
+    out = {"sf_loc_raw": torch.as_tensor(eng.get_params("sf_loc_raw").astype(np.float64)),
+           "sf_scale_raw": torch.as_tensor(eng.get_params("sf_scale_raw").astype(np.float64))}
+    out.update(mlp_unflat(eng.get_params("mlp"), like, ocfg))
+    if "image_scales" in like:
+        out["image_scales"] = torch.as_tensor(eng.get_params("image_scales").astype(np.float64))
+    if "dw_r_logit" in like:
+        out["dw_r_logit"] = torch.as_tensor(eng.get_params("dw_r_logit").astype(np.float64))
+    return out
+
+
+def engine_grads(eng, ocfg, like):
+    g = {"sf_loc_raw": eng.get_grads("sf_loc_raw").astype(np.float64),
+         "sf_scale_raw": eng.get_grads("sf_scale_raw").astype(np.float64),
+         "mlp": eng.get_grads("mlp").astype(np.float64)}
+    if "image_scales" in like:
+        g["image_scales"] = eng.get_grads("image_scales").astype(np.float64)
+    if "dw_r_logit" in like:
+        g["dw_r_logit"] = eng.get_grads("dw_r_logit").astype(np.float64)
+    return g
+
+
+def oracle_grads_grouped(g, ocfg):
+    out = {"sf_loc_raw": g["sf_loc_raw"].numpy(), "sf_scale_raw": g["sf_scale_raw"].numpy()}
+    if all(n in g for n in mlp_names(ocfg)):
+        out["mlp"] = mlp_flat(g, ocfg)
+    for k in ("image_scales", "dw_r_logit"):
+        if k in g:
+            out[k] = g[k].numpy()
+    return out
+
+
+def rel_err(a, b):
+    """max |a-b| / (|b| + 1e-3*max|b|): elementwise relative error with a floor tied to the array scale."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    scale = np.max(np.abs(b)) if b.size else 1.0
+    return float(np.max(np.abs(a - b) / (np.abs(b) + 1e-3 * scale + 1e-30))) if b.size else 0.0

@@ -1,0 +1,204 @@
+"""GPU parity: the CUDA step (through the C-ABI) vs the float64 CPU oracle on identical inputs.
+
+Tolerances (north_star: rtol 1e-4, FP32):
+* scalars (loss, NLL, KL, grad norm): relative 1e-4;
+* gradients / parameters: ``_util.rel_err`` <= 1e-4, i.e. |a-b| <= 1e-4 (|b| + 1e-3 max|b|) -- a
+  relative test whose floor is tied to the scale of the array (FP32 sums over thousands of
+  observations cannot be relatively exact on elements that cancel to ~0).
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from careless_b200 import synth
+from oracle import model as om
+from oracle import philox
+
+import _util as U
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4
+
+
+def _draws(rng, S, R, N, n_steps=1):
+    u = rng.random((n_steps, S, R))
+    u = (np.floor(u * 2 ** 24) + 0.5) / 2 ** 24          # on the float32-exact grid
+    e = rng.standard_normal((n_steps, S, N)).astype(np.float32).astype(np.float64)
+    return u, e
+
+
+def _compare_step(problem, label, frozen=(), **kw):
+    rng = np.random.default_rng(7)
+    ocfg, oprior, eng = U.build(problem, **kw)
+    try:
+        params = U.perturbed_params(ocfg, oprior, rng)
+        U.push_params(eng, params, ocfg)
+        for f in frozen:
+            eng.set_trainable(f, False)
+        S, R, N = ocfg.mc_samples, ocfg.n_refl, len(problem["refl_id"])
+        u, e = _draws(rng, S, R, N)
+        eng.enable_ipred(True)
+        hist = eng.step(1, u_f=u, eps_s=e)
+        ofrozen = tuple(frozen)
+        metrics, g, out = om.loss_and_grads(params, problem, oprior, ocfg, u[0], e[0], frozen=ofrozen)
+        z = eng.get_samples()
+        ip = eng.get_ipred()
+        errs = {
+            "z_f": U.rel_err(z, out["z_f"].detach().numpy()),
+            "ipred": U.rel_err(ip, out["ipred"].detach().numpy()),
+        }
+        for k in ("loss", "NLL", "F KLDiv", "Grad Norm"):
+            errs[k] = abs(hist[0][k] - metrics[k]) / (abs(metrics[k]) + 1e-12)
+        ge = U.engine_grads(eng, ocfg, params)
+        go = U.oracle_grads_grouped(g, ocfg)
+        for k in go:
+            errs["g:" + k] = U.rel_err(ge[k], go[k])
+        print(f"\n[{label}] " + "  ".join(f"{k}={v:.2e}" for k, v in errs.items()))
+        print(f"[{label}] metrics gpu={hist[0]}  oracle={metrics}")
+        bad = {k: v for k, v in errs.items() if not (v <= RTOL)}
+        assert not bad, f"{label}: parity failures {bad}"
+    finally:
+        eng.close()
+
+
+def test_mono_normal_small():
+    p = synth.make_mono(3000, 400, d=3, n_images=11, seed=1)
+    _compare_step(p, "mono-normal-W8L3", mlp_width=8, mlp_layers=3)
+
+
+def test_mono_studentt_hybrid_default_mlp():
+    p = synth.make_mono(5000, 700, d=2, n_images=23, seed=2)
+    _compare_step(p, "mono-t-hybrid-W10L20", mlp_width=10, mlp_layers=20, likelihood="studentt", dof=12.0,
+                  image_scales=True, mc_samples=2)
+
+
+def test_mono_w32_l20():
+    p = synth.make_mono(9000, 900, d=5, n_images=30, seed=3)
+    _compare_step(p, "mono-t-W32L20", mlp_width=32, mlp_layers=20, likelihood="studentt", dof=12.0)
+
+
+def test_mono_no_hidden_layers_and_softplus_shift():
+    p = synth.make_mono(2000, 300, d=4, n_images=5, seed=4)
+    _compare_step(p, "mono-L0-softplus", mlp_width=4, mlp_layers=0, scale_bijector="softplus", scale_shift=0.75,
+                  image_scales=True)
+
+
+def test_kl_weight_mean_reduction():
+    p = synth.make_mono(2500, 350, d=3, n_images=7, seed=5)
+    _compare_step(p, "mono-klw", mlp_width=6, mlp_layers=4, kl_weight=2.5, mc_samples=3)
+
+
+def test_wilson_b_sigma():
+    p = synth.make_mono(2500, 350, d=3, n_images=7, seed=6)
+    rng = np.random.default_rng(0)
+    sigma = np.exp(-0.25 * 20.0 * rng.random(350) * 0.04).astype(np.float32)     # manager.py:43-46
+    _compare_step(p, "mono-wilson-b", mlp_width=6, mlp_layers=4, sigma=sigma)
+
+
+def test_laue_normal():
+    p = synth.make_laue(6000, 800, d=4, n_images=40, seed=7)
+    _compare_step(p, "laue-normal", mlp_width=12, mlp_layers=5, laue=True, image_scales=True)
+
+
+def test_laue_studentt_gaps():
+    p = synth.make_laue(4000, 500, d=3, n_images=20, seed=8)
+    _compare_step(p, "laue-t", mlp_width=8, mlp_layers=3, laue=True, likelihood="studentt", dof=4.0, mc_samples=2)
+
+
+@pytest.mark.parametrize("optimize_r", [False, True])
+def test_double_wilson(optimize_r):
+    p = synth.make_double_wilson(1500, 250, n_datasets=3, d=3, n_images=6, r=0.95, seed=9)
+    # exercise absent parents too
+    p["dw_parent"] = p["dw_parent"].copy(); p["reflids"] = p["reflids"].copy()
+    child = np.where(p["dw_parent"] >= 0)[0][::7]
+    p["dw_parent"][child] = -1; p["reflids"][child] = -1
+    _compare_step(p, f"dw-opt{int(optimize_r)}", mlp_width=8, mlp_layers=3, prior="double_wilson", optimize_dw_r=optimize_r)
+
+
+def test_frozen_scaler():
+    p = synth.make_mono(2000, 300, d=3, n_images=5, seed=10)
+    _compare_step(p, "frozen-mlp", frozen=("mlp",), mlp_width=8, mlp_layers=3)
+
+
+@pytest.mark.parametrize("clip", ["none", "clipnorm", "clipvalue", "global_clipnorm"])
+def test_adam_trajectory(clip):
+    """Five full steps: parameters, Adam moments and the metric history follow the oracle."""
+    p = synth.make_mono(3000, 300, d=3, n_images=9, seed=11)
+    opt = om.AdamConfig(lr=1e-2)
+    if clip == "clipnorm": opt.clipnorm = 5.0
+    if clip == "clipvalue": opt.clipvalue = 0.5
+    if clip == "global_clipnorm": opt.global_clipnorm = 20.0
+    rng = np.random.default_rng(3)
+    ocfg, oprior, eng = U.build(p, mlp_width=8, mlp_layers=4, image_scales=True, opt=opt)
+    try:
+        params = U.perturbed_params(ocfg, oprior, rng, amount=0.05)
+        U.push_params(eng, params, ocfg)
+        n = 5
+        u, e = _draws(rng, 1, ocfg.n_refl, len(p["refl_id"]), n)
+        hist = eng.step(n, u_f=u, eps_s=e)
+        oparams, ohist, ostate = om.train(params, p, oprior, ocfg, opt, [(u[i], e[i]) for i in range(n)])
+        assert len(hist) == n
+        for i in range(n):
+            for k in ("loss", "NLL", "F KLDiv", "Grad Norm"):
+                assert abs(hist[i][k] - ohist[i][k]) <= 2e-4 * abs(ohist[i][k]) + 1e-6, (i, k, hist[i], ohist[i])
+        got = U.pull_params(eng, params, ocfg)
+        errs = {k: U.rel_err(got[k].numpy(), oparams[k].numpy()) for k in got}
+        print(f"\n[adam-{clip}] " + "  ".join(f"{k}={v:.2e}" for k, v in errs.items()))
+        assert max(errs.values()) <= 2e-4, errs
+        m, v, t = eng.get_adam_state("sf_loc_raw")
+        assert t == n
+        assert U.rel_err(m, ostate["m"]["sf_loc_raw"].numpy()) <= 1e-3
+    finally:
+        eng.close()
+
+
+def test_philox_mode_matches_oracle_stream():
+    """No injected draws: the in-kernel Philox stream equals oracle/philox.py, so parity still holds."""
+    p = synth.make_mono(3000, 400, d=3, n_images=9, seed=12)
+    rng = np.random.default_rng(5)
+    seed = 987654321123
+    ocfg, oprior, eng = U.build(p, mlp_width=8, mlp_layers=3, mc_samples=2, seed=seed)
+    try:
+        params = U.perturbed_params(ocfg, oprior, rng)
+        U.push_params(eng, params, ocfg)
+        hist = eng.step(2)
+        N = len(p["refl_id"])
+        draws = [(philox.refl_uniforms(seed, s, 2, np.arange(ocfg.n_refl)), philox.obs_normals(seed, s, 2, np.arange(N))) for s in range(2)]
+        _, ohist, _ = om.train(params, p, oprior, ocfg, om.AdamConfig(), draws)
+        for i in range(2):
+            for k in ("loss", "NLL", "F KLDiv", "Grad Norm"):
+                assert abs(hist[i][k] - ohist[i][k]) <= 2e-4 * abs(ohist[i][k]) + 1e-6, (i, k, hist[i], ohist[i])
+    finally:
+        eng.close()
+
+
+def test_nonfinite_gradient_stops_training():
+    """variational.py:208,271-274: non-finite elements are zeroed, the norm is reported, the loop stops."""
+    p = synth.make_mono(1000, 100, d=2, n_images=3, seed=13)
+    p["uncertainties"] = p["uncertainties"].copy()
+    p["uncertainties"][5] = 0.0                      # -> inf/nan in the likelihood gradient
+    ocfg, oprior, eng = U.build(p, mlp_width=4, mlp_layers=2)
+    try:
+        hist = eng.step(4)
+        assert len(hist) == 1
+        assert not math.isfinite(hist[0]["Grad Norm"])
+        assert np.all(np.isfinite(eng.get_params("mlp")))
+    finally:
+        eng.close()
+
+
+def test_errors_are_reported():
+    from careless_b200 import ClbError, EngineConfig, Engine
+    with pytest.raises(ClbError):
+        Engine(EngineConfig(n_refl=10, n_meta=3, mlp_width=64, mlp_layers=2))       # unsupported width
+    eng = Engine(EngineConfig(n_refl=10, n_meta=2, mlp_width=4, mlp_layers=1))
+    try:
+        with pytest.raises(ClbError):
+            eng.step(1)                                                              # no data yet
+        with pytest.raises(ClbError):
+            eng.set_observations(np.array([11]), None, np.zeros((1, 2)), np.ones(1), np.ones(1))   # refl_id out of range
+    finally:
+        eng.close()
