@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""bench.py -- reflection observations/sec through the ELBO gradient + Adam step.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--obs N] [--refl R]
+
+Workload at every N: BASELINE.json configs[1] per GPU ("synthetic mono: 10M observations, 500k unique
+reflections, StudentTLikelihood, MLPScaler width 32 x 20 layers"; d=5 metadata columns), i.e. weak
+scaling: each rank owns its own 500k reflections and their 10M observations; the scale-MLP gradients
+and the scalar ELBO terms are all-reduced over NCCL every step.
+
+One "step" = one full-batch ELBO gradient + Adam step over the resident observations.
+* value  : obs/s with the inputs resident in HBM (K steps, CUDA events on the launch stream, max over ranks)
+* e2e    : obs/s through the C-ABI with HOST buffers: every step re-uploads the prepared rows from pinned
+           host memory (clb_upload_observations), runs the step and reads the metrics back.
+* roofline: the dominant kernel (k_obs), timed live with CUDA events inside the same K steps.
+* cpu_baseline / --impl reference: the float32 torch-CPU restatement of the reference graph (oracle/,
+  "port": TensorFlow is not installable here) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "reflection observations/sec through ELBO grad+Adam step"
+UNIT = "obs/s"
+D_META, WIDTH, LAYERS, DOF = 5, 32, 20, 12.0
+
+
+def flops_per_obs(d=D_META, w=WIDTH, layers=LAYERS):
+    """forward + backward (dX, dW) of the scale MLP = 6 (dW + (L-1)W^2 + 2W)."""
+    return 6 * (d * w + (layers - 1) * w * w + 2 * w)
+
+
+def bytes_per_step(n_obs, n_refl, d=D_META):
+    """compulsory HBM bytes of the non-MLP stages: N(16+4d) + 72R (no image ids here: -4)."""
+    return n_obs * (12 + 4 * d + 4) + n_refl * 72
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"], "bf16_tflops_sustained": p.get("bf16_tflops_sustained"),
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------
+# reference arm / cpu baseline: float32 torch-CPU restatement of the reference graph
+# ----------------------------------------------------------------------------------------
+def cpu_reference(budget_s, n_obs, n_refl, steps=None, warmup=1):
+    import torch
+    from careless_b200 import synth
+    from oracle import model as om
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    p = synth.make_mono(n_obs, n_refl, d=D_META, n_images=max(2, n_obs // 2000), seed=1234)
+    cfg = om.ModelConfig(n_refl=n_refl, n_meta=D_META, mlp_width=WIDTH, mlp_layers=LAYERS, likelihood="studentt", dof=DOF)
+    prior = om.PriorData(p["centric"], p["multiplicity"])
+    params = om.init_params(cfg, prior, dtype=torch.float32)
+    state = om.adam_init(params)
+    opt = om.AdamConfig()
+    rng = np.random.default_rng(0)
+
+    def one(params):
+        u = rng.random((1, n_refl)).astype(np.float32) * 0.999 + 0.0005
+        e = rng.standard_normal((1, n_obs)).astype(np.float32)
+        _, g, _ = om.loss_and_grads(params, p, prior, cfg, u, e)
+        return om.adam_apply(params, g, state, opt)
+
+    for _ in range(warmup):
+        params = one(params)
+    done, t0 = 0, time.perf_counter()
+    while True:
+        params = one(params)
+        done += 1
+        el = time.perf_counter() - t0
+        if (steps is not None and done >= steps) or (steps is None and el >= budget_s and done >= 2):
+            break
+    el = time.perf_counter() - t0
+    return {"value": n_obs * done / el, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{done} steps x {n_obs} obs / {n_refl} reflections of the same config (float32 torch {torch.__version__} CPU restatement, "
+                      f"{el:.1f} s)", "ms_per_step": 1e3 * el / done}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_obs, n_refl = 500_000, 25_000
+    steps = max(1, min(args.steps, 6))
+    r = cpu_reference(20.0, n_obs, n_refl, steps=steps, warmup=min(args.warmup, 1))
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": min(args.warmup, 1), "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, 1), "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {"workload": f"BASELINE configs[1] per GPU: synthetic mono, {args.obs} obs, {args.refl} unique reflections, "
+                        f"StudentT(dof={DOF:g}), MLPScaler {WIDTH}x{LAYERS}, d={D_META}, WilsonPrior, 1 MC sample",
+            "obs_per_gpu": args.obs, "refl_per_gpu": args.refl, "world_size": world,
+            "l2_note": "inputs per step (>= 360 MB/GPU) exceed the 126 MB L2, no flush needed",
+            "parallelism": f"reflection-partitioned dp{world}" if world > 1 else "single GPU"}
+
+
+# ----------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------
+class _DevView:
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from careless_b200 import synth
+    from careless_b200.engine import Engine, EngineConfig
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: careless_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    stream = torch.cuda.current_stream()
+
+    N, R = args.obs, args.refl
+    p = synth.make_mono(N, R, d=D_META, n_images=5000, seed=1234 + rank)
+    cfg = EngineConfig(n_refl=R, n_refl_total=R * world, n_meta=D_META, mlp_width=WIDTH, mlp_layers=LAYERS,
+                       likelihood="studentt", dof=DOF, seed=1234, device=local, stream=stream.cuda_stream,
+                       rank=rank, world_size=world)
+    eng = Engine(cfg)
+    t_prep = time.perf_counter()
+    eng.set_observations(p["refl_id"], None, p["metadata"], p["intensities"], p["uncertainties"],
+                         obs_index=np.arange(N, dtype=np.int64) + rank * N, n_rows_total=N * world)
+    eng.set_prior(p["centric"], p["multiplicity"], refl_index=np.arange(R, dtype=np.int64) + rank * R)
+    eng.synchronize()
+    t_prep = time.perf_counter() - t_prep
+
+    if world > 1:
+        pf, nf, pd, nd = eng.reduce_buffers()
+        gbuf = torch.as_tensor(_DevView(pf, nf, "<f4"), device=f"cuda:{local}")
+        sbuf = torch.as_tensor(_DevView(pd, nd, "<f8"), device=f"cuda:{local}")
+
+    def step(want_metrics=False):
+        if world == 1:
+            return eng.step(1)[0] if want_metrics else (eng.step_begin(), eng.step_norms(), eng.step_end(False))
+        eng.step_begin()
+        dist.all_reduce(gbuf)
+        eng.step_norms()
+        dist.all_reduce(sbuf)
+        return eng.step_end(want_metrics)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+
+    # ---- timed region 1: resident inputs ----
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    eng.reset_timers(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    kt = eng.kernel_times()
+    eng.reset_timers(False)
+    last = step(True)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- timed region 2: end to end through the C-ABI with host buffers ----
+    h2d = 0
+    barrier()
+    t0 = time.perf_counter()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record(stream)
+    for _ in range(args.steps):
+        eng.upload_observations()          # pinned host -> device copy of this step's inputs
+        m = step(True)                     # device -> host read of the step's metrics (4 doubles)
+    e3.record(stream)
+    barrier()
+    ms_e2e = max(e2.elapsed_time(e3), 1e3 * (time.perf_counter() - t0))
+    h2d = N * (4 + 4 + 4 * D_META + 4 + 4)
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e, kt["obs_kernel_ms"]], device=f"cuda:{local}", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e, obs_ms = [float(x) for x in t.tolist()]
+    else:
+        obs_ms = kt["obs_kernel_ms"]
+
+    if rank == 0:
+        peaks = load_peaks()
+        ms_step = ms / args.steps
+        value = N * world * args.steps / (ms * 1e-3)
+        launches_per_step = kt["total_launches"] / max(1, args.steps)
+        obs_avg_ms = obs_ms / max(1, kt["obs_kernel_launches"])
+        tflops = N * flops_per_obs() / (obs_avg_ms * 1e-3) / 1e12
+        hbm_gbs = bytes_per_step(N, R) / (obs_avg_ms * 1e-3) / 1e9
+        fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12
+        roofline = {"kernel": "k_obs<32,studentt> (scale MLP fwd+bwd + likelihood + segmented dL/dz_f reduction)",
+                    "bound": "tensor", "achieved": tflops, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                    "frac": tflops / peaks["bf16_tflops"], "traffic": None, "peak_source": peaks["source"] + " bf16 cuBLAS burst",
+                    "note": "this round's k_obs runs the MLP on the FP32 FMA pipe (no tensor cores yet); fractions of the other roofs follow",
+                    "fp32_fma": {"achieved": tflops, "peak": fp32_peak, "frac": tflops / fp32_peak, "peak_source": "computed 148x128x2x1.965GHz"},
+                    "hbm": {"achieved": hbm_gbs, "peak": peaks["hbm_gbs"], "frac": hbm_gbs / peaks["hbm_gbs"], "unit": "GB/s",
+                            "algorithmic_bytes_per_step": bytes_per_step(N, R)},
+                    "kernel_ms": obs_avg_ms, "kernel_share_of_step": obs_avg_ms / ms_step,
+                    "flops_per_obs": flops_per_obs()}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu = cpu_reference(12.0, 250_000, 12_500)
+            cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": workload_config(args, world),
+                "e2e": {"value": N * world * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d * world,
+                        "d2h_bytes_per_step": 32 * world, "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": int(round(launches_per_step * args.steps)), "launches_per_step": launches_per_step,
+                "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+                "last_metrics": last, "host_prep_s": t_prep}
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--obs", type=int, default=10_000_000)
+    ap.add_argument("--refl", type=int, default=500_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

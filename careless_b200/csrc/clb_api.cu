@@ -195,6 +195,101 @@ double lik_logpdf_zero(const clb_config& c, double loc, double scale) {
          - 0.5 * (v + 1.0) * std::log1p(t * t / v);
 }
 
+// ---------------------------------------------------------------------------------------
+// Host prep: reference input tuple (base.py:22-31) -> sorted / padded SoA rows.
+//   mono: stable counting sort by refl_id  (segmented reduction of dL/dz_f inside warps)
+//   Laue: stable counting sort by harmonic_id; spots padded so none straddles a 32-row warp chunk
+// ---------------------------------------------------------------------------------------
+struct RowPlan {
+  int order = CLB_ORDER_REFL;
+  int64_t npad = 0;
+  double ll_const = 0.0;              // sum over empty Laue slots of logpdf(0; I_k, sigma_k)
+  std::vector<int32_t> perm;          // sorted position -> original row
+  std::vector<int64_t> pos;           // sorted position -> padded row
+};
+
+int plan_rows(std::string& err, RowPlan& plan, int64_t n, int64_t n_total, int64_t R, int n_images, int laue,
+              int likelihood, float dof, const int64_t* refl_id, const int64_t* image_id, const float* metadata,
+              const float* iobs, const float* sig, const int64_t* harmonic_id, const int64_t* obs_index, int order) {
+  char buf[256];
+  auto bad = [&](const char* fmt, long long a, long long b, long long c2) { snprintf(buf, sizeof buf, fmt, a, b, c2); err = buf; return 1; };
+  if (n <= 0 || !refl_id || !metadata || !iobs || !sig) { err = "clb_set_observations: null/empty input"; return 1; }
+  if (laue && !harmonic_id) { err = "Laue model needs harmonic_id"; return 1; }
+  if (n >= ((int64_t)1 << 31) - 64) return bad("n_rows %lld exceeds 2^31 per handle", n, 0, 0);
+  if (order == CLB_ORDER_AUTO) order = laue ? CLB_ORDER_SPOT : CLB_ORDER_REFL;
+  if (laue && order != CLB_ORDER_SPOT) { err = "Laue rows must use CLB_ORDER_SPOT"; return 1; }
+  if (!laue && order == CLB_ORDER_SPOT) { err = "CLB_ORDER_SPOT needs a Laue model"; return 1; }
+  if (order == CLB_ORDER_IMAGE && !image_id) { err = "CLB_ORDER_IMAGE needs image_id"; return 1; }
+  plan.order = order;
+  for (int64_t i = 0; i < n; ++i) {
+    if (refl_id[i] < 0 || refl_id[i] >= R) return bad("refl_id[%lld]=%lld outside [0,%lld)", i, refl_id[i], R);
+    if (n_images > 0 && image_id && (image_id[i] < 0 || image_id[i] >= n_images)) return bad("image_id[%lld]=%lld outside [0,%lld)", i, image_id[i], n_images);
+    if (obs_index && (obs_index[i] < 0 || obs_index[i] >= n_total)) return bad("obs_index[%lld]=%lld outside [0,%lld)", i, obs_index[i], n_total);
+    if (laue && (harmonic_id[i] < 0 || harmonic_id[i] >= n)) return bad("harmonic_id[%lld]=%lld outside [0,%lld)", i, harmonic_id[i], n);
+  }
+  std::vector<int32_t> key;
+  int64_t n_keys = 0;
+  if (order == CLB_ORDER_REFL) { key.resize(n); for (int64_t i = 0; i < n; ++i) key[i] = (int32_t)refl_id[i]; n_keys = R; }
+  else if (order == CLB_ORDER_SPOT) { key.resize(n); for (int64_t i = 0; i < n; ++i) key[i] = (int32_t)harmonic_id[i]; n_keys = n; }
+  else if (order == CLB_ORDER_IMAGE) {
+    int64_t mx = 0; for (int64_t i = 0; i < n; ++i) mx = std::max(mx, image_id[i]);
+    key.resize(n); for (int64_t i = 0; i < n; ++i) key[i] = (int32_t)image_id[i]; n_keys = mx + 1;
+  }
+  plan.perm.resize(n);
+  std::vector<int64_t> count;
+  if (n_keys > 0) {
+    count.assign((size_t)n_keys + 1, 0);
+    for (int64_t i = 0; i < n; ++i) count[key[i] + 1]++;
+    for (int64_t k = 0; k < n_keys; ++k) count[k + 1] += count[k];
+    std::vector<int64_t> cur(count.begin(), count.end() - 1);
+    for (int64_t i = 0; i < n; ++i) plan.perm[cur[key[i]]++] = (int32_t)i;
+  } else {
+    for (int64_t i = 0; i < n; ++i) plan.perm[i] = (int32_t)i;
+  }
+  plan.pos.resize(n);
+  plan.ll_const = 0.0;
+  int64_t npad = n;
+  if (order == CLB_ORDER_SPOT) {
+    clb_config lc{}; lc.likelihood = likelihood; lc.dof = dof;
+    int64_t p = 0;
+    for (int64_t k = 0; k < n_keys; ++k) {
+      const int64_t len = count[k + 1] - count[k];
+      if (len == 0) { plan.ll_const += lik_logpdf_zero(lc, iobs[k], sig[k]); continue; }
+      if (len > 32) return bad("spot %lld has %lld harmonics; at most 32 are supported", k, len, 0);
+      if ((p & 31) + len > 32) p = (p + 31) & ~(int64_t)31;
+      for (int64_t j = 0; j < len; ++j) plan.pos[count[k] + j] = p + j;
+      p += len;
+    }
+    npad = p;
+  } else {
+    for (int64_t i = 0; i < n; ++i) plan.pos[i] = i;
+  }
+  plan.npad = (npad + 31) & ~(int64_t)31;
+  return 0;
+}
+
+void fill_rows(const RowPlan& plan, int64_t n, int d, const int64_t* refl_id, const int64_t* image_id,
+               const float* metadata, const float* iobs, const float* sig, const int64_t* harmonic_id,
+               const int64_t* obs_index, int32_t* p_refl, int32_t* p_img, int32_t* p_spot, uint32_t* p_oidx,
+               float* p_meta, float* p_iobs, float* p_sig) {
+  const int64_t npad = plan.npad;
+  for (int64_t i = 0; i < npad; ++i) { p_refl[i] = -1; p_oidx[i] = 0; p_iobs[i] = 0.f; p_sig[i] = 1.f; }
+  if (p_img) std::fill(p_img, p_img + npad, 0);
+  if (p_spot) std::fill(p_spot, p_spot + npad, -1);
+  std::fill(p_meta, p_meta + (size_t)npad * d, 0.f);
+  for (int64_t sidx = 0; sidx < n; ++sidx) {
+    const int64_t i = plan.perm[sidx], p = plan.pos[sidx];
+    p_refl[p] = (int32_t)refl_id[i];
+    if (p_img) p_img[p] = (int32_t)image_id[i];
+    p_oidx[p] = (uint32_t)(obs_index ? obs_index[i] : i);
+    for (int j = 0; j < d; ++j) p_meta[(size_t)j * npad + p] = metadata[(size_t)i * d + j];
+    if (p_spot) {
+      const int64_t k = harmonic_id[i];
+      p_spot[p] = (int32_t)k; p_iobs[p] = iobs[k]; p_sig[p] = sig[k];     // formatter.py:637-640: spot k's value sits at index k
+    } else { p_iobs[p] = iobs[i]; p_sig[p] = sig[i]; }
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -294,72 +389,16 @@ int clb_set_observations(clb_handle* h, int64_t n, int64_t n_total, const int64_
                          const int64_t* harmonic_id, const int64_t* obs_index, int32_t order) {
   if (!h) return CLB_ERR_INVALID;
   const clb_config& c = h->cfg;
-  if (n <= 0 || !refl_id || !metadata || !iobs || !sig) return fail(h, CLB_ERR_INVALID, "clb_set_observations: null/empty input");
-  if (c.laue && !harmonic_id) return fail(h, CLB_ERR_INVALID, "Laue model needs harmonic_id");
   if (c.image_scales && !image_id) return fail(h, CLB_ERR_INVALID, "image scales need image_id");
-  if (n >= (int64_t)1 << 31) return fail(h, CLB_ERR_INVALID, "n_rows %lld exceeds 2^31-1 per handle", (long long)n);
   if (n_total <= 0) n_total = n;
+  RowPlan plan;
+  std::string err;
+  if (plan_rows(err, plan, n, n_total, h->R, c.image_scales ? c.n_images : 0, c.laue, c.likelihood, c.dof,
+                refl_id, image_id, metadata, iobs, sig, harmonic_id, obs_index, order))
+    return fail(h, CLB_ERR_INVALID, "%s", err.c_str());
   CLB_CUDA(h, cudaSetDevice(c.device));
-  if (order == CLB_ORDER_AUTO) order = c.laue ? CLB_ORDER_SPOT : CLB_ORDER_REFL;
-  if (c.laue && order != CLB_ORDER_SPOT) return fail(h, CLB_ERR_INVALID, "Laue rows must use CLB_ORDER_SPOT");
   const int d = c.n_meta;
-
-  // ---- validate ids and build the sort key ----
-  std::vector<int32_t> key((size_t)n);
-  int64_t n_keys = 0;
-  for (int64_t i = 0; i < n; ++i) {
-    if (refl_id[i] < 0 || refl_id[i] >= h->R) return fail(h, CLB_ERR_INVALID, "refl_id[%lld]=%lld outside [0,%lld)", (long long)i, (long long)refl_id[i], (long long)h->R);
-    if (c.image_scales && (image_id[i] < 0 || image_id[i] >= c.n_images)) return fail(h, CLB_ERR_INVALID, "image_id[%lld]=%lld outside [0,%d)", (long long)i, (long long)image_id[i], c.n_images);
-    if (obs_index && (obs_index[i] < 0 || obs_index[i] >= n_total)) return fail(h, CLB_ERR_INVALID, "obs_index[%lld] outside [0,n_rows_total)", (long long)i);
-  }
-  if (order == CLB_ORDER_REFL) { for (int64_t i = 0; i < n; ++i) key[i] = (int32_t)refl_id[i]; n_keys = h->R; }
-  else if (order == CLB_ORDER_SPOT) {
-    for (int64_t i = 0; i < n; ++i) {
-      if (harmonic_id[i] < 0 || harmonic_id[i] >= n) return fail(h, CLB_ERR_INVALID, "harmonic_id[%lld] outside [0,n_rows)", (long long)i);
-      key[i] = (int32_t)harmonic_id[i];
-    }
-    n_keys = n;
-  } else if (order == CLB_ORDER_IMAGE) {
-    if (!image_id) return fail(h, CLB_ERR_INVALID, "CLB_ORDER_IMAGE needs image_id");
-    int64_t mx = 0; for (int64_t i = 0; i < n; ++i) mx = std::max(mx, image_id[i]);
-    for (int64_t i = 0; i < n; ++i) key[i] = (int32_t)image_id[i]; n_keys = mx + 1;
-  } else { n_keys = 0; }
-
-  // ---- stable counting sort -> perm[sorted position] = original row ----
-  std::vector<int32_t> perm((size_t)n);
-  std::vector<int64_t> count;
-  if (n_keys > 0) {
-    count.assign((size_t)n_keys + 1, 0);
-    for (int64_t i = 0; i < n; ++i) count[key[i] + 1]++;
-    for (int64_t k = 0; k < n_keys; ++k) count[k + 1] += count[k];
-    std::vector<int64_t> cur(count.begin(), count.end() - 1);
-    for (int64_t i = 0; i < n; ++i) perm[cur[key[i]]++] = (int32_t)i;
-  } else {
-    for (int64_t i = 0; i < n; ++i) perm[i] = (int32_t)i;
-  }
-
-  // ---- padded positions (Laue: no spot may straddle a 32-row warp chunk) ----
-  std::vector<int64_t> pos((size_t)n);
-  int64_t npad = 0;
-  h->ll_const = 0.0;
-  if (order == CLB_ORDER_SPOT) {
-    int64_t p = 0;
-    for (int64_t k = 0; k < n_keys; ++k) {
-      const int64_t len = count[k + 1] - count[k];
-      if (len == 0) { h->ll_const += lik_logpdf_zero(c, iobs[k], sig[k]); continue; }
-      if (len > 32) return fail(h, CLB_ERR_INVALID, "spot %lld has %lld harmonics; at most 32 are supported", (long long)k, (long long)len);
-      if ((p & 31) + len > 32) p = (p + 31) & ~(int64_t)31;
-      for (int64_t j = 0; j < len; ++j) pos[count[k] + j] = p + j;
-      p += len;
-    }
-    npad = p;
-  } else {
-    for (int64_t i = 0; i < n; ++i) pos[i] = i;
-    npad = n;
-  }
-  npad = (npad + 31) & ~(int64_t)31;
-
-  // ---- build the SoA device layout in pinned memory ----
+  const int64_t npad = plan.npad;
   const bool has_img = image_id != nullptr;
   const bool has_spot = c.laue != 0;
   size_t bytes = 0;
@@ -374,28 +413,11 @@ int clb_set_observations(clb_handle* h, int64_t n, int64_t n_total, const int64_
   CLB_CUDA(h, h->rows_host.alloc(bytes));
   CLB_CUDA(h, h->rows.alloc(bytes));
   char* hb = h->rows_host.as<char>();
-  int32_t* p_refl = reinterpret_cast<int32_t*>(hb + o_refl);
-  int32_t* p_img = has_img ? reinterpret_cast<int32_t*>(hb + o_img) : nullptr;
-  int32_t* p_spot = has_spot ? reinterpret_cast<int32_t*>(hb + o_spot) : nullptr;
-  uint32_t* p_oidx = reinterpret_cast<uint32_t*>(hb + o_oidx);
-  float* p_meta = reinterpret_cast<float*>(hb + o_meta);
-  float* p_iobs = reinterpret_cast<float*>(hb + o_iobs);
-  float* p_sig = reinterpret_cast<float*>(hb + o_sig);
-  for (int64_t i = 0; i < npad; ++i) { p_refl[i] = -1; p_oidx[i] = 0; p_iobs[i] = 0.f; p_sig[i] = 1.f; }
-  if (p_img) std::fill(p_img, p_img + npad, 0);
-  if (p_spot) std::fill(p_spot, p_spot + npad, -1);
-  std::fill(p_meta, p_meta + (size_t)npad * d, 0.f);
-  for (int64_t sidx = 0; sidx < n; ++sidx) {
-    const int64_t i = perm[sidx], p = pos[sidx];
-    p_refl[p] = (int32_t)refl_id[i];
-    if (p_img) p_img[p] = (int32_t)image_id[i];
-    p_oidx[p] = (uint32_t)(obs_index ? obs_index[i] : i);
-    for (int j = 0; j < d; ++j) p_meta[(size_t)j * npad + p] = metadata[(size_t)i * d + j];
-    if (has_spot) {
-      const int64_t k = harmonic_id[i];
-      p_spot[p] = (int32_t)k; p_iobs[p] = iobs[k]; p_sig[p] = sig[k];     // formatter.py:637-640: spot k's value sits at index k
-    } else { p_iobs[p] = iobs[i]; p_sig[p] = sig[i]; }
-  }
+  fill_rows(plan, n, d, refl_id, image_id, metadata, iobs, sig, harmonic_id, obs_index,
+            reinterpret_cast<int32_t*>(hb + o_refl), has_img ? reinterpret_cast<int32_t*>(hb + o_img) : nullptr,
+            has_spot ? reinterpret_cast<int32_t*>(hb + o_spot) : nullptr, reinterpret_cast<uint32_t*>(hb + o_oidx),
+            reinterpret_cast<float*>(hb + o_meta), reinterpret_cast<float*>(hb + o_iobs), reinterpret_cast<float*>(hb + o_sig));
+  h->ll_const = plan.ll_const;
   h->rows_bytes = bytes;
   char* db = h->rows.as<char>();
   h->d_refl = reinterpret_cast<int32_t*>(db + o_refl);
@@ -405,7 +427,7 @@ int clb_set_observations(clb_handle* h, int64_t n, int64_t n_total, const int64_
   h->d_meta = reinterpret_cast<float*>(db + o_meta);
   h->d_iobs = reinterpret_cast<float*>(db + o_iobs);
   h->d_sig = reinterpret_cast<float*>(db + o_sig);
-  h->n_rows_raw = n; h->n_rows = npad; h->n_rows_total = n_total; h->order = order;
+  h->n_rows_raw = n; h->n_rows = npad; h->n_rows_total = n_total; h->order = plan.order;
 
   // ---- launch geometry + per-CTA buffers of the observation kernel ----
   const int64_t n_tiles = (npad + kObsThreads - 1) / kObsThreads;
@@ -414,6 +436,28 @@ int clb_set_observations(clb_handle* h, int64_t n, int64_t n_total, const int64_
   CLB_CUDA(h, h->scratch.alloc(sizeof(float4) * (size_t)h->grid_obs * std::max(1, c.mlp_layers) * (h->WP / 4) * kObsThreads));
   h->have_obs = true;
   return clb_upload_observations(h);
+}
+
+// Host prep only (no CUDA): the sorted / padded SoA device layout of clb_set_observations, written to
+// caller arrays of `capacity` rows.  *n_padded receives the padded row count; when capacity is too
+// small nothing else is written.  Used by the CPU test-suite to check the layout bit-exactly.
+int clb_prepare_rows(int64_t n, int64_t n_refl, int32_t n_meta, int32_t n_images, int32_t laue, int32_t likelihood, float dof,
+                     const int64_t* refl_id, const int64_t* image_id, const float* metadata, const float* iobs,
+                     const float* sig, const int64_t* harmonic_id, const int64_t* obs_index, int32_t order,
+                     int64_t capacity, int64_t* n_padded, int32_t* refl_out, int32_t* image_out, int32_t* spot_out,
+                     uint32_t* oidx_out, float* meta_out, float* iobs_out, float* sig_out, double* ll_const) {
+  RowPlan plan;
+  std::string err;
+  if (plan_rows(err, plan, n, n, n_refl, n_images, laue, likelihood, dof, refl_id, image_id, metadata, iobs, sig,
+                harmonic_id, obs_index, order))
+    return fail(nullptr, CLB_ERR_INVALID, "%s", err.c_str());
+  if (n_padded) *n_padded = plan.npad;
+  if (ll_const) *ll_const = plan.ll_const;
+  if (capacity < plan.npad) return CLB_OK;
+  if (!refl_out || !oidx_out || !meta_out || !iobs_out || !sig_out) return fail(nullptr, CLB_ERR_INVALID, "clb_prepare_rows: null output");
+  fill_rows(plan, n, n_meta, refl_id, image_id, metadata, iobs, sig, harmonic_id, obs_index,
+            refl_out, image_id ? image_out : nullptr, laue ? spot_out : nullptr, oidx_out, meta_out, iobs_out, sig_out);
+  return CLB_OK;
 }
 
 int clb_upload_observations(clb_handle* h) {

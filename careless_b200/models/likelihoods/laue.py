@@ -1,0 +1,29 @@
+"""Laue likelihoods (mirror of careless/models/likelihoods/laue.py:36-100): predicted harmonics are
+summed per spot (harmonic_id) before the mono log-density; done inside the CUDA observation kernel."""
+import numpy as np
+
+from .mono import Likelihood
+
+
+class LaueBase(Likelihood):
+    laue = True
+
+    @staticmethod
+    def convolve(value, harmonic_id):
+        """laue.py:17-25 on the host (post-processing helper): sum rows per spot, zeros elsewhere."""
+        value = np.asarray(value)
+        hid = np.asarray(harmonic_id).reshape(-1)
+        out = np.zeros_like(value)
+        np.add.at(out.T, hid, value.T)
+        return out
+
+
+class NormalLikelihood(LaueBase):
+    kind = "normal"
+
+
+class StudentTLikelihood(LaueBase):
+    kind = "studentt"
+
+    def __init__(self, dof):
+        self.dof = float(dof)

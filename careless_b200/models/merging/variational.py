@@ -1,0 +1,147 @@
+"""VariationalMergingModel: the reference's public training interface on top of the CUDA engine.
+
+Mirror of careless/models/merging/variational.py:11-275.  ``train_model(data, steps)`` uploads the input
+tuple once, runs ``steps`` fused ELBO-gradient + Adam steps on the GPU and returns the same history
+dict (keys ``loss``, ``NLL``, ``F KLDiv``, ``Grad Norm``), stopping early on a non-finite gradient
+norm exactly like the reference loop (:271-274).  Trained parameters are written back into the
+surrogate / scaler objects so ``mean() / stddev() / save_weights`` behave as in careless.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from ..base import BaseModel
+from ..priors.wilson import DoubleWilsonPrior, WilsonPrior
+from ..scaling.image import HybridImageScaler
+from ..scaling.nn import MetadataScaler
+from ...engine import Engine, EngineConfig
+from ...optimizers import Adam
+
+
+class VariationalMergingModel(BaseModel):
+    def __init__(self, surrogate_posterior, prior, likelihood, scaling_model, mc_sample_size=1, kl_weight=None,
+                 scale_kl_weight=None, scale_prior=None):
+        if scale_prior is not None:
+            raise NotImplementedError("scale_prior is never enabled by the reference CLI (variational.py:159-163) and is not implemented")
+        self.prior = prior
+        self.surrogate_posterior = surrogate_posterior
+        self.likelihood = likelihood
+        self.scaling_model = scaling_model
+        self.mc_sample_size = mc_sample_size
+        self.kl_weight = kl_weight
+        self.optimizer = Adam(beta_2=0.99)
+        self.seed = 1234
+        self.device = 0
+        self._engine = None
+        self._engine_key = None
+
+    def compile(self, optimizer=None, run_eagerly=None, **kwargs):
+        if optimizer is not None and not isinstance(optimizer, str):
+            self.optimizer = optimizer
+        return self
+
+    # ------------------------------------------------------------------ engine plumbing
+    def _parts(self):
+        sm = self.scaling_model
+        if isinstance(sm, HybridImageScaler):
+            return sm.mlp_scaler, sm.image_scaler
+        if isinstance(sm, MetadataScaler):
+            return sm, None
+        raise TypeError(f"unsupported scaling model {type(sm).__name__}")
+
+    def _build_engine(self, data):
+        mlp, img = self._parts()
+        metadata = self.get_metadata(data)
+        refl_id = np.asarray(self.get_refl_id(data)).reshape(-1)
+        n_meta = metadata.shape[-1]
+        mlp.build(n_meta)
+        laue = bool(getattr(self.likelihood, "laue", False))
+        if laue != self.is_laue(data):
+            raise ValueError("Laue likelihood needs the 8-entry Laue input tuple (and vice versa)")
+        q, prior, opt = self.surrogate_posterior, self.prior, self.optimizer
+        R = q.loc_raw.shape[0]
+        dw = isinstance(prior, DoubleWilsonPrior)
+        cfg = EngineConfig(
+            n_refl=R, n_meta=n_meta, mlp_width=mlp.width, mlp_layers=mlp.n_layers,
+            n_images=(img.max_images if img is not None else 0), image_scales=img is not None,
+            mc_samples=int(self.mc_sample_size), likelihood=self.likelihood.kind, dof=self.likelihood.dof, laue=laue,
+            prior="double_wilson" if dw else "wilson", n_asu=(len(prior.r) if dw else 0),
+            optimize_dw_r=(prior.optimize_r if dw else False), scale_bijector=mlp.scale_bijector,
+            scale_shift=mlp.scale_multiplier, epsilon=q.scale_shift, kl_weight=self.kl_weight,
+            learning_rate=opt.learning_rate, beta_1=opt.beta_1, beta_2=opt.beta_2, adam_epsilon=opt.epsilon,
+            clipnorm=opt.clipnorm, clipvalue=opt.clipvalue, global_clipnorm=opt.global_clipnorm,
+            seed=self.seed, device=self.device)
+        key = (tuple(sorted(cfg.__dict__.items())), id(data))
+        if self._engine is not None and self._engine_key == key:
+            return self._engine
+        if self._engine is not None:
+            self._engine.close()
+        eng = Engine(cfg)
+        eng.set_observations(refl_id, self.get_image_id(data), metadata, self.get_intensities(data),
+                             self.get_uncertainties(data), harmonic_id=self.get_harmonic_id(data) if laue else None)
+        eng.set_prior(prior.centric, prior.epsilon, prior.sigma, dw_parent=prior.dw_parent if dw else None,
+                      asu_id=prior.asu_ids if dw else None, r=prior.r if dw else None, init_scale=-1.0)
+        self._engine, self._engine_key = eng, key
+        return eng
+
+    def _push(self, eng):
+        mlp, img = self._parts()
+        q = self.surrogate_posterior
+        eng.set_params("sf_loc_raw", q.loc_raw)
+        eng.set_params("sf_scale_raw", q.scale_raw)
+        eng.set_params("mlp", mlp.flat())
+        if img is not None:
+            eng.set_params("image_scales", img._scales)
+        eng.set_trainable("sf_loc_raw", q.trainable)
+        eng.set_trainable("sf_scale_raw", q.trainable)
+        eng.set_trainable("mlp", self.scaling_model.trainable and mlp.trainable)
+        if img is not None:
+            eng.set_trainable("image_scales", self.scaling_model.trainable and img.trainable)
+
+    def _pull(self, eng):
+        mlp, img = self._parts()
+        q = self.surrogate_posterior
+        q.loc_raw, q.scale_raw = eng.get_params("sf_loc_raw"), eng.get_params("sf_scale_raw")
+        mlp.from_flat(eng.get_params("mlp"))
+        if img is not None:
+            img._scales = eng.get_params("image_scales")
+        if isinstance(self.prior, DoubleWilsonPrior) and self.prior.optimize_r:
+            self.prior.r = (1.0 / (1.0 + np.exp(-eng.get_params("dw_r_logit")))).astype(np.float32)
+
+    # ------------------------------------------------------------------ the reference's training entry
+    def train_model(self, data, steps, message=None, format_string="{:0.2e}", validation_data=None,
+                    validation_frequency=10, progress=True, use_custom_train_step=True, jit_compile=None,
+                    reduce_retracing=False, chunk=100):
+        """variational.py:226-275.  Returns history: dict[str, list[float]], one entry per step taken."""
+        if validation_data is not None:
+            raise NotImplementedError("validation NLL (variational.py:257-260) is a 'next' row of the scope table")
+        eng = self._build_engine(data)
+        self._push(eng)
+        history = {}
+        done = 0
+        bar = None
+        if progress:
+            from tqdm import tqdm
+            bar = tqdm(total=steps, desc=message)
+        while done < steps:
+            n = min(chunk, steps - done)
+            rows = eng.step(n)            # metrics stay on the device for the whole chunk (no per-step host sync)
+            for row in rows:
+                for k, v in row.items():
+                    history.setdefault(k, []).append(float(v))
+            done += len(rows)
+            if bar is not None:
+                bar.update(len(rows))
+                bar.set_postfix({k: format_string.format(v[-1]) for k, v in history.items()})
+            if len(rows) < n:
+                print("Encountered numerical issues, terminating optimization early!")
+                break
+        if bar is not None:
+            bar.close()
+        self._pull(eng)
+        return history
+
+    def close(self):
+        if self._engine is not None:
+            self._engine.close()
+            self._engine = None

@@ -118,6 +118,17 @@ int clb_set_observations(clb_handle* h, int64_t n_rows, int64_t n_rows_total,
                          const int64_t* refl_id, const int64_t* image_id,
                          const float* metadata, const float* intensities, const float* uncertainties,
                          const int64_t* harmonic_id, const int64_t* obs_index, int32_t order);
+/* The host prep of clb_set_observations alone (no CUDA, usable without a GPU): writes the sorted /
+ * padded SoA rows into caller arrays of `capacity` rows (meta_out: n_meta x capacity is NOT the
+ * layout -- it is n_meta x *n_padded, row stride *n_padded).  Call once with capacity 0 to learn
+ * *n_padded.  Exists so the layout (refl_id order, harmonic grouping) can be checked bit-exactly. */
+int clb_prepare_rows(int64_t n_rows, int64_t n_refl, int32_t n_meta, int32_t n_images, int32_t laue,
+                     int32_t likelihood, float dof,
+                     const int64_t* refl_id, const int64_t* image_id, const float* metadata,
+                     const float* intensities, const float* uncertainties, const int64_t* harmonic_id,
+                     const int64_t* obs_index, int32_t order,
+                     int64_t capacity, int64_t* n_padded, int32_t* refl_out, int32_t* image_out, int32_t* spot_out,
+                     uint32_t* oidx_out, float* meta_out, float* iobs_out, float* sig_out, double* ll_const);
 /* Re-upload of the already prepared (pinned) device-layout rows: the host->device copy of
  * one step's inputs, used by the end-to-end measurement. */
 int clb_upload_observations(clb_handle* h);

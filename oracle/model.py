@@ -164,7 +164,7 @@ def tn_log_prob(z, loc, scale, low, high):
 # priors
 # ----------------------------------------------------------------------------------------
 def _as(x, like):
-    return torch.as_tensor(np.asarray(x), dtype=like.dtype)
+    return torch.as_tensor(np.array(x, copy=True), dtype=like.dtype)
 
 
 def wilson_log_prob(z, centric, eps_mult, sigma):
@@ -359,7 +359,8 @@ def loss_and_grads(params, data, prior, cfg, u_f, eps_s, frozen=()):
     grads = torch.autograd.grad(out["loss"], [leaves[k] for k in names], allow_unused=True)
     g = {k: (torch.zeros_like(leaves[k]) if gi is None else gi) for k, gi in zip(names, grads)}
     gn = math.sqrt(sum(float((gi.double() ** 2).sum()) for gi in g.values()))
-    metrics = {"loss": float(out["loss"]), "NLL": float(out["nll"]), "F KLDiv": float(out["kl"]), "Grad Norm": gn}
+    metrics = {"loss": float(out["loss"].detach()), "NLL": float(out["nll"].detach()),
+               "F KLDiv": float(out["kl"].detach()), "Grad Norm": gn}
     return metrics, g, out
 
 
