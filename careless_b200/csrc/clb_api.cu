@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -71,6 +72,7 @@ struct clb_handle {
   int64_t adam_t = 0;
   uint32_t step_counter = 0;   // RNG step index
   bool have_obs = false, have_prior = false, in_step = false;
+  bool debug_sync = false;   // CLB_DEBUG_SYNC=1: synchronise + log after every kernel launch
   int order = CLB_ORDER_REFL;
   double ll_const = 0.0;   // per-sample constant log-likelihood of empty Laue slots
 
@@ -114,6 +116,11 @@ int fail(clb_handle* h, int code, const char* fmt, ...) {
   do { cudaError_t e_ = (expr);                                                                \
        if (e_ != cudaSuccess) return fail(h, CLB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,     \
                                           cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+#define CLB_LAUNCHED(h)                                                                        \
+  do { CLB_CUDA(h, cudaGetLastError()); (h)->total_launches++;                                 \
+       if ((h)->debug_sync) { fprintf(stderr, "[clb] launch %lld at %s:%d ...", (long long)(h)->total_launches, __FILE__, __LINE__); \
+                              fflush(stderr); CLB_CUDA(h, cudaStreamSynchronize((h)->stream)); fprintf(stderr, " done\n"); } } while (0)
 
 int round_width(int w) { return w <= 8 ? 8 : w <= 16 ? 16 : w <= 32 ? 32 : -1; }
 
@@ -323,6 +330,7 @@ int clb_create(const clb_config* cfg, clb_handle** out) {
   h->cfg = *cfg;
   if (h->cfg.n_refl_total <= 0) h->cfg.n_refl_total = h->cfg.n_refl;
   if (h->cfg.world_size <= 0) { h->cfg.world_size = 1; h->cfg.rank = 0; }
+  { const char* dbg = getenv("CLB_DEBUG_SYNC"); h->debug_sync = dbg && dbg[0] == '1'; }
   h->R = cfg->n_refl; h->S = cfg->mc_samples; h->WP = WP; h->KS = ks_for(WP);
   auto bail = [&](int code) { g_create_error = h->err; delete h; return code; };
 #define CREATE_CUDA(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { fail(h, CLB_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); return bail(CLB_ERR_CUDA); } } while (0)
@@ -661,7 +669,7 @@ static int step_begin_impl(clb_handle* h, const float* inj_u, const float* inj_e
     a.R = R; a.S = S; a.eps = c.epsilon; a.cq = cq; a.seed = c.seed; a.step = h->step_counter;
     const int64_t nthr = R * S;
     k_refl_sample<<<(unsigned)((nthr + 255) / 256), 256, 0, st>>>(a);
-    CLB_CUDA(h, cudaGetLastError()); h->total_launches++;
+    CLB_LAUNCHED(h);
   }
   if (dw) {
     DwArgs a{};
@@ -674,7 +682,7 @@ static int step_begin_impl(clb_handle* h, const float* inj_u, const float* inj_e
     a.acc = h->acc.as<double>(); a.R = R; a.S = S; a.cq = cq;
     const int64_t nthr = R * S;
     k_dw_prior<<<(unsigned)((nthr + 255) / 256), 256, 0, st>>>(a);
-    CLB_CUDA(h, cudaGetLastError()); h->total_launches++;
+    CLB_LAUNCHED(h);
   }
   {
     ObsArgs a{};
@@ -699,13 +707,13 @@ static int step_begin_impl(clb_handle* h, const float* inj_u, const float* inj_e
       while (h->ev.size() < h->ev_used + 2) { cudaEvent_t e; CLB_CUDA(h, cudaEventCreate(&e)); h->ev.push_back(e); }
       CLB_CUDA(h, cudaEventRecord(h->ev[h->ev_used], st));
     }
-    CLB_CUDA(h, dispatch_obs(h, a)); h->total_launches++; h->obs_launches++;
+    CLB_CUDA(h, dispatch_obs(h, a)); h->obs_launches++; CLB_LAUNCHED(h);
     if (h->timing) { CLB_CUDA(h, cudaEventRecord(h->ev[h->ev_used + 1], st)); h->ev_used += 2; }
   }
   if (train_mlp) {
     const int np = h->lay.n_params;
     k_reduce_partials<<<(np + 255) / 256, 256, 0, st>>>(h->partials.as<float>(), h->grid_obs * h->KS, np, grad + h->goff[CLB_GROUP_MLP]);
-    CLB_CUDA(h, cudaGetLastError()); h->total_launches++;
+    CLB_LAUNCHED(h);
   }
   {
     ReflBwdArgs a{};
@@ -715,7 +723,7 @@ static int step_begin_impl(clb_handle* h, const float* inj_u, const float* inj_e
     a.g_loc = grad + h->goff[CLB_GROUP_SF_LOC]; a.g_scale = grad + h->goff[CLB_GROUP_SF_SCALE];
     a.R = R; a.S = S; a.eps = c.epsilon; a.cq = cq; a.seed = c.seed; a.step = h->step_counter;
     k_refl_backward<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(a);
-    CLB_CUDA(h, cudaGetLastError()); h->total_launches++;
+    CLB_LAUNCHED(h);
   }
   h->in_step = true;
   return CLB_OK;
@@ -730,10 +738,10 @@ static int step_norms_impl(clb_handle* h) {
   for (int v = 0; v < h->vt.n_vars; ++v) maxsz = std::max(maxsz, h->vt.size[v]);
   const int chunks = (int)std::min<int64_t>((maxsz + 256 * 8 - 1) / (256 * 8), 4 * h->n_sms);
   k_var_sumsq<<<dim3(std::max(chunks, 1), h->vt.n_vars), 256, 0, st>>>(h->grad.as<float>(), h->vt, h->var_sums.as<double>());
-  CLB_CUDA(h, cudaGetLastError()); h->total_launches++;
+  CLB_LAUNCHED(h);
   k_pack_scalars<<<1, 128, 0, st>>>(h->acc.as<double>(), h->var_sums.as<double>(), h->vt, h->red.as<double>(), h->cfg.rank,
                                   (double)h->S * h->ll_const);
-  CLB_CUDA(h, cudaGetLastError()); h->total_launches++;
+  CLB_LAUNCHED(h);
   return CLB_OK;
 }
 
@@ -752,14 +760,14 @@ static int step_end_impl(clb_handle* h, double* d_metrics) {
   f.clipnorm = c.clipnorm; f.global_clipnorm = c.global_clipnorm;
   f.lr = c.learning_rate; f.beta1 = c.beta_1; f.beta2 = c.beta_2; f.t = h->adam_t + 1;
   k_finalize<<<1, 32, 0, st>>>(f);
-  CLB_CUDA(h, cudaGetLastError()); h->total_launches++;
+  CLB_LAUNCHED(h);
   int64_t maxsz = 1;
   for (int v = 0; v < h->vt.n_vars; ++v) if (h->vt.trainable[v]) maxsz = std::max(maxsz, h->vt.size[v]);
   const int chunks = (int)std::min<int64_t>((maxsz + 256 * 4 - 1) / (256 * 4), 8 * h->n_sms);
   k_adam<<<dim3(std::max(chunks, 1), h->vt.n_vars), 256, 0, st>>>(h->theta.as<float>(), h->m.as<float>(), h->v.as<float>(), h->grad.as<float>(),
                                                                    h->vt, h->var_scale.as<float>(), h->adam_alpha.as<float>(),
                                                                    c.clipvalue, c.beta_1, c.beta_2, c.adam_epsilon, h->stop_step.as<int>(), (int)h->step_counter);
-  CLB_CUDA(h, cudaGetLastError()); h->total_launches++;
+  CLB_LAUNCHED(h);
   h->adam_t += 1;
   h->step_counter += 1;
   h->in_step = false;

@@ -328,7 +328,8 @@ __global__ void __launch_bounds__(kObsThreads, 1) k_obs(ObsArgs a) {
       {
         const int key = active ? refl : -1 - lane;
         const float tot = warp_segsum(d_zf, key, lane);
-        if (active && warp_run_tail(key, lane)) atomicAdd(&a.gz[(size_t)s * a.R + refl], tot);
+        const bool tail = warp_run_tail(key, lane);      // all 32 lanes must execute the shuffles
+        if (active && tail) atomicAdd(&a.gz[(size_t)s * a.R + refl], tot);
       }
       const float d_base = aimg * d_zs;
       d_aimg += base * d_zs;
@@ -338,7 +339,8 @@ __global__ void __launch_bounds__(kObsThreads, 1) k_obs(ObsArgs a) {
     if (a.g_img != nullptr) {
       const int key = (active && img > 0) ? img : -1 - lane;
       const float tot = warp_segsum(d_aimg, key, lane);
-      if (key > 0 && warp_run_tail(key, lane)) atomicAdd(&a.g_img[img - 1], tot);
+      const bool tail = warp_run_tail(key, lane);
+      if (key > 0 && tail) atomicAdd(&a.g_img[img - 1], tot);
     }
     if (!a.train_mlp) continue;
     // ---------------- backward through the MLP ----------------
