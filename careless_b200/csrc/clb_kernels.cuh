@@ -140,7 +140,7 @@ struct ObsArgs {
   const float* z; float* gz; int64_t R; int S;
   const float* inj_eps;            // (S, N_total) or null
   float* g_img;                    // gradient of image scales or null
-  float* partials;                 // [grid*KS][n_params]
+  double* partials;                // [grid*KS][n_params], FP64 so that the cross-tile accumulation adds no FP32 rounding
   float4* scratch;                 // [grid][L][WP/4][T]
   float* ipred_out;                // (S, N_total) original order, or null
   double* acc;
@@ -165,7 +165,7 @@ template <int WP> struct ObsSmem {
 template <int WP>
 __device__ __forceinline__ void stage_and_accumulate(const float (&ain)[WP], const float (&dp)[WP],
                                                      float* S_h, float4* S_d, float* dbacc_k,
-                                                     float* part_rows, int koff, int boff, int in_dim, int out_dim,
+                                                     double* part_rows, int koff, int boff, int in_dim, int out_dim,
                                                      int tid) {
   constexpr int T = kObsThreads, HS = T + 4, NC = WP / 4;
   constexpr int TPL = WP * NC;            // threads covering one WPxWP matrix with 1x4 patches
@@ -198,7 +198,7 @@ __device__ __forceinline__ void stage_and_accumulate(const float (&ain)[WP], con
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       const int j = 4 * pjq + c;
-      if (j < out_dim) part_rows[koff + pi * out_dim + j] += av[c];
+      if (j < out_dim) part_rows[koff + pi * out_dim + j] += (double)av[c];
     }
   }
   // bias gradient: column sums of dp
@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(kObsThreads, 1) k_obs(ObsArgs a) {
   }
   __syncthreads();
 
-  float* part_rows = a.partials + ((size_t)blockIdx.x * KS + (tid / TPL)) * a.lay.n_params;
+  double* part_rows = a.partials + ((size_t)blockIdx.x * KS + (tid / TPL)) * a.lay.n_params;
   float4* scr = a.scratch + (size_t)blockIdx.x * L * NC * T;
   double ll_sum = 0.0;
   const int64_t n_tiles = (a.n_rows + T - 1) / T;
@@ -298,7 +298,12 @@ __global__ void __launch_bounds__(kObsThreads, 1) k_obs(ObsArgs a) {
     const uint32_t oi = inb ? a.oidx[row] : 0u;
     const float iobs = inb ? a.iobs[row] : 0.f;
     const float sg = inb ? a.sig[row] : 1.f;
-    const int spot = (a.laue && inb) ? a.spot[row] : -1 - lane;   // unique keys when not Laue
+    // runs of equal keys inside the warp (same for every MC sample)
+    const WarpRuns refl_runs = warp_runs(active ? refl : -1 - lane, lane);
+    WarpRuns spot_runs = refl_runs, img_runs = refl_runs;
+    if (a.laue) spot_runs = warp_runs(inb ? a.spot[row] : -1, lane);   // padding rows carry spot -1
+    const bool img_live = active && img > 0;
+    if (a.g_img != nullptr) img_runs = warp_runs(img_live ? img : -1 - lane, lane);
     float dmu = 0.f, drho = 0.f, d_aimg = 0.f;
     for (int s = 0; s < a.S; ++s) {
       float e = 0.f;
@@ -311,12 +316,8 @@ __global__ void __launch_bounds__(kObsThreads, 1) k_obs(ObsArgs a) {
       float x = ip;
       bool eval = active;
       if (a.laue) {           // harmonic segment-sum within the warp (spots never straddle a warp)
-        const float tot = warp_segsum(active ? ip : 0.f, spot, lane);
-        const bool tail = warp_run_tail(spot, lane);
-        const unsigned tails = __ballot_sync(0xffffffffu, tail);
-        const int my_tail = __ffs(tails >> lane) - 1 + lane;
-        x = __shfl_sync(0xffffffffu, tot, my_tail);
-        eval = active && tail;   // count each spot once
+        x = warp_segtotal(active ? ip : 0.f, spot_runs, lane);
+        eval = active && spot_runs.tail;   // count each spot once
       }
       float ll = 0.f, g = 0.f;
       if (active) lik_eval<LIK>(x, iobs, sg, a.lik, ll, g);
@@ -325,22 +326,16 @@ __global__ void __launch_bounds__(kObsThreads, 1) k_obs(ObsArgs a) {
       const float d_zs = G * zf * zf;
       const float d_zf = G * zs * 2.0f * zf;
       // segmented reduction of dL/dz_f over runs of equal refl_id, one atomic per run
-      {
-        const int key = active ? refl : -1 - lane;
-        const float tot = warp_segsum(d_zf, key, lane);
-        const bool tail = warp_run_tail(key, lane);      // all 32 lanes must execute the shuffles
-        if (active && tail) atomicAdd(&a.gz[(size_t)s * a.R + refl], tot);
-      }
+      const float tot = warp_segsum(d_zf, refl_runs, lane);
+      if (active && refl_runs.tail) atomicAdd(&a.gz[(size_t)s * a.R + refl], tot);
       const float d_base = aimg * d_zs;
       d_aimg += base * d_zs;
       dmu += d_base;
       drho += d_base * e * dsig;
     }
     if (a.g_img != nullptr) {
-      const int key = (active && img > 0) ? img : -1 - lane;
-      const float tot = warp_segsum(d_aimg, key, lane);
-      const bool tail = warp_run_tail(key, lane);
-      if (key > 0 && tail) atomicAdd(&a.g_img[img - 1], tot);
+      const float tot = warp_segsum(d_aimg, img_runs, lane);
+      if (img_live && img_runs.tail) atomicAdd(&a.g_img[img - 1], tot);
     }
     if (!a.train_mlp) continue;
     // ---------------- backward through the MLP ----------------
@@ -400,7 +395,7 @@ __global__ void __launch_bounds__(kObsThreads, 1) k_obs(ObsArgs a) {
   if (a.train_mlp) {
     for (int idx = tid; idx < NL * WP; idx += T) {
       const int k = idx / WP, j = idx % WP;
-      if (j < a.lay.out_dim[k]) a.partials[(size_t)blockIdx.x * KS * a.lay.n_params + a.lay.boff[k] + j] += dbacc[idx];
+      if (j < a.lay.out_dim[k]) a.partials[(size_t)blockIdx.x * KS * a.lay.n_params + a.lay.boff[k] + j] += (double)dbacc[idx];
     }
   }
   ll_sum = warp_sum(ll_sum);
@@ -414,12 +409,12 @@ __global__ void __launch_bounds__(kObsThreads, 1) k_obs(ObsArgs a) {
 }
 
 // Sum the per-CTA partial weight gradients: grad[p] = sum_rows partials[row][p]  (deterministic order).
-__global__ void __launch_bounds__(256) k_reduce_partials(const float* partials, int rows, int n_params, float* grad) {
+__global__ void __launch_bounds__(256) k_reduce_partials(const double* partials, int rows, int n_params, float* grad) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n_params) return;
-  float s = 0.f;
+  double s = 0.0;
   for (int r = 0; r < rows; ++r) s += partials[(size_t)r * n_params + p];
-  grad[p] = s;
+  grad[p] = (float)s;
 }
 
 // ---------------------------------------------------------------------------------------

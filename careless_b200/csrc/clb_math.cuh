@@ -195,21 +195,40 @@ CLB_DEV float warp_sum(float v) {
   return v;
 }
 
-// Inclusive segmented sum over runs of equal keys in consecutive lanes.  After the call the
-// LAST lane of every run holds the run total.  All 32 lanes must participate.
-CLB_DEV float warp_segsum(float v, int key, int lane) {
+// Runs of equal keys in consecutive lanes of a warp (keys need not be sorted: a run ends as soon as
+// the key changes).  All 32 lanes must call these.
+struct WarpRuns {
+  int start;        // lane of the first element of my run
+  bool tail;        // am I the last lane of my run
+  unsigned tails;   // bit l set <=> lane l is the last lane of its run
+};
+
+CLB_DEV WarpRuns warp_runs(int key, int lane) {
+  const int pk = __shfl_up_sync(0xffffffffu, key, 1);
+  const bool head = (lane == 0) || (pk != key);
+  const unsigned heads = __ballot_sync(0xffffffffu, head);
+  WarpRuns r;
+  r.start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+  r.tails = (heads >> 1) | 0x80000000u;
+  r.tail = (r.tails >> lane) & 1u;
+  return r;
+}
+
+// Inclusive segmented sum: afterwards the tail lane of every run holds the run total.
+CLB_DEV float warp_segsum(float v, const WarpRuns& r, int lane) {
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
     const float ov = __shfl_up_sync(0xffffffffu, v, o);
-    const int ok = __shfl_up_sync(0xffffffffu, key, o);
-    if (lane >= o && ok == key) v += ov;
+    if (lane - o >= r.start) v += ov;
   }
   return v;
 }
-// true for the last lane of each run of equal keys
-CLB_DEV bool warp_run_tail(int key, int lane) {
-  const int nk = __shfl_down_sync(0xffffffffu, key, 1);
-  return (lane == 31) || (nk != key);
+
+// Run total broadcast to every lane of the run.
+CLB_DEV float warp_segtotal(float v, const WarpRuns& r, int lane) {
+  const float tot = warp_segsum(v, r, lane);
+  const int my_tail = __ffs(r.tails >> lane) - 1 + lane;
+  return __shfl_sync(0xffffffffu, tot, my_tail);
 }
 
 }  // namespace clb

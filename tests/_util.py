@@ -114,3 +114,9 @@ def rel_err(a, b):
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
     scale = np.max(np.abs(b)) if b.size else 1.0
     return float(np.max(np.abs(a - b) / (np.abs(b) + 1e-3 * scale + 1e-30))) if b.size else 0.0
+
+
+def rms_err(a, b):
+    """||a-b||_2 / ||b||_2"""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-300))
