@@ -184,7 +184,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=local)      # a real (non-legacy) stream shared by the engine, NCCL and the events
+    torch.cuda.set_stream(stream)
 
     N, R = args.obs, args.refl
     p = synth.make_mono(N, R, d=D_META, n_images=5000, seed=1234 + rank)

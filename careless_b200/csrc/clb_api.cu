@@ -440,7 +440,7 @@ int clb_set_observations(clb_handle* h, int64_t n, int64_t n_total, const int64_
   // ---- launch geometry + per-CTA buffers of the observation kernel ----
   const int64_t n_tiles = (npad + kObsThreads - 1) / kObsThreads;
   h->grid_obs = (int)std::min<int64_t>(n_tiles, h->n_sms);
-  CLB_CUDA(h, h->partials.alloc(sizeof(double) * (size_t)h->grid_obs * h->KS * h->lay.n_params));
+  CLB_CUDA(h, h->partials.alloc(sizeof(double) * (size_t)h->grid_obs * h->KS * partial_row_size(h->NL, h->WP)));
   CLB_CUDA(h, h->scratch.alloc(sizeof(float4) * (size_t)h->grid_obs * std::max(1, c.mlp_layers) * (h->WP / 4) * kObsThreads));
   h->have_obs = true;
   return clb_upload_observations(h);
@@ -656,7 +656,7 @@ static int step_begin_impl(clb_handle* h, const float* inj_u, const float* inj_e
   // gradients of the replicated groups are accumulated with atomics / overwritten by the reduction
   if (h->P > 2 * R) CLB_CUDA(h, cudaMemsetAsync(grad + 2 * R, 0, sizeof(float) * (h->P - 2 * R), st));
   const bool train_mlp = h->gtrain[CLB_GROUP_MLP] != 0;
-  if (train_mlp) CLB_CUDA(h, cudaMemsetAsync(h->partials.p, 0, sizeof(double) * (size_t)h->grid_obs * h->KS * h->lay.n_params, st));
+  if (train_mlp) CLB_CUDA(h, cudaMemsetAsync(h->partials.p, 0, sizeof(double) * (size_t)h->grid_obs * h->KS * partial_row_size(h->NL, h->WP), st));
 
   const bool dw = c.prior == CLB_PRIOR_DOUBLE_WILSON;
   {
@@ -712,7 +712,7 @@ static int step_begin_impl(clb_handle* h, const float* inj_u, const float* inj_e
   }
   if (train_mlp) {
     const int np = h->lay.n_params;
-    k_reduce_partials<<<(np + 255) / 256, 256, 0, st>>>(h->partials.as<double>(), h->grid_obs * h->KS, np, grad + h->goff[CLB_GROUP_MLP]);
+    k_reduce_partials<<<(np + 255) / 256, 256, 0, st>>>(h->partials.as<double>(), h->grid_obs * h->KS, h->lay, h->WP, grad + h->goff[CLB_GROUP_MLP]);
     CLB_LAUNCHED(h);
   }
   {

@@ -161,16 +161,19 @@ template <int WP> struct ObsSmem {
 };
 
 // One layer's weight gradient over the CTA tile: dW[i][j] = sum_obs a[obs][i] * dp[obs][j].
-// a is staged transposed (S_h[i][obs]), dp row-major with XOR-swizzled float4 chunks.
+// a is staged transposed (S_h[i][obs]), dp row-major with XOR-swizzled float4 chunks.  Each thread owns
+// a 1x4 patch of dW (exclusive: no atomics); its FP64 running sum lives in the CTA's L2-resident partial
+// buffer at `part` (4 consecutive doubles).  The partial is fetched BEFORE the staging barriers so the L2
+// round trip overlaps the 256-observation loop.
 template <int WP>
 __device__ __forceinline__ void stage_and_accumulate(const float (&ain)[WP], const float (&dp)[WP],
-                                                     float* S_h, float4* S_d, float* dbacc_k,
-                                                     double* part_rows, int koff, int boff, int in_dim, int out_dim,
-                                                     int tid) {
+                                                     float* S_h, float4* S_d, float* dbacc_k, double* part, int tid) {
   constexpr int T = kObsThreads, HS = T + 4, NC = WP / 4;
   constexpr int TPL = WP * NC;            // threads covering one WPxWP matrix with 1x4 patches
   constexpr int KS = T / TPL;             // K (observation) split
   static_assert(KS >= 1, "WP too large for the tile");
+  const double2 p01 = __ldcg(reinterpret_cast<const double2*>(part));
+  const double2 p23 = __ldcg(reinterpret_cast<const double2*>(part) + 1);
   __syncthreads();                        // previous consumer of the staging buffers is done
 #pragma unroll
   for (int i = 0; i < WP; ++i) S_h[i * HS + tid] = ain[i];
@@ -178,7 +181,7 @@ __device__ __forceinline__ void stage_and_accumulate(const float (&ain)[WP], con
   for (int c = 0; c < NC; ++c)
     S_d[tid * NC + (c ^ (tid & (NC - 1)))] = make_float4(dp[4 * c], dp[4 * c + 1], dp[4 * c + 2], dp[4 * c + 3]);
   __syncthreads();
-  const int pi = tid % WP, pjq = (tid / WP) % NC, ks = tid / TPL;   // part_rows already points at row ks
+  const int pi = tid % WP, pjq = (tid / WP) % NC, ks = tid / TPL;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   const int o0 = ks * (T / KS);
 #pragma unroll 4
@@ -192,15 +195,8 @@ __device__ __forceinline__ void stage_and_accumulate(const float (&ain)[WP], con
       acc.z = fmaf(hv[q], d4.z, acc.z); acc.w = fmaf(hv[q], d4.w, acc.w);
     }
   }
-  // read-modify-write of this CTA's private partial (exclusive ownership: no atomics)
-  if (pi < in_dim) {
-    const float av[4] = {acc.x, acc.y, acc.z, acc.w};
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const int j = 4 * pjq + c;
-      if (j < out_dim) part_rows[koff + pi * out_dim + j] += (double)av[c];
-    }
-  }
+  __stcg(reinterpret_cast<double2*>(part), make_double2(p01.x + (double)acc.x, p01.y + (double)acc.y));
+  __stcg(reinterpret_cast<double2*>(part) + 1, make_double2(p23.x + (double)acc.z, p23.y + (double)acc.w));
   // bias gradient: column sums of dp
   {
     constexpr int G = T / WP;
@@ -210,10 +206,13 @@ __device__ __forceinline__ void stage_and_accumulate(const float (&ain)[WP], con
       const float4 d4 = S_d[o * NC + ((j >> 2) ^ (o & (NC - 1)))];
       s += (j & 3) == 0 ? d4.x : (j & 3) == 1 ? d4.y : (j & 3) == 2 ? d4.z : d4.w;
     }
-    if (j < out_dim) atomicAdd(&dbacc_k[j], s);
+    atomicAdd(&dbacc_k[j], s);
   }
-  (void)boff;
 }
+
+// Padded per-CTA partial layout: [NL][TPL][4] kernel patches (element (i, j) of layer k at
+// k*WP*WP + ((j/4)*WP + i)*4 + j%4) followed by [NL][WP] bias sums.
+__host__ __device__ inline int partial_row_size(int n_layers, int WP) { return n_layers * (WP * WP + WP); }
 
 template <int WP, int LIK>
 __global__ void __launch_bounds__(kObsThreads, 1) k_obs(ObsArgs a) {
@@ -244,7 +243,8 @@ __global__ void __launch_bounds__(kObsThreads, 1) k_obs(ObsArgs a) {
   }
   __syncthreads();
 
-  double* part_rows = a.partials + ((size_t)blockIdx.x * KS + (tid / TPL)) * a.lay.n_params;
+  const int PP = partial_row_size(NL, WP);
+  double* part_rows = a.partials + ((size_t)blockIdx.x * KS + (tid / TPL)) * PP + (size_t)(tid % TPL) * 4;
   float4* scr = a.scratch + (size_t)blockIdx.x * L * NC * T;
   double ll_sum = 0.0;
   const int64_t n_tiles = (a.n_rows + T - 1) / T;
@@ -339,13 +339,29 @@ __global__ void __launch_bounds__(kObsThreads, 1) k_obs(ObsArgs a) {
     }
     if (!a.train_mlp) continue;
     // ---------------- backward through the MLP ----------------
-    float dp[WP], ain[WP];
+    float dp[WP], nxt[WP];
+    // prefetch the input activations of the last hidden layer while the head is processed
+    auto load_act = [&](float (&dst)[WP], int k) {     // a_k: input of hidden layer k
+      if (k > 0) {
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          const float4 v = __ldcg(&scr[((size_t)(k - 1) * NC + c) * T + tid]);
+          dst[4 * c] = v.x; dst[4 * c + 1] = v.y; dst[4 * c + 2] = v.z; dst[4 * c + 3] = v.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < WP; ++i) dst[i] = (inb && i < a.d) ? a.meta[(size_t)i * a.n_rows + row] : 0.f;
+      }
+    };
+    if (L > 0) load_act(nxt, L - 1);
 #pragma unroll
     for (int j = 0; j < WP; ++j) dp[j] = 0.f;
     dp[0] = dmu; dp[1] = drho;
     // head: dW_out = a_L^T [dmu, drho]
-    stage_and_accumulate<WP>(h, dp, S_h, S_d, dbacc + L * WP, part_rows, a.lay.koff[L], a.lay.boff[L],
-                             a.lay.in_dim[L], a.lay.out_dim[L], tid);
+    stage_and_accumulate<WP>(h, dp, S_h, S_d, dbacc + L * WP, part_rows + (size_t)L * WP * WP, tid);
+    unsigned mask = 0u;                        // sign bits of a_{k+1}: leaky'(pre-activation)
+#pragma unroll
+    for (int j = 0; j < WP; ++j) mask |= (h[j] > 0.f ? 1u : 0u) << j;
     {
       const float* Wk = Wsm + (size_t)L * WP * WP;
 #pragma unroll
@@ -354,23 +370,16 @@ __global__ void __launch_bounds__(kObsThreads, 1) k_obs(ObsArgs a) {
         dp[i] = w.x * dmu + w.y * drho;          // delta a_L
       }
     }
-    // h currently holds a_L (output of hidden layer L-1)
     for (int k = L - 1; k >= 0; --k) {
       // delta p_k = delta a_{k+1} * leaky'(a_{k+1});  sign(a) == sign(pre-activation)
 #pragma unroll
-      for (int j = 0; j < WP; ++j) dp[j] = h[j] > 0.f ? dp[j] : kLeak * dp[j];
-      if (k > 0) {
+      for (int j = 0; j < WP; ++j) dp[j] = ((mask >> j) & 1u) ? dp[j] : kLeak * dp[j];
+      float ain[WP];
+      mask = 0u;
 #pragma unroll
-        for (int c = 0; c < NC; ++c) {
-          const float4 v = scr[((size_t)(k - 1) * NC + c) * T + tid];
-          ain[4 * c] = v.x; ain[4 * c + 1] = v.y; ain[4 * c + 2] = v.z; ain[4 * c + 3] = v.w;
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < WP; ++i) ain[i] = (inb && i < a.d) ? a.meta[(size_t)i * a.n_rows + row] : 0.f;
-      }
-      stage_and_accumulate<WP>(ain, dp, S_h, S_d, dbacc + k * WP, part_rows, a.lay.koff[k], a.lay.boff[k],
-                               a.lay.in_dim[k], a.lay.out_dim[k], tid);
+      for (int i = 0; i < WP; ++i) { ain[i] = nxt[i]; mask |= (ain[i] > 0.f ? 1u : 0u) << i; }
+      if (k > 0) load_act(nxt, k - 1);           // in flight during this layer's dW loop
+      stage_and_accumulate<WP>(ain, dp, S_h, S_d, dbacc + k * WP, part_rows + (size_t)k * WP * WP, tid);
       if (k > 0) {
         const float* Wk = Wsm + (size_t)k * WP * WP;
         float da[WP];
@@ -386,17 +395,15 @@ __global__ void __launch_bounds__(kObsThreads, 1) k_obs(ObsArgs a) {
           da[i] = (s0 + s1) + (s2 + s3);
         }
 #pragma unroll
-        for (int i = 0; i < WP; ++i) { dp[i] = da[i]; h[i] = ain[i]; }
+        for (int i = 0; i < WP; ++i) dp[i] = da[i];
       }
     }
   }
   // ---- flush: bias gradients and the log-likelihood sum ----
   __syncthreads();
   if (a.train_mlp) {
-    for (int idx = tid; idx < NL * WP; idx += T) {
-      const int k = idx / WP, j = idx % WP;
-      if (j < a.lay.out_dim[k]) a.partials[(size_t)blockIdx.x * KS * a.lay.n_params + a.lay.boff[k] + j] += (double)dbacc[idx];
-    }
+    for (int idx = tid; idx < NL * WP; idx += T)
+      a.partials[(size_t)blockIdx.x * KS * PP + (size_t)NL * WP * WP + idx] += (double)dbacc[idx];
   }
   ll_sum = warp_sum(ll_sum);
   if (lane == 0) red[tid >> 5] = ll_sum;
@@ -408,12 +415,27 @@ __global__ void __launch_bounds__(kObsThreads, 1) k_obs(ObsArgs a) {
   }
 }
 
-// Sum the per-CTA partial weight gradients: grad[p] = sum_rows partials[row][p]  (deterministic order).
-__global__ void __launch_bounds__(256) k_reduce_partials(const double* partials, int rows, int n_params, float* grad) {
+// Sum the per-CTA partial weight gradients (padded layout, see partial_row_size) into the flat keras-order
+// gradient: grad[p] = sum_rows partials[row][src(p)]  (fixed order => deterministic).
+__global__ void __launch_bounds__(256) k_reduce_partials(const double* partials, int rows, MlpLayout lay, int WP, float* grad) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n_params) return;
+  if (p >= lay.n_params) return;
+  const int PP = partial_row_size(lay.n_layers, WP);
+  int src = -1;
+  for (int k = 0; k < lay.n_layers; ++k) {
+    const int nk = lay.in_dim[k] * lay.out_dim[k];
+    if (p >= lay.koff[k] && p < lay.koff[k] + nk) {
+      const int i = (p - lay.koff[k]) / lay.out_dim[k], j = (p - lay.koff[k]) % lay.out_dim[k];
+      src = k * WP * WP + ((j >> 2) * WP + i) * 4 + (j & 3);
+      break;
+    }
+    if (p >= lay.boff[k] && p < lay.boff[k] + lay.out_dim[k]) {
+      src = lay.n_layers * WP * WP + k * WP + (p - lay.boff[k]);
+      break;
+    }
+  }
   double s = 0.0;
-  for (int r = 0; r < rows; ++r) s += partials[(size_t)r * n_params + p];
+  for (int r = 0; r < rows; ++r) s += partials[(size_t)r * PP + src];
   grad[p] = (float)s;
 }
 
