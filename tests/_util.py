@@ -109,11 +109,23 @@ def oracle_grads_grouped(g, ocfg):
     return out
 
 
-def rel_err(a, b):
-    """max |a-b| / (|b| + 1e-3*max|b|): elementwise relative error with a floor tied to the array scale."""
-    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+def rel_err_all(a, b):
+    """elementwise |a-b| / (|b| + 1e-3*max|b|): relative error with a floor tied to the array scale."""
+    a, b = np.asarray(a, dtype=np.float64).reshape(-1), np.asarray(b, dtype=np.float64).reshape(-1)
     scale = np.max(np.abs(b)) if b.size else 1.0
-    return float(np.max(np.abs(a - b) / (np.abs(b) + 1e-3 * scale + 1e-30))) if b.size else 0.0
+    return np.abs(a - b) / (np.abs(b) + 1e-3 * scale + 1e-30)
+
+
+def rel_err(a, b):
+    """max over elements of rel_err_all."""
+    e = rel_err_all(a, b)
+    return float(e.max()) if e.size else 0.0
+
+
+def rel_err_q(a, b, q=0.995):
+    """q-quantile over elements of rel_err_all (robust to the few cancellation-dominated elements)."""
+    e = rel_err_all(a, b)
+    return float(np.quantile(e, q)) if e.size else 0.0
 
 
 def rms_err(a, b):

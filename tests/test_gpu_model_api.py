@@ -1,0 +1,119 @@
+"""GPU tests of the careless-shaped public API (careless_b200.models), written like the reference's own
+tests/models/merging/test_variational_{mono,laue}.py: every likelihood x prior x scaler combination trains
+and stays finite -- plus what the reference never checks: the history matches the oracle."""
+import numpy as np
+import pytest
+
+from careless_b200 import synth
+from careless_b200.models.likelihoods import laue as laue_lik
+from careless_b200.models.likelihoods import mono as mono_lik
+from careless_b200.models.merging.surrogate_posteriors import TruncatedNormal
+from careless_b200.models.merging.variational import VariationalMergingModel
+from careless_b200.models.priors.wilson import DoubleWilsonPrior, WilsonPrior
+from careless_b200.models.scaling.image import HybridImageScaler, ImageScaler
+from careless_b200.models.scaling.nn import MLPScaler
+from careless_b200.optimizers import Adam
+
+pytestmark = pytest.mark.gpu
+
+
+def _inputs(p, laue):
+    col = lambda a: np.asarray(a).reshape(-1, 1)
+    t = (col(p["refl_id"]), col(p["image_id"]), col(p["file_id"]), p["metadata"], col(p["intensities"]), col(p["uncertainties"]))
+    if laue:
+        t = t + (col(p["wavelength"]), col(p["harmonic_id"]))
+    return t
+
+
+def _model(p, laue, likelihood, prior_kind, scaler_kind, mc_samples):
+    if prior_kind == "wilson":
+        prior = WilsonPrior(p["centric"], p["multiplicity"])
+    else:
+        prior = DoubleWilsonPrior(p["centric"], p["multiplicity"], p["asu_id"], p["reflids"], p["root"], p["r"],
+                                  optimize_r=(prior_kind == "dw_opt"))
+    loc, scale = prior.mean(), prior.stddev()
+    low = (1e-32 * ~np.asarray(p["centric"], dtype=bool)).astype("float32")          # manager.py:434
+    q = TruncatedNormal.from_loc_and_scale(loc, scale, low)
+    mod = laue_lik if laue else mono_lik
+    lik = mod.NormalLikelihood() if likelihood == "normal" else mod.StudentTLikelihood(4.0)
+    mlp = MLPScaler(3, 6, scale_bijector="exp")
+    scaler = mlp if scaler_kind == "mlp" else HybridImageScaler(mlp, ImageScaler(int(p["n_images"])))
+    model = VariationalMergingModel(q, prior, lik, scaler, mc_samples)
+    model.compile(Adam(1e-2, 0.9, 0.99))
+    return model
+
+
+@pytest.mark.parametrize("laue", [False, True])
+@pytest.mark.parametrize("likelihood", ["normal", "studentt"])
+@pytest.mark.parametrize("scaler_kind", ["mlp", "hybrid"])
+@pytest.mark.parametrize("mc_samples", [1, 3])
+def test_train_model_runs_and_improves(laue, likelihood, scaler_kind, mc_samples):
+    p = synth.make_laue(3000, 300, d=3, n_images=12, seed=4) if laue else synth.make_mono(3000, 300, d=3, n_images=12, seed=4)
+    model = _model(p, laue, likelihood, "wilson", scaler_kind, mc_samples)
+    data = _inputs(p, laue)
+    hist = model.train_model(data, 40, progress=False)
+    assert set(hist) >= {"loss", "NLL", "F KLDiv", "Grad Norm"}
+    assert all(len(v) == 40 for v in hist.values())
+    assert np.all(np.isfinite([hist[k] for k in hist]))
+    assert np.mean(hist["loss"][-5:]) < np.mean(hist["loss"][:5])
+    q = model.surrogate_posterior
+    assert np.all(np.isfinite(q.mean())) and np.all(q.stddev() > 0) and np.all(np.isfinite(q.moment_4()))
+    model.close()
+
+
+@pytest.mark.parametrize("prior_kind", ["dw", "dw_opt"])
+def test_double_wilson_model(prior_kind):
+    p = synth.make_double_wilson(1500, 200, n_datasets=3, d=3, n_images=5, r=0.9, seed=5)
+    model = _model(p, False, "normal", prior_kind, "hybrid", 1)
+    r0 = model.prior.r.copy()
+    hist = model.train_model(_inputs(p, False), 30, progress=False)
+    assert np.all(np.isfinite(hist["loss"]))
+    if prior_kind == "dw_opt":
+        assert not np.allclose(model.prior.r[1:], r0[1:])
+    else:
+        assert np.allclose(model.prior.r, r0)
+    with pytest.raises(ValueError):
+        DoubleWilsonPrior(p["centric"], p["multiplicity"], p["asu_id"], p["reflids"], p["root"], [0.0, 1.0, 0.5])
+    model.close()
+
+
+def test_freezing_and_weight_roundtrip(tmp_path):
+    """careless.py:48-56,79-80,104: save/load weights, frozen scaler for the half-dataset re-merge."""
+    p = synth.make_mono(2000, 200, d=3, n_images=8, seed=6)
+    model = _model(p, False, "normal", "wilson", "hybrid", 1)
+    data = _inputs(p, False)
+    model.train_model(data, 10, progress=False)
+    mlp = model.scaling_model.mlp_scaler
+    w_before = [w.copy() for w in mlp.get_weights()]
+    s_before = model.scaling_model.image_scaler._scales.copy()
+    q_before = model.surrogate_posterior.loc_raw.copy()
+    mlp.save_weights(tmp_path / "scale"); model.surrogate_posterior.save_weights(tmp_path / "sf")
+    model.scaling_model.trainable = False                     # careless.py:104
+    model.train_model(data, 5, progress=False)
+    assert all(np.array_equal(a, b) for a, b in zip(w_before, mlp.get_weights()))
+    assert np.array_equal(s_before, model.scaling_model.image_scaler._scales)
+    assert not np.array_equal(q_before, model.surrogate_posterior.loc_raw)
+    model.surrogate_posterior.load_weights(tmp_path / "sf"); mlp.load_weights(tmp_path / "scale")
+    assert np.array_equal(q_before, model.surrogate_posterior.loc_raw)
+    model.close()
+
+
+def test_history_matches_oracle_through_public_api():
+    import torch
+    from oracle import model as om
+    from oracle import philox
+    p = synth.make_mono(2500, 250, d=3, n_images=9, seed=7)
+    model = _model(p, False, "studentt", "wilson", "hybrid", 2)
+    model.seed = 4242
+    hist = model.train_model(_inputs(p, False), 3, progress=False)
+    ocfg = om.ModelConfig(n_refl=250, n_meta=3, mlp_width=6, mlp_layers=3, likelihood="studentt", dof=4.0,
+                          mc_samples=2, image_scales=True, n_images=12)
+    ocfg.n_images = int(p["n_images"])
+    oprior = om.PriorData(p["centric"], p["multiplicity"])
+    params = om.init_params(ocfg, oprior)
+    draws = [(philox.refl_uniforms(4242, s, 2, np.arange(250)), philox.obs_normals(4242, s, 2, np.arange(2500))) for s in range(3)]
+    _, ohist, _ = om.train(params, p, oprior, ocfg, om.AdamConfig(lr=1e-2), draws)
+    for i in range(3):
+        for k in ("loss", "NLL", "F KLDiv", "Grad Norm"):
+            assert abs(hist[k][i] - ohist[i][k]) <= 2e-4 * abs(ohist[i][k]) + 1e-6, (i, k, hist[k][i], ohist[i][k])
+    model.close()
