@@ -331,7 +331,7 @@ int clb_create(const clb_config* cfg, clb_handle** out) {
   if (h->cfg.n_refl_total <= 0) h->cfg.n_refl_total = h->cfg.n_refl;
   if (h->cfg.world_size <= 0) { h->cfg.world_size = 1; h->cfg.rank = 0; }
   { const char* dbg = getenv("CLB_DEBUG_SYNC"); h->debug_sync = dbg && dbg[0] == '1'; }
-  h->R = cfg->n_refl; h->S = cfg->mc_samples; h->WP = WP; h->KS = ks_for(WP);
+  h->R = cfg->n_refl; h->S = cfg->mc_samples; h->WP = WP; h->KS = 1;
   auto bail = [&](int code) { g_create_error = h->err; delete h; return code; };
 #define CREATE_CUDA(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { fail(h, CLB_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); return bail(CLB_ERR_CUDA); } } while (0)
   CREATE_CUDA(cudaSetDevice(cfg->device));

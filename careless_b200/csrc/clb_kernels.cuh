@@ -156,68 +156,115 @@ template <int WP> struct ObsSmem {
   static size_t bytes(int n_layers) {
     return sizeof(float) * ((size_t)n_layers * WP * WP + (size_t)n_layers * WP   // W, b
                             + (size_t)n_layers * WP                                // bias-grad accumulators
-                            + (size_t)WP * HS + (size_t)T * WP) + 64 * sizeof(double);
+                            + (size_t)WP * HS + (size_t)T * WP      // staged activation / delta tiles
+                            + (size_t)T * 16)                         // K-split reduction buffer
+           + 64 * sizeof(double);
   }
 };
 
 // One layer's weight gradient over the CTA tile: dW[i][j] = sum_obs a[obs][i] * dp[obs][j].
-// a is staged transposed (S_h[i][obs]), dp row-major with XOR-swizzled float4 chunks.  Each thread owns
-// a 1x4 patch of dW (exclusive: no atomics); its FP64 running sum lives in the CTA's L2-resident partial
-// buffer at `part` (4 consecutive doubles).  The partial is fetched BEFORE the staging barriers so the L2
-// round trip overlaps the 256-observation loop.
+// a is staged transposed (S_h[i][obs], padded stride), dp row-major with XOR-swizzled float4 chunks.
+// Each thread accumulates a 4x4 patch of dW (rows pi + (WP/4) r, float4 column chunk pj) over its share
+// of the tile's observations (K-split over KS4 thread groups): 8 LDS.128 feed 64 FFMA.  The K-split
+// partial sums are combined through shared memory (Rbuf) and the first WP*WP/4 threads add the result to
+// the CTA's FP64 running sum in its L2-resident partial buffer (`part`, 4 consecutive doubles each;
+// exclusive ownership, no atomics).  The partial is fetched BEFORE the barriers so the L2 round trip
+// overlaps the loop.
 template <int WP>
 __device__ __forceinline__ void stage_and_accumulate(const float (&ain)[WP], const float (&dp)[WP],
-                                                     float* S_h, float4* S_d, float* dbacc_k, double* part, int tid) {
+                                                     float* S_h, float4* S_d, float4* Rbuf, float* dbacc_k,
+                                                     double* part, int tid) {
   constexpr int T = kObsThreads, HS = T + 4, NC = WP / 4;
-  constexpr int TPL = WP * NC;            // threads covering one WPxWP matrix with 1x4 patches
-  constexpr int KS = T / TPL;             // K (observation) split
-  static_assert(KS >= 1, "WP too large for the tile");
-  const double2 p01 = __ldcg(reinterpret_cast<const double2*>(part));
-  const double2 p23 = __ldcg(reinterpret_cast<const double2*>(part) + 1);
-  __syncthreads();                        // previous consumer of the staging buffers is done
+  constexpr int Q = WP / 4;               // patch rows are strided by Q, patch columns are one float4 chunk
+  constexpr int TPL4 = Q * Q;             // threads covering one WPxWP matrix with 4x4 patches
+  constexpr int KS4 = T / TPL4;           // K (observation) split
+  constexpr int OBS = T / KS4;            // observations per K-split group
+  constexpr int NOUT4 = WP * WP / 4;      // float4 outputs of one layer
+  static_assert(OBS % 4 == 0 && OBS >= 4, "tile too small for the K split");
+  const bool owner = tid < NOUT4;
+  double2 p01 = make_double2(0.0, 0.0), p23 = make_double2(0.0, 0.0);
+  if (owner) {
+    p01 = __ldcg(reinterpret_cast<const double2*>(part));
+    p23 = __ldcg(reinterpret_cast<const double2*>(part) + 1);
+  }
+  __syncthreads();                        // previous consumers of the staging / reduction buffers are done
 #pragma unroll
   for (int i = 0; i < WP; ++i) S_h[i * HS + tid] = ain[i];
 #pragma unroll
   for (int c = 0; c < NC; ++c)
     S_d[tid * NC + (c ^ (tid & (NC - 1)))] = make_float4(dp[4 * c], dp[4 * c + 1], dp[4 * c + 2], dp[4 * c + 3]);
   __syncthreads();
-  const int pi = tid % WP, pjq = (tid / WP) % NC, ks = tid / TPL;
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  const int o0 = ks * (T / KS);
-#pragma unroll 4
-  for (int o = o0; o < o0 + T / KS; o += 4) {
-    const float4 h4 = *reinterpret_cast<const float4*>(&S_h[pi * HS + o]);
-    const float hv[4] = {h4.x, h4.y, h4.z, h4.w};
+  const int pp = tid % TPL4, ks = tid / TPL4;
+  const int pi = pp % Q, pj = pp / Q;
+  float acc[4][4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float4 d4 = S_d[(o + q) * NC + (pjq ^ ((o + q) & (NC - 1)))];
-      acc.x = fmaf(hv[q], d4.x, acc.x); acc.y = fmaf(hv[q], d4.y, acc.y);
-      acc.z = fmaf(hv[q], d4.z, acc.z); acc.w = fmaf(hv[q], d4.w, acc.w);
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+  const float* hrow = S_h + pi * HS + ks * OBS;
+  const float4* drow = S_d + (size_t)(ks * OBS) * NC;
+  const int o0 = ks * OBS;
+  float4 hb[2][4], db[2][4];
+  auto load = [&](int buf, int o) {       // o: offset inside this group's observation range
+#pragma unroll
+    for (int r = 0; r < 4; ++r) hb[buf][r] = *reinterpret_cast<const float4*>(hrow + r * Q * HS + o);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) db[buf][q] = drow[(o + q) * NC + (pj ^ ((o0 + o + q) & (NC - 1)))];
+  };
+  load(0, 0);
+#pragma unroll
+  for (int st = 0; st < OBS / 4; ++st) {
+    const int cur = st & 1;
+    if (st + 1 < OBS / 4) load(cur ^ 1, 4 * (st + 1));
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const float hv[4] = {hb[cur][r].x, hb[cur][r].y, hb[cur][r].z, hb[cur][r].w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        acc[r][0] = fmaf(hv[q], db[cur][q].x, acc[r][0]); acc[r][1] = fmaf(hv[q], db[cur][q].y, acc[r][1]);
+        acc[r][2] = fmaf(hv[q], db[cur][q].z, acc[r][2]); acc[r][3] = fmaf(hv[q], db[cur][q].w, acc[r][3]);
+      }
     }
   }
-  __stcg(reinterpret_cast<double2*>(part), make_double2(p01.x + (double)acc.x, p01.y + (double)acc.y));
-  __stcg(reinterpret_cast<double2*>(part) + 1, make_double2(p23.x + (double)acc.z, p23.y + (double)acc.w));
-  // bias gradient: column sums of dp
+  // K-split partial sums -> Rbuf[ks][r][pp]
+#pragma unroll
+  for (int r = 0; r < 4; ++r) Rbuf[(ks * 4 + r) * TPL4 + pp] = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+  // bias gradient: column sums of dp (reads S_d only)
   {
     constexpr int G = T / WP;
     const int j = tid % WP, g = tid / WP;
     float s = 0.f;
+#pragma unroll 4
     for (int o = g * (T / G); o < (g + 1) * (T / G); ++o) {
       const float4 d4 = S_d[o * NC + ((j >> 2) ^ (o & (NC - 1)))];
       s += (j & 3) == 0 ? d4.x : (j & 3) == 1 ? d4.y : (j & 3) == 2 ? d4.z : d4.w;
     }
     atomicAdd(&dbacc_k[j], s);
   }
+  __syncthreads();
+  if (owner) {
+    float4 t = Rbuf[tid];
+#pragma unroll
+    for (int k2 = 1; k2 < KS4; ++k2) {
+      const float4 v = Rbuf[k2 * NOUT4 + tid];
+      t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+    }
+    __stcg(reinterpret_cast<double2*>(part), make_double2(p01.x + (double)t.x, p01.y + (double)t.y));
+    __stcg(reinterpret_cast<double2*>(part) + 1, make_double2(p23.x + (double)t.z, p23.y + (double)t.w));
+  }
 }
 
-// Padded per-CTA partial layout: [NL][TPL][4] kernel patches (element (i, j) of layer k at
-// k*WP*WP + ((j/4)*WP + i)*4 + j%4) followed by [NL][WP] bias sums.
+// Padded per-CTA partial layout: [NL][WP*WP] kernel sums in patch order -- element (i, j) of layer k at
+// k*WP*WP + partial_elem(i, j, WP) -- followed by [NL][WP] bias sums.
+__host__ __device__ inline int partial_elem(int i, int j, int WP) {
+  const int Q = WP / 4;
+  return (((i / Q) * Q * Q + (j >> 2) * Q + (i % Q)) << 2) + (j & 3);
+}
 __host__ __device__ inline int partial_row_size(int n_layers, int WP) { return n_layers * (WP * WP + WP); }
 
 template <int WP, int LIK>
 __global__ void __launch_bounds__(kObsThreads, 1) k_obs(ObsArgs a) {
   constexpr int T = kObsThreads, HS = T + 4, NC = WP / 4;
-  constexpr int TPL = WP * NC, KS = T / TPL;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int NL = a.lay.n_layers;          // incl. head
   const int L = NL - 1;                   // hidden layers
@@ -226,7 +273,8 @@ __global__ void __launch_bounds__(kObsThreads, 1) k_obs(ObsArgs a) {
   float* dbacc = bsm + (size_t)NL * WP;                     // [NL][WP]
   float* S_h = dbacc + (size_t)NL * WP;                     // [WP][HS]
   float4* S_d = reinterpret_cast<float4*>(S_h + (size_t)WP * HS);   // [T][NC]
-  double* red = reinterpret_cast<double*>(reinterpret_cast<float*>(S_d) + (size_t)T * WP);
+  float4* Rbuf = S_d + (size_t)T * NC;                      // [KS4][4][TPL4] float4 = T*16 floats
+  double* red = reinterpret_cast<double*>(reinterpret_cast<float*>(Rbuf) + (size_t)T * 16);
 
   const int tid = threadIdx.x, lane = tid & 31;
   // ---- stage the weights (zero padded to WP x WP) ----
@@ -244,7 +292,7 @@ __global__ void __launch_bounds__(kObsThreads, 1) k_obs(ObsArgs a) {
   __syncthreads();
 
   const int PP = partial_row_size(NL, WP);
-  double* part_rows = a.partials + ((size_t)blockIdx.x * KS + (tid / TPL)) * PP + (size_t)(tid % TPL) * 4;
+  double* part_rows = a.partials + (size_t)blockIdx.x * PP + (size_t)tid * 4;   // valid for tid < WP*WP/4
   float4* scr = a.scratch + (size_t)blockIdx.x * L * NC * T;
   double ll_sum = 0.0;
   const int64_t n_tiles = (a.n_rows + T - 1) / T;
@@ -358,7 +406,7 @@ __global__ void __launch_bounds__(kObsThreads, 1) k_obs(ObsArgs a) {
     for (int j = 0; j < WP; ++j) dp[j] = 0.f;
     dp[0] = dmu; dp[1] = drho;
     // head: dW_out = a_L^T [dmu, drho]
-    stage_and_accumulate<WP>(h, dp, S_h, S_d, dbacc + L * WP, part_rows + (size_t)L * WP * WP, tid);
+    stage_and_accumulate<WP>(h, dp, S_h, S_d, Rbuf, dbacc + L * WP, part_rows + (size_t)L * WP * WP, tid);
     unsigned mask = 0u;                        // sign bits of a_{k+1}: leaky'(pre-activation)
 #pragma unroll
     for (int j = 0; j < WP; ++j) mask |= (h[j] > 0.f ? 1u : 0u) << j;
@@ -379,7 +427,7 @@ __global__ void __launch_bounds__(kObsThreads, 1) k_obs(ObsArgs a) {
 #pragma unroll
       for (int i = 0; i < WP; ++i) { ain[i] = nxt[i]; mask |= (ain[i] > 0.f ? 1u : 0u) << i; }
       if (k > 0) load_act(nxt, k - 1);           // in flight during this layer's dW loop
-      stage_and_accumulate<WP>(ain, dp, S_h, S_d, dbacc + k * WP, part_rows + (size_t)k * WP * WP, tid);
+      stage_and_accumulate<WP>(ain, dp, S_h, S_d, Rbuf, dbacc + k * WP, part_rows + (size_t)k * WP * WP, tid);
       if (k > 0) {
         const float* Wk = Wsm + (size_t)k * WP * WP;
         float da[WP];
@@ -403,7 +451,7 @@ __global__ void __launch_bounds__(kObsThreads, 1) k_obs(ObsArgs a) {
   __syncthreads();
   if (a.train_mlp) {
     for (int idx = tid; idx < NL * WP; idx += T)
-      a.partials[(size_t)blockIdx.x * KS * PP + (size_t)NL * WP * WP + idx] += (double)dbacc[idx];
+      a.partials[(size_t)blockIdx.x * PP + (size_t)NL * WP * WP + idx] += (double)dbacc[idx];
   }
   ll_sum = warp_sum(ll_sum);
   if (lane == 0) red[tid >> 5] = ll_sum;
@@ -426,7 +474,7 @@ __global__ void __launch_bounds__(256) k_reduce_partials(const double* partials,
     const int nk = lay.in_dim[k] * lay.out_dim[k];
     if (p >= lay.koff[k] && p < lay.koff[k] + nk) {
       const int i = (p - lay.koff[k]) / lay.out_dim[k], j = (p - lay.koff[k]) % lay.out_dim[k];
-      src = k * WP * WP + ((j >> 2) * WP + i) * 4 + (j & 3);
+      src = k * WP * WP + partial_elem(i, j, WP);
       break;
     }
     if (p >= lay.boff[k] && p < lay.boff[k] + lay.out_dim[k]) {
