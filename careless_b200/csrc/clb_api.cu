@@ -72,6 +72,7 @@ struct clb_handle {
   int64_t adam_t = 0;
   uint32_t step_counter = 0;   // RNG step index
   bool have_obs = false, have_prior = false, in_step = false;
+  bool use_tc = false;       // tensor-core (tcgen05) path of k_obs: padded width 32, unless CLB_NO_TC=1
   bool debug_sync = false;   // CLB_DEBUG_SYNC=1: synchronise + log after every kernel launch
   int order = CLB_ORDER_REFL;
   double ll_const = 0.0;   // per-sample constant log-likelihood of empty Laue slots
@@ -124,19 +125,21 @@ int fail(clb_handle* h, int code, const char* fmt, ...) {
 
 int round_width(int w) { return w <= 8 ? 8 : w <= 16 ? 16 : w <= 32 ? 32 : -1; }
 
-template <int WP, int LIK> cudaError_t launch_obs(clb_handle* h, const ObsArgs& a) {
-  cudaError_t e = cudaFuncSetAttribute(k_obs<WP, LIK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_obs);
+template <int WP, int LIK, bool TC> cudaError_t launch_obs(clb_handle* h, const ObsArgs& a) {
+  cudaError_t e = cudaFuncSetAttribute(k_obs<WP, LIK, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_obs);
   if (e != cudaSuccess) return e;
-  k_obs<WP, LIK><<<h->grid_obs, kObsThreads, h->smem_obs, h->stream>>>(a);
+  k_obs<WP, LIK, TC><<<h->grid_obs, kObsThreads, h->smem_obs, h->stream>>>(a);
   return cudaGetLastError();
 }
 
 cudaError_t dispatch_obs(clb_handle* h, const ObsArgs& a) {
   const int lik = h->cfg.likelihood;
   switch (h->WP) {
-    case 8:  return lik ? launch_obs<8, 1>(h, a) : launch_obs<8, 0>(h, a);
-    case 16: return lik ? launch_obs<16, 1>(h, a) : launch_obs<16, 0>(h, a);
-    case 32: return lik ? launch_obs<32, 1>(h, a) : launch_obs<32, 0>(h, a);
+    case 8:  return lik ? launch_obs<8, 1, false>(h, a) : launch_obs<8, 0, false>(h, a);
+    case 16: return lik ? launch_obs<16, 1, false>(h, a) : launch_obs<16, 0, false>(h, a);
+    case 32:
+      if (h->use_tc) return lik ? launch_obs<32, 1, true>(h, a) : launch_obs<32, 0, true>(h, a);
+      return lik ? launch_obs<32, 1, false>(h, a) : launch_obs<32, 0, false>(h, a);
   }
   return cudaErrorInvalidValue;
 }
@@ -341,10 +344,11 @@ int clb_create(const clb_config* cfg, clb_handle** out) {
   build_layout(h);
   build_vars(h);
   h->NL = h->lay.n_layers;
+  { const char* no_tc = getenv("CLB_NO_TC"); h->use_tc = (WP == 32) && cfg->mlp_layers > 0 && !(no_tc && no_tc[0] == '1'); }
   switch (WP) {
     case 8: h->smem_obs = ObsSmem<8>::bytes(h->NL); break;
     case 16: h->smem_obs = ObsSmem<16>::bytes(h->NL); break;
-    default: h->smem_obs = ObsSmem<32>::bytes(h->NL); break;
+    default: h->smem_obs = ObsSmem<32>::bytes(h->NL, h->use_tc); break;
   }
   if (h->smem_obs > (size_t)prop.sharedMemPerBlockOptin) {
     fail(h, CLB_ERR_INVALID, "scale MLP (%d layers x padded width %d) needs %zu B of shared memory; the device offers %zu",

@@ -5,6 +5,7 @@
 // See DESIGN.md for the data layout and the roofline of each kernel.
 #pragma once
 #include "clb_math.cuh"
+#include "clb_tc.cuh"
 
 namespace clb {
 
@@ -153,8 +154,9 @@ struct ObsArgs {
 template <int WP> struct ObsSmem {
   static constexpr int T = kObsThreads;
   static constexpr int HS = T + 4;                    // padded stride of the transposed activation tile
-  static size_t bytes(int n_layers) {
-    return sizeof(float) * ((size_t)n_layers * WP * WP + (size_t)n_layers * WP   // W, b
+  static size_t bytes(int n_layers, bool tensor_cores = false) {
+    return (tensor_cores ? 2 * (size_t)tc::kImgBytes + 128 : 0) +                  // B operand images, barrier, TMEM slot
+           sizeof(float) * ((size_t)n_layers * WP * WP + (size_t)n_layers * WP   // W, b
                             + (size_t)n_layers * WP                                // bias-grad accumulators
                             + (size_t)WP * HS + (size_t)T * WP      // staged activation / delta tiles
                             + (size_t)T * 16)                         // K-split reduction buffer
@@ -262,8 +264,12 @@ __host__ __device__ inline int partial_elem(int i, int j, int WP) {
 }
 __host__ __device__ inline int partial_row_size(int n_layers, int WP) { return n_layers * (WP * WP + WP); }
 
-template <int WP, int LIK>
+// TC = true (WP == 32 only): the forward and dX products of the hidden layers run on the tensor cores
+// (tcgen05.mma kind::tf32, 3xTF32 error-compensated, operands/accumulators in tensor memory; clb_tc.cuh);
+// TC = false: everything on the FP32 FMA pipe.
+template <int WP, int LIK, bool TC>
 __global__ void __launch_bounds__(kObsThreads, 1) k_obs(ObsArgs a) {
+  static_assert(!TC || WP == 32, "the tensor-core path is built for the padded width 32");
   constexpr int T = kObsThreads, HS = T + 4, NC = WP / 4;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int NL = a.lay.n_layers;          // incl. head
@@ -275,8 +281,17 @@ __global__ void __launch_bounds__(kObsThreads, 1) k_obs(ObsArgs a) {
   float4* S_d = reinterpret_cast<float4*>(S_h + (size_t)WP * HS);   // [T][NC]
   float4* Rbuf = S_d + (size_t)T * NC;                      // [KS4][4][TPL4] float4 = T*16 floats
   double* red = reinterpret_cast<double*>(reinterpret_cast<float*>(Rbuf) + (size_t)T * 16);
+  char* tc_img = reinterpret_cast<char*>(red + 64);         // [2][kImgBytes] B operand images (TC only)
+  uint64_t* tc_bar = reinterpret_cast<uint64_t*>(tc_img + 2 * tc::kImgBytes);
+  uint32_t* tc_slot = reinterpret_cast<uint32_t*>(tc_bar + 1);
 
   const int tid = threadIdx.x, lane = tid & 31;
+  tc::Ctx tcx{};
+  if constexpr (TC) {
+    if (tid == 0) tc::mbar_init(tc::smem_u32(tc_bar), 6);
+    if (tid < 32) tc::tmem_alloc(tc::smem_u32(tc_slot));
+    tc::fence_before();
+  }
   // ---- stage the weights (zero padded to WP x WP) ----
   for (int idx = tid; idx < NL * WP * WP; idx += T) {
     const int k = idx / (WP * WP), i = (idx / WP) % WP, j = idx % WP;
@@ -290,6 +305,18 @@ __global__ void __launch_bounds__(kObsThreads, 1) k_obs(ObsArgs a) {
     dbacc[idx] = 0.f;
   }
   __syncthreads();
+  if constexpr (TC) {
+    tc::fence_after();
+    const uint32_t tbase = *tc_slot;
+    const int warp = tid >> 5;
+    tcx.half_addr = tbase + tc::kHalfCols * (uint32_t)(warp >> 2);
+    tcx.row_addr = tcx.half_addr + ((uint32_t)(32 * (warp & 3)) << 16);
+    tcx.mbar = tc::smem_u32(tc_bar);
+    tcx.parity = 0;
+    tcx.img_hi = tc_img; tcx.img_lo = tc_img + tc::kImgBytes;
+    tcx.desc_hi = tc::make_desc(tc::smem_u32(tcx.img_hi)); tcx.desc_lo = tc::make_desc(tc::smem_u32(tcx.img_lo));
+    tcx.tid = tid;
+  }
 
   const int PP = partial_row_size(NL, WP);
   double* part_rows = a.partials + (size_t)blockIdx.x * PP + (size_t)tid * 4;   // valid for tid < WP*WP/4
@@ -309,15 +336,22 @@ __global__ void __launch_bounds__(kObsThreads, 1) k_obs(ObsArgs a) {
     for (int k = 0; k < L; ++k) {
       const float* Wk = Wsm + (size_t)k * WP * WP;
       float o[WP];
+      if constexpr (TC) {
+        tc::issue<false>(tcx, h, Wk);
+        tc::collect(tcx, o);
 #pragma unroll
-      for (int j = 0; j < WP; ++j) o[j] = bsm[k * WP + j];
+        for (int j = 0; j < WP; ++j) o[j] += bsm[k * WP + j];
+      } else {
 #pragma unroll
-      for (int i = 0; i < WP; ++i) {
+        for (int j = 0; j < WP; ++j) o[j] = bsm[k * WP + j];
 #pragma unroll
-        for (int c = 0; c < NC; ++c) {
-          const float4 w = *reinterpret_cast<const float4*>(&Wk[i * WP + 4 * c]);
-          o[4 * c] = fmaf(h[i], w.x, o[4 * c]); o[4 * c + 1] = fmaf(h[i], w.y, o[4 * c + 1]);
-          o[4 * c + 2] = fmaf(h[i], w.z, o[4 * c + 2]); o[4 * c + 3] = fmaf(h[i], w.w, o[4 * c + 3]);
+        for (int i = 0; i < WP; ++i) {
+#pragma unroll
+          for (int c = 0; c < NC; ++c) {
+            const float4 w = *reinterpret_cast<const float4*>(&Wk[i * WP + 4 * c]);
+            o[4 * c] = fmaf(h[i], w.x, o[4 * c]); o[4 * c + 1] = fmaf(h[i], w.y, o[4 * c + 1]);
+            o[4 * c + 2] = fmaf(h[i], w.z, o[4 * c + 2]); o[4 * c + 3] = fmaf(h[i], w.w, o[4 * c + 3]);
+          }
         }
       }
 #pragma unroll
@@ -427,6 +461,13 @@ __global__ void __launch_bounds__(kObsThreads, 1) k_obs(ObsArgs a) {
 #pragma unroll
       for (int i = 0; i < WP; ++i) { ain[i] = nxt[i]; mask |= (ain[i] > 0.f ? 1u : 0u) << i; }
       if (k > 0) load_act(nxt, k - 1);           // in flight during this layer's dW loop
+      if constexpr (TC) {
+        // delta a_k = delta p_k W_k^T on the tensor cores, in flight while the FP32 pipe accumulates dW_k
+        if (k > 0) tc::issue<true>(tcx, dp, Wsm + (size_t)k * WP * WP);
+        stage_and_accumulate<WP>(ain, dp, S_h, S_d, Rbuf, dbacc + k * WP, part_rows + (size_t)k * WP * WP, tid);
+        if (k > 0) tc::collect(tcx, dp);
+        continue;
+      }
       stage_and_accumulate<WP>(ain, dp, S_h, S_d, Rbuf, dbacc + k * WP, part_rows + (size_t)k * WP * WP, tid);
       if (k > 0) {
         const float* Wk = Wsm + (size_t)k * WP * WP;
@@ -455,11 +496,15 @@ __global__ void __launch_bounds__(kObsThreads, 1) k_obs(ObsArgs a) {
   }
   ll_sum = warp_sum(ll_sum);
   if (lane == 0) red[tid >> 5] = ll_sum;
+  if constexpr (TC) tc::fence_before();
   __syncthreads();
   if (tid == 0) {
     double t = 0.0;
     for (int i = 0; i < T / 32; ++i) t += red[i];
     atomicAdd(&a.acc[ACC_LL], t);
+  }
+  if constexpr (TC) {
+    if (tid < 32) tc::tmem_dealloc(*tc_slot);
   }
 }
 

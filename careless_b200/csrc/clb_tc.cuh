@@ -1,0 +1,169 @@
+// clb_tc.cuh -- tcgen05 / TMEM building blocks for the scale-MLP products of k_obs (sm_100a only).
+//
+// One "pass" multiplies the CTA's 256x32 activation (or delta) tile by one 32x32 weight matrix on the
+// 5th-generation tensor cores, error-compensated 3xTF32 so that the result keeps FP32 accuracy:
+//     X W  ~=  X_hi W_hi + X_hi W_lo + X_lo W_hi          (X_hi = tf32(X), X_lo = tf32(X - X_hi), same for W)
+// * A operand (X): one row per thread, written to TENSOR MEMORY with tcgen05.st (lane = row) -- no layout puzzle;
+// * B operand (W): built per pass in shared memory in the canonical K-major / no-swizzle UMMA layout
+//   (8x16-byte core matrices, LBO = 528 B between K-adjacent core matrices, SBO = 128 B between 8-row groups);
+// * D (FP32 accumulators): tensor memory, read back one row per thread with tcgen05.ld.
+// The 256-row tile is two M=128 halves; each (half, product) pair has its own accumulator columns and its own
+// issuing warp (a single thread issues a tcgen05.mma only every ~60-110 cycles, but issuers run concurrently --
+// measured with tools/tc_rate.cu), so a pass is 6 issuers x 4 k-steps (K = 8 per tf32 instruction).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace clb {
+namespace tc {
+
+constexpr uint32_t kLBO = 528;           // bytes between K-adjacent core matrices (528 % 128 == 16: conflict-free image builds)
+constexpr uint32_t kSBO = 128;           // bytes between 8-row groups
+constexpr uint32_t kImgBytes = 8 * kLBO; // one 32x32 tf32 operand image
+constexpr uint32_t kTmemCols = 512;
+// tensor-memory column map of one 128-row half (half h starts at column 256 h)
+constexpr uint32_t kColAhi = 0, kColAlo = 32, kColD = 64;   // D0, D1, D2 at 64, 96, 128
+constexpr uint32_t kHalfCols = 256;
+// instruction descriptor: D=F32 (1<<4), A=B=TF32 (2<<7, 2<<10), both K-major, N=32 (4<<17), M=128 (8<<24)
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((kLBO >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((kSBO >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);   // version 1, no swizzle
+}
+
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n"
+               :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(kIdesc), "r"(accumulate) : "memory");
+}
+
+__device__ __forceinline__ void commit(uint32_t mbar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(mbar), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+  asm volatile("{\n\t.reg .pred P1;\n\tCLB_WAIT:\n\t"
+               "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+               "@P1 bra CLB_DONE;\n\tbra CLB_WAIT;\n\tCLB_DONE:\n\t}\n" :: "r"(mbar), "r"(parity) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem) {   // one full warp
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(slot_smem), "r"(kTmemCols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t tbase) {     // the same warp
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tbase), "r"(kTmemCols) : "memory");
+}
+
+#define CLB_TMEM_ST32(taddr, v) asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" \
+  :: "r"(taddr), "r"(v[0]),"r"(v[1]),"r"(v[2]),"r"(v[3]),"r"(v[4]),"r"(v[5]),"r"(v[6]),"r"(v[7]),"r"(v[8]),"r"(v[9]),"r"(v[10]),"r"(v[11]),"r"(v[12]),"r"(v[13]),"r"(v[14]),"r"(v[15]), \
+     "r"(v[16]),"r"(v[17]),"r"(v[18]),"r"(v[19]),"r"(v[20]),"r"(v[21]),"r"(v[22]),"r"(v[23]),"r"(v[24]),"r"(v[25]),"r"(v[26]),"r"(v[27]),"r"(v[28]),"r"(v[29]),"r"(v[30]),"r"(v[31]) : "memory")
+
+#define CLB_TMEM_LD32(taddr, v) asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];" \
+  : "=r"(v[0]),"=r"(v[1]),"=r"(v[2]),"=r"(v[3]),"=r"(v[4]),"=r"(v[5]),"=r"(v[6]),"=r"(v[7]),"=r"(v[8]),"=r"(v[9]),"=r"(v[10]),"=r"(v[11]),"=r"(v[12]),"=r"(v[13]),"=r"(v[14]),"=r"(v[15]), \
+    "=r"(v[16]),"=r"(v[17]),"=r"(v[18]),"=r"(v[19]),"=r"(v[20]),"=r"(v[21]),"=r"(v[22]),"=r"(v[23]),"=r"(v[24]),"=r"(v[25]),"=r"(v[26]),"=r"(v[27]),"=r"(v[28]),"=r"(v[29]),"=r"(v[30]),"=r"(v[31]) \
+  : "r"(taddr) : "memory")
+
+// Per-thread view of the CTA's tensor-core state.
+struct Ctx {
+  uint32_t row_addr;     // tensor-memory address of this thread's row: base + (32 (warp%4)) << 16 + 256 (warp/4)
+  uint32_t half_addr;    // base + 256 (warp/4): operand / accumulator columns of this warp's half (lane field 0)
+  uint32_t mbar;         // shared-memory address of the pass barrier (6 arrivals per pass)
+  uint32_t parity;
+  char* img_hi; char* img_lo;          // B operand images in shared memory
+  uint64_t desc_hi, desc_lo;
+  int tid;
+};
+
+// Start one pass:  Y = X W_k (BWD = false)  or  Y = X W_k^T (BWD = true) for the CTA's 256 rows.
+// x: this thread's row.  Wk: the layer's 32x32 FP32 weights in shared memory, row-major [in][out].
+// Ends with the tcgen05.mma's in flight; tc::collect() waits for them.  Contains one __syncthreads().
+template <bool BWD>
+__device__ __forceinline__ void issue(Ctx& c, const float (&x)[32], const float* Wk) {
+  {
+    uint32_t hi[32], lo[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const float h = tf32_rna(x[k]);
+      hi[k] = __float_as_uint(h);
+      lo[k] = __float_as_uint(tf32_rna(x[k] - h));
+    }
+    CLB_TMEM_ST32(c.row_addr + kColAhi, hi);
+    CLB_TMEM_ST32(c.row_addr + kColAlo, lo);
+  }
+  {   // B image: element (n, k) of the [N][K] operand at (k/4) LBO + (n/8) SBO + (n%8) 16 + (k%4) 4 bytes
+    float4 w;
+    uint32_t off;
+    if (!BWD) {            // B[n][k] = W[k][n]: thread (n = tid%32, kq = tid/32) gathers 4 consecutive k
+      const int n = c.tid & 31, kq = c.tid >> 5;
+      w = make_float4(Wk[(4 * kq) * 32 + n], Wk[(4 * kq + 1) * 32 + n], Wk[(4 * kq + 2) * 32 + n], Wk[(4 * kq + 3) * 32 + n]);
+      off = kq * kLBO + (n >> 3) * kSBO + (n & 7) * 16;
+    } else {               // B[n][k] = W[n][k]: thread (kq = tid%8, n = tid/8) copies 4 consecutive k
+      const int kq = c.tid & 7, n = c.tid >> 3;
+      w = *reinterpret_cast<const float4*>(&Wk[n * 32 + 4 * kq]);
+      off = kq * kLBO + (n >> 3) * kSBO + (n & 7) * 16;
+    }
+    float4 h, l;
+    h.x = tf32_rna(w.x); h.y = tf32_rna(w.y); h.z = tf32_rna(w.z); h.w = tf32_rna(w.w);
+    l.x = tf32_rna(w.x - h.x); l.y = tf32_rna(w.y - h.y); l.z = tf32_rna(w.z - h.z); l.w = tf32_rna(w.w - h.w);
+    *reinterpret_cast<float4*>(c.img_hi + off) = h;
+    *reinterpret_cast<float4*>(c.img_lo + off) = l;
+  }
+  wait_st();
+  fence_async_smem();           // generic-proxy smem writes -> visible to the tensor core's async proxy
+  fence_before();
+  __syncthreads();
+  const int warp = c.tid >> 5;
+  if ((c.tid & 31) == 0 && (warp & 3) < 3) {     // 6 issuers: (half, product) = (warp/4, warp%4)
+    fence_after();
+    const int part = warp & 3;
+    const uint32_t a = c.half_addr + (part == 2 ? kColAlo : kColAhi);
+    const uint64_t b = (part == 1) ? c.desc_lo : c.desc_hi;
+    const uint32_t d = c.half_addr + kColD + 32u * (uint32_t)part;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks)
+      mma_tf32_ts(d, a + 8u * (uint32_t)ks, b + (uint64_t)((2u * kLBO * (uint32_t)ks) >> 4), ks > 0 ? 1u : 0u);
+    commit(c.mbar);
+  }
+}
+
+// Wait for the pass and read this thread's row of the result: y = D0 + D1 + D2.
+__device__ __forceinline__ void collect(Ctx& c, float (&y)[32]) {
+  mbar_wait(c.mbar, c.parity);
+  c.parity ^= 1u;
+  fence_after();
+  uint32_t v[32];
+  CLB_TMEM_LD32(c.row_addr + kColD + 32, v);     // small cross terms first: (X_hi W_lo + X_lo W_hi) + X_hi W_hi
+  wait_ld();
+#pragma unroll
+  for (int k = 0; k < 32; ++k) y[k] = __uint_as_float(v[k]);
+  CLB_TMEM_LD32(c.row_addr + kColD + 64, v);
+  wait_ld();
+#pragma unroll
+  for (int k = 0; k < 32; ++k) y[k] += __uint_as_float(v[k]);
+  CLB_TMEM_LD32(c.row_addr + kColD, v);
+  wait_ld();
+#pragma unroll
+  for (int k = 0; k < 32; ++k) y[k] += __uint_as_float(v[k]);
+}
+
+}  // namespace tc
+}  // namespace clb

@@ -1,0 +1,178 @@
+// tc_probe.cu -- bring-up probe for the tcgen05 path of the scale MLP (not part of the product library).
+//
+// One CTA, 128 threads.  D[128x32] (TMEM) = A[128x32] (TMEM, one row per thread/lane) x W[32x32] (smem),
+// error-compensated 3xTF32:  A_hi*W_hi + A_hi*W_lo + A_lo*W_hi.  Checks the result against a double CPU
+// product and times the full per-layer round trip (tcgen05.st -> fence -> mma x12 -> commit -> wait -> ld).
+//
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tc_probe tools/tc_probe.cu && ./tc_probe
+#include <cstdio>
+#include <cstdlib>
+#include <cstdint>
+#include <cmath>
+#include <vector>
+#include <cuda_runtime.h>
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(1); } } while (0)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return __uint_as_float(r);
+}
+
+// K-major, no-swizzle canonical layout of a [N=32][K=32] tf32 operand: core matrix = 8 rows x 16 B.
+// element (n, k) at (k/4)*LBO + (n/8)*SBO + (n%8)*16 + (k%4)*4 bytes
+constexpr uint32_t LBO = 512, SBO = 128;
+__host__ __device__ inline uint32_t b_off_kmajor(int n, int k) { return (k / 4) * LBO + (n / 8) * SBO + (n % 8) * 16 + (k % 4) * 4; }
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;            // descriptor version 1 (Blackwell)
+  return d;                          // layout_type = 0 (no swizzle), base_offset = 0
+}
+
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n"
+               :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+#define TMEM_ST32(taddr, v) asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" \
+  :: "r"(taddr), "r"(v[0]),"r"(v[1]),"r"(v[2]),"r"(v[3]),"r"(v[4]),"r"(v[5]),"r"(v[6]),"r"(v[7]),"r"(v[8]),"r"(v[9]),"r"(v[10]),"r"(v[11]),"r"(v[12]),"r"(v[13]),"r"(v[14]),"r"(v[15]), \
+     "r"(v[16]),"r"(v[17]),"r"(v[18]),"r"(v[19]),"r"(v[20]),"r"(v[21]),"r"(v[22]),"r"(v[23]),"r"(v[24]),"r"(v[25]),"r"(v[26]),"r"(v[27]),"r"(v[28]),"r"(v[29]),"r"(v[30]),"r"(v[31]) : "memory")
+
+#define TMEM_LD32(taddr, v) asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];" \
+  : "=r"(v[0]),"=r"(v[1]),"=r"(v[2]),"=r"(v[3]),"=r"(v[4]),"=r"(v[5]),"=r"(v[6]),"=r"(v[7]),"=r"(v[8]),"=r"(v[9]),"=r"(v[10]),"=r"(v[11]),"=r"(v[12]),"=r"(v[13]),"=r"(v[14]),"=r"(v[15]), \
+    "=r"(v[16]),"=r"(v[17]),"=r"(v[18]),"=r"(v[19]),"=r"(v[20]),"=r"(v[21]),"=r"(v[22]),"=r"(v[23]),"=r"(v[24]),"=r"(v[25]),"=r"(v[26]),"=r"(v[27]),"=r"(v[28]),"=r"(v[29]),"=r"(v[30]),"=r"(v[31]) \
+  : "r"(taddr) : "memory")
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile("{\n\t.reg .pred P1;\n\tWAIT_LOOP:\n\t"
+               "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+               "@P1 bra DONE;\n\tbra WAIT_LOOP;\n\tDONE:\n\t}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+constexpr int kCols = 128;   // TMEM columns: D [0,32)  A_hi [32,64)  A_lo [64,96)
+
+__global__ void __launch_bounds__(128, 1) probe(const float* A, const float* W, float* D, int mode, int iters, long long* cycles) {
+  __shared__ __align__(1024) float Bhi[32 * 32];
+  __shared__ __align__(1024) float Blo[32 * 32];
+  __shared__ __align__(8) uint64_t mbar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+
+  // ---- B operand (weights) in canonical K-major layout: B[n][k] = W[k][n] ----
+  for (int idx = tid; idx < 1024; idx += 128) {
+    const int n = idx / 32, k = idx % 32;
+    const float w = W[k * 32 + n];
+    const float hi = tf32_rna(w), lo = tf32_rna(w - hi);
+    *reinterpret_cast<float*>(reinterpret_cast<char*>(Bhi) + b_off_kmajor(n, k)) = hi;
+    *reinterpret_cast<float*>(reinterpret_cast<char*>(Blo) + b_off_kmajor(n, k)) = lo;
+  }
+  if (tid == 0) { mbar_init(&mbar, 1); }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // smem writes -> visible to the tensor core (async proxy)
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_s)), "r"(kCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tbase = tmem_base_s;
+  const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
+  const uint32_t t_d = tbase + lane_base + 0, t_ahi = tbase + lane_base + 32, t_alo = tbase + lane_base + 64;
+
+  // idesc: c=F32 (1<<4), a=b=TF32 (2<<7, 2<<10), K-major A/B, N=32 (4<<17), M=128 (8<<24)
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+  const uint64_t dhi = make_desc(smem_u32(Bhi), LBO, SBO), dlo = make_desc(smem_u32(Blo), LBO, SBO);
+
+  float a[32];
+  for (int k = 0; k < 32; ++k) a[k] = A[tid * 32 + k];
+  uint32_t out[32];
+  uint32_t parity = 0;
+  long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    uint32_t hi[32], lo[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const float h = tf32_rna(a[k]);
+      hi[k] = __float_as_uint(h);
+      lo[k] = __float_as_uint(tf32_rna(a[k] - h));
+    }
+    TMEM_ST32(t_ahi, hi);
+    TMEM_ST32(t_alo, lo);
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      uint32_t acc = 0;
+      const int nparts = (mode == 0) ? 1 : 3;
+      for (int part = 0; part < nparts; ++part) {
+        const uint32_t ta = (part == 2) ? (tbase + 64) : (tbase + 32);       // A_lo for the third product
+        const uint64_t db = (part == 1) ? dlo : dhi;                         // W_lo for the second product
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          mma_tf32_ts(tbase, ta + 8 * ks, db + (uint64_t)((2 * LBO * ks) >> 4), idesc, acc);
+          acc = 1;
+        }
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&mbar)) : "memory");
+    }
+    mbar_wait(&mbar, parity);
+    parity ^= 1;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    TMEM_LD32(t_d, out);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    if (it + 1 < iters) {     // chain: feed a squashed copy of the output back in (keeps the loop honest)
+#pragma unroll
+      for (int k = 0; k < 32; ++k) a[k] = a[k] + 1e-6f * __uint_as_float(out[k]);
+    }
+  }
+  long long t1 = clock64();
+  if (tid == 0) cycles[0] = t1 - t0;
+  for (int k = 0; k < 32; ++k) D[tid * 32 + k] = __uint_as_float(out[k]);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tbase), "r"(kCols) : "memory");
+}
+
+int main() {
+  std::vector<float> A(128 * 32), W(32 * 32), D(128 * 32);
+  srand(1);
+  for (auto& x : A) x = (float)rand() / RAND_MAX * 2.f - 1.f;
+  for (auto& x : W) x = (float)rand() / RAND_MAX * 2.f - 1.f;
+  float *dA, *dW, *dD; long long* dC;
+  CK(cudaMalloc(&dA, A.size() * 4)); CK(cudaMalloc(&dW, W.size() * 4)); CK(cudaMalloc(&dD, D.size() * 4)); CK(cudaMalloc(&dC, 8));
+  CK(cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dW, W.data(), W.size() * 4, cudaMemcpyHostToDevice));
+  for (int mode = 0; mode < 2; ++mode) {
+    probe<<<1, 128>>>(dA, dW, dD, mode, 1, dC);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost));
+    double maxerr = 0, maxref = 0;
+    for (int m = 0; m < 128; ++m)
+      for (int n = 0; n < 32; ++n) {
+        double ref = 0;
+        for (int k = 0; k < 32; ++k) ref += (double)A[m * 32 + k] * (double)W[k * 32 + n];
+        maxerr = fmax(maxerr, fabs(ref - D[m * 32 + n])); maxref = fmax(maxref, fabs(ref));
+      }
+    printf("mode %d (%s): max abs err %.3e (max |ref| %.3f)  D[0][0..3] = %f %f %f %f\n", mode, mode ? "3xTF32" : "1xTF32", maxerr, maxref,
+           D[0], D[1], D[2], D[3]);
+  }
+  for (int mode = 0; mode < 2; ++mode) {
+    long long c = 0;
+    probe<<<1, 128>>>(dA, dW, dD, mode, 1000, dC);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(&c, dC, 8, cudaMemcpyDeviceToHost));
+    printf("mode %d: %.1f cycles per layer round trip (1 CTA, 128 threads)\n", mode, (double)c / 1000);
+  }
+  return 0;
+}
