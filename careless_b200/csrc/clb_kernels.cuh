@@ -155,14 +155,44 @@ template <int WP> struct ObsSmem {
   static constexpr int T = kObsThreads;
   static constexpr int HS = T + 4;                    // padded stride of the transposed activation tile
   static size_t bytes(int n_layers, bool tensor_cores = false) {
-    return (tensor_cores ? 2 * (size_t)tc::kImgBytes + 128 : 0) +                  // B operand images, barrier, TMEM slot
-           sizeof(float) * ((size_t)n_layers * WP * WP + (size_t)n_layers * WP   // W, b
+    if (tensor_cores)     // dW operand images, hidden-layer weights, compact head, biases, bias sums, reductions, chain images
+      return 2 * (size_t)tc::kDwImgBytes + sizeof(float) * ((size_t)(n_layers - 1) * WP * WP + 2 * WP + 2 * (size_t)n_layers * WP
+                                                              + (size_t)(T / 32) * WP) + 64 * sizeof(double) + 2 * (size_t)tc::kImgBytes + 128;
+    return sizeof(float) * ((size_t)n_layers * WP * WP + (size_t)n_layers * WP   // W, b
                             + (size_t)n_layers * WP                                // bias-grad accumulators
                             + (size_t)WP * HS + (size_t)T * WP      // staged activation / delta tiles
-                            + (size_t)T * 16)                         // K-split reduction buffer
+                            + (size_t)T * 16                          // K-split reduction buffer
+                            + (size_t)(T / 32) * WP)                  // per-warp bias-gradient sums
            + 64 * sizeof(double);
   }
 };
+
+
+// Bias gradient, step 1: column sums of dp over the 32 observations of a warp.  A recursive-halving exchange
+// leaves one lane per column with the warp's sum (WP-1 shuffles), stored to bias_part[warp][column].
+template <int WP>
+__device__ __forceinline__ void bias_partial(const float (&dp)[WP], float* bias_part, int tid) {
+  constexpr int NH = (WP == 32) ? 5 : (WP == 16) ? 4 : 3;      // log2(WP) halving steps
+  float v[WP];
+#pragma unroll
+  for (int j = 0; j < WP; ++j) v[j] = dp[j];
+  const int lane = tid & 31;
+#pragma unroll
+  for (int st = 0; st < NH; ++st) {
+    const int bit = 16 >> st, half = WP >> (st + 1);
+    const bool up = (lane & bit) != 0;
+#pragma unroll
+    for (int j = 0; j < half; ++j) {
+      const float send = up ? v[j] : v[j + half];
+      const float recv = __shfl_xor_sync(0xffffffffu, send, bit);
+      v[j] = (up ? v[j + half] : v[j]) + recv;
+    }
+  }
+#pragma unroll
+  for (int st = NH; st < 5; ++st) v[0] += __shfl_xor_sync(0xffffffffu, v[0], 16 >> st);
+  constexpr int SH = 5 - NH;                                     // lanes sharing a column
+  if ((lane & ((1 << SH) - 1)) == 0) bias_part[(tid >> 5) * WP + (lane >> SH)] = v[0];
+}
 
 // One layer's weight gradient over the CTA tile: dW[i][j] = sum_obs a[obs][i] * dp[obs][j].
 // a is staged transposed (S_h[i][obs], padded stride), dp row-major with XOR-swizzled float4 chunks.
@@ -174,8 +204,8 @@ template <int WP> struct ObsSmem {
 // overlaps the loop.
 template <int WP>
 __device__ __forceinline__ void stage_and_accumulate(const float (&ain)[WP], const float (&dp)[WP],
-                                                     float* S_h, float4* S_d, float4* Rbuf, float* dbacc_k,
-                                                     double* part, int tid) {
+                                                     float* S_h, float4* S_d, float4* Rbuf, float* bias_part,
+                                                     float* dbacc_k, double* part, int tid) {
   constexpr int T = kObsThreads, HS = T + 4, NC = WP / 4;
   constexpr int Q = WP / 4;               // patch rows are strided by Q, patch columns are one float4 chunk
   constexpr int TPL4 = Q * Q;             // threads covering one WPxWP matrix with 4x4 patches
@@ -231,19 +261,14 @@ __device__ __forceinline__ void stage_and_accumulate(const float (&ain)[WP], con
   // K-split partial sums -> Rbuf[ks][r][pp]
 #pragma unroll
   for (int r = 0; r < 4; ++r) Rbuf[(ks * 4 + r) * TPL4 + pp] = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
-  // bias gradient: column sums of dp (reads S_d only)
-  {
-    constexpr int G = T / WP;
-    const int j = tid % WP, g = tid / WP;
-    float s = 0.f;
-#pragma unroll 4
-    for (int o = g * (T / G); o < (g + 1) * (T / G); ++o) {
-      const float4 d4 = S_d[o * NC + ((j >> 2) ^ (o & (NC - 1)))];
-      s += (j & 3) == 0 ? d4.x : (j & 3) == 1 ? d4.y : (j & 3) == 2 ? d4.z : d4.w;
-    }
-    atomicAdd(&dbacc_k[j], s);
-  }
+  bias_partial<WP>(dp, bias_part, tid);
   __syncthreads();
+  if (tid < WP) {
+    float sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < T / 32; ++w) sum += bias_part[w * WP + tid];
+    dbacc_k[tid] += sum;                    // column tid of this layer is owned by thread tid: no atomics
+  }
   if (owner) {
     float4 t = Rbuf[tid];
 #pragma unroll
@@ -254,6 +279,40 @@ __device__ __forceinline__ void stage_and_accumulate(const float (&ain)[WP], con
     __stcg(reinterpret_cast<double2*>(part), make_double2(p01.x + (double)t.x, p01.y + (double)t.y));
     __stcg(reinterpret_cast<double2*>(part) + 1, make_double2(p23.x + (double)t.z, p23.y + (double)t.w));
   }
+}
+
+// Tensor-core version of one layer's backward (TC kernels, WP == 32): dW_k = a_k^T dp_k and, when need_dx,
+// dp <- delta a_k = dp_k W_k^T, both on tcgen05 (clb_tc.cuh); the FP32 pipe only splits operands, folds the
+// accumulator copies and adds the result to the CTA's FP64 partial (same layout as the FP32 path).
+__device__ __forceinline__ void tc_layer_backward(tc::Ctx& tcx, float (&dp)[32], const float (&ain)[32], const float* Wk,
+                                                  bool need_dx, float* bias_part, float* dbacc_k, double* part, int tid) {
+  const double2 p01 = __ldcg(reinterpret_cast<const double2*>(part));
+  const double2 p23 = __ldcg(reinterpret_cast<const double2*>(part) + 1);
+  bias_partial<32>(dp, bias_part, tid);
+  tc::issue_backward(tcx, dp, ain, Wk, need_dx);
+  if (need_dx) tc::collect(tcx, dp);
+  tc::collect_dw(tcx);
+  __syncthreads();
+  {
+    // element (i, j0..j0+3) owned by this thread in the partial layout (see partial_elem): i = pi + 8 r, j0 = 4 pj
+    const int r = tid >> 6, pj = (tid & 63) >> 3, pi = tid & 7;
+    const float* st = reinterpret_cast<const float*>(tcx.dw_a) + (size_t)(pi + 8 * r) * tc::kStageStride + 4 * pj;
+    float4 t = *reinterpret_cast<const float4*>(st);
+#pragma unroll
+    for (int c = 1; c < 4; ++c) {
+      const float4 v = *reinterpret_cast<const float4*>(st + (size_t)c * 32 * tc::kStageStride);
+      t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+    }
+    if (tid < 32) {
+      float sum = 0.f;
+#pragma unroll
+      for (int w = 0; w < kObsThreads / 32; ++w) sum += bias_part[w * 32 + tid];
+      dbacc_k[tid] += sum;
+    }
+    __stcg(reinterpret_cast<double2*>(part), make_double2(p01.x + (double)t.x, p01.y + (double)t.y));
+    __stcg(reinterpret_cast<double2*>(part) + 1, make_double2(p23.x + (double)t.z, p23.y + (double)t.w));
+  }
+  __syncthreads();      // the stage aliases the operand image of the next layer
 }
 
 // Padded per-CTA partial layout: [NL][WP*WP] kernel sums in patch order -- element (i, j) of layer k at
@@ -271,33 +330,48 @@ template <int WP, int LIK, bool TC>
 __global__ void __launch_bounds__(kObsThreads, 1) k_obs(ObsArgs a) {
   static_assert(!TC || WP == 32, "the tensor-core path is built for the padded width 32");
   constexpr int T = kObsThreads, HS = T + 4, NC = WP / 4;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
   const int NL = a.lay.n_layers;          // incl. head
   const int L = NL - 1;                   // hidden layers
-  float* Wsm = reinterpret_cast<float*>(smem_raw);          // [NL][WP][WP]
-  float* bsm = Wsm + (size_t)NL * WP * WP;                  // [NL][WP]
+  constexpr int HSTR = TC ? 2 : WP;       // row stride of the head weights (compact [WP][2] in the TC kernels)
+  unsigned char* sp = smem_raw;
+  char* tc_dwa = nullptr; char* tc_dwb = nullptr;
+  if constexpr (TC) { tc_dwa = reinterpret_cast<char*>(sp); tc_dwb = tc_dwa + tc::kDwImgBytes; sp += 2 * tc::kDwImgBytes; }
+  float* Wsm = reinterpret_cast<float*>(sp);                // [L][WP][WP] hidden layers, then the head [WP][HSTR]
+  float* Whead = Wsm + (size_t)L * WP * WP;
+  float* bsm = Whead + (size_t)WP * HSTR;                   // [NL][WP]
   float* dbacc = bsm + (size_t)NL * WP;                     // [NL][WP]
-  float* S_h = dbacc + (size_t)NL * WP;                     // [WP][HS]
-  float4* S_d = reinterpret_cast<float4*>(S_h + (size_t)WP * HS);   // [T][NC]
-  float4* Rbuf = S_d + (size_t)T * NC;                      // [KS4][4][TPL4] float4 = T*16 floats
-  double* red = reinterpret_cast<double*>(reinterpret_cast<float*>(Rbuf) + (size_t)T * 16);
+  float* nxtp = dbacc + (size_t)NL * WP;
+  float* S_h = nullptr; float4* S_d = nullptr; float4* Rbuf = nullptr;
+  if constexpr (!TC) {
+    S_h = nxtp;                                             // [WP][HS]
+    S_d = reinterpret_cast<float4*>(S_h + (size_t)WP * HS); // [T][NC]
+    Rbuf = S_d + (size_t)T * NC;                            // [KS4][4][TPL4] float4 = T*16 floats
+    nxtp = reinterpret_cast<float*>(Rbuf) + (size_t)T * 16;
+  }
+  float* bias_part = nxtp;                                  // [T/32][WP]
+  double* red = reinterpret_cast<double*>(bias_part + (size_t)(T / 32) * WP);
   char* tc_img = reinterpret_cast<char*>(red + 64);         // [2][kImgBytes] B operand images (TC only)
-  uint64_t* tc_bar = reinterpret_cast<uint64_t*>(tc_img + 2 * tc::kImgBytes);
-  uint32_t* tc_slot = reinterpret_cast<uint32_t*>(tc_bar + 1);
+  uint64_t* tc_bar = reinterpret_cast<uint64_t*>(tc_img + 2 * tc::kImgBytes);   // [0] chain, [1] dW
+  uint32_t* tc_slot = reinterpret_cast<uint32_t*>(tc_bar + 2);
 
   const int tid = threadIdx.x, lane = tid & 31;
   tc::Ctx tcx{};
   if constexpr (TC) {
-    if (tid == 0) tc::mbar_init(tc::smem_u32(tc_bar), 6);
+    if (tid == 0) { tc::mbar_init(tc::smem_u32(tc_bar), 6); tc::mbar_init(tc::smem_u32(tc_bar + 1), 2); }
     if (tid < 32) tc::tmem_alloc(tc::smem_u32(tc_slot));
     tc::fence_before();
   }
   // ---- stage the weights (zero padded to WP x WP) ----
-  for (int idx = tid; idx < NL * WP * WP; idx += T) {
+  for (int idx = tid; idx < L * WP * WP; idx += T) {
     const int k = idx / (WP * WP), i = (idx / WP) % WP, j = idx % WP;
     float w = 0.f;
     if (i < a.lay.in_dim[k] && j < a.lay.out_dim[k]) w = a.theta_mlp[a.lay.koff[k] + i * a.lay.out_dim[k] + j];
     Wsm[idx] = w;
+  }
+  for (int idx = tid; idx < WP * HSTR; idx += T) {
+    const int i = idx / HSTR, j = idx % HSTR;
+    Whead[idx] = (i < a.lay.in_dim[L] && j < a.lay.out_dim[L]) ? a.theta_mlp[a.lay.koff[L] + i * a.lay.out_dim[L] + j] : 0.f;
   }
   for (int idx = tid; idx < NL * WP; idx += T) {
     const int k = idx / WP, j = idx % WP;
@@ -316,6 +390,10 @@ __global__ void __launch_bounds__(kObsThreads, 1) k_obs(ObsArgs a) {
     tcx.img_hi = tc_img; tcx.img_lo = tc_img + tc::kImgBytes;
     tcx.desc_hi = tc::make_desc(tc::smem_u32(tcx.img_hi)); tcx.desc_lo = tc::make_desc(tc::smem_u32(tcx.img_lo));
     tcx.tid = tid;
+    tcx.base = tbase;
+    tcx.mbar_dw = tc::smem_u32(tc_bar + 1); tcx.parity_dw = 0;
+    tcx.dw_a = tc_dwa; tcx.dw_b = tc_dwb;
+    tcx.desc_dwa = tc::make_desc_mn(tc::smem_u32(tc_dwa)); tcx.desc_dwb = tc::make_desc_mn(tc::smem_u32(tc_dwb));
   }
 
   const int PP = partial_row_size(NL, WP);
@@ -363,11 +441,10 @@ __global__ void __launch_bounds__(kObsThreads, 1) k_obs(ObsArgs a) {
     }
     float out0, out1;
     {
-      const float* Wk = Wsm + (size_t)L * WP * WP;
       out0 = bsm[L * WP]; out1 = bsm[L * WP + 1];
 #pragma unroll
       for (int i = 0; i < WP; ++i) {
-        const float2 w = *reinterpret_cast<const float2*>(&Wk[i * WP]);
+        const float2 w = *reinterpret_cast<const float2*>(&Whead[i * HSTR]);
         out0 = fmaf(h[i], w.x, out0); out1 = fmaf(h[i], w.y, out1);
       }
     }
@@ -440,17 +517,15 @@ __global__ void __launch_bounds__(kObsThreads, 1) k_obs(ObsArgs a) {
     for (int j = 0; j < WP; ++j) dp[j] = 0.f;
     dp[0] = dmu; dp[1] = drho;
     // head: dW_out = a_L^T [dmu, drho]
-    stage_and_accumulate<WP>(h, dp, S_h, S_d, Rbuf, dbacc + L * WP, part_rows + (size_t)L * WP * WP, tid);
+    if constexpr (TC) tc_layer_backward(tcx, dp, h, nullptr, false, bias_part, dbacc + L * WP, part_rows + (size_t)L * WP * WP, tid);
+    else stage_and_accumulate<WP>(h, dp, S_h, S_d, Rbuf, bias_part, dbacc + L * WP, part_rows + (size_t)L * WP * WP, tid);
     unsigned mask = 0u;                        // sign bits of a_{k+1}: leaky'(pre-activation)
 #pragma unroll
     for (int j = 0; j < WP; ++j) mask |= (h[j] > 0.f ? 1u : 0u) << j;
-    {
-      const float* Wk = Wsm + (size_t)L * WP * WP;
 #pragma unroll
-      for (int i = 0; i < WP; ++i) {
-        const float2 w = *reinterpret_cast<const float2*>(&Wk[i * WP]);
-        dp[i] = w.x * dmu + w.y * drho;          // delta a_L
-      }
+    for (int i = 0; i < WP; ++i) {
+      const float2 w = *reinterpret_cast<const float2*>(&Whead[i * HSTR]);
+      dp[i] = w.x * dmu + w.y * drho;            // delta a_L
     }
     for (int k = L - 1; k >= 0; --k) {
       // delta p_k = delta a_{k+1} * leaky'(a_{k+1});  sign(a) == sign(pre-activation)
@@ -462,13 +537,12 @@ __global__ void __launch_bounds__(kObsThreads, 1) k_obs(ObsArgs a) {
       for (int i = 0; i < WP; ++i) { ain[i] = nxt[i]; mask |= (ain[i] > 0.f ? 1u : 0u) << i; }
       if (k > 0) load_act(nxt, k - 1);           // in flight during this layer's dW loop
       if constexpr (TC) {
-        // delta a_k = delta p_k W_k^T on the tensor cores, in flight while the FP32 pipe accumulates dW_k
-        if (k > 0) tc::issue<true>(tcx, dp, Wsm + (size_t)k * WP * WP);
-        stage_and_accumulate<WP>(ain, dp, S_h, S_d, Rbuf, dbacc + k * WP, part_rows + (size_t)k * WP * WP, tid);
-        if (k > 0) tc::collect(tcx, dp);
+        // delta a_k = delta p_k W_k^T and dW_k = a_k^T delta p_k, both on the tensor cores
+        tc_layer_backward(tcx, dp, ain, Wsm + (size_t)k * WP * WP, k > 0, bias_part, dbacc + k * WP,
+                          part_rows + (size_t)k * WP * WP, tid);
         continue;
       }
-      stage_and_accumulate<WP>(ain, dp, S_h, S_d, Rbuf, dbacc + k * WP, part_rows + (size_t)k * WP * WP, tid);
+      stage_and_accumulate<WP>(ain, dp, S_h, S_d, Rbuf, bias_part, dbacc + k * WP, part_rows + (size_t)k * WP * WP, tid);
       if (k > 0) {
         const float* Wk = Wsm + (size_t)k * WP * WP;
         float da[WP];

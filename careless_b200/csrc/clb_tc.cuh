@@ -24,20 +24,42 @@ constexpr uint32_t kTmemCols = 512;
 // tensor-memory column map of one 128-row half (half h starts at column 256 h)
 constexpr uint32_t kColAhi = 0, kColAlo = 32, kColD = 64;   // D0, D1, D2 at 64, 96, 128
 constexpr uint32_t kHalfCols = 256;
+// dW = A^T dP (contraction over the 256 observations of the tile): both operands come from shared memory in the
+// MN-major layout, which for 32-bit types exists only as SWIZZLE_128B_BASE32B (layout type 1): atoms of 4 K-rows
+// x 128 B (32 MN elements), 32-byte chunk index XOR (row % 4); SBO = 512 B between 4-row K groups, LBO = 32 KB
+// between 32-element MN groups (group 0 = hi parts, group 1 = lo parts).  M = N = 64, K = 8 per instruction:
+// D = [A_hi; A_lo]^T [dP_hi | dP_lo]  ->  dW = D[0:32,0:32] + D[0:32,32:64] + D[32:64,0:32] (+ lo*lo).
+// M = 64 accumulators occupy lanes (r % 16) + 32 (r / 16) (verified with tools/tc_probe2.cu).
+constexpr uint32_t kDwSBO = 512, kDwLBO = (256 / 4) * 512;
+constexpr uint32_t kDwImgBytes = 2 * kDwLBO;                 // 64 KB per operand
+constexpr uint32_t kColDw0 = 160, kColDw1 = 416;             // accumulator columns of the two dW issuers (64 each)
+constexpr uint32_t kIdescDw = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((64u >> 3) << 17) | ((64u >> 4) << 24);
+constexpr int kStageStride = 36;                             // floats per row of the dW reduction stage (padded)
 // instruction descriptor: D=F32 (1<<4), A=B=TF32 (2<<7, 2<<10), both K-major, N=32 (4<<17), M=128 (8<<24)
 constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// Round to the nearest TF32 (10-bit mantissa), ties away from zero: integer add + mask (2 instructions;
+// cvt.rna.tf32.f32 expands to ~5).  Overflow into the exponent is the correct rounding; inf/nan stay inf/nan-like.
 __device__ __forceinline__ float tf32_rna(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((kLBO >> 4) & 0x3FFF) << 16) |
          ((uint64_t)((kSBO >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);   // version 1, no swizzle
+}
+
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((kDwLBO >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((kDwSBO >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) | ((uint64_t)1 << 61);   // SWIZZLE_128B_BASE32B
+}
+
+__device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+               :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
 __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t accumulate) {
@@ -91,48 +113,61 @@ struct Ctx {
   char* img_hi; char* img_lo;          // B operand images in shared memory
   uint64_t desc_hi, desc_lo;
   int tid;
+  // dW
+  uint32_t mbar_dw, parity_dw;         // barrier of the dW product (2 arrivals)
+  char* dw_a; char* dw_b;              // MN-major operand images (kDwImgBytes each); dw_a doubles as the reduction stage
+  uint64_t desc_dwa, desc_dwb;
+  uint32_t base;                       // tensor-memory base address
 };
 
-// Start one pass:  Y = X W_k (BWD = false)  or  Y = X W_k^T (BWD = true) for the CTA's 256 rows.
-// x: this thread's row.  Wk: the layer's 32x32 FP32 weights in shared memory, row-major [in][out].
-// Ends with the tcgen05.mma's in flight; tc::collect() waits for them.  Contains one __syncthreads().
-template <bool BWD>
-__device__ __forceinline__ void issue(Ctx& c, const float (&x)[32], const float* Wk) {
-  {
-    uint32_t hi[32], lo[32];
+__device__ __forceinline__ void split32(const float (&x)[32], uint32_t (&hi)[32], uint32_t (&lo)[32]) {
 #pragma unroll
-    for (int k = 0; k < 32; ++k) {
-      const float h = tf32_rna(x[k]);
-      hi[k] = __float_as_uint(h);
-      lo[k] = __float_as_uint(tf32_rna(x[k] - h));
-    }
-    CLB_TMEM_ST32(c.row_addr + kColAhi, hi);
-    CLB_TMEM_ST32(c.row_addr + kColAlo, lo);
+  for (int k = 0; k < 32; ++k) {
+    const float h = tf32_rna(x[k]);
+    hi[k] = __float_as_uint(h);
+    lo[k] = __float_as_uint(tf32_rna(x[k] - h));
   }
-  {   // B image: element (n, k) of the [N][K] operand at (k/4) LBO + (n/8) SBO + (n%8) 16 + (k%4) 4 bytes
-    float4 w;
-    uint32_t off;
-    if (!BWD) {            // B[n][k] = W[k][n]: thread (n = tid%32, kq = tid/32) gathers 4 consecutive k
-      const int n = c.tid & 31, kq = c.tid >> 5;
-      w = make_float4(Wk[(4 * kq) * 32 + n], Wk[(4 * kq + 1) * 32 + n], Wk[(4 * kq + 2) * 32 + n], Wk[(4 * kq + 3) * 32 + n]);
-      off = kq * kLBO + (n >> 3) * kSBO + (n & 7) * 16;
-    } else {               // B[n][k] = W[n][k]: thread (kq = tid%8, n = tid/8) copies 4 consecutive k
-      const int kq = c.tid & 7, n = c.tid >> 3;
-      w = *reinterpret_cast<const float4*>(&Wk[n * 32 + 4 * kq]);
-      off = kq * kLBO + (n >> 3) * kSBO + (n & 7) * 16;
-    }
-    float4 h, l;
-    h.x = tf32_rna(w.x); h.y = tf32_rna(w.y); h.z = tf32_rna(w.z); h.w = tf32_rna(w.w);
-    l.x = tf32_rna(w.x - h.x); l.y = tf32_rna(w.y - h.y); l.z = tf32_rna(w.z - h.z); l.w = tf32_rna(w.w - h.w);
-    *reinterpret_cast<float4*>(c.img_hi + off) = h;
-    *reinterpret_cast<float4*>(c.img_lo + off) = l;
+}
+
+// One row (observation k) of an MN-major operand image: 32 hi values in MN group 0, 32 lo values in group 1.
+__device__ __forceinline__ void dw_store_row(char* img, int k, const uint32_t (&hi)[32], const uint32_t (&lo)[32]) {
+  const int r = k & 3;
+  char* row = img + (size_t)(k >> 2) * kDwSBO + r * 128;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    char* p = row + ((c ^ r) * 32);
+    *reinterpret_cast<uint4*>(p) = make_uint4(hi[8 * c], hi[8 * c + 1], hi[8 * c + 2], hi[8 * c + 3]);
+    *reinterpret_cast<uint4*>(p + 16) = make_uint4(hi[8 * c + 4], hi[8 * c + 5], hi[8 * c + 6], hi[8 * c + 7]);
+    *reinterpret_cast<uint4*>(p + kDwLBO) = make_uint4(lo[8 * c], lo[8 * c + 1], lo[8 * c + 2], lo[8 * c + 3]);
+    *reinterpret_cast<uint4*>(p + kDwLBO + 16) = make_uint4(lo[8 * c + 4], lo[8 * c + 5], lo[8 * c + 6], lo[8 * c + 7]);
   }
-  wait_st();
-  fence_async_smem();           // generic-proxy smem writes -> visible to the tensor core's async proxy
-  fence_before();
-  __syncthreads();
+}
+
+// Build the chain's B operand image of one layer (see issue<>): 4 weights per thread.
+template <bool BWD>
+__device__ __forceinline__ void build_weight_image(Ctx& c, const float* Wk) {
+  float4 w;
+  uint32_t off;
+  if (!BWD) {            // B[n][k] = W[k][n]: thread (n = tid%32, kq = tid/32) gathers 4 consecutive k
+    const int n = c.tid & 31, kq = c.tid >> 5;
+    w = make_float4(Wk[(4 * kq) * 32 + n], Wk[(4 * kq + 1) * 32 + n], Wk[(4 * kq + 2) * 32 + n], Wk[(4 * kq + 3) * 32 + n]);
+    off = kq * kLBO + (n >> 3) * kSBO + (n & 7) * 16;
+  } else {               // B[n][k] = W[n][k]: thread (kq = tid%8, n = tid/8) copies 4 consecutive k
+    const int kq = c.tid & 7, n = c.tid >> 3;
+    w = *reinterpret_cast<const float4*>(&Wk[n * 32 + 4 * kq]);
+    off = kq * kLBO + (n >> 3) * kSBO + (n & 7) * 16;
+  }
+  float4 h, l;
+  h.x = tf32_rna(w.x); h.y = tf32_rna(w.y); h.z = tf32_rna(w.z); h.w = tf32_rna(w.w);
+  l.x = tf32_rna(w.x - h.x); l.y = tf32_rna(w.y - h.y); l.z = tf32_rna(w.z - h.z); l.w = tf32_rna(w.w - h.w);
+  *reinterpret_cast<float4*>(c.img_hi + off) = h;
+  *reinterpret_cast<float4*>(c.img_lo + off) = l;
+}
+
+// The 6 chain issuers: (half, product) = (warp/4, warp%4 < 3), 4 k-steps each.
+__device__ __forceinline__ void issue_chain_mmas(Ctx& c) {
   const int warp = c.tid >> 5;
-  if ((c.tid & 31) == 0 && (warp & 3) < 3) {     // 6 issuers: (half, product) = (warp/4, warp%4)
+  if ((c.tid & 31) == 0 && (warp & 3) < 3) {
     fence_after();
     const int part = warp & 3;
     const uint32_t a = c.half_addr + (part == 2 ? kColAlo : kColAhi);
@@ -143,6 +178,85 @@ __device__ __forceinline__ void issue(Ctx& c, const float (&x)[32], const float*
       mma_tf32_ts(d, a + 8u * (uint32_t)ks, b + (uint64_t)((2u * kLBO * (uint32_t)ks) >> 4), ks > 0 ? 1u : 0u);
     commit(c.mbar);
   }
+}
+
+// Backward of one layer: start delta_a = dp W^T (if need_dx) and dW = ain^T dp on the tensor cores.
+// Contains one __syncthreads().  collect() returns delta_a; collect_dw() the weight gradient.
+__device__ __forceinline__ void issue_backward(Ctx& c, const float (&dp)[32], const float (&ain)[32], const float* Wk, bool need_dx) {
+  {
+    uint32_t hi[32], lo[32];
+    split32(dp, hi, lo);
+    if (need_dx) {
+      CLB_TMEM_ST32(c.row_addr + kColAhi, hi);
+      CLB_TMEM_ST32(c.row_addr + kColAlo, lo);
+    }
+    dw_store_row(c.dw_b, c.tid, hi, lo);
+    split32(ain, hi, lo);
+    dw_store_row(c.dw_a, c.tid, hi, lo);
+  }
+  if (need_dx) build_weight_image<true>(c, Wk);
+  wait_st();
+  fence_async_smem();
+  fence_before();
+  __syncthreads();
+  if (need_dx) issue_chain_mmas(c);
+  const int warp = c.tid >> 5;
+  if ((c.tid & 31) == 0 && (warp & 3) == 3) {      // 2 dW issuers: observations [0,128) and [128,256)
+    fence_after();
+    const uint32_t half = (uint32_t)(warp >> 2);
+    const uint32_t d = c.base + (half ? kColDw1 : kColDw0);
+    const uint64_t a0 = c.desc_dwa + (uint64_t)((half * 16u * 2u * kDwSBO) >> 4);
+    const uint64_t b0 = c.desc_dwb + (uint64_t)((half * 16u * 2u * kDwSBO) >> 4);
+#pragma unroll
+    for (int ks = 0; ks < 16; ++ks)
+      mma_tf32_ss(d, a0 + (uint64_t)((2u * kDwSBO * (uint32_t)ks) >> 4), b0 + (uint64_t)((2u * kDwSBO * (uint32_t)ks) >> 4), kIdescDw, ks > 0 ? 1u : 0u);
+    commit(c.mbar_dw);
+  }
+}
+
+// Wait for dW and combine: D rows live at lanes (r%16) + 32 (r/16); every thread with lane < 16 folds its row's
+// two column halves and parks it in the stage [region*2 + (r >= 32)][i = r % 32][kStageStride] (aliases dw_a).
+// After the caller's __syncthreads() the stage holds 4 partial copies of the 32x32 gradient.
+__device__ __forceinline__ void collect_dw(Ctx& c) {
+  mbar_wait(c.mbar_dw, c.parity_dw);
+  c.parity_dw ^= 1u;
+  fence_after();
+  const int warp = c.tid >> 5, lane = c.tid & 31;
+  const uint32_t addr = c.base + ((uint32_t)(32 * (warp & 3)) << 16) + ((warp >> 2) ? kColDw1 : kColDw0);
+  uint32_t v0[32], v1[32];
+  CLB_TMEM_LD32(addr, v0);
+  CLB_TMEM_LD32(addr + 32, v1);
+  wait_ld();
+  if (lane < 16) {
+    const int r = 16 * (warp & 3) + lane;
+    float* dst = reinterpret_cast<float*>(c.dw_a) + ((size_t)((warp >> 2) * 2 + (r >> 5)) * 32 + (r & 31)) * kStageStride;
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      *reinterpret_cast<float4*>(dst + 4 * q) = make_float4(__uint_as_float(v0[4 * q]) + __uint_as_float(v1[4 * q]),
+                                                            __uint_as_float(v0[4 * q + 1]) + __uint_as_float(v1[4 * q + 1]),
+                                                            __uint_as_float(v0[4 * q + 2]) + __uint_as_float(v1[4 * q + 2]),
+                                                            __uint_as_float(v0[4 * q + 3]) + __uint_as_float(v1[4 * q + 3]));
+  }
+}
+
+
+// Start one pass:  Y = X W_k (BWD = false)  or  Y = X W_k^T (BWD = true) for the CTA's 256 rows.
+// x: this thread's row.  Wk: the layer's 32x32 FP32 weights in shared memory, row-major [in][out].
+// Ends with the tcgen05.mma's in flight; tc::collect() waits for them.  Contains one __syncthreads().
+template <bool BWD>
+__device__ __forceinline__ void issue(Ctx& c, const float (&x)[32], const float* Wk) {
+  {
+    uint32_t hi[32], lo[32];
+    split32(x, hi, lo);
+    CLB_TMEM_ST32(c.row_addr + kColAhi, hi);
+    CLB_TMEM_ST32(c.row_addr + kColAlo, lo);
+  }
+  build_weight_image<BWD>(c, Wk);
+  wait_st();
+  fence_async_smem();           // generic-proxy smem writes -> visible to the tensor core's async proxy
+  fence_before();
+  __syncthreads();
+  issue_chain_mmas(c);
 }
 
 // Wait for the pass and read this thread's row of the result: y = D0 + D1 + D2.
