@@ -68,6 +68,18 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, ui
                :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(kIdesc), "r"(accumulate) : "memory");
 }
 
+// Warp-uniform helpers: the compiler keeps values produced by a constant-lane shuffle in uniform registers,
+// so the tcgen05.mma operands need no per-instruction R2UR "waterfall" loop (which costs ~100 cycles per MMA).
+__device__ __forceinline__ uint32_t uniform32(uint32_t x) { return __shfl_sync(0xffffffffu, x, 0); }
+__device__ __forceinline__ uint64_t uniform64(uint64_t x) {
+  return ((uint64_t)__shfl_sync(0xffffffffu, (uint32_t)(x >> 32), 0) << 32) | (uint64_t)__shfl_sync(0xffffffffu, (uint32_t)x, 0);
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void commit(uint32_t mbar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(mbar) : "memory");
 }
@@ -164,19 +176,25 @@ __device__ __forceinline__ void build_weight_image(Ctx& c, const float* Wk) {
   *reinterpret_cast<float4*>(c.img_lo + off) = l;
 }
 
-// The 6 chain issuers: (half, product) = (warp/4, warp%4 < 3), 4 k-steps each.
+// The 6 chain issuers: (half, product) = (warp/4, warp%4 < 3), 4 k-steps each.  Whole warps take the branch
+// (warp-uniform operands), one elected lane issues.
 __device__ __forceinline__ void issue_chain_mmas(Ctx& c) {
-  const int warp = c.tid >> 5;
-  if ((c.tid & 31) == 0 && (warp & 3) < 3) {
+  const uint32_t warp = uniform32((uint32_t)c.tid >> 5);
+  if ((warp & 3u) < 3u) {
     fence_after();
-    const int part = warp & 3;
-    const uint32_t a = c.half_addr + (part == 2 ? kColAlo : kColAhi);
-    const uint64_t b = (part == 1) ? c.desc_lo : c.desc_hi;
-    const uint32_t d = c.half_addr + kColD + 32u * (uint32_t)part;
+    const uint32_t part = warp & 3u;
+    const uint32_t half = uniform32(c.base) + kHalfCols * (warp >> 2);
+    const uint32_t a = half + (part == 2u ? kColAlo : kColAhi);
+    const uint64_t b = uniform64((part == 1u) ? c.desc_lo : c.desc_hi);
+    const uint32_t d = half + kColD + 32u * part;
+    const uint32_t bar = uniform32(c.mbar);
+    if (elect_one()) {
 #pragma unroll
-    for (int ks = 0; ks < 4; ++ks)
-      mma_tf32_ts(d, a + 8u * (uint32_t)ks, b + (uint64_t)((2u * kLBO * (uint32_t)ks) >> 4), ks > 0 ? 1u : 0u);
-    commit(c.mbar);
+      for (int ks = 0; ks < 4; ++ks)
+        mma_tf32_ts(d, a + 8u * (uint32_t)ks, b + (uint64_t)((2u * kLBO * (uint32_t)ks) >> 4), ks > 0 ? 1u : 0u);
+      commit(bar);
+    }
+    __syncwarp();
   }
 }
 
@@ -200,17 +218,21 @@ __device__ __forceinline__ void issue_backward(Ctx& c, const float (&dp)[32], co
   fence_before();
   __syncthreads();
   if (need_dx) issue_chain_mmas(c);
-  const int warp = c.tid >> 5;
-  if ((c.tid & 31) == 0 && (warp & 3) == 3) {      // 2 dW issuers: observations [0,128) and [128,256)
+  const uint32_t warp = uniform32((uint32_t)c.tid >> 5);
+  if ((warp & 3u) == 3u) {                          // 2 dW issuers: observations [0,128) and [128,256)
     fence_after();
-    const uint32_t half = (uint32_t)(warp >> 2);
-    const uint32_t d = c.base + (half ? kColDw1 : kColDw0);
-    const uint64_t a0 = c.desc_dwa + (uint64_t)((half * 16u * 2u * kDwSBO) >> 4);
-    const uint64_t b0 = c.desc_dwb + (uint64_t)((half * 16u * 2u * kDwSBO) >> 4);
+    const uint32_t half = warp >> 2;
+    const uint32_t d = uniform32(c.base) + (half ? kColDw1 : kColDw0);
+    const uint64_t a0 = uniform64(c.desc_dwa) + (uint64_t)((half * 16u * 2u * kDwSBO) >> 4);
+    const uint64_t b0 = uniform64(c.desc_dwb) + (uint64_t)((half * 16u * 2u * kDwSBO) >> 4);
+    const uint32_t bar = uniform32(c.mbar_dw);
+    if (elect_one()) {
 #pragma unroll
-    for (int ks = 0; ks < 16; ++ks)
-      mma_tf32_ss(d, a0 + (uint64_t)((2u * kDwSBO * (uint32_t)ks) >> 4), b0 + (uint64_t)((2u * kDwSBO * (uint32_t)ks) >> 4), kIdescDw, ks > 0 ? 1u : 0u);
-    commit(c.mbar_dw);
+      for (int ks = 0; ks < 16; ++ks)
+        mma_tf32_ss(d, a0 + (uint64_t)((2u * kDwSBO * (uint32_t)ks) >> 4), b0 + (uint64_t)((2u * kDwSBO * (uint32_t)ks) >> 4), kIdescDw, ks > 0 ? 1u : 0u);
+      commit(bar);
+    }
+    __syncwarp();
   }
 }
 
