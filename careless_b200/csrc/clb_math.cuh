@@ -39,8 +39,8 @@ CLB_DEV uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, 
   return make_uint4(c0, c1, c2, c3);
 }
 
-// uint32 -> (0,1) on the 24-bit grid; exact in float32, never 0 or 1.
-CLB_DEV float u01(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+// uint32 -> (0,1) on the 23-bit grid ((x>>9)+0.5)/2^23: exact in float32 (24 significant bits), never 0 or 1.
+CLB_DEV float u01(uint32_t x) { return ((float)(x >> 9) + 0.5f) * (1.0f / 8388608.0f); }
 
 CLB_DEV float refl_uniform(uint64_t seed, uint32_t step, uint32_t s, uint32_t refl_index) {
   uint4 x = philox4x32_10(refl_index, s, step, kStreamRefl, (uint32_t)seed, (uint32_t)(seed >> 32));
@@ -70,6 +70,7 @@ struct TnSample {
 // de/dbeta = exp((e^2-b^2)/2) u', u' = clip(u, FLT_MIN, 1-FLT_EPS).
 CLB_DEV TnSample tn_forward(float v_loc, float v_scale, float low, float eps, float u) {
   TnSample t;
+  u = fminf(fmaxf(u, 5.9604645e-8f), 1.0f - 5.9604645e-8f);   // keep injected draws strictly inside (0,1): [2^-24, 1-2^-24]
   t.mu = expf(v_loc);
   t.sigma = expf(v_scale) + eps;
   const float inv_s = 1.0f / t.sigma;

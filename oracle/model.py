@@ -114,6 +114,7 @@ class _StdTruncatedNormal(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, alpha, beta, u):
+        u = torch.clamp(u, 2.0 ** -24, 1.0 - 2.0 ** -24)     # draws strictly inside (0,1), as in the CUDA sampler
         Pa = ndtr(alpha)
         Z = ndtr(beta) - Pa
         p = Pa + u * Z

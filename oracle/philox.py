@@ -42,8 +42,8 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
 
 
 def u01(x):
-    """uint32 -> float in (0,1) on the 24-bit grid ((x>>8)+0.5)/2^24, exact in float32."""
-    return ((np.asarray(x, dtype=np.uint32) >> np.uint32(8)).astype(np.float64) + 0.5) / 16777216.0
+    """uint32 -> float in (0,1) on the 23-bit grid ((x>>9)+0.5)/2^23, exact in float32 (24 significant bits)."""
+    return ((np.asarray(x, dtype=np.uint32) >> np.uint32(9)).astype(np.float64) + 0.5) / 8388608.0
 
 
 def _key(seed):

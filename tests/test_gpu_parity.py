@@ -32,7 +32,7 @@ RTOL = 1e-4
 
 def _draws(rng, S, R, N, n_steps=1):
     u = rng.random((n_steps, S, R))
-    u = (np.floor(u * 2 ** 24) + 0.5) / 2 ** 24          # on the float32-exact grid
+    u = (np.floor(u * 2 ** 23) + 0.5) / 2 ** 23          # on the float32-exact grid
     e = rng.standard_normal((n_steps, S, N)).astype(np.float32).astype(np.float64)
     return u, e
 

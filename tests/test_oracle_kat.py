@@ -188,3 +188,17 @@ def test_philox_known_answers():
     assert u.shape == (2, 1000) and u.min() > 0 and u.max() < 1
     e = philox.obs_normals(1234, 3, 1, np.arange(200000))
     assert abs(e.mean()) < 0.01 and abs(e.std() - 1) < 0.01
+
+
+def test_uniform_grid_is_exact_in_float32_and_never_hits_the_ends():
+    """The in-kernel draw u = ((x >> 9) + 0.5) / 2^23 needs 24 significant bits: float32 holds it exactly, so the
+    CUDA kernels and this float64 restatement see the same numbers and u can never round to 0 or 1
+    (a 24-bit grid would: (2^24 - 0.5) / 2^24 rounds to 1.0f and the inverse CDF returns +inf)."""
+    x = np.array([0, 1, 511, 512, 2 ** 31, 2 ** 32 - 512, 2 ** 32 - 1], dtype=np.uint64).astype(np.uint32)
+    u = philox.u01(x)
+    assert np.array_equal(u.astype(np.float32).astype(np.float64), u)
+    assert u.min() == 2.0 ** -24 and u.max() == 1.0 - 2.0 ** -24
+    assert np.float32(u.max()) < np.float32(1.0)
+    # the oracle sampler clamps injected draws like the kernel does
+    z = om.tn_sample(T([1.0]), T([0.5]), T([0.0]), T([1e10]), T([[1.0], [0.0]]))
+    assert np.all(np.isfinite(z.numpy()))

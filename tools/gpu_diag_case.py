@@ -14,7 +14,7 @@ ocfg, oprior, eng = U.build(p, **kw)
 params = U.perturbed_params(ocfg, oprior, rng)
 U.push_params(eng, params, ocfg)
 S, R, N = 2, 500, 4000
-u = rng.random((1, S, R)); u = (np.floor(u * 2 ** 24) + 0.5) / 2 ** 24
+u = rng.random((1, S, R)); u = (np.floor(u * 2 ** 23) + 0.5) / 2 ** 23
 e = rng.standard_normal((1, S, N)).astype(np.float32).astype(np.float64)
 hist = eng.step(1, u_f=u, eps_s=e)
 m, g, out = om.loss_and_grads(params, p, oprior, ocfg, u[0], e[0])
