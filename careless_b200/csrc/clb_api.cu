@@ -86,7 +86,8 @@ struct clb_handle {
   size_t rows_bytes = 0;
   int32_t *d_refl = nullptr, *d_image = nullptr, *d_spot = nullptr; uint32_t* d_oidx = nullptr;
   float *d_meta = nullptr, *d_iobs = nullptr, *d_sig = nullptr;
-  DevBuf partials, scratch;
+  DevBuf partials, scratch, wpack;
+  int obs_threads = kObsThreads;   // rows per CTA tile: 256 (FP32 kernels) or 128 (tensor-core kernels, 2 CTAs per SM)
   DevBuf acc, var_sums, red, metrics, var_scale, adam_alpha, stop_step;
   DevBuf inj_u, inj_eps, ipred;
   bool want_ipred = false;
@@ -128,7 +129,7 @@ int round_width(int w) { return w <= 8 ? 8 : w <= 16 ? 16 : w <= 32 ? 32 : -1; }
 template <int WP, int LIK, bool TC> cudaError_t launch_obs(clb_handle* h, const ObsArgs& a) {
   cudaError_t e = cudaFuncSetAttribute(k_obs<WP, LIK, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_obs);
   if (e != cudaSuccess) return e;
-  k_obs<WP, LIK, TC><<<h->grid_obs, kObsThreads, h->smem_obs, h->stream>>>(a);
+  k_obs<WP, LIK, TC><<<h->grid_obs, TC ? tc::kThreads : kObsThreads, h->smem_obs, h->stream>>>(a);
   return cudaGetLastError();
 }
 
@@ -345,6 +346,7 @@ int clb_create(const clb_config* cfg, clb_handle** out) {
   build_vars(h);
   h->NL = h->lay.n_layers;
   { const char* no_tc = getenv("CLB_NO_TC"); h->use_tc = (WP == 32) && cfg->mlp_layers > 0 && !(no_tc && no_tc[0] == '1'); }
+  h->obs_threads = h->use_tc ? tc::kThreads : kObsThreads;
   switch (WP) {
     case 8: h->smem_obs = ObsSmem<8>::bytes(h->NL); break;
     case 16: h->smem_obs = ObsSmem<16>::bytes(h->NL); break;
@@ -442,10 +444,11 @@ int clb_set_observations(clb_handle* h, int64_t n, int64_t n_total, const int64_
   h->n_rows_raw = n; h->n_rows = npad; h->n_rows_total = n_total; h->order = plan.order;
 
   // ---- launch geometry + per-CTA buffers of the observation kernel ----
-  const int64_t n_tiles = (npad + kObsThreads - 1) / kObsThreads;
-  h->grid_obs = (int)std::min<int64_t>(n_tiles, h->n_sms);
+  const int64_t n_tiles = (npad + h->obs_threads - 1) / h->obs_threads;
+  h->grid_obs = (int)std::min<int64_t>(n_tiles, (int64_t)h->n_sms * (h->use_tc ? 2 : 1));
   CLB_CUDA(h, h->partials.alloc(sizeof(double) * (size_t)h->grid_obs * h->KS * partial_row_size(h->NL, h->WP)));
-  CLB_CUDA(h, h->scratch.alloc(sizeof(float4) * (size_t)h->grid_obs * std::max(1, c.mlp_layers) * (h->WP / 4) * kObsThreads));
+  CLB_CUDA(h, h->scratch.alloc(sizeof(float4) * (size_t)h->grid_obs * std::max(1, c.mlp_layers) * (h->WP / 4) * h->obs_threads));
+  if (h->use_tc) CLB_CUDA(h, h->wpack.alloc(sizeof(float) * (size_t)std::max(1, c.mlp_layers) * 1024));
   h->have_obs = true;
   return clb_upload_observations(h);
 }
@@ -695,6 +698,11 @@ static int step_begin_impl(clb_handle* h, const float* inj_u, const float* inj_e
     a.n_rows = h->n_rows; a.n_rows_total = h->n_rows_total; a.d = c.n_meta;
     a.theta_mlp = theta + h->goff[CLB_GROUP_MLP];
     a.theta_img = c.image_scales ? theta + h->goff[CLB_GROUP_IMAGE_SCALES] : nullptr;
+    a.wpack = h->use_tc ? h->wpack.as<float>() : nullptr;
+    if (h->use_tc) {
+      k_pack_weights<<<(c.mlp_layers * 1024 + 255) / 256, 256, 0, st>>>(a.theta_mlp, h->lay, h->wpack.as<float>());
+      CLB_LAUNCHED(h);
+    }
     a.lay = h->lay;
     a.z = h->z.as<float>(); a.gz = h->gz.as<float>(); a.R = R; a.S = S;
     a.inj_eps = d_inj_eps;

@@ -137,6 +137,7 @@ struct ObsArgs {
   int d;
   // model
   const float* theta_mlp; const float* theta_img;   // image scales (n_img-1) or null
+  const float* wpack;              // [L][32][32] zero-padded FP32 copy of the hidden-layer kernels (TC kernels)
   MlpLayout lay;
   const float* z; float* gz; int64_t R; int S;
   const float* inj_eps;            // (S, N_total) or null
@@ -155,9 +156,9 @@ template <int WP> struct ObsSmem {
   static constexpr int T = kObsThreads;
   static constexpr int HS = T + 4;                    // padded stride of the transposed activation tile
   static size_t bytes(int n_layers, bool tensor_cores = false) {
-    if (tensor_cores)     // dW operand images, hidden-layer weights, compact head, biases, bias sums, reductions, chain images
-      return 2 * (size_t)tc::kDwImgBytes + sizeof(float) * ((size_t)(n_layers - 1) * WP * WP + 2 * WP + 2 * (size_t)n_layers * WP
-                                                              + (size_t)(T / 32) * WP) + 64 * sizeof(double) + 2 * (size_t)tc::kImgBytes + 128;
+    if (tensor_cores)     // dW operand images, compact head weights, biases, bias sums, reductions, chain images (128-thread CTA)
+      return 2 * (size_t)tc::kDwImgBytes + sizeof(float) * (2 * WP + 2 * (size_t)n_layers * WP + (size_t)(tc::kThreads / 32) * WP)
+             + 64 * sizeof(double) + 2 * (size_t)tc::kImgBytes + 128;
     return sizeof(float) * ((size_t)n_layers * WP * WP + (size_t)n_layers * WP   // W, b
                             + (size_t)n_layers * WP                                // bias-grad accumulators
                             + (size_t)WP * HS + (size_t)T * WP      // staged activation / delta tiles
@@ -281,36 +282,40 @@ __device__ __forceinline__ void stage_and_accumulate(const float (&ain)[WP], con
   }
 }
 
-// Tensor-core version of one layer's backward (TC kernels, WP == 32): dW_k = a_k^T dp_k and, when need_dx,
-// dp <- delta a_k = dp_k W_k^T, both on tcgen05 (clb_tc.cuh); the FP32 pipe only splits operands, folds the
-// accumulator copies and adds the result to the CTA's FP64 partial (same layout as the FP32 path).
-__device__ __forceinline__ void tc_layer_backward(tc::Ctx& tcx, float (&dp)[32], const float (&ain)[32], const float* Wk,
+// Tensor-core version of one layer's backward (TC kernels: WP == 32, 128-thread CTAs): dW_k = a_k^T dp_k and,
+// when need_dx, dp <- delta a_k = dp_k W_k^T, both on tcgen05 (clb_tc.cuh); the FP32 pipe only splits operands,
+// folds the accumulator copies and adds the result to the CTA's FP64 partial (same layout as the FP32 path:
+// float4 output o4 = r*64 + pj*8 + pi holds element (i = pi + 8 r, j = 4 pj ..); thread tid owns o4 = tid, tid+128).
+__device__ __forceinline__ void tc_layer_backward(tc::Ctx& tcx, float (&dp)[32], const float (&ain)[32], const float (&w)[8],
                                                   bool need_dx, float* bias_part, float* dbacc_k, double* part, int tid) {
-  const double2 p01 = __ldcg(reinterpret_cast<const double2*>(part));
-  const double2 p23 = __ldcg(reinterpret_cast<const double2*>(part) + 1);
+  double2 pr[2][2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    pr[h][0] = __ldcg(reinterpret_cast<const double2*>(part + 512 * h));
+    pr[h][1] = __ldcg(reinterpret_cast<const double2*>(part + 512 * h) + 1);
+  }
   bias_partial<32>(dp, bias_part, tid);
-  tc::issue_backward(tcx, dp, ain, Wk, need_dx);
+  tc::issue_backward(tcx, dp, ain, w, need_dx);
   if (need_dx) tc::collect(tcx, dp);
   tc::collect_dw(tcx);
   __syncthreads();
   {
-    // element (i, j0..j0+3) owned by this thread in the partial layout (see partial_elem): i = pi + 8 r, j0 = 4 pj
-    const int r = tid >> 6, pj = (tid & 63) >> 3, pi = tid & 7;
-    const float* st = reinterpret_cast<const float*>(tcx.dw_a) + (size_t)(pi + 8 * r) * tc::kStageStride + 4 * pj;
-    float4 t = *reinterpret_cast<const float4*>(st);
+    const int pj = (tid & 63) >> 3, pi = tid & 7;
 #pragma unroll
-    for (int c = 1; c < 4; ++c) {
-      const float4 v = *reinterpret_cast<const float4*>(st + (size_t)c * 32 * tc::kStageStride);
-      t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+    for (int h = 0; h < 2; ++h) {
+      const int r = (tid >> 6) + 2 * h;
+      const float* st = reinterpret_cast<const float*>(tcx.dw_a) + (size_t)(pi + 8 * r) * tc::kStageStride + 4 * pj;
+      const float4 t0 = *reinterpret_cast<const float4*>(st);
+      const float4 t1 = *reinterpret_cast<const float4*>(st + (size_t)32 * tc::kStageStride);
+      __stcg(reinterpret_cast<double2*>(part + 512 * h), make_double2(pr[h][0].x + (double)(t0.x + t1.x), pr[h][0].y + (double)(t0.y + t1.y)));
+      __stcg(reinterpret_cast<double2*>(part + 512 * h) + 1, make_double2(pr[h][1].x + (double)(t0.z + t1.z), pr[h][1].y + (double)(t0.w + t1.w)));
     }
     if (tid < 32) {
       float sum = 0.f;
 #pragma unroll
-      for (int w = 0; w < kObsThreads / 32; ++w) sum += bias_part[w * 32 + tid];
+      for (int w2 = 0; w2 < tc::kThreads / 32; ++w2) sum += bias_part[w2 * 32 + tid];
       dbacc_k[tid] += sum;
     }
-    __stcg(reinterpret_cast<double2*>(part), make_double2(p01.x + (double)t.x, p01.y + (double)t.y));
-    __stcg(reinterpret_cast<double2*>(part) + 1, make_double2(p23.x + (double)t.z, p23.y + (double)t.w));
   }
   __syncthreads();      // the stage aliases the operand image of the next layer
 }
@@ -327,9 +332,9 @@ __host__ __device__ inline int partial_row_size(int n_layers, int WP) { return n
 // (tcgen05.mma kind::tf32, 3xTF32 error-compensated, operands/accumulators in tensor memory; clb_tc.cuh);
 // TC = false: everything on the FP32 FMA pipe.
 template <int WP, int LIK, bool TC>
-__global__ void __launch_bounds__(kObsThreads, 1) k_obs(ObsArgs a) {
+__global__ void __launch_bounds__(TC ? tc::kThreads : kObsThreads, TC ? 2 : 1) k_obs(ObsArgs a) {
   static_assert(!TC || WP == 32, "the tensor-core path is built for the padded width 32");
-  constexpr int T = kObsThreads, HS = T + 4, NC = WP / 4;
+  constexpr int T = TC ? tc::kThreads : kObsThreads, HS = T + 4, NC = WP / 4;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const int NL = a.lay.n_layers;          // incl. head
   const int L = NL - 1;                   // hidden layers
@@ -337,8 +342,8 @@ __global__ void __launch_bounds__(kObsThreads, 1) k_obs(ObsArgs a) {
   unsigned char* sp = smem_raw;
   char* tc_dwa = nullptr; char* tc_dwb = nullptr;
   if constexpr (TC) { tc_dwa = reinterpret_cast<char*>(sp); tc_dwb = tc_dwa + tc::kDwImgBytes; sp += 2 * tc::kDwImgBytes; }
-  float* Wsm = reinterpret_cast<float*>(sp);                // [L][WP][WP] hidden layers, then the head [WP][HSTR]
-  float* Whead = Wsm + (size_t)L * WP * WP;
+  float* Wsm = reinterpret_cast<float*>(sp);                // [L][WP][WP] hidden layers (FP32 path only), then the head [WP][HSTR]
+  float* Whead = Wsm + (TC ? 0 : (size_t)L * WP * WP);
   float* bsm = Whead + (size_t)WP * HSTR;                   // [NL][WP]
   float* dbacc = bsm + (size_t)NL * WP;                     // [NL][WP]
   float* nxtp = dbacc + (size_t)NL * WP;
@@ -358,16 +363,18 @@ __global__ void __launch_bounds__(kObsThreads, 1) k_obs(ObsArgs a) {
   const int tid = threadIdx.x, lane = tid & 31;
   tc::Ctx tcx{};
   if constexpr (TC) {
-    if (tid == 0) { tc::mbar_init(tc::smem_u32(tc_bar), 6); tc::mbar_init(tc::smem_u32(tc_bar + 1), 2); }
+    if (tid == 0) { tc::mbar_init(tc::smem_u32(tc_bar), 3); tc::mbar_init(tc::smem_u32(tc_bar + 1), 1); }
     if (tid < 32) tc::tmem_alloc(tc::smem_u32(tc_slot));
     tc::fence_before();
   }
   // ---- stage the weights (zero padded to WP x WP) ----
-  for (int idx = tid; idx < L * WP * WP; idx += T) {
-    const int k = idx / (WP * WP), i = (idx / WP) % WP, j = idx % WP;
-    float w = 0.f;
-    if (i < a.lay.in_dim[k] && j < a.lay.out_dim[k]) w = a.theta_mlp[a.lay.koff[k] + i * a.lay.out_dim[k] + j];
-    Wsm[idx] = w;
+  if constexpr (!TC) {
+    for (int idx = tid; idx < L * WP * WP; idx += T) {
+      const int k = idx / (WP * WP), i = (idx / WP) % WP, j = idx % WP;
+      float w = 0.f;
+      if (i < a.lay.in_dim[k] && j < a.lay.out_dim[k]) w = a.theta_mlp[a.lay.koff[k] + i * a.lay.out_dim[k] + j];
+      Wsm[idx] = w;
+    }
   }
   for (int idx = tid; idx < WP * HSTR; idx += T) {
     const int i = idx / HSTR, j = idx % HSTR;
@@ -383,8 +390,7 @@ __global__ void __launch_bounds__(kObsThreads, 1) k_obs(ObsArgs a) {
     tc::fence_after();
     const uint32_t tbase = *tc_slot;
     const int warp = tid >> 5;
-    tcx.half_addr = tbase + tc::kHalfCols * (uint32_t)(warp >> 2);
-    tcx.row_addr = tcx.half_addr + ((uint32_t)(32 * (warp & 3)) << 16);
+    tcx.row_addr = tbase + ((uint32_t)(32 * warp) << 16);
     tcx.mbar = tc::smem_u32(tc_bar);
     tcx.parity = 0;
     tcx.img_hi = tc_img; tcx.img_lo = tc_img + tc::kImgBytes;
@@ -411,11 +417,16 @@ __global__ void __launch_bounds__(kObsThreads, 1) k_obs(ObsArgs a) {
     float h[WP];
 #pragma unroll
     for (int i = 0; i < WP; ++i) h[i] = (inb && i < a.d) ? a.meta[(size_t)i * a.n_rows + row] : 0.f;
+    float wreg[8];                       // TC: this thread's share of the next pass's weights
+    if constexpr (TC) { if (L > 0) tc::load_w<false>(a.wpack, tid, wreg); }
     for (int k = 0; k < L; ++k) {
       const float* Wk = Wsm + (size_t)k * WP * WP;
       float o[WP];
       if constexpr (TC) {
-        tc::issue<false>(tcx, h, Wk);
+        tc::issue<false>(tcx, h, wreg);
+        // prefetch the next pass's weights while the tensor cores work: next forward layer, or the first backward layer
+        if (k + 1 < L) tc::load_w<false>(a.wpack + (size_t)(k + 1) * 1024, tid, wreg);
+        else if (a.train_mlp && L > 1) tc::load_w<true>(a.wpack + (size_t)(L - 1) * 1024, tid, wreg);
         tc::collect(tcx, o);
 #pragma unroll
         for (int j = 0; j < WP; ++j) o[j] += bsm[k * WP + j];
@@ -517,7 +528,7 @@ __global__ void __launch_bounds__(kObsThreads, 1) k_obs(ObsArgs a) {
     for (int j = 0; j < WP; ++j) dp[j] = 0.f;
     dp[0] = dmu; dp[1] = drho;
     // head: dW_out = a_L^T [dmu, drho]
-    if constexpr (TC) tc_layer_backward(tcx, dp, h, nullptr, false, bias_part, dbacc + L * WP, part_rows + (size_t)L * WP * WP, tid);
+    if constexpr (TC) tc_layer_backward(tcx, dp, h, wreg, false, bias_part, dbacc + L * WP, part_rows + (size_t)L * WP * WP, tid);
     else stage_and_accumulate<WP>(h, dp, S_h, S_d, Rbuf, bias_part, dbacc + L * WP, part_rows + (size_t)L * WP * WP, tid);
     unsigned mask = 0u;                        // sign bits of a_{k+1}: leaky'(pre-activation)
 #pragma unroll
@@ -538,8 +549,11 @@ __global__ void __launch_bounds__(kObsThreads, 1) k_obs(ObsArgs a) {
       if (k > 0) load_act(nxt, k - 1);           // in flight during this layer's dW loop
       if constexpr (TC) {
         // delta a_k = delta p_k W_k^T and dW_k = a_k^T delta p_k, both on the tensor cores
-        tc_layer_backward(tcx, dp, ain, Wsm + (size_t)k * WP * WP, k > 0, bias_part, dbacc + k * WP,
-                          part_rows + (size_t)k * WP * WP, tid);
+        float wcur[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) wcur[q] = wreg[q];
+        if (k > 1) tc::load_w<true>(a.wpack + (size_t)(k - 1) * 1024, tid, wreg);     // next backward layer
+        tc_layer_backward(tcx, dp, ain, wcur, k > 0, bias_part, dbacc + k * WP, part_rows + (size_t)k * WP * WP, tid);
         continue;
       }
       stage_and_accumulate<WP>(ain, dp, S_h, S_d, Rbuf, bias_part, dbacc + k * WP, part_rows + (size_t)k * WP * WP, tid);
@@ -580,6 +594,16 @@ __global__ void __launch_bounds__(kObsThreads, 1) k_obs(ObsArgs a) {
   if constexpr (TC) {
     if (tid < 32) tc::tmem_dealloc(*tc_slot);
   }
+}
+
+// Zero-padded [L][32][32] FP32 copy of the hidden-layer kernels for the tensor-core kernels (they read 4 KB per
+// pass through L1/L2 instead of keeping 80 KB of weights in shared memory, which makes room for two CTAs per SM).
+__global__ void __launch_bounds__(256) k_pack_weights(const float* theta_mlp, MlpLayout lay, float* wpack) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int L = lay.n_layers - 1;
+  if (idx >= L * 1024) return;
+  const int k = idx >> 10, i = (idx >> 5) & 31, j = idx & 31;
+  wpack[idx] = (i < lay.in_dim[k] && j < lay.out_dim[k]) ? theta_mlp[lay.koff[k] + i * lay.out_dim[k] + j] : 0.f;
 }
 
 // Sum the per-CTA partial weight gradients (padded layout, see partial_row_size) into the flat keras-order

@@ -7,9 +7,11 @@
 // * B operand (W): built per pass in shared memory in the canonical K-major / no-swizzle UMMA layout
 //   (8x16-byte core matrices, LBO = 528 B between K-adjacent core matrices, SBO = 128 B between 8-row groups);
 // * D (FP32 accumulators): tensor memory, read back one row per thread with tcgen05.ld.
-// The 256-row tile is two M=128 halves; each (half, product) pair has its own accumulator columns and its own
-// issuing warp (a single thread issues a tcgen05.mma only every ~60-110 cycles, but issuers run concurrently --
-// measured with tools/tc_rate.cu), so a pass is 6 issuers x 4 k-steps (K = 8 per tf32 instruction).
+// A CTA is 128 threads = one M=128 tile (thread = row = tensor-memory lane); two CTAs share an SM so that one
+// CTA's st -> barrier -> mma -> commit -> wait -> ld latencies hide behind the other's work.  Each of the three
+// products has its own accumulator columns and its own issuing warp (several warps issue concurrently, one
+// thread alone only manages a tcgen05.mma every ~60 cycles -- tools/tc_rate.cu): a pass is 3 issuers x 4
+// k-steps (K = 8 per tf32 instruction); the dW product is issued by the fourth warp.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -20,19 +22,19 @@ namespace tc {
 constexpr uint32_t kLBO = 528;           // bytes between K-adjacent core matrices (528 % 128 == 16: conflict-free image builds)
 constexpr uint32_t kSBO = 128;           // bytes between 8-row groups
 constexpr uint32_t kImgBytes = 8 * kLBO; // one 32x32 tf32 operand image
-constexpr uint32_t kTmemCols = 512;
-// tensor-memory column map of one 128-row half (half h starts at column 256 h)
-constexpr uint32_t kColAhi = 0, kColAlo = 32, kColD = 64;   // D0, D1, D2 at 64, 96, 128
-constexpr uint32_t kHalfCols = 256;
-// dW = A^T dP (contraction over the 256 observations of the tile): both operands come from shared memory in the
+constexpr uint32_t kTmemCols = 256;      // per CTA (two CTAs per SM)
+constexpr int kThreads = 128;            // rows per CTA tile
+// tensor-memory column map of the CTA
+constexpr uint32_t kColAhi = 0, kColAlo = 32, kColD = 64;   // D0, D1, D2 at 64, 96, 128; dW accumulators at 160
+// dW = A^T dP (contraction over the 128 observations of the tile): both operands come from shared memory in the
 // MN-major layout, which for 32-bit types exists only as SWIZZLE_128B_BASE32B (layout type 1): atoms of 4 K-rows
-// x 128 B (32 MN elements), 32-byte chunk index XOR (row % 4); SBO = 512 B between 4-row K groups, LBO = 32 KB
+// x 128 B (32 MN elements), 32-byte chunk index XOR (row % 4); SBO = 512 B between 4-row K groups, LBO = 16 KB
 // between 32-element MN groups (group 0 = hi parts, group 1 = lo parts).  M = N = 64, K = 8 per instruction:
 // D = [A_hi; A_lo]^T [dP_hi | dP_lo]  ->  dW = D[0:32,0:32] + D[0:32,32:64] + D[32:64,0:32] (+ lo*lo).
 // M = 64 accumulators occupy lanes (r % 16) + 32 (r / 16) (verified with tools/tc_probe2.cu).
-constexpr uint32_t kDwSBO = 512, kDwLBO = (256 / 4) * 512;
-constexpr uint32_t kDwImgBytes = 2 * kDwLBO;                 // 64 KB per operand
-constexpr uint32_t kColDw0 = 160, kColDw1 = 416;             // accumulator columns of the two dW issuers (64 each)
+constexpr uint32_t kDwSBO = 512, kDwLBO = (kThreads / 4) * 512;
+constexpr uint32_t kDwImgBytes = 2 * kDwLBO;                 // 32 KB per operand
+constexpr uint32_t kColDw = 160;                              // 64 accumulator columns of the dW product
 constexpr uint32_t kIdescDw = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((64u >> 3) << 17) | ((64u >> 4) << 24);
 constexpr int kStageStride = 36;                             // floats per row of the dW reduction stage (padded)
 // instruction descriptor: D=F32 (1<<4), A=B=TF32 (2<<7, 2<<10), both K-major, N=32 (4<<17), M=128 (8<<24)
@@ -118,15 +120,14 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t tbase) {     // the same w
 
 // Per-thread view of the CTA's tensor-core state.
 struct Ctx {
-  uint32_t row_addr;     // tensor-memory address of this thread's row: base + (32 (warp%4)) << 16 + 256 (warp/4)
-  uint32_t half_addr;    // base + 256 (warp/4): operand / accumulator columns of this warp's half (lane field 0)
-  uint32_t mbar;         // shared-memory address of the pass barrier (6 arrivals per pass)
+  uint32_t row_addr;     // tensor-memory address of this thread's row: base + (32 warp) << 16
+  uint32_t mbar;         // shared-memory address of the pass barrier (3 arrivals per pass)
   uint32_t parity;
   char* img_hi; char* img_lo;          // B operand images in shared memory
   uint64_t desc_hi, desc_lo;
   int tid;
   // dW
-  uint32_t mbar_dw, parity_dw;         // barrier of the dW product (2 arrivals)
+  uint32_t mbar_dw, parity_dw;         // barrier of the dW product (1 arrival)
   char* dw_a; char* dw_b;              // MN-major operand images (kDwImgBytes each); dw_a doubles as the reduction stage
   uint64_t desc_dwa, desc_dwb;
   uint32_t base;                       // tensor-memory base address
@@ -155,38 +156,57 @@ __device__ __forceinline__ void dw_store_row(char* img, int k, const uint32_t (&
   }
 }
 
-// Build the chain's B operand image of one layer (see issue<>): 4 weights per thread.
+// The 8 weights this thread contributes to the B operand image of one layer, fetched from the padded FP32
+// copy in global memory (L2/L1 resident, 4 KB per layer) one pass ahead of their use.
+//   forward  (B[n][k] = W[k][n]): thread (n = tid%32, kq = tid/32 and kq+4) gathers 4 consecutive k each;
+//   backward (B[n][k] = W[n][k]): thread (kq = tid%8, n = tid/8 and n+16) copies 4 consecutive k each.
 template <bool BWD>
-__device__ __forceinline__ void build_weight_image(Ctx& c, const float* Wk) {
-  float4 w;
-  uint32_t off;
-  if (!BWD) {            // B[n][k] = W[k][n]: thread (n = tid%32, kq = tid/32) gathers 4 consecutive k
-    const int n = c.tid & 31, kq = c.tid >> 5;
-    w = make_float4(Wk[(4 * kq) * 32 + n], Wk[(4 * kq + 1) * 32 + n], Wk[(4 * kq + 2) * 32 + n], Wk[(4 * kq + 3) * 32 + n]);
-    off = kq * kLBO + (n >> 3) * kSBO + (n & 7) * 16;
-  } else {               // B[n][k] = W[n][k]: thread (kq = tid%8, n = tid/8) copies 4 consecutive k
-    const int kq = c.tid & 7, n = c.tid >> 3;
-    w = *reinterpret_cast<const float4*>(&Wk[n * 32 + 4 * kq]);
-    off = kq * kLBO + (n >> 3) * kSBO + (n & 7) * 16;
+__device__ __forceinline__ void load_w(const float* __restrict__ Wg, int tid, float (&w)[8]) {
+  if (!BWD) {
+    const int n = tid & 31, kq = tid >> 5;
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) w[4 * h + r] = __ldg(&Wg[(4 * (kq + 4 * h) + r) * 32 + n]);
+  } else {
+    const int kq = tid & 7, n = tid >> 3;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(&Wg[(n + 16 * h) * 32 + 4 * kq]));
+      w[4 * h] = v.x; w[4 * h + 1] = v.y; w[4 * h + 2] = v.z; w[4 * h + 3] = v.w;
+    }
   }
-  float4 h, l;
-  h.x = tf32_rna(w.x); h.y = tf32_rna(w.y); h.z = tf32_rna(w.z); h.w = tf32_rna(w.w);
-  l.x = tf32_rna(w.x - h.x); l.y = tf32_rna(w.y - h.y); l.z = tf32_rna(w.z - h.z); l.w = tf32_rna(w.w - h.w);
-  *reinterpret_cast<float4*>(c.img_hi + off) = h;
-  *reinterpret_cast<float4*>(c.img_lo + off) = l;
 }
 
-// The 6 chain issuers: (half, product) = (warp/4, warp%4 < 3), 4 k-steps each.  Whole warps take the branch
-// (warp-uniform operands), one elected lane issues.
+// Build the chain's B operand image (hi and lo) from the prefetched weights.
+// element (n, k) of the [N][K] operand at (k/4) LBO + (n/8) SBO + (n%8) 16 + (k%4) 4 bytes
+template <bool BWD>
+__device__ __forceinline__ void build_weight_image(Ctx& c, const float (&w)[8]) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    int n, kq;
+    if (!BWD) { n = c.tid & 31; kq = (c.tid >> 5) + 4 * h; }
+    else { kq = c.tid & 7; n = (c.tid >> 3) + 16 * h; }
+    const uint32_t off = kq * kLBO + (n >> 3) * kSBO + (n & 7) * 16;
+    float4 hi, lo;
+    hi.x = tf32_rna(w[4 * h]); hi.y = tf32_rna(w[4 * h + 1]); hi.z = tf32_rna(w[4 * h + 2]); hi.w = tf32_rna(w[4 * h + 3]);
+    lo.x = tf32_rna(w[4 * h] - hi.x); lo.y = tf32_rna(w[4 * h + 1] - hi.y);
+    lo.z = tf32_rna(w[4 * h + 2] - hi.z); lo.w = tf32_rna(w[4 * h + 3] - hi.w);
+    *reinterpret_cast<float4*>(c.img_hi + off) = hi;
+    *reinterpret_cast<float4*>(c.img_lo + off) = lo;
+  }
+}
+
+// The 3 chain issuers: product = warp (0: X_hi W_hi, 1: X_hi W_lo, 2: X_lo W_hi), 4 k-steps each.  Whole warps
+// take the branch (warp-uniform operands), one elected lane issues.
 __device__ __forceinline__ void issue_chain_mmas(Ctx& c) {
   const uint32_t warp = uniform32((uint32_t)c.tid >> 5);
-  if ((warp & 3u) < 3u) {
+  if (warp < 3u) {
     fence_after();
-    const uint32_t part = warp & 3u;
-    const uint32_t half = uniform32(c.base) + kHalfCols * (warp >> 2);
-    const uint32_t a = half + (part == 2u ? kColAlo : kColAhi);
-    const uint64_t b = uniform64((part == 1u) ? c.desc_lo : c.desc_hi);
-    const uint32_t d = half + kColD + 32u * part;
+    const uint32_t base = uniform32(c.base);
+    const uint32_t a = base + (warp == 2u ? kColAlo : kColAhi);
+    const uint64_t b = uniform64((warp == 1u) ? c.desc_lo : c.desc_hi);
+    const uint32_t d = base + kColD + 32u * warp;
     const uint32_t bar = uniform32(c.mbar);
     if (elect_one()) {
 #pragma unroll
@@ -198,9 +218,9 @@ __device__ __forceinline__ void issue_chain_mmas(Ctx& c) {
   }
 }
 
-// Backward of one layer: start delta_a = dp W^T (if need_dx) and dW = ain^T dp on the tensor cores.
-// Contains one __syncthreads().  collect() returns delta_a; collect_dw() the weight gradient.
-__device__ __forceinline__ void issue_backward(Ctx& c, const float (&dp)[32], const float (&ain)[32], const float* Wk, bool need_dx) {
+// Backward of one layer: start delta_a = dp W^T (if need_dx; w = prefetched weights) and dW = ain^T dp on the
+// tensor cores.  Contains one __syncthreads().  collect() returns delta_a; collect_dw() the weight gradient.
+__device__ __forceinline__ void issue_backward(Ctx& c, const float (&dp)[32], const float (&ain)[32], const float (&w)[8], bool need_dx) {
   {
     uint32_t hi[32], lo[32];
     split32(dp, hi, lo);
@@ -212,23 +232,21 @@ __device__ __forceinline__ void issue_backward(Ctx& c, const float (&dp)[32], co
     split32(ain, hi, lo);
     dw_store_row(c.dw_a, c.tid, hi, lo);
   }
-  if (need_dx) build_weight_image<true>(c, Wk);
+  if (need_dx) build_weight_image<true>(c, w);
   wait_st();
   fence_async_smem();
   fence_before();
   __syncthreads();
   if (need_dx) issue_chain_mmas(c);
   const uint32_t warp = uniform32((uint32_t)c.tid >> 5);
-  if ((warp & 3u) == 3u) {                          // 2 dW issuers: observations [0,128) and [128,256)
+  if (warp == 3u) {                                 // the dW issuer: 16 k-steps over the tile's 128 observations
     fence_after();
-    const uint32_t half = warp >> 2;
-    const uint32_t d = uniform32(c.base) + (half ? kColDw1 : kColDw0);
-    const uint64_t a0 = uniform64(c.desc_dwa) + (uint64_t)((half * 16u * 2u * kDwSBO) >> 4);
-    const uint64_t b0 = uniform64(c.desc_dwb) + (uint64_t)((half * 16u * 2u * kDwSBO) >> 4);
+    const uint32_t d = uniform32(c.base) + kColDw;
+    const uint64_t a0 = uniform64(c.desc_dwa), b0 = uniform64(c.desc_dwb);
     const uint32_t bar = uniform32(c.mbar_dw);
     if (elect_one()) {
 #pragma unroll
-      for (int ks = 0; ks < 16; ++ks)
+      for (int ks = 0; ks < kThreads / 8; ++ks)
         mma_tf32_ss(d, a0 + (uint64_t)((2u * kDwSBO * (uint32_t)ks) >> 4), b0 + (uint64_t)((2u * kDwSBO * (uint32_t)ks) >> 4), kIdescDw, ks > 0 ? 1u : 0u);
       commit(bar);
     }
@@ -237,21 +255,21 @@ __device__ __forceinline__ void issue_backward(Ctx& c, const float (&dp)[32], co
 }
 
 // Wait for dW and combine: D rows live at lanes (r%16) + 32 (r/16); every thread with lane < 16 folds its row's
-// two column halves and parks it in the stage [region*2 + (r >= 32)][i = r % 32][kStageStride] (aliases dw_a).
-// After the caller's __syncthreads() the stage holds 4 partial copies of the 32x32 gradient.
+// two column halves and parks it in the stage [r >= 32][i = r % 32][kStageStride] (aliases dw_a).
+// After the caller's __syncthreads() the stage holds the 2 partial copies of the 32x32 gradient.
 __device__ __forceinline__ void collect_dw(Ctx& c) {
   mbar_wait(c.mbar_dw, c.parity_dw);
   c.parity_dw ^= 1u;
   fence_after();
   const int warp = c.tid >> 5, lane = c.tid & 31;
-  const uint32_t addr = c.base + ((uint32_t)(32 * (warp & 3)) << 16) + ((warp >> 2) ? kColDw1 : kColDw0);
+  const uint32_t addr = c.row_addr + kColDw;
   uint32_t v0[32], v1[32];
   CLB_TMEM_LD32(addr, v0);
   CLB_TMEM_LD32(addr + 32, v1);
   wait_ld();
   if (lane < 16) {
-    const int r = 16 * (warp & 3) + lane;
-    float* dst = reinterpret_cast<float*>(c.dw_a) + ((size_t)((warp >> 2) * 2 + (r >> 5)) * 32 + (r & 31)) * kStageStride;
+    const int r = 16 * warp + lane;
+    float* dst = reinterpret_cast<float*>(c.dw_a) + ((size_t)(r >> 5) * 32 + (r & 31)) * kStageStride;
 #pragma unroll
     for (int q = 0; q < 8; ++q)
       *reinterpret_cast<float4*>(dst + 4 * q) = make_float4(__uint_as_float(v0[4 * q]) + __uint_as_float(v1[4 * q]),
@@ -261,19 +279,18 @@ __device__ __forceinline__ void collect_dw(Ctx& c) {
   }
 }
 
-
-// Start one pass:  Y = X W_k (BWD = false)  or  Y = X W_k^T (BWD = true) for the CTA's 256 rows.
-// x: this thread's row.  Wk: the layer's 32x32 FP32 weights in shared memory, row-major [in][out].
+// Start one pass:  Y = X W_k (BWD = false)  or  Y = X W_k^T (BWD = true) for the CTA's 128 rows.
+// x: this thread's row; w: the thread's share of the layer's weights (load_w<BWD>).
 // Ends with the tcgen05.mma's in flight; tc::collect() waits for them.  Contains one __syncthreads().
 template <bool BWD>
-__device__ __forceinline__ void issue(Ctx& c, const float (&x)[32], const float* Wk) {
+__device__ __forceinline__ void issue(Ctx& c, const float (&x)[32], const float (&w)[8]) {
   {
     uint32_t hi[32], lo[32];
     split32(x, hi, lo);
     CLB_TMEM_ST32(c.row_addr + kColAhi, hi);
     CLB_TMEM_ST32(c.row_addr + kColAlo, lo);
   }
-  build_weight_image<BWD>(c, Wk);
+  build_weight_image<BWD>(c, w);
   wait_st();
   fence_async_smem();           // generic-proxy smem writes -> visible to the tensor core's async proxy
   fence_before();
