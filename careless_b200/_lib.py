@@ -18,9 +18,9 @@ LIK_NORMAL, LIK_STUDENTT = 0, 1
 PRIOR_WILSON, PRIOR_DOUBLE_WILSON = 0, 1
 BIJ_EXP, BIJ_SOFTPLUS = 0, 1
 ORDER_AUTO, ORDER_REFL, ORDER_SPOT, ORDER_IMAGE, ORDER_NONE = 0, 1, 2, 3, 4
-GROUP_SF_LOC, GROUP_SF_SCALE, GROUP_MLP, GROUP_IMAGE_SCALES, GROUP_DW_R = 0, 1, 2, 3, 4
+GROUP_SF_LOC, GROUP_SF_SCALE, GROUP_MLP, GROUP_IMAGE_SCALES, GROUP_DW_R, GROUP_IMAGE_LAYERS = 0, 1, 2, 3, 4, 5
 GROUPS = {"sf_loc_raw": GROUP_SF_LOC, "sf_scale_raw": GROUP_SF_SCALE, "mlp": GROUP_MLP,
-          "image_scales": GROUP_IMAGE_SCALES, "dw_r_logit": GROUP_DW_R}
+          "image_scales": GROUP_IMAGE_SCALES, "dw_r_logit": GROUP_DW_R, "image_layers": GROUP_IMAGE_LAYERS}
 
 
 class clb_config(C.Structure):
@@ -35,7 +35,7 @@ class clb_config(C.Structure):
         ("use_kl_weight", C.c_int32), ("kl_weight", C.c_float),
         ("learning_rate", C.c_float), ("beta_1", C.c_float), ("beta_2", C.c_float), ("adam_epsilon", C.c_float),
         ("clipnorm", C.c_float), ("clipvalue", C.c_float), ("global_clipnorm", C.c_float),
-        ("seed", C.c_uint64), ("rank", C.c_int32), ("world_size", C.c_int32),
+        ("seed", C.c_uint64), ("rank", C.c_int32), ("world_size", C.c_int32), ("image_layers", C.c_int32),
     ]
 
 
@@ -56,7 +56,7 @@ SYMBOLS = {
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
     "clb_prepare_rows": (C.c_int, [C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                   C.c_int32, C.c_int64, _I64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_int32, C.c_int32, C.c_int64, _I64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]),
     "clb_upload_observations": (C.c_int, [_H]),
     "clb_set_prior": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -68,6 +68,7 @@ SYMBOLS = {
     "clb_get_adam_state": (C.c_int, [_H, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, _I64]),
     "clb_set_trainable": (C.c_int, [_H, C.c_int32, C.c_int32]),
     "clb_step": (C.c_int, [_H, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(clb_metrics), C.POINTER(C.c_int32)]),
+    "clb_eval": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.POINTER(clb_metrics)]),
     "clb_step_begin": (C.c_int, [_H, C.c_void_p, C.c_void_p]),
     "clb_step_norms": (C.c_int, [_H]),
     "clb_step_end": (C.c_int, [_H, C.POINTER(clb_metrics)]),

@@ -72,6 +72,7 @@ struct clb_handle {
   int64_t adam_t = 0;
   uint32_t step_counter = 0;   // RNG step index
   bool have_obs = false, have_prior = false, in_step = false;
+  bool eval_mode = false;    // clb_eval: forward only (no gradients, no Adam)
   bool use_tc = false;       // tensor-core (tcgen05) path of k_obs: padded width 32, unless CLB_NO_TC=1
   bool debug_sync = false;   // CLB_DEBUG_SYNC=1: synchronise + log after every kernel launch
   int order = CLB_ORDER_REFL;
@@ -172,6 +173,7 @@ void build_vars(clb_handle* h) {
   h->gsize[CLB_GROUP_MLP] = h->lay.n_params;
   h->gsize[CLB_GROUP_IMAGE_SCALES] = c.image_scales ? std::max(0, c.n_images - 1) : 0;
   h->gsize[CLB_GROUP_DW_R] = (c.prior == CLB_PRIOR_DOUBLE_WILSON && c.optimize_dw_r) ? c.n_asu : 0;
+  h->gsize[CLB_GROUP_IMAGE_LAYERS] = (int64_t)c.image_layers * c.n_images * c.mlp_width * (c.mlp_width + 1);
   int64_t off = 0;
   for (int g = 0; g < CLB_N_GROUPS; ++g) { h->goff[g] = off; off += h->gsize[g]; h->gtrain[g] = 1; }
   h->P = off;
@@ -188,6 +190,11 @@ void build_vars(clb_handle* h) {
   }
   if (h->gsize[CLB_GROUP_IMAGE_SCALES] > 0) add(CLB_GROUP_IMAGE_SCALES, h->goff[CLB_GROUP_IMAGE_SCALES], h->gsize[CLB_GROUP_IMAGE_SCALES], 1);
   if (h->gsize[CLB_GROUP_DW_R] > 0) add(CLB_GROUP_DW_R, h->goff[CLB_GROUP_DW_R], h->gsize[CLB_GROUP_DW_R], 1);
+  for (int l = 0; l < c.image_layers; ++l) {       // keras variables of each ImageLayer: kernel, bias
+    const int64_t w = c.mlp_width, stride = (int64_t)c.n_images * w * (w + 1);
+    add(CLB_GROUP_IMAGE_LAYERS, h->goff[CLB_GROUP_IMAGE_LAYERS] + l * stride, (int64_t)c.n_images * w * w, 1);
+    add(CLB_GROUP_IMAGE_LAYERS, h->goff[CLB_GROUP_IMAGE_LAYERS] + l * stride + (int64_t)c.n_images * w * w, (int64_t)c.n_images * w, 1);
+  }
   vt.n_vars = n;
 }
 
@@ -221,13 +228,17 @@ struct RowPlan {
 
 int plan_rows(std::string& err, RowPlan& plan, int64_t n, int64_t n_total, int64_t R, int n_images, int laue,
               int likelihood, float dof, const int64_t* refl_id, const int64_t* image_id, const float* metadata,
-              const float* iobs, const float* sig, const int64_t* harmonic_id, const int64_t* obs_index, int order) {
+              const float* iobs, const float* sig, const int64_t* harmonic_id, const int64_t* obs_index, int order,
+              int image_tile = 0) {
+  // image_tile > 0 (image layers): rows are image-major and no image may straddle a tile of image_tile rows
   char buf[256];
   auto bad = [&](const char* fmt, long long a, long long b, long long c2) { snprintf(buf, sizeof buf, fmt, a, b, c2); err = buf; return 1; };
   if (n <= 0 || !refl_id || !metadata || !iobs || !sig) { err = "clb_set_observations: null/empty input"; return 1; }
   if (laue && !harmonic_id) { err = "Laue model needs harmonic_id"; return 1; }
   if (n >= ((int64_t)1 << 31) - 64) return bad("n_rows %lld exceeds 2^31 per handle", n, 0, 0);
-  if (order == CLB_ORDER_AUTO) order = laue ? CLB_ORDER_SPOT : CLB_ORDER_REFL;
+  if (order == CLB_ORDER_AUTO) order = laue ? CLB_ORDER_SPOT : (image_tile > 0 ? CLB_ORDER_IMAGE : CLB_ORDER_REFL);
+  if (image_tile > 0 && !image_id) { err = "image layers need image_id"; return 1; }
+  if (image_tile > 0 && order != CLB_ORDER_SPOT && order != CLB_ORDER_IMAGE) { err = "image layers need image-major rows (CLB_ORDER_IMAGE or CLB_ORDER_SPOT)"; return 1; }
   if (laue && order != CLB_ORDER_SPOT) { err = "Laue rows must use CLB_ORDER_SPOT"; return 1; }
   if (!laue && order == CLB_ORDER_SPOT) { err = "CLB_ORDER_SPOT needs a Laue model"; return 1; }
   if (order == CLB_ORDER_IMAGE && !image_id) { err = "CLB_ORDER_IMAGE needs image_id"; return 1; }
@@ -262,14 +273,29 @@ int plan_rows(std::string& err, RowPlan& plan, int64_t n, int64_t n_total, int64
   int64_t npad = n;
   if (order == CLB_ORDER_SPOT) {
     clb_config lc{}; lc.likelihood = likelihood; lc.dof = dof;
-    int64_t p = 0;
+    int64_t p = 0, prev_img = -1;
     for (int64_t k = 0; k < n_keys; ++k) {
       const int64_t len = count[k + 1] - count[k];
       if (len == 0) { plan.ll_const += lik_logpdf_zero(lc, iobs[k], sig[k]); continue; }
       if (len > 32) return bad("spot %lld has %lld harmonics; at most 32 are supported", k, len, 0);
+      if (image_tile > 0) {                          // harmonic ids are image-major (formatter.py:617)
+        const int64_t img = image_id[plan.perm[count[k]]];
+        if (img < prev_img) return bad("image layers need harmonic_id to be image-major (spot %lld)", k, 0, 0);
+        if (img != prev_img) p = (p + image_tile - 1) / image_tile * image_tile;
+        prev_img = img;
+      }
       if ((p & 31) + len > 32) p = (p + 31) & ~(int64_t)31;
       for (int64_t j = 0; j < len; ++j) plan.pos[count[k] + j] = p + j;
       p += len;
+    }
+    npad = p;
+  } else if (order == CLB_ORDER_IMAGE && image_tile > 0) {
+    int64_t p = 0, prev_img = -1;
+    for (int64_t sidx = 0; sidx < n; ++sidx) {
+      const int64_t img = image_id[plan.perm[sidx]];
+      if (img != prev_img) p = (p + image_tile - 1) / image_tile * image_tile;
+      prev_img = img;
+      plan.pos[sidx] = p++;
     }
     npad = p;
   } else {
@@ -325,6 +351,10 @@ int clb_create(const clb_config* cfg, clb_handle** out) {
   if (cfg->mlp_layers + 1 > kMaxLayers) return fail(nullptr, CLB_ERR_INVALID, "mlp_layers %d exceeds the supported maximum %d", cfg->mlp_layers, kMaxLayers - 1);
   if (cfg->likelihood == CLB_LIK_STUDENTT && !(cfg->dof > 0.f)) return fail(nullptr, CLB_ERR_INVALID, "student-t likelihood needs dof > 0");
   if (cfg->image_scales && cfg->n_images <= 0) return fail(nullptr, CLB_ERR_INVALID, "image scales need n_images > 0");
+  if (cfg->image_layers < 0 || (cfg->image_layers > 0 && cfg->n_images <= 0)) return fail(nullptr, CLB_ERR_INVALID, "image layers need n_images > 0");
+  if (cfg->image_layers > 0 && cfg->mlp_layers == 0 && cfg->n_meta != cfg->mlp_width)
+    return fail(nullptr, CLB_ERR_INVALID, "image layers without MLP layers need n_meta == mlp_width");
+  if (cfg->mlp_layers + cfg->image_layers + 1 > kMaxLayers) return fail(nullptr, CLB_ERR_INVALID, "too many layers");
   if (cfg->prior == CLB_PRIOR_DOUBLE_WILSON && cfg->n_asu <= 0) return fail(nullptr, CLB_ERR_INVALID, "DoubleWilson needs n_asu > 0");
   const int wmax = std::max(std::max(cfg->n_meta, cfg->mlp_width), 2);
   const int WP = round_width(wmax);
@@ -345,12 +375,12 @@ int clb_create(const clb_config* cfg, clb_handle** out) {
   build_layout(h);
   build_vars(h);
   h->NL = h->lay.n_layers;
-  { const char* no_tc = getenv("CLB_NO_TC"); h->use_tc = (WP == 32) && cfg->mlp_layers > 0 && !(no_tc && no_tc[0] == '1'); }
+  { const char* no_tc = getenv("CLB_NO_TC"); h->use_tc = (WP == 32) && (cfg->mlp_layers + cfg->image_layers) > 0 && !(no_tc && no_tc[0] == '1'); }
   h->obs_threads = h->use_tc ? tc::kThreads : kObsThreads;
   switch (WP) {
-    case 8: h->smem_obs = ObsSmem<8>::bytes(h->NL); break;
-    case 16: h->smem_obs = ObsSmem<16>::bytes(h->NL); break;
-    default: h->smem_obs = ObsSmem<32>::bytes(h->NL, h->use_tc); break;
+    case 8: h->smem_obs = ObsSmem<8>::bytes(h->NL, false, cfg->image_layers); break;
+    case 16: h->smem_obs = ObsSmem<16>::bytes(h->NL, false, cfg->image_layers); break;
+    default: h->smem_obs = ObsSmem<32>::bytes(h->NL, h->use_tc, cfg->image_layers); break;
   }
   if (h->smem_obs > (size_t)prop.sharedMemPerBlockOptin) {
     fail(h, CLB_ERR_INVALID, "scale MLP (%d layers x padded width %d) needs %zu B of shared memory; the device offers %zu",
@@ -376,6 +406,11 @@ int clb_create(const clb_config* cfg, clb_handle** out) {
   for (int k = 0; k < h->lay.n_layers; ++k)
     for (int i = 0; i < std::min(h->lay.in_dim[k], h->lay.out_dim[k]); ++i) mlp[h->lay.koff[k] + i * h->lay.out_dim[k] + i] = 1.f;
   for (int64_t i = 0; i < h->gsize[CLB_GROUP_IMAGE_SCALES]; ++i) init[h->goff[CLB_GROUP_IMAGE_SCALES] + i] = 1.f;
+  for (int l = 0; l < cfg->image_layers; ++l) {            // image.py:73-80: eye(units, in) for every image
+    const int64_t w = cfg->mlp_width, stride = (int64_t)cfg->n_images * w * (w + 1);
+    float* kern = init.data() + h->goff[CLB_GROUP_IMAGE_LAYERS] + l * stride;
+    for (int64_t im = 0; im < cfg->n_images; ++im) for (int64_t j = 0; j < w; ++j) kern[(im * w + j) * w + j] = 1.f;
+  }
   CREATE_CUDA(cudaMemcpyAsync(h->theta.p, init.data(), pb, cudaMemcpyHostToDevice, h->stream));
   const int big = 0x7fffffff;
   CREATE_CUDA(cudaMemcpyAsync(h->stop_step.p, &big, sizeof(int), cudaMemcpyHostToDevice, h->stream));
@@ -403,12 +438,12 @@ int clb_set_observations(clb_handle* h, int64_t n, int64_t n_total, const int64_
                          const int64_t* harmonic_id, const int64_t* obs_index, int32_t order) {
   if (!h) return CLB_ERR_INVALID;
   const clb_config& c = h->cfg;
-  if (c.image_scales && !image_id) return fail(h, CLB_ERR_INVALID, "image scales need image_id");
+  if ((c.image_scales || c.image_layers > 0) && !image_id) return fail(h, CLB_ERR_INVALID, "image scales / image layers need image_id");
   if (n_total <= 0) n_total = n;
   RowPlan plan;
   std::string err;
-  if (plan_rows(err, plan, n, n_total, h->R, c.image_scales ? c.n_images : 0, c.laue, c.likelihood, c.dof,
-                refl_id, image_id, metadata, iobs, sig, harmonic_id, obs_index, order))
+  if (plan_rows(err, plan, n, n_total, h->R, (c.image_scales || c.image_layers > 0) ? c.n_images : 0, c.laue, c.likelihood, c.dof,
+                refl_id, image_id, metadata, iobs, sig, harmonic_id, obs_index, order, c.image_layers > 0 ? h->obs_threads : 0))
     return fail(h, CLB_ERR_INVALID, "%s", err.c_str());
   CLB_CUDA(h, cudaSetDevice(c.device));
   const int d = c.n_meta;
@@ -447,7 +482,7 @@ int clb_set_observations(clb_handle* h, int64_t n, int64_t n_total, const int64_
   const int64_t n_tiles = (npad + h->obs_threads - 1) / h->obs_threads;
   h->grid_obs = (int)std::min<int64_t>(n_tiles, (int64_t)h->n_sms * (h->use_tc ? 2 : 1));
   CLB_CUDA(h, h->partials.alloc(sizeof(double) * (size_t)h->grid_obs * h->KS * partial_row_size(h->NL, h->WP)));
-  CLB_CUDA(h, h->scratch.alloc(sizeof(float4) * (size_t)h->grid_obs * std::max(1, c.mlp_layers) * (h->WP / 4) * h->obs_threads));
+  CLB_CUDA(h, h->scratch.alloc(sizeof(float4) * (size_t)h->grid_obs * std::max(1, c.mlp_layers + c.image_layers) * (h->WP / 4) * h->obs_threads));
   if (h->use_tc) CLB_CUDA(h, h->wpack.alloc(sizeof(float) * (size_t)std::max(1, c.mlp_layers) * 1024));
   h->have_obs = true;
   return clb_upload_observations(h);
@@ -458,13 +493,13 @@ int clb_set_observations(clb_handle* h, int64_t n, int64_t n_total, const int64_
 // small nothing else is written.  Used by the CPU test-suite to check the layout bit-exactly.
 int clb_prepare_rows(int64_t n, int64_t n_refl, int32_t n_meta, int32_t n_images, int32_t laue, int32_t likelihood, float dof,
                      const int64_t* refl_id, const int64_t* image_id, const float* metadata, const float* iobs,
-                     const float* sig, const int64_t* harmonic_id, const int64_t* obs_index, int32_t order,
+                     const float* sig, const int64_t* harmonic_id, const int64_t* obs_index, int32_t order, int32_t image_tile,
                      int64_t capacity, int64_t* n_padded, int32_t* refl_out, int32_t* image_out, int32_t* spot_out,
                      uint32_t* oidx_out, float* meta_out, float* iobs_out, float* sig_out, double* ll_const) {
   RowPlan plan;
   std::string err;
   if (plan_rows(err, plan, n, n, n_refl, n_images, laue, likelihood, dof, refl_id, image_id, metadata, iobs, sig,
-                harmonic_id, obs_index, order))
+                harmonic_id, obs_index, order, image_tile))
     return fail(nullptr, CLB_ERR_INVALID, "%s", err.c_str());
   if (n_padded) *n_padded = plan.npad;
   if (ll_const) *ll_const = plan.ll_const;
@@ -662,7 +697,7 @@ static int step_begin_impl(clb_handle* h, const float* inj_u, const float* inj_e
   CLB_CUDA(h, cudaMemsetAsync(h->var_sums.p, 0, sizeof(double) * 2 * kMaxVars, st));
   // gradients of the replicated groups are accumulated with atomics / overwritten by the reduction
   if (h->P > 2 * R) CLB_CUDA(h, cudaMemsetAsync(grad + 2 * R, 0, sizeof(float) * (h->P - 2 * R), st));
-  const bool train_mlp = h->gtrain[CLB_GROUP_MLP] != 0;
+  const bool train_mlp = h->gtrain[CLB_GROUP_MLP] != 0 && !h->eval_mode;
   if (train_mlp) CLB_CUDA(h, cudaMemsetAsync(h->partials.p, 0, sizeof(double) * (size_t)h->grid_obs * h->KS * partial_row_size(h->NL, h->WP), st));
 
   const bool dw = c.prior == CLB_PRIOR_DOUBLE_WILSON;
@@ -699,14 +734,19 @@ static int step_begin_impl(clb_handle* h, const float* inj_u, const float* inj_e
     a.theta_mlp = theta + h->goff[CLB_GROUP_MLP];
     a.theta_img = c.image_scales ? theta + h->goff[CLB_GROUP_IMAGE_SCALES] : nullptr;
     a.wpack = h->use_tc ? h->wpack.as<float>() : nullptr;
+    a.n_img_layers = c.image_layers; a.il_width = c.mlp_width; a.il_n_images = c.n_images;
+    a.theta_il = c.image_layers > 0 ? theta + h->goff[CLB_GROUP_IMAGE_LAYERS] : nullptr;
+    a.g_il = (c.image_layers > 0 && h->gtrain[CLB_GROUP_IMAGE_LAYERS] && !h->eval_mode) ? grad + h->goff[CLB_GROUP_IMAGE_LAYERS] : nullptr;
     if (h->use_tc) {
-      k_pack_weights<<<(c.mlp_layers * 1024 + 255) / 256, 256, 0, st>>>(a.theta_mlp, h->lay, h->wpack.as<float>());
-      CLB_LAUNCHED(h);
+      if (c.mlp_layers > 0) {
+        k_pack_weights<<<(c.mlp_layers * 1024 + 255) / 256, 256, 0, st>>>(a.theta_mlp, h->lay, h->wpack.as<float>());
+        CLB_LAUNCHED(h);
+      }
     }
     a.lay = h->lay;
     a.z = h->z.as<float>(); a.gz = h->gz.as<float>(); a.R = R; a.S = S;
     a.inj_eps = d_inj_eps;
-    a.g_img = (c.image_scales && h->gtrain[CLB_GROUP_IMAGE_SCALES]) ? grad + h->goff[CLB_GROUP_IMAGE_SCALES] : nullptr;
+    a.g_img = (c.image_scales && h->gtrain[CLB_GROUP_IMAGE_SCALES] && !h->eval_mode) ? grad + h->goff[CLB_GROUP_IMAGE_SCALES] : nullptr;
     a.partials = h->partials.as<double>(); a.scratch = h->scratch.as<float4>();
     a.ipred_out = h->want_ipred ? h->ipred.as<float>() : nullptr;
     a.acc = h->acc.as<double>();
@@ -727,7 +767,7 @@ static int step_begin_impl(clb_handle* h, const float* inj_u, const float* inj_e
     k_reduce_partials<<<(np + 255) / 256, 256, 0, st>>>(h->partials.as<double>(), h->grid_obs * h->KS, h->lay, h->WP, grad + h->goff[CLB_GROUP_MLP]);
     CLB_LAUNCHED(h);
   }
-  {
+  if (!h->eval_mode) {
     ReflBwdArgs a{};
     a.v_loc = theta + h->goff[CLB_GROUP_SF_LOC]; a.v_scale = theta + h->goff[CLB_GROUP_SF_SCALE];
     a.centric = h->centric.as<uint8_t>(); a.refl_index = h->refl_index.as<uint32_t>();
@@ -783,6 +823,43 @@ static int step_end_impl(clb_handle* h, double* d_metrics) {
   h->adam_t += 1;
   h->step_counter += 1;
   h->in_step = false;
+  return CLB_OK;
+}
+
+// Forward only: the "NLL" / "F KLDiv" / "loss" of the current parameters on this handle's observations with fresh
+// draws and no update (keras test_on_batch at variational.py:257-260).  grad_norm is reported as 0.
+int clb_eval(clb_handle* h, const float* inj_u_f, const float* inj_eps_s, clb_metrics* out) {
+  if (!h) return CLB_ERR_INVALID;
+  if (h->cfg.world_size > 1) return fail(h, CLB_ERR_STATE, "clb_eval is single-GPU");
+  int rc = ensure_metrics(h, 1); if (rc) return rc;
+  h->eval_mode = true;
+  rc = step_begin_impl(h, inj_u_f, inj_eps_s);
+  h->eval_mode = false;
+  if (rc) return rc;
+  cudaStream_t st = h->stream;
+  CLB_CUDA(h, cudaMemsetAsync(h->var_sums.p, 0, sizeof(double) * 2 * kMaxVars, st));
+  k_pack_scalars<<<1, 128, 0, st>>>(h->acc.as<double>(), h->var_sums.as<double>(), h->vt, h->red.as<double>(), h->cfg.rank,
+                                    (double)h->S * h->ll_const);
+  CLB_LAUNCHED(h);
+  const clb_config& c = h->cfg;
+  FinalizeArgs f{};
+  f.acc = h->acc.as<double>(); f.red = h->red.as<double>(); f.vt = h->vt; f.vt.n_vars = 0;
+  f.metrics = h->metrics.as<double>(); f.var_scale = h->var_scale.as<float>(); f.adam_alpha = h->adam_alpha.as<float>() + 1;
+  f.stop_step = h->stop_step.as<int>() + 1; f.step = 0;      // scratch slots: the training early-stop state is untouched
+  f.kl_div = c.use_kl_weight ? (double)h->S * (double)c.n_refl_total : (double)h->S;
+  f.kl_coef = c.use_kl_weight ? (double)c.kl_weight : 1.0;
+  f.ll_div = c.use_kl_weight ? (double)h->S * (double)h->n_rows_total : (double)h->S;
+  f.lr = c.learning_rate; f.beta1 = c.beta_1; f.beta2 = c.beta_2; f.t = 1;
+  k_finalize<<<1, 32, 0, st>>>(f);
+  CLB_LAUNCHED(h);
+  h->step_counter += 1;
+  h->in_step = false;
+  if (out) {
+    double m[4];
+    CLB_CUDA(h, cudaMemcpyAsync(m, h->metrics.p, sizeof m, cudaMemcpyDeviceToHost, st));
+    CLB_CUDA(h, cudaStreamSynchronize(st));
+    out->loss = m[0]; out->nll = m[1]; out->kl = m[2]; out->grad_norm = m[3];
+  }
   return CLB_OK;
 }
 

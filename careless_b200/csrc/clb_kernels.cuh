@@ -138,6 +138,9 @@ struct ObsArgs {
   // model
   const float* theta_mlp; const float* theta_img;   // image scales (n_img-1) or null
   const float* wpack;              // [L][32][32] zero-padded FP32 copy of the hidden-layer kernels (TC kernels)
+  // image layers (scaling/image.py:66-125): per layer a kernel [n_img][W][W] (out, in) and a bias [n_img][W]
+  int n_img_layers; int il_width; int il_n_images;
+  const float* theta_il; float* g_il;   // parameter group and its gradient (null: frozen / eval)
   MlpLayout lay;
   const float* z; float* gz; int64_t R; int S;
   const float* inj_eps;            // (S, N_total) or null
@@ -155,7 +158,10 @@ struct ObsArgs {
 template <int WP> struct ObsSmem {
   static constexpr int T = kObsThreads;
   static constexpr int HS = T + 4;                    // padded stride of the transposed activation tile
-  static size_t bytes(int n_layers, bool tensor_cores = false) {
+  static size_t bytes(int n_layers, bool tensor_cores = false, int n_img_layers = 0) {
+    return bytes_base(n_layers, tensor_cores) + sizeof(float) * (size_t)n_img_layers * (WP * WP + WP);
+  }
+  static size_t bytes_base(int n_layers, bool tensor_cores) {
     if (tensor_cores)     // dW operand images, compact head weights, biases, bias sums, reductions, chain images (128-thread CTA)
       return 2 * (size_t)tc::kDwImgBytes + sizeof(float) * (2 * WP + 2 * (size_t)n_layers * WP + (size_t)(tc::kThreads / 32) * WP)
              + 64 * sizeof(double) + 2 * (size_t)tc::kImgBytes + 128;
@@ -206,7 +212,8 @@ __device__ __forceinline__ void bias_partial(const float (&dp)[WP], float* bias_
 template <int WP>
 __device__ __forceinline__ void stage_and_accumulate(const float (&ain)[WP], const float (&dp)[WP],
                                                      float* S_h, float4* S_d, float4* Rbuf, float* bias_part,
-                                                     float* dbacc_k, double* part, int tid) {
+                                                     float* dbacc_k, double* part, int tid,
+                                                     float* il_gk = nullptr, float* il_gb = nullptr, int il_w = 0) {
   constexpr int T = kObsThreads, HS = T + 4, NC = WP / 4;
   constexpr int Q = WP / 4;               // patch rows are strided by Q, patch columns are one float4 chunk
   constexpr int TPL4 = Q * Q;             // threads covering one WPxWP matrix with 4x4 patches
@@ -215,8 +222,9 @@ __device__ __forceinline__ void stage_and_accumulate(const float (&ain)[WP], con
   constexpr int NOUT4 = WP * WP / 4;      // float4 outputs of one layer
   static_assert(OBS % 4 == 0 && OBS >= 4, "tile too small for the K split");
   const bool owner = tid < NOUT4;
+  const bool to_image = il_w > 0;         // image layer: the tile's gradient goes to that image's slot (atomics)
   double2 p01 = make_double2(0.0, 0.0), p23 = make_double2(0.0, 0.0);
-  if (owner) {
+  if (owner && !to_image) {
     p01 = __ldcg(reinterpret_cast<const double2*>(part));
     p23 = __ldcg(reinterpret_cast<const double2*>(part) + 1);
   }
@@ -268,7 +276,8 @@ __device__ __forceinline__ void stage_and_accumulate(const float (&ain)[WP], con
     float sum = 0.f;
 #pragma unroll
     for (int w = 0; w < T / 32; ++w) sum += bias_part[w * WP + tid];
-    dbacc_k[tid] += sum;                    // column tid of this layer is owned by thread tid: no atomics
+    if (!to_image) dbacc_k[tid] += sum;     // column tid of this layer is owned by thread tid: no atomics
+    else if (il_gb != nullptr && tid < il_w) atomicAdd(&il_gb[tid], sum);
   }
   if (owner) {
     float4 t = Rbuf[tid];
@@ -277,8 +286,19 @@ __device__ __forceinline__ void stage_and_accumulate(const float (&ain)[WP], con
       const float4 v = Rbuf[k2 * NOUT4 + tid];
       t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
     }
-    __stcg(reinterpret_cast<double2*>(part), make_double2(p01.x + (double)t.x, p01.y + (double)t.y));
-    __stcg(reinterpret_cast<double2*>(part) + 1, make_double2(p23.x + (double)t.z, p23.y + (double)t.w));
+    if (!to_image) {
+      __stcg(reinterpret_cast<double2*>(part), make_double2(p01.x + (double)t.x, p01.y + (double)t.y));
+      __stcg(reinterpret_cast<double2*>(part) + 1, make_double2(p23.x + (double)t.z, p23.y + (double)t.w));
+    } else if (il_gk != nullptr) {
+      // float4 output tid = r*Q*Q + pj*Q + pi holds dK[i = pi + Q r][j = 4 pj ..]; image kernels are stored (out, in)
+      const int r4 = tid / TPL4, pj4 = (tid % TPL4) / Q, pi4 = tid % Q;
+      const int i = pi4 + Q * r4;
+      const float tv[4] = {t.x, t.y, t.z, t.w};
+      if (i < il_w) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { const int j = 4 * pj4 + c; if (j < il_w) atomicAdd(&il_gk[j * il_w + i], tv[c]); }
+      }
+    }
   }
 }
 
@@ -287,12 +307,17 @@ __device__ __forceinline__ void stage_and_accumulate(const float (&ain)[WP], con
 // folds the accumulator copies and adds the result to the CTA's FP64 partial (same layout as the FP32 path:
 // float4 output o4 = r*64 + pj*8 + pi holds element (i = pi + 8 r, j = 4 pj ..); thread tid owns o4 = tid, tid+128).
 __device__ __forceinline__ void tc_layer_backward(tc::Ctx& tcx, float (&dp)[32], const float (&ain)[32], const float (&w)[8],
-                                                  bool need_dx, float* bias_part, float* dbacc_k, double* part, int tid) {
+                                                  bool need_dx, float* bias_part, float* dbacc_k, double* part, int tid,
+                                                  float* il_gk = nullptr, float* il_gb = nullptr, int il_w = 0) {
+  const bool to_image = il_w > 0;          // image layer: the tile's gradient goes to that image's slot (atomics)
   double2 pr[2][2];
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
-    pr[h][0] = __ldcg(reinterpret_cast<const double2*>(part + 512 * h));
-    pr[h][1] = __ldcg(reinterpret_cast<const double2*>(part + 512 * h) + 1);
+    pr[h][0] = pr[h][1] = make_double2(0.0, 0.0);
+    if (!to_image) {
+      pr[h][0] = __ldcg(reinterpret_cast<const double2*>(part + 512 * h));
+      pr[h][1] = __ldcg(reinterpret_cast<const double2*>(part + 512 * h) + 1);
+    }
   }
   bias_partial<32>(dp, bias_part, tid);
   tc::issue_backward(tcx, dp, ain, w, need_dx);
@@ -307,14 +332,24 @@ __device__ __forceinline__ void tc_layer_backward(tc::Ctx& tcx, float (&dp)[32],
       const float* st = reinterpret_cast<const float*>(tcx.dw_a) + (size_t)(pi + 8 * r) * tc::kStageStride + 4 * pj;
       const float4 t0 = *reinterpret_cast<const float4*>(st);
       const float4 t1 = *reinterpret_cast<const float4*>(st + (size_t)32 * tc::kStageStride);
-      __stcg(reinterpret_cast<double2*>(part + 512 * h), make_double2(pr[h][0].x + (double)(t0.x + t1.x), pr[h][0].y + (double)(t0.y + t1.y)));
-      __stcg(reinterpret_cast<double2*>(part + 512 * h) + 1, make_double2(pr[h][1].x + (double)(t0.z + t1.z), pr[h][1].y + (double)(t0.w + t1.w)));
+      if (!to_image) {
+        __stcg(reinterpret_cast<double2*>(part + 512 * h), make_double2(pr[h][0].x + (double)(t0.x + t1.x), pr[h][0].y + (double)(t0.y + t1.y)));
+        __stcg(reinterpret_cast<double2*>(part + 512 * h) + 1, make_double2(pr[h][1].x + (double)(t0.z + t1.z), pr[h][1].y + (double)(t0.w + t1.w)));
+      } else if (il_gk != nullptr) {
+        const int i = pi + 8 * r;
+        const float tv[4] = {t0.x + t1.x, t0.y + t1.y, t0.z + t1.z, t0.w + t1.w};
+        if (i < il_w) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) { const int j = 4 * pj + c; if (j < il_w) atomicAdd(&il_gk[j * il_w + i], tv[c]); }
+        }
+      }
     }
     if (tid < 32) {
       float sum = 0.f;
 #pragma unroll
       for (int w2 = 0; w2 < tc::kThreads / 32; ++w2) sum += bias_part[w2 * 32 + tid];
-      dbacc_k[tid] += sum;
+      if (!to_image) dbacc_k[tid] += sum;
+      else if (il_gb != nullptr && tid < il_w) atomicAdd(&il_gb[tid], sum);
     }
   }
   __syncthreads();      // the stage aliases the operand image of the next layer
@@ -346,7 +381,11 @@ __global__ void __launch_bounds__(TC ? tc::kThreads : kObsThreads, TC ? 2 : 1) k
   float* Whead = Wsm + (TC ? 0 : (size_t)L * WP * WP);
   float* bsm = Whead + (size_t)WP * HSTR;                   // [NL][WP]
   float* dbacc = bsm + (size_t)NL * WP;                     // [NL][WP]
-  float* nxtp = dbacc + (size_t)NL * WP;
+  const int K = a.n_img_layers;           // image layers sit between the hidden layers and the head
+  const int LT = L + K;                   // layers of the chain
+  float* Wimg = dbacc + (size_t)NL * WP;                    // [K][WP][WP] this tile's image-layer kernels as [in][out]
+  float* bimg = Wimg + (size_t)K * WP * WP;                 // [K][WP]
+  float* nxtp = bimg + (size_t)K * WP;
   float* S_h = nullptr; float4* S_d = nullptr; float4* Rbuf = nullptr;
   if constexpr (!TC) {
     S_h = nxtp;                                             // [WP][HS]
@@ -404,7 +443,7 @@ __global__ void __launch_bounds__(TC ? tc::kThreads : kObsThreads, TC ? 2 : 1) k
 
   const int PP = partial_row_size(NL, WP);
   double* part_rows = a.partials + (size_t)blockIdx.x * PP + (size_t)tid * 4;   // valid for tid < WP*WP/4
-  float4* scr = a.scratch + (size_t)blockIdx.x * L * NC * T;
+  float4* scr = a.scratch + (size_t)blockIdx.x * LT * NC * T;
   double ll_sum = 0.0;
   const int64_t n_tiles = (a.n_rows + T - 1) / T;
 
@@ -413,26 +452,47 @@ __global__ void __launch_bounds__(TC ? tc::kThreads : kObsThreads, TC ? 2 : 1) k
     const bool inb = row < a.n_rows;
     const int refl = inb ? a.refl[row] : -1;
     const bool active = refl >= 0;
+    // image layers: the host prep never lets an image straddle a tile, so the whole tile uses one image's weights
+    const int timg = (K > 0) ? a.image[tile * T] : 0;
+    if (K > 0) {
+      __syncthreads();                     // the previous tile is done with Wimg
+      const int w = a.il_width;
+      const size_t lstride = (size_t)a.il_n_images * w * (w + 1);
+      for (int idx = tid; idx < K * WP * WP; idx += T) {
+        const int l = idx / (WP * WP), i = (idx / WP) % WP, j = idx % WP;
+        Wimg[idx] = (i < w && j < w) ? a.theta_il[l * lstride + ((size_t)timg * w + j) * w + i] : 0.f;   // stored (out, in)
+      }
+      for (int idx = tid; idx < K * WP; idx += T) {
+        const int l = idx / WP, j = idx % WP;
+        bimg[idx] = (j < w) ? a.theta_il[l * lstride + (size_t)a.il_n_images * w * w + (size_t)timg * w + j] : 0.f;
+      }
+      __syncthreads();
+    }
     // ---------------- forward ----------------
     float h[WP];
 #pragma unroll
     for (int i = 0; i < WP; ++i) h[i] = (inb && i < a.d) ? a.meta[(size_t)i * a.n_rows + row] : 0.f;
     float wreg[8];                       // TC: this thread's share of the next pass's weights
-    if constexpr (TC) { if (L > 0) tc::load_w<false>(a.wpack, tid, wreg); }
-    for (int k = 0; k < L; ++k) {
-      const float* Wk = Wsm + (size_t)k * WP * WP;
+    auto wsrc = [&](int k) -> const float* {      // FP32 weights of chain layer k as [in][out] (TC: 32x32 padded)
+      if (k >= L) return Wimg + (size_t)(k - L) * WP * WP;
+      if constexpr (TC) return a.wpack + (size_t)k * 1024; else return Wsm + (size_t)k * WP * WP;
+    };
+    if constexpr (TC) { if (LT > 0) tc::load_w<false>(wsrc(0), tid, wreg); }
+    for (int k = 0; k < LT; ++k) {
+      const float* Wk = wsrc(k);
+      const float* bk = (k >= L) ? bimg + (size_t)(k - L) * WP : bsm + (size_t)k * WP;
       float o[WP];
       if constexpr (TC) {
         tc::issue<false>(tcx, h, wreg);
         // prefetch the next pass's weights while the tensor cores work: next forward layer, or the first backward layer
-        if (k + 1 < L) tc::load_w<false>(a.wpack + (size_t)(k + 1) * 1024, tid, wreg);
-        else if (a.train_mlp && L > 1) tc::load_w<true>(a.wpack + (size_t)(L - 1) * 1024, tid, wreg);
+        if (k + 1 < LT) tc::load_w<false>(wsrc(k + 1), tid, wreg);
+        else if (a.train_mlp && LT > 1) tc::load_w<true>(wsrc(LT - 1), tid, wreg);
         tc::collect(tcx, o);
 #pragma unroll
-        for (int j = 0; j < WP; ++j) o[j] += bsm[k * WP + j];
+        for (int j = 0; j < WP; ++j) o[j] += bk[j];
       } else {
 #pragma unroll
-        for (int j = 0; j < WP; ++j) o[j] = bsm[k * WP + j];
+        for (int j = 0; j < WP; ++j) o[j] = bk[j];
 #pragma unroll
         for (int i = 0; i < WP; ++i) {
 #pragma unroll
@@ -523,7 +583,7 @@ __global__ void __launch_bounds__(TC ? tc::kThreads : kObsThreads, TC ? 2 : 1) k
         for (int i = 0; i < WP; ++i) dst[i] = (inb && i < a.d) ? a.meta[(size_t)i * a.n_rows + row] : 0.f;
       }
     };
-    if (L > 0) load_act(nxt, L - 1);
+    if (LT > 0) load_act(nxt, LT - 1);
 #pragma unroll
     for (int j = 0; j < WP; ++j) dp[j] = 0.f;
     dp[0] = dmu; dp[1] = drho;
@@ -538,7 +598,19 @@ __global__ void __launch_bounds__(TC ? tc::kThreads : kObsThreads, TC ? 2 : 1) k
       const float2 w = *reinterpret_cast<const float2*>(&Whead[i * HSTR]);
       dp[i] = w.x * dmu + w.y * drho;            // delta a_L
     }
-    for (int k = L - 1; k >= 0; --k) {
+    for (int k = LT - 1; k >= 0; --k) {
+      // image layers send their gradient to the tile's image slot; hidden layers to the CTA partial
+      const bool is_il = k >= L;
+      float* il_gk = nullptr; float* il_gb = nullptr;
+      if (is_il && a.g_il != nullptr) {
+        const int w = a.il_width;
+        const size_t lstride = (size_t)a.il_n_images * w * (w + 1);
+        il_gk = a.g_il + (size_t)(k - L) * lstride + (size_t)timg * w * w;
+        il_gb = a.g_il + (size_t)(k - L) * lstride + (size_t)a.il_n_images * w * w + (size_t)timg * w;
+      }
+      const int il_w = is_il ? a.il_width : 0;
+      float* dbk = dbacc + (size_t)(is_il ? L : k) * WP;            // unused for image layers
+      double* partk = part_rows + (size_t)(is_il ? L : k) * WP * WP;  // unused for image layers
       // delta p_k = delta a_{k+1} * leaky'(a_{k+1});  sign(a) == sign(pre-activation)
 #pragma unroll
       for (int j = 0; j < WP; ++j) dp[j] = ((mask >> j) & 1u) ? dp[j] : kLeak * dp[j];
@@ -552,13 +624,13 @@ __global__ void __launch_bounds__(TC ? tc::kThreads : kObsThreads, TC ? 2 : 1) k
         float wcur[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) wcur[q] = wreg[q];
-        if (k > 1) tc::load_w<true>(a.wpack + (size_t)(k - 1) * 1024, tid, wreg);     // next backward layer
-        tc_layer_backward(tcx, dp, ain, wcur, k > 0, bias_part, dbacc + k * WP, part_rows + (size_t)k * WP * WP, tid);
+        if (k > 1) tc::load_w<true>(wsrc(k - 1), tid, wreg);     // next backward layer
+        tc_layer_backward(tcx, dp, ain, wcur, k > 0, bias_part, dbk, partk, tid, il_gk, il_gb, il_w);
         continue;
       }
-      stage_and_accumulate<WP>(ain, dp, S_h, S_d, Rbuf, bias_part, dbacc + k * WP, part_rows + (size_t)k * WP * WP, tid);
+      stage_and_accumulate<WP>(ain, dp, S_h, S_d, Rbuf, bias_part, dbk, partk, tid, il_gk, il_gb, il_w);
       if (k > 0) {
-        const float* Wk = Wsm + (size_t)k * WP * WP;
+        const float* Wk = wsrc(k);
         float da[WP];
 #pragma unroll
         for (int i = 0; i < WP; ++i) {

@@ -157,22 +157,23 @@ __device__ __forceinline__ void dw_store_row(char* img, int k, const uint32_t (&
 }
 
 // The 8 weights this thread contributes to the B operand image of one layer, fetched from the padded FP32
-// copy in global memory (L2/L1 resident, 4 KB per layer) one pass ahead of their use.
+// copy in global memory (L2/L1 resident, 4 KB per layer; image layers: the tile's copy in shared memory, hence
+// generic loads) one pass ahead of their use.
 //   forward  (B[n][k] = W[k][n]): thread (n = tid%32, kq = tid/32 and kq+4) gathers 4 consecutive k each;
 //   backward (B[n][k] = W[n][k]): thread (kq = tid%8, n = tid/8 and n+16) copies 4 consecutive k each.
 template <bool BWD>
-__device__ __forceinline__ void load_w(const float* __restrict__ Wg, int tid, float (&w)[8]) {
+__device__ __forceinline__ void load_w(const float* Wg, int tid, float (&w)[8]) {
   if (!BWD) {
     const int n = tid & 31, kq = tid >> 5;
 #pragma unroll
     for (int h = 0; h < 2; ++h)
 #pragma unroll
-      for (int r = 0; r < 4; ++r) w[4 * h + r] = __ldg(&Wg[(4 * (kq + 4 * h) + r) * 32 + n]);
+      for (int r = 0; r < 4; ++r) w[4 * h + r] = Wg[(4 * (kq + 4 * h) + r) * 32 + n];
   } else {
     const int kq = tid & 7, n = tid >> 3;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(&Wg[(n + 16 * h) * 32 + 4 * kq]));
+      const float4 v = *reinterpret_cast<const float4*>(&Wg[(n + 16 * h) * 32 + 4 * kq]);
       w[4 * h] = v.x; w[4 * h + 1] = v.y; w[4 * h + 2] = v.z; w[4 * h + 3] = v.w;
     }
   }

@@ -24,6 +24,7 @@ class EngineConfig:
     n_refl_total: int = 0
     n_images: int = 0
     image_scales: bool = False
+    image_layers: int = 0
     mc_samples: int = 1
     likelihood: str = "normal"
     dof: Optional[float] = None
@@ -56,7 +57,8 @@ class EngineConfig:
         c.n_refl = self.n_refl
         c.n_refl_total = self.n_refl_total or self.n_refl
         c.n_meta, c.mlp_width, c.mlp_layers = self.n_meta, self.mlp_width, self.mlp_layers
-        c.n_images = self.n_images if self.image_scales else 0
+        c.n_images = self.n_images if (self.image_scales or self.image_layers > 0) else 0
+        c.image_layers = self.image_layers
         c.image_scales = int(self.image_scales)
         c.mc_samples = self.mc_samples
         c.likelihood = {"normal": L.LIK_NORMAL, "studentt": L.LIK_STUDENTT}[self.likelihood]
@@ -187,6 +189,17 @@ class Engine:
         done = C.c_int32()
         self._check(self.lib.clb_step(self._h, n_steps, _ptr(u_f), _ptr(eps_s), out, C.byref(done)))
         return [{"loss": m.loss, "NLL": m.nll, "F KLDiv": m.kl, "Grad Norm": m.grad_norm} for m in out[:done.value]]
+
+    def eval(self, u_f=None, eps_s=None):
+        """Forward only (keras test_on_batch): metrics of the current parameters on this engine's rows."""
+        S, R, N = self.cfg.mc_samples, self.cfg.n_refl, self.n_rows_total
+        if u_f is not None:
+            u_f = np.ascontiguousarray(np.asarray(u_f, dtype=np.float32).reshape(S, R))
+        if eps_s is not None:
+            eps_s = np.ascontiguousarray(np.asarray(eps_s, dtype=np.float32).reshape(S, N))
+        m = L.clb_metrics()
+        self._check(self.lib.clb_eval(self._h, _ptr(u_f), _ptr(eps_s), C.byref(m)))
+        return {"loss": m.loss, "NLL": m.nll, "F KLDiv": m.kl}
 
     def step_begin(self, u_f=None, eps_s=None):
         S, R, N = self.cfg.mc_samples, self.cfg.n_refl, self.n_rows_total

@@ -12,7 +12,7 @@ import numpy as np
 
 from ..base import BaseModel
 from ..priors.wilson import DoubleWilsonPrior, WilsonPrior
-from ..scaling.image import HybridImageScaler
+from ..scaling.image import HybridImageScaler, NeuralImageScaler
 from ..scaling.nn import MetadataScaler
 from ...engine import Engine, EngineConfig
 from ...optimizers import Adam
@@ -43,6 +43,8 @@ class VariationalMergingModel(BaseModel):
     # ------------------------------------------------------------------ engine plumbing
     def _parts(self):
         sm = self.scaling_model
+        if isinstance(sm, NeuralImageScaler):
+            return sm.metadata_scaler, None
         if isinstance(sm, HybridImageScaler):
             return sm.mlp_scaler, sm.image_scaler
         if isinstance(sm, MetadataScaler):
@@ -61,9 +63,11 @@ class VariationalMergingModel(BaseModel):
         q, prior, opt = self.surrogate_posterior, self.prior, self.optimizer
         R = q.loc_raw.shape[0]
         dw = isinstance(prior, DoubleWilsonPrior)
+        nis = self.scaling_model if isinstance(self.scaling_model, NeuralImageScaler) else None
         cfg = EngineConfig(
             n_refl=R, n_meta=n_meta, mlp_width=mlp.width, mlp_layers=mlp.n_layers,
-            n_images=(img.max_images if img is not None else 0), image_scales=img is not None,
+            n_images=(img.max_images if img is not None else (nis.max_images if nis is not None else 0)), image_scales=img is not None,
+            image_layers=(len(nis.image_layers) if nis is not None else 0),
             mc_samples=int(self.mc_sample_size), likelihood=self.likelihood.kind, dof=self.likelihood.dof, laue=laue,
             prior="double_wilson" if dw else "wilson", n_asu=(len(prior.r) if dw else 0),
             optimize_dw_r=(prior.optimize_r if dw else False), scale_bijector=mlp.scale_bijector,
@@ -92,6 +96,9 @@ class VariationalMergingModel(BaseModel):
         eng.set_params("mlp", mlp.flat())
         if img is not None:
             eng.set_params("image_scales", img._scales)
+        if isinstance(self.scaling_model, NeuralImageScaler) and self.scaling_model.image_layers:
+            eng.set_params("image_layers", self.scaling_model.flat())
+            eng.set_trainable("image_layers", self.scaling_model.trainable)
         eng.set_trainable("sf_loc_raw", q.trainable)
         eng.set_trainable("sf_scale_raw", q.trainable)
         eng.set_trainable("mlp", self.scaling_model.trainable and mlp.trainable)
@@ -105,6 +112,8 @@ class VariationalMergingModel(BaseModel):
         mlp.from_flat(eng.get_params("mlp"))
         if img is not None:
             img._scales = eng.get_params("image_scales")
+        if isinstance(self.scaling_model, NeuralImageScaler) and self.scaling_model.image_layers:
+            self.scaling_model.from_flat(eng.get_params("image_layers"))
         if isinstance(self.prior, DoubleWilsonPrior) and self.prior.optimize_r:
             self.prior.r = (1.0 / (1.0 + np.exp(-eng.get_params("dw_r_logit")))).astype(np.float32)
 
@@ -112,34 +121,71 @@ class VariationalMergingModel(BaseModel):
     def train_model(self, data, steps, message=None, format_string="{:0.2e}", validation_data=None,
                     validation_frequency=10, progress=True, use_custom_train_step=True, jit_compile=None,
                     reduce_retracing=False, chunk=100):
-        """variational.py:226-275.  Returns history: dict[str, list[float]], one entry per step taken."""
-        if validation_data is not None:
-            raise NotImplementedError("validation NLL (variational.py:257-260) is a 'next' row of the scope table")
+        """variational.py:226-275.  Returns history: dict[str, list[float]], one entry per step taken.
+        With ``validation_data`` the held-out NLL (keras test_on_batch, :257-260) is evaluated after every
+        ``validation_frequency``-th step on a second engine and logged as ``NLL_val`` scaled by
+        len(train)/len(validation) (:249)."""
         eng = self._build_engine(data)
         self._push(eng)
+        veng, val_scale, nll_val = None, None, None
+        if validation_data is not None:
+            val_scale = len(data[0]) / len(validation_data[0])
+            veng = self._validation_engine(validation_data)
         history = {}
         done = 0
         bar = None
         if progress:
             from tqdm import tqdm
             bar = tqdm(total=steps, desc=message)
-        while done < steps:
-            n = min(chunk, steps - done)
+        stopped = False
+        while done < steps and not stopped:
+            if veng is not None:
+                to_val = (-done) % validation_frequency           # steps until the next validated step
+                n = 1 if to_val == 0 else min(chunk, to_val, steps - done)
+            else:
+                n = min(chunk, steps - done)
             rows = eng.step(n)            # metrics stay on the device for the whole chunk (no per-step host sync)
+            if veng is not None and done % validation_frequency == 0 and rows:
+                for g in ("sf_loc_raw", "sf_scale_raw", "mlp", "image_scales", "dw_r_logit", "image_layers"):
+                    if eng.group_size(g) > 0:
+                        veng.set_params(g, eng.get_params(g))
+                nll_val = val_scale * veng.eval()["NLL"]
             for row in rows:
                 for k, v in row.items():
                     history.setdefault(k, []).append(float(v))
+                if veng is not None:
+                    history.setdefault("NLL_val", []).append(float(nll_val))
             done += len(rows)
             if bar is not None:
                 bar.update(len(rows))
                 bar.set_postfix({k: format_string.format(v[-1]) for k, v in history.items()})
             if len(rows) < n:
                 print("Encountered numerical issues, terminating optimization early!")
-                break
+                stopped = True
         if bar is not None:
             bar.close()
+        if veng is not None:
+            veng.close()
         self._pull(eng)
         return history
+
+    def _validation_engine(self, validation_data):
+        """A second engine holding the held-out rows (same model configuration, its own RNG stream)."""
+        import dataclasses
+        eng = self._engine
+        mlp, img = self._parts()
+        laue = bool(getattr(self.likelihood, "laue", False))
+        prior = self.prior
+        dw = isinstance(prior, DoubleWilsonPrior)
+        cfg = dataclasses.replace(eng.cfg, seed=eng.cfg.seed + 0x9E3779B9)
+        veng = Engine(cfg)
+        veng.set_observations(np.asarray(self.get_refl_id(validation_data)).reshape(-1), self.get_image_id(validation_data),
+                              self.get_metadata(validation_data), self.get_intensities(validation_data),
+                              self.get_uncertainties(validation_data),
+                              harmonic_id=self.get_harmonic_id(validation_data) if laue else None)
+        veng.set_prior(prior.centric, prior.epsilon, prior.sigma, dw_parent=prior.dw_parent if dw else None,
+                       asu_id=prior.asu_ids if dw else None, r=prior.r if dw else None, init_scale=-1.0)
+        return veng
 
     def close(self):
         if self._engine is not None:

@@ -50,9 +50,10 @@ enum { CLB_ORDER_AUTO = 0, CLB_ORDER_REFL = 1, CLB_ORDER_SPOT = 2, CLB_ORDER_IMA
  *   MLP               scaling/nn.py:55-79, keras order [kernel_0, bias_0, ..., kernel_out, bias_out]
  *   IMAGE_SCALES      scaling/image.py:21   (n_images-1 values; image 0 is pinned to 1)
  *   DW_R              priors/wilson.py:105-110 (logits of r, one per ASU; --optimize-double-wilson-r)
+ *   IMAGE_LAYERS      scaling/image.py:73-88 (--image-layers): per layer kernel (n_images, W, W) as (out, in), bias (n_images, W)
  */
 enum { CLB_GROUP_SF_LOC = 0, CLB_GROUP_SF_SCALE = 1, CLB_GROUP_MLP = 2, CLB_GROUP_IMAGE_SCALES = 3,
-       CLB_GROUP_DW_R = 4, CLB_N_GROUPS = 5 };
+       CLB_GROUP_DW_R = 4, CLB_GROUP_IMAGE_LAYERS = 5, CLB_N_GROUPS = 6 };
 
 /* Everything DataManager.build_model (careless/io/manager.py:380-507) decides, flattened. */
 typedef struct {
@@ -65,7 +66,7 @@ typedef struct {
   int32_t n_meta;             /* d: metadata columns */
   int32_t mlp_width;          /* W   (--mlp-width, args/scaling.py:27-31) */
   int32_t mlp_layers;         /* L   (--mlp-layers, args/scaling.py:21-25) */
-  int32_t n_images;           /* max(image_id)+1 when image scales are on, else 0 */
+  int32_t n_images;           /* max(image_id)+1 when image scales or image layers are on, else 0 */
   int32_t image_scales;       /* HybridImageScaler(MLPScaler, ImageScaler): manager.py:484-487 */
   int32_t mc_samples;         /* S   (--mc-samples, args/common.py:11-15) */
   int32_t likelihood;         /* CLB_LIK_* */
@@ -86,6 +87,7 @@ typedef struct {
 
   uint64_t seed;              /* Philox key for in-kernel draws (--seed, args/tf_options.py:50-54) */
   int32_t rank, world_size;   /* reflection-partitioned data parallelism; 0,1 on one GPU */
+  int32_t image_layers;       /* NeuralImageScaler per-image dense layers (--image-layers, args/scaling.py:33-37); needs n_images */
 } clb_config;
 
 /* Per-step metrics: the keys of the history dict returned by train_model (variational.py:214-224, 262-268). */
@@ -126,7 +128,7 @@ int clb_prepare_rows(int64_t n_rows, int64_t n_refl, int32_t n_meta, int32_t n_i
                      int32_t likelihood, float dof,
                      const int64_t* refl_id, const int64_t* image_id, const float* metadata,
                      const float* intensities, const float* uncertainties, const int64_t* harmonic_id,
-                     const int64_t* obs_index, int32_t order,
+                     const int64_t* obs_index, int32_t order, int32_t image_tile /* > 0: image layers, rows per tile */,
                      int64_t capacity, int64_t* n_padded, int32_t* refl_out, int32_t* image_out, int32_t* spot_out,
                      uint32_t* oidx_out, float* meta_out, float* iobs_out, float* sig_out, double* ll_const);
 /* Re-upload of the already prepared (pinned) device-layout rows: the host->device copy of
@@ -161,6 +163,11 @@ int clb_set_trainable(clb_handle* h, int32_t group, int32_t trainable);
  * of steps taken in *steps_done (may be NULL). */
 int clb_step(clb_handle* h, int32_t n_steps, const float* inj_u_f, const float* inj_eps_s,
              clb_metrics* metrics_out, int32_t* steps_done);
+
+/* Replaces: keras test_on_batch on held-out data (variational.py:257-260): forward pass only -- fresh draws,
+ * no gradients, no update -- of the CURRENT parameters on this handle's observations.  Typical use: a second
+ * handle holds the validation rows and receives the training handle's parameters through clb_set_params. */
+int clb_eval(clb_handle* h, const float* inj_u_f, const float* inj_eps_s, clb_metrics* metrics_out);
 
 /* Multi-GPU form of one step, split around the two all-reduces (sum) over NCCL:
  *   clb_step_begin  -> kernels up to the local gradients

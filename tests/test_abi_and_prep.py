@@ -53,7 +53,7 @@ def test_no_cpu_fallback():
     assert ei.value.code == -3 and "no CPU fallback" in str(ei.value)
 
 
-def _prepare(p, n_refl, laue, order=L.ORDER_AUTO, likelihood=0, dof=0.0, obs_index=None):
+def _prepare(p, n_refl, laue, order=L.ORDER_AUTO, likelihood=0, dof=0.0, obs_index=None, image_tile=0):
     lib = L.load()
     n = len(p["refl_id"]); d = p["metadata"].shape[1]
     refl = np.ascontiguousarray(p["refl_id"], dtype=np.int64)
@@ -66,7 +66,7 @@ def _prepare(p, n_refl, laue, order=L.ORDER_AUTO, likelihood=0, dof=0.0, obs_ind
     ptr = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
     npad = C.c_int64(); llc = C.c_double()
     args = [n, n_refl, d, int(p["n_images"]), int(laue), likelihood, dof, ptr(refl), ptr(img), ptr(meta), ptr(iobs), ptr(sig),
-            ptr(hid), ptr(oi), order]
+            ptr(hid), ptr(oi), order, image_tile]
     rc = lib.clb_prepare_rows(*args, 0, C.byref(npad), None, None, None, None, None, None, None, C.byref(llc))
     L.check(rc)
     m = npad.value
@@ -136,3 +136,25 @@ def test_prep_rejects_bad_input():
     q["harmonic_id"] = np.zeros(200, dtype=np.int64)       # one spot with 200 harmonics
     with pytest.raises(L.ClbError):
         _prepare(q, 20, laue=True)
+
+
+@pytest.mark.parametrize("laue", [False, True])
+def test_image_layer_prep_keeps_one_image_per_tile(laue):
+    """--image-layers: rows become image-major and every 128-row tile holds rows of a single image."""
+    p = synth.make_laue(3000, 200, d=2, n_images=9, seed=5) if laue else synth.make_mono(3000, 200, d=2, n_images=9, seed=5)
+    out = _prepare(p, 200, laue=laue, image_tile=128)
+    live = out["refl"] >= 0
+    assert live.sum() == 3000 and np.array_equal(np.sort(out["oidx"][live]), np.arange(3000))
+    assert np.array_equal(out["image"][live], p["image_id"][out["oidx"][live]])
+    assert len(out["refl"]) % 32 == 0
+    for t in range(0, len(out["refl"]), 128):
+        imgs = np.unique(out["image"][t:t + 128][live[t:t + 128]])
+        assert len(imgs) <= 1
+        if live[t:t + 128].any():
+            assert live[t]                      # the tile's first row is real: the kernel reads its image id
+    assert np.all(np.diff(out["image"][live]) >= 0)
+    if laue:
+        s = out["spot"][live]; rows = np.nonzero(live)[0]
+        for k in np.unique(s):
+            r = rows[s == k]
+            assert r[0] // 32 == r[-1] // 32 and r[-1] - r[0] + 1 == len(r)

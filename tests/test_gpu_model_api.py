@@ -10,7 +10,7 @@ from careless_b200.models.likelihoods import mono as mono_lik
 from careless_b200.models.merging.surrogate_posteriors import TruncatedNormal
 from careless_b200.models.merging.variational import VariationalMergingModel
 from careless_b200.models.priors.wilson import DoubleWilsonPrior, WilsonPrior
-from careless_b200.models.scaling.image import HybridImageScaler, ImageScaler
+from careless_b200.models.scaling.image import HybridImageScaler, ImageScaler, NeuralImageScaler
 from careless_b200.models.scaling.nn import MLPScaler
 from careless_b200.optimizers import Adam
 
@@ -116,4 +116,60 @@ def test_history_matches_oracle_through_public_api():
     for i in range(3):
         for k in ("loss", "NLL", "F KLDiv", "Grad Norm"):
             assert abs(hist[k][i] - ohist[i][k]) <= 2e-4 * abs(ohist[i][k]) + 1e-6, (i, k, hist[k][i], ohist[i][k])
+    model.close()
+
+
+def test_validation_nll_follows_the_reference_loop():
+    """variational.py:249,257-260: NLL_val = len(train)/len(val) * test_on_batch NLL, refreshed every
+    validation_frequency steps; checked against the oracle's forward pass with the validation engine's own draws."""
+    from oracle import model as om
+    from oracle import philox
+    p = synth.make_mono(3000, 250, d=3, n_images=9, seed=8)
+    rng = np.random.default_rng(1)
+    test = rng.random(3000) < 0.2
+    split = lambda m: {k: (v[m] if isinstance(v, np.ndarray) and v.shape[:1] == (3000,) else v) for k, v in p.items()}
+    ptr, pte = split(~test), split(test)
+    model = _model(p, False, "normal", "wilson", "mlp", 1)
+    model.seed = 77
+    hist = model.train_model(_inputs(ptr, False), 25, validation_data=_inputs(pte, False), validation_frequency=10, progress=False)
+    assert len(hist["NLL_val"]) == 25 and np.all(np.isfinite(hist["NLL_val"]))
+    v = np.array(hist["NLL_val"])
+    assert np.all(v[0:10] == v[0]) and np.all(v[10:20] == v[10]) and np.all(v[20:25] == v[20]) and v[0] != v[10]
+    # oracle: forward on the held-out rows with the trained-at-step-21 parameters is not reproducible here, so check step 0:
+    model2 = _model(p, False, "normal", "wilson", "mlp", 1)
+    model2.seed = 77
+    h2 = model2.train_model(_inputs(ptr, False), 1, validation_data=_inputs(pte, False), validation_frequency=10, progress=False)
+    ocfg = om.ModelConfig(n_refl=250, n_meta=3, mlp_width=6, mlp_layers=3)
+    oprior = om.PriorData(p["centric"], p["multiplicity"])
+    import torch
+    q = model2.surrogate_posterior
+    params = om.init_params(ocfg, oprior)
+    params["sf_loc_raw"] = torch.as_tensor(q.loc_raw.astype(np.float64)); params["sf_scale_raw"] = torch.as_tensor(q.scale_raw.astype(np.float64))
+    ws = model2.scaling_model.get_weights()
+    names = [f"mlp.{k}.{n}" for k in range(3) for n in ("kernel", "bias")] + ["mlp.out.kernel", "mlp.out.bias"]
+    for n, w in zip(names, ws):
+        params[n] = torch.as_tensor(w.astype(np.float64))
+    vseed = 77 + 0x9E3779B9
+    nte = int(test.sum())
+    out = om.forward(params, pte, oprior, ocfg, philox.refl_uniforms(vseed, 0, 1, np.arange(250)), philox.obs_normals(vseed, 0, 1, np.arange(nte)))
+    expect = (3000 - nte) / nte * float(out["nll"])
+    assert abs(h2["NLL_val"][0] - expect) <= 2e-4 * abs(expect), (h2["NLL_val"][0], expect)
+    model.close(); model2.close()
+
+
+@pytest.mark.parametrize("laue", [False, True])
+def test_neural_image_scaler_trains(laue):
+    """careless --image-layers=2 (tests/test_cli.py:211-228 exercises it through the CLI)."""
+    p = synth.make_laue(3000, 300, d=3, n_images=6, seed=9) if laue else synth.make_mono(3000, 300, d=3, n_images=6, seed=9)
+    prior = WilsonPrior(p["centric"], p["multiplicity"])
+    low = (1e-32 * ~np.asarray(p["centric"], dtype=bool)).astype("float32")
+    q = TruncatedNormal.from_loc_and_scale(prior.mean(), prior.stddev(), low)
+    lik = (laue_lik if laue else mono_lik).NormalLikelihood()
+    scaler = NeuralImageScaler(2, int(p["n_images"]), 3, 6, scale_bijector="exp")
+    model = VariationalMergingModel(q, prior, lik, scaler, 1)
+    model.compile(Adam(1e-2, 0.9, 0.99))
+    w0 = scaler.image_layers[0].w.copy()
+    hist = model.train_model(_inputs(p, laue), 30, progress=False)
+    assert np.all(np.isfinite(hist["loss"])) and np.mean(hist["loss"][-5:]) < np.mean(hist["loss"][:5])
+    assert scaler.image_layers[0].w.shape == (6, 6, 6) and not np.allclose(scaler.image_layers[0].w, w0)
     model.close()

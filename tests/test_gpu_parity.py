@@ -136,6 +136,15 @@ def test_double_wilson(optimize_r):
     _compare_step(p, f"dw-opt{int(optimize_r)}", mlp_width=8, mlp_layers=3, prior="double_wilson", optimize_dw_r=optimize_r)
 
 
+@pytest.mark.parametrize("width,laue", [(10, False), (32, False), (12, True)])
+def test_image_layers(width, laue):
+    """NeuralImageScaler (scaling/image.py:66-125, --image-layers): per-image dense layers after the MLP.
+    width 10/12 runs the FP32 kernel, width 32 the tensor-core kernel; rows are image-major, one image per tile."""
+    p = synth.make_laue(5000, 600, d=3, n_images=7, seed=14) if laue else synth.make_mono(5000, 600, d=3, n_images=7, seed=14)
+    _compare_step(p, f"image-layers-W{width}{'-laue' if laue else ''}", mlp_width=width, mlp_layers=3, image_layers=2, laue=laue,
+                  likelihood="studentt", dof=6.0)
+
+
 def test_frozen_scaler():
     p = synth.make_mono(2000, 300, d=3, n_images=5, seed=10)
     _compare_step(p, "frozen-mlp", frozen=("mlp",), mlp_width=8, mlp_layers=3)
