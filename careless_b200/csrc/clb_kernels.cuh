@@ -402,7 +402,7 @@ __global__ void __launch_bounds__(TC ? tc::kThreads : kObsThreads, TC ? 2 : 1) k
   const int tid = threadIdx.x, lane = tid & 31;
   tc::Ctx tcx{};
   if constexpr (TC) {
-    if (tid == 0) { tc::mbar_init(tc::smem_u32(tc_bar), 3); tc::mbar_init(tc::smem_u32(tc_bar + 1), 1); }
+    if (tid == 0) { tc::mbar_init(tc::smem_u32(tc_bar), 1); tc::mbar_init(tc::smem_u32(tc_bar + 1), 1); }
     if (tid < 32) tc::tmem_alloc(tc::smem_u32(tc_slot));
     tc::fence_before();
   }

@@ -198,21 +198,26 @@ __device__ __forceinline__ void build_weight_image(Ctx& c, const float (&w)[8]) 
   }
 }
 
-// The 3 chain issuers: product = warp (0: X_hi W_hi, 1: X_hi W_lo, 2: X_lo W_hi), 4 k-steps each.  Whole warps
-// take the branch (warp-uniform operands), one elected lane issues.
+// The chain issuer: warp 0 issues the 12 tcgen05.mma of the three products back to back into ONE accumulator
+// (X_hi W_lo, X_lo W_hi first, then X_hi W_hi), so that collect() needs a single tensor-memory load.
 __device__ __forceinline__ void issue_chain_mmas(Ctx& c) {
   const uint32_t warp = uniform32((uint32_t)c.tid >> 5);
-  if (warp < 3u) {
+  if (warp == 0u) {
     fence_after();
     const uint32_t base = uniform32(c.base);
-    const uint32_t a = base + (warp == 2u ? kColAlo : kColAhi);
-    const uint64_t b = uniform64((warp == 1u) ? c.desc_lo : c.desc_hi);
-    const uint32_t d = base + kColD + 32u * warp;
+    const uint64_t bhi = uniform64(c.desc_hi), blo = uniform64(c.desc_lo);
+    const uint32_t d = base + kColD;
     const uint32_t bar = uniform32(c.mbar);
     if (elect_one()) {
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks)
-        mma_tf32_ts(d, a + 8u * (uint32_t)ks, b + (uint64_t)((2u * kLBO * (uint32_t)ks) >> 4), ks > 0 ? 1u : 0u);
+        mma_tf32_ts(d, base + kColAhi + 8u * (uint32_t)ks, blo + (uint64_t)((2u * kLBO * (uint32_t)ks) >> 4), ks > 0 ? 1u : 0u);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)
+        mma_tf32_ts(d, base + kColAlo + 8u * (uint32_t)ks, bhi + (uint64_t)((2u * kLBO * (uint32_t)ks) >> 4), 1u);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)
+        mma_tf32_ts(d, base + kColAhi + 8u * (uint32_t)ks, bhi + (uint64_t)((2u * kLBO * (uint32_t)ks) >> 4), 1u);
       commit(bar);
     }
     __syncwarp();
@@ -299,24 +304,16 @@ __device__ __forceinline__ void issue(Ctx& c, const float (&x)[32], const float 
   issue_chain_mmas(c);
 }
 
-// Wait for the pass and read this thread's row of the result: y = D0 + D1 + D2.
+// Wait for the pass and read this thread's row of the result.
 __device__ __forceinline__ void collect(Ctx& c, float (&y)[32]) {
   mbar_wait(c.mbar, c.parity);
   c.parity ^= 1u;
   fence_after();
   uint32_t v[32];
-  CLB_TMEM_LD32(c.row_addr + kColD + 32, v);     // small cross terms first: (X_hi W_lo + X_lo W_hi) + X_hi W_hi
-  wait_ld();
-#pragma unroll
-  for (int k = 0; k < 32; ++k) y[k] = __uint_as_float(v[k]);
-  CLB_TMEM_LD32(c.row_addr + kColD + 64, v);
-  wait_ld();
-#pragma unroll
-  for (int k = 0; k < 32; ++k) y[k] += __uint_as_float(v[k]);
   CLB_TMEM_LD32(c.row_addr + kColD, v);
   wait_ld();
 #pragma unroll
-  for (int k = 0; k < 32; ++k) y[k] += __uint_as_float(v[k]);
+  for (int k = 0; k < 32; ++k) y[k] = __uint_as_float(v[k]);
 }
 
 }  // namespace tc
