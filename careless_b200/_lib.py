@@ -76,6 +76,8 @@ SYMBOLS = {
     "clb_get_samples": (C.c_int, [_H, C.c_void_p, C.c_int64]),
     "clb_enable_ipred": (C.c_int, [_H, C.c_int32]),
     "clb_get_ipred": (C.c_int, [_H, C.c_void_p, C.c_int64]),
+    "clb_get_results": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
+    "clb_get_scale_moments": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int64]),
     "clb_synchronize": (C.c_int, [_H]),
     "clb_kernel_time_ms": (C.c_int, [_H, C.POINTER(C.c_double), _I64, _I64]),
     "clb_reset_timers": (C.c_int, [_H, C.c_int32]),

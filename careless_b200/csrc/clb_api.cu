@@ -90,7 +90,8 @@ struct clb_handle {
   DevBuf partials, scratch, wpack;
   int obs_threads = kObsThreads;   // rows per CTA tile: 256 (FP32 kernels) or 128 (tensor-core kernels, 2 CTAs per SM)
   DevBuf acc, var_sums, red, metrics, var_scale, adam_alpha, stop_step;
-  DevBuf inj_u, inj_eps, ipred;
+  DevBuf inj_u, inj_eps, ipred, scale_mom, results;
+  bool want_scale_moments = false;
   bool want_ipred = false;
   int metrics_cap = 0;
 
@@ -749,6 +750,8 @@ static int step_begin_impl(clb_handle* h, const float* inj_u, const float* inj_e
     a.g_img = (c.image_scales && h->gtrain[CLB_GROUP_IMAGE_SCALES] && !h->eval_mode) ? grad + h->goff[CLB_GROUP_IMAGE_SCALES] : nullptr;
     a.partials = h->partials.as<double>(); a.scratch = h->scratch.as<float4>();
     a.ipred_out = h->want_ipred ? h->ipred.as<float>() : nullptr;
+    a.scale_mean_out = h->want_scale_moments ? h->scale_mom.as<float>() : nullptr;
+    a.scale_std_out = h->want_scale_moments ? h->scale_mom.as<float>() + h->n_rows_total : nullptr;
     a.acc = h->acc.as<double>();
     a.lik.dof = c.dof; a.lik.half_dofp1 = 0.5f * (c.dof + 1.0f);
     a.lik.lnorm = (c.likelihood == CLB_LIK_STUDENTT)
@@ -860,6 +863,50 @@ int clb_eval(clb_handle* h, const float* inj_u_f, const float* inj_eps_s, clb_me
     CLB_CUDA(h, cudaStreamSynchronize(st));
     out->loss = m[0]; out->nll = m[1]; out->kl = m[2]; out->grad_norm = m[3];
   }
+  return CLB_OK;
+}
+
+// Replaces: scale_dist.mean() / scale_dist.stddev() of VariationalMergingModel.scale_mean_stddev and
+// prediction_mean_stddev (variational.py:47-121): per-observation moments of the scale distribution in the
+// caller's row order (rows of other ranks / unused slots are 0).
+int clb_get_scale_moments(clb_handle* h, float* mean, float* stddev, int64_t n) {
+  if (!h || !mean || !stddev || n != h->n_rows_total) return fail(h, CLB_ERR_INVALID, "clb_get_scale_moments: expected %lld values", h ? (long long)h->n_rows_total : 0LL);
+  CLB_CUDA(h, cudaSetDevice(h->cfg.device));
+  CLB_CUDA(h, h->scale_mom.alloc(sizeof(float) * 2 * n));
+  CLB_CUDA(h, cudaMemsetAsync(h->scale_mom.p, 0, sizeof(float) * 2 * n, h->stream));
+  h->eval_mode = true; h->want_scale_moments = true;
+  const bool ip = h->want_ipred; h->want_ipred = false;
+  int rc = step_begin_impl(h, nullptr, nullptr);
+  h->eval_mode = false; h->want_scale_moments = false; h->want_ipred = ip; h->in_step = false;
+  if (rc) return rc;
+  CLB_CUDA(h, cudaMemcpyAsync(mean, h->scale_mom.p, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
+  CLB_CUDA(h, cudaMemcpyAsync(stddev, h->scale_mom.as<float>() + n, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
+  CLB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return CLB_OK;
+}
+
+// Replaces: the numeric part of DataManager.get_results (io/manager.py:188-197, :209): merged F, SigF, I, SigI and
+// the redundancy N of every surrogate entry of this handle.  Any output may be NULL.
+int clb_get_results(clb_handle* h, float* F, float* SigF, float* I, float* SigI, float* N, int64_t n) {
+  if (!h || n != h->R) return fail(h, CLB_ERR_INVALID, "clb_get_results: expected %lld values", h ? (long long)h->R : 0LL);
+  if (!h->have_prior) return fail(h, CLB_ERR_STATE, "clb_get_results before clb_set_prior");
+  CLB_CUDA(h, cudaSetDevice(h->cfg.device));
+  cudaStream_t st = h->stream;
+  CLB_CUDA(h, h->results.alloc(sizeof(float) * 5 * n));
+  float* d = h->results.as<float>();
+  float* theta = h->theta.as<float>();
+  k_results<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(theta + h->goff[CLB_GROUP_SF_LOC], theta + h->goff[CLB_GROUP_SF_SCALE],
+                                                          h->centric.as<uint8_t>(), n, h->cfg.epsilon, d, d + n, d + 2 * n, d + 3 * n);
+  CLB_LAUNCHED(h);
+  CLB_CUDA(h, cudaMemsetAsync(d + 4 * n, 0, sizeof(float) * n, st));
+  if (h->have_obs) {
+    k_count_obs<<<(unsigned)((h->n_rows + 255) / 256), 256, 0, st>>>(h->d_refl, h->n_rows, d + 4 * n);
+    CLB_LAUNCHED(h);
+  }
+  float* outs[5] = {F, SigF, I, SigI, N};
+  for (int q = 0; q < 5; ++q)
+    if (outs[q]) CLB_CUDA(h, cudaMemcpyAsync(outs[q], d + (size_t)q * n, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
+  CLB_CUDA(h, cudaStreamSynchronize(st));
   return CLB_OK;
 }
 

@@ -148,6 +148,7 @@ struct ObsArgs {
   double* partials;                // [grid*KS][n_params], FP64 so that the cross-tile accumulation adds no FP32 rounding
   float4* scratch;                 // [grid][L][WP/4][T]
   float* ipred_out;                // (S, N_total) original order, or null
+  float* scale_mean_out; float* scale_std_out;   // (N_total) moments of the scale distribution, original order, or null
   double* acc;
   LikConst lik; float cl;          // likelihood coefficient (1/S or 1/(S*N))
   int bijector; float shift; float eps;
@@ -528,6 +529,10 @@ __global__ void __launch_bounds__(TC ? tc::kThreads : kObsThreads, TC ? 2 : 1) k
     const uint32_t oi = inb ? a.oidx[row] : 0u;
     const float iobs = inb ? a.iobs[row] : 0.f;
     const float sg = inb ? a.sig[row] : 1.f;
+    if (a.scale_mean_out != nullptr && active) {     // variational.py:67-69: scale_dist.mean() / .stddev()
+      a.scale_mean_out[oi] = aimg * (out0 + a.shift);
+      a.scale_std_out[oi] = fabsf(aimg) * sig_s;
+    }
     // runs of equal keys inside the warp (same for every MC sample)
     const WarpRuns refl_runs = warp_runs(active ? refl : -1 - lane, lane);
     WarpRuns spot_runs = refl_runs, img_runs = refl_runs;
@@ -666,6 +671,38 @@ __global__ void __launch_bounds__(TC ? tc::kThreads : kObsThreads, TC ? 2 : 1) k
   if constexpr (TC) {
     if (tid < 32) tc::tmem_dealloc(*tc_slot);
   }
+}
+
+// Merged results per reflection (io/manager.py:188-197, :209): F = <z>, SigF = sd(z) of the truncated-normal
+// surrogate on [low, 1e10] ([3P] tfd.TruncatedNormal mean/variance), I = SigF^2 + F^2, <F^4> on [low, inf)
+// (surrogate_posteriors.py:55-72 closed form == scipy truncnorm.moment(4)), SigI = sqrt(max((1e-5 I)^2, <F^4> - I^2)).
+// FP64 arithmetic (R is small), FP32 outputs like the reference.
+__global__ void __launch_bounds__(256) k_results(const float* v_loc, const float* v_scale, const uint8_t* centric, int64_t R, float eps,
+                                                 float* F, float* SigF, float* I, float* SigI) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  const double mu = exp((double)v_loc[r]), sg = exp((double)v_scale[r]) + (double)eps;
+  const double low = centric[r] ? 0.0 : 1e-32, high = 1e10;
+  const double al = (low - mu) / sg, be = (high - mu) / sg;
+  const double isq = 0.3989422804014327;
+  const double pa = isq * exp(-0.5 * al * al), pb = isq * exp(-0.5 * be * be);
+  const double Z = normcdf(-al) - normcdf(-be);
+  const double bpb = (pb == 0.0) ? 0.0 : be * pb;
+  const double d1 = (pa - pb) / Z;
+  const double mean = mu + sg * d1;
+  const double var = sg * sg * (1.0 + (al * pa - bpb) / Z - d1 * d1);
+  const double a = low;
+  const double aterm = (a * a * a + a * a * mu + a * mu * mu + sg * sg * (3.0 * a + 5.0 * mu) + mu * mu * mu) * pa;
+  const double m4 = mu * mu * mu * mu + 6.0 * mu * mu * sg * sg + 3.0 * sg * sg * sg * sg + sg * aterm / normcdf(-al);
+  const double sd = sqrt(fmax(var, 0.0));
+  const double inten = sd * sd + mean * mean;
+  const double ivar = fmax((inten * 1e-5) * (inten * 1e-5), m4 - inten * inten);
+  F[r] = (float)mean; SigF[r] = (float)sd; I[r] = (float)inten; SigI[r] = (float)sqrt(ivar);
+}
+
+__global__ void __launch_bounds__(256) k_count_obs(const int32_t* refl, int64_t n_rows, float* N) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_rows && refl[i] >= 0) atomicAdd(&N[refl[i]], 1.0f);
 }
 
 // Zero-padded [L][32][32] FP32 copy of the hidden-layer kernels for the tensor-core kernels (they read 4 KB per

@@ -241,6 +241,21 @@ class Engine:
         self._check(self.lib.clb_get_ipred(self._h, _ptr(out), out.size))
         return out
 
+    def get_results(self):
+        """Merged F, SigF, I, SigI and redundancy N per surrogate entry (io/manager.py:188-197, :209)."""
+        R = self.cfg.n_refl
+        out = {k: np.empty(R, dtype=np.float32) for k in ("F", "SigF", "I", "SigI", "N")}
+        self._check(self.lib.clb_get_results(self._h, _ptr(out["F"]), _ptr(out["SigF"]), _ptr(out["I"]), _ptr(out["SigI"]),
+                                             _ptr(out["N"]), R))
+        return out
+
+    def get_scale_moments(self):
+        """(mean, stddev) of the scale distribution of every observation, original row order (variational.py:67-69)."""
+        n = self.n_rows_total
+        mean, std = np.empty(n, dtype=np.float32), np.empty(n, dtype=np.float32)
+        self._check(self.lib.clb_get_scale_moments(self._h, _ptr(mean), _ptr(std), n))
+        return mean, std
+
     def synchronize(self):
         self._check(self.lib.clb_synchronize(self._h))
 

@@ -187,6 +187,42 @@ class VariationalMergingModel(BaseModel):
                        asu_id=prior.asu_ids if dw else None, r=prior.r if dw else None, init_scale=-1.0)
         return veng
 
+    # ------------------------------------------------------------------ post-hoc moments ("next" row 2)
+    def scale_mean_stddev(self, inputs):
+        """variational.py:47-78: moments of the posterior of the scale of every observation (Laue: convolved)."""
+        eng = self._build_engine(inputs)
+        self._push(eng)
+        mean, stddev = eng.get_scale_moments()
+        if getattr(self.likelihood, "laue", False):
+            hid = self.get_harmonic_id(inputs)
+            mean = self.likelihood.convolve(mean, hid)
+            stddev = np.sqrt(self.likelihood.convolve(stddev * stddev, hid))
+        return mean, stddev
+
+    def prediction_mean_stddev(self, inputs):
+        """variational.py:80-121: expected intensity <Sigma><F^2> and its standard deviation per observation."""
+        eng = self._build_engine(inputs)
+        self._push(eng)
+        smean, sstd = eng.get_scale_moments()
+        res = eng.get_results()
+        refl_id = np.asarray(self.get_refl_id(inputs)).reshape(-1)
+        f2 = np.square(res["F"]) + np.square(res["SigF"])
+        iexp = smean * f2[refl_id]
+        f4 = self.surrogate_posterior.moment_4(method='scipy')
+        s2 = np.square(smean) + np.square(sstd)
+        ivar = f4[refl_id] * s2 - iexp * iexp
+        if getattr(self.likelihood, "laue", False):
+            hid = self.get_harmonic_id(inputs)
+            iexp = self.likelihood.convolve(iexp, hid)
+            ivar = self.likelihood.convolve(ivar, hid)
+        return iexp, np.sqrt(ivar)
+
+    def get_results(self, inputs):
+        """Numeric part of DataManager.get_results (io/manager.py:188-209): dict of F, SigF, I, SigI, N per reflection."""
+        eng = self._build_engine(inputs)
+        self._push(eng)
+        return eng.get_results()
+
     def close(self):
         if self._engine is not None:
             self._engine.close()

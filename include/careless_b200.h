@@ -189,6 +189,11 @@ int clb_enable_ipred(clb_handle* h, int32_t enable);
 int clb_get_ipred(clb_handle* h, float* ipred, int64_t n);
 int clb_synchronize(clb_handle* h);
 
+/* "Next" rows of the scope table: the numeric part of DataManager.get_results
+ * (io/manager.py:188-197, :209) and the scale moments behind get_predictions (variational.py:47-121). */
+int clb_get_results(clb_handle* h, float* F, float* SigF, float* I, float* SigI, float* N, int64_t n_refl);
+int clb_get_scale_moments(clb_handle* h, float* mean, float* stddev, int64_t n_rows_total);
+
 /* Device timing of the dominant kernel (CUDA events on the handle's stream), for bench.py's roofline. */
 int clb_kernel_time_ms(clb_handle* h, double* obs_kernel_ms_sum, int64_t* obs_kernel_launches, int64_t* total_launches);
 int clb_reset_timers(clb_handle* h, int32_t enable_event_timing);

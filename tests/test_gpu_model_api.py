@@ -173,3 +173,47 @@ def test_neural_image_scaler_trains(laue):
     assert np.all(np.isfinite(hist["loss"])) and np.mean(hist["loss"][-5:]) < np.mean(hist["loss"][:5])
     assert scaler.image_layers[0].w.shape == (6, 6, 6) and not np.allclose(scaler.image_layers[0].w, w0)
     model.close()
+
+
+@pytest.mark.parametrize("laue", [False, True])
+def test_results_and_predictions(laue):
+    """DataManager.get_results / get_predictions numerics (io/manager.py:188-209, variational.py:47-121):
+    merged F/SigF/I/SigI vs scipy.stats.truncnorm, scale moments vs the oracle's scale network."""
+    import torch
+    from scipy.stats import truncnorm
+    from oracle import model as om
+    p = synth.make_laue(3000, 300, d=3, n_images=8, seed=10) if laue else synth.make_mono(3000, 300, d=3, n_images=8, seed=10)
+    model = _model(p, laue, "normal", "wilson", "hybrid", 1)
+    data = _inputs(p, laue)
+    model.train_model(data, 20, progress=False)
+    res = model.get_results(data)
+    q = model.surrogate_posterior
+    loc, scale = q.loc.astype(np.float64), q.scale.astype(np.float64)
+    low = q.low.astype(np.float64)
+    a, b = (low - loc) / scale, (1e10 - loc) / scale
+    F, SigF = truncnorm.mean(a, b, loc, scale), truncnorm.std(a, b, loc, scale)
+    assert np.allclose(res["F"], F, rtol=1e-5) and np.allclose(res["SigF"], SigF, rtol=1e-5)
+    I = SigF ** 2 + F ** 2
+    f4 = truncnorm.moment(4, a, np.inf, loc, scale)
+    SigI = np.sqrt(np.maximum((I * 1e-5) ** 2, f4 - I * I))
+    assert np.allclose(res["I"], I, rtol=1e-5) and np.allclose(res["SigI"], SigI, rtol=2e-4)
+    assert np.array_equal(res["N"], np.bincount(p["refl_id"], minlength=300).astype(np.float32))
+    # scale moments against the oracle's network with the trained weights
+    ocfg = om.ModelConfig(n_refl=300, n_meta=3, mlp_width=6, mlp_layers=3, image_scales=True, n_images=int(p["n_images"]), laue=laue)
+    mlp = model.scaling_model.mlp_scaler
+    names = [f"mlp.{k}.{n}" for k in range(3) for n in ("kernel", "bias")] + ["mlp.out.kernel", "mlp.out.bias"]
+    params = {n: torch.as_tensor(w.astype(np.float64)) for n, w in zip(names, mlp.get_weights())}
+    params["image_scales"] = torch.as_tensor(model.scaling_model.image_scaler._scales.astype(np.float64))
+    mu_s, sig_s, shift = om.scale_network(params, p, ocfg, torch.float64)
+    aimg = om.image_scale_vector(params, p, ocfg, torch.float64)
+    smean, sstd = (aimg * mu_s).numpy(), (aimg.abs() * sig_s).numpy()
+    iexp = smean * (F ** 2 + SigF ** 2)[p["refl_id"]]
+    ivar = f4[p["refl_id"]] * (smean ** 2 + sstd ** 2) - iexp ** 2
+    if laue:
+        conv = lambda v: np.bincount(p["harmonic_id"], weights=v, minlength=len(v))
+        smean, sstd, iexp, ivar = conv(smean), np.sqrt(conv(sstd ** 2)), conv(iexp), conv(ivar)
+    m, sd = model.scale_mean_stddev(data)
+    assert np.allclose(m, smean, rtol=2e-4, atol=1e-5) and np.allclose(sd, sstd, rtol=2e-4, atol=1e-6)
+    ip, sip = model.prediction_mean_stddev(data)
+    assert np.allclose(ip, iexp, rtol=5e-4, atol=1e-4) and np.allclose(sip, np.sqrt(ivar), rtol=2e-3, atol=1e-4)
+    model.close()
