@@ -143,3 +143,21 @@ def rms_err(a, b):
     """||a-b||_2 / ||b||_2"""
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
     return float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-300))
+
+
+def load_fixture(name, to_observed=True):
+    """tests/golden/fixture_mtz.npz -> careless_b200.io DataSet (same result as read_mtz on the reference's fixture file)."""
+    import os
+    from careless_b200.io.mtz import DataSet
+    from careless_b200.io.symmetry import SpaceGroup, UnitCell
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fixture_mtz.npz"))
+    keys, types, data = [str(k) for k in z[f"{name}/keys"]], [str(t) for t in z[f"{name}/types"]], z[f"{name}/data"]
+    sg = SpaceGroup.from_triplets([str(s) for s in z[f"{name}/symm"]], name=str(z[f"{name}/spacegroup"]))
+    cols = {}
+    for j, (k, t) in enumerate(zip(keys, types)):
+        cols[k] = data[:, j].astype(np.int32) if t in ("H", "B", "Y", "I") else data[:, j].astype(np.float32)
+    ds = DataSet(cols, dict(zip(keys, types)), UnitCell(*z[f"{name}/cell"]), sg, merged=False)
+    if to_observed:
+        ds.set_hkls(sg.hkl_to_observed(ds.get_hkls(), ds["M/ISYM"]))
+        del ds.columns["M/ISYM"]
+    return ds

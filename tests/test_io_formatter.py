@@ -1,0 +1,247 @@
+"""CPU tests of the input formatter: symmetry algebra, ASU numbering, MTZ i/o, mono and Laue
+formatters.  Models: tests/io/test_asu.py:8-81, tests/io/test_data_formatter.py:10-120, tests/utils/test_laue.py of the
+reference.  The ASU mapping is pinned against the reference fixtures' own H,K,L + M/ISYM columns (tests/golden/)."""
+import itertools
+import os
+
+import numpy as np
+import pytest
+
+import _util as U
+from careless_b200.io import symmetry as S
+from careless_b200.io.asu import ReciprocalASU, ReciprocalASUCollection
+from careless_b200.io.formatter import LaueFormatter, MonoFormatter, expand_harmonics, ngroup, positional_encoding
+from careless_b200.io.mtz import read_mtz, write_mtz
+from careless_b200.models.base import BaseModel
+
+FIXTURES = ("pyp_off", "pyp_2ms", "pyp_2ms_P3")
+CELLS = [((10., 20., 30., 90., 80., 75.), "P 1"), ((30., 50., 80., 90., 100., 90.), "P 1 21 1"),
+         ((10., 20., 30., 90., 90., 90.), "P 21 21 21"), ((89., 89., 105., 90., 90., 120.), "P 31 2 1"),
+         ((30., 30., 30., 90., 90., 120.), "R 32")]          # tests/conftest.py:31-40 of the reference
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_hkl_to_asu_reproduces_fixture_columns(name):
+    """Un-map the stored ASU indices with the stored M/ISYM, map them back: H,K,L and M/ISYM must match bit for bit."""
+    raw = U.load_fixture(name, to_observed=False)
+    obs = U.load_fixture(name)
+    assert not np.array_equal(obs.get_hkls(), raw.get_hkls())          # the un-mapping did something
+    asu, isym = obs.spacegroup.hkl_to_asu(obs.get_hkls())
+    assert np.array_equal(asu, raw.get_hkls())
+    assert np.array_equal(isym, raw["M/ISYM"] % 256)
+    assert obs.spacegroup.in_asu(raw.get_hkls()).all()
+
+
+def test_sohncke_tables_close_and_have_one_asu_image_per_orbit():
+    point_order = lambda num: (1 if num < 3 else 2 if num < 16 else 4 if num < 89 else 8 if num < 143 else 3 if num < 149
+                               else 6 if num < 177 else 12 if num < 207 else 24)
+    special = [[1, 0, 0], [0, 1, 0], [0, 0, 1], [1, 1, 0], [1, -1, 0], [1, 1, 1], [2, 1, 0], [0, 0, -1], [1, 0, 1], [0, 1, 1],
+               [-1, -1, 0], [1, 2, 0], [2, -1, 0], [1, 1, -1], [-2, 1, 1]]
+    for name, (num, _) in S._SOHNCKE.items():
+        sg = S.SpaceGroup.from_name(name)
+        assert len(sg.sym_ops) == point_order(num), name
+        rng = np.random.default_rng(num)
+        hkl = np.concatenate([rng.integers(-6, 7, size=(200, 3)), special])
+        hkl = hkl[np.any(hkl != 0, 1)]
+        imgs = sg._images(hkl)
+        imgs = np.concatenate([imgs, -imgs])
+        for j in range(len(hkl)):
+            orbit = np.unique(imgs[:, j, :], axis=0)
+            assert sg.in_asu(orbit).sum() == 1, (name, hkl[j])
+        asu, isym = sg.hkl_to_asu(hkl)
+        assert np.array_equal(sg.hkl_to_observed(asu, isym), hkl)
+        # epsilon, centricity and absences are class functions of the orbit
+        assert np.array_equal(sg.epsilon(asu), sg.epsilon(hkl))
+        assert np.array_equal(sg.is_centric(asu), sg.is_centric(hkl))
+        assert np.array_equal(sg.is_absent(asu), sg.is_absent(hkl))
+
+
+def test_known_absences_centrics_epsilon():
+    p212121 = S.SpaceGroup.from_name("P 21 21 21")
+    h = np.array([[1, 0, 0], [2, 0, 0], [0, 3, 0], [0, 0, 4], [1, 2, 0], [1, 2, 3]])
+    assert p212121.is_absent(h).tolist() == [True, False, True, False, False, False]
+    assert p212121.is_centric(h).tolist() == [True, True, True, True, True, False]
+    assert p212121.epsilon(h).tolist() == [2, 2, 2, 2, 1, 1]
+    p63 = S.SpaceGroup.from_name("P 63")
+    h = np.array([[0, 0, 1], [0, 0, 2], [1, 0, 0], [1, 2, 3]])
+    assert p63.is_absent(h).tolist() == [True, False, False, False]
+    assert p63.epsilon(h).tolist() == [6, 6, 1, 1]
+    assert p63.is_centric(h).tolist() == [False, False, True, False]
+    c2 = S.SpaceGroup.from_name("C 1 2 1")
+    h = np.array([[1, 0, 0], [1, 1, 0], [0, 2, 0], [2, 0, 1]])
+    assert c2.is_absent(h).tolist() == [True, False, False, False]
+    assert c2.epsilon(h).tolist() == [2, 2, 4, 2]                   # centering included, like rs.compute_multiplicity
+    assert c2.is_centric(h).tolist() == [True, False, False, True]
+    p41212 = S.SpaceGroup.from_name("P 41 21 2")
+    h = np.array([[0, 0, 1], [0, 0, 4], [1, 0, 0], [2, 0, 0], [1, 1, 0]])
+    assert p41212.is_absent(h).tolist() == [True, False, True, False, False]
+
+
+def test_triplet_round_trip():
+    for t in ("x,y,z", "x-y,x,z+1/2", "-y,x-y,z+1/3", "-x+1/2,-y,z+1/2", "y+1/4,x+3/4,-z+3/4"):
+        assert S.parse_triplet(t).triplet() == t
+    assert S.parse_triplet("X-Y, X, Z+1/2").triplet() == "x-y,x,z+1/2"
+
+
+@pytest.mark.parametrize("anomalous", [True, False])
+@pytest.mark.parametrize("dmin", [10., 5.])
+def test_reciprocal_asu(dmin, anomalous):
+    for cellp, name in CELLS:
+        cell, sg = S.UnitCell(*cellp), S.SpaceGroup.from_name(name)
+        rasu = ReciprocalASU(cell, sg, dmin, anomalous)
+        Hall = S.generate_reciprocal_asu(cell, sg, dmin, anomalous)
+        assert len(Hall) > 0
+        assert np.all(rasu.centric == sg.is_centric(Hall))
+        assert np.all(rasu.multiplicity == sg.epsilon(Hall))
+        assert np.all(cell.calculate_d_array(Hall).astype(np.float32) >= dmin)
+        assert not sg.is_absent(Hall).any()
+        assert np.all(rasu.to_refl_id(Hall) == np.arange(len(Hall)))
+        assert np.all(rasu.to_miller_index(np.arange(len(Hall))) == Hall)
+        assert np.all(np.isfinite(rasu.dHKL))
+        assert len(np.unique(Hall, axis=0)) == len(Hall)
+        # completeness: every non-absent reflection of the sphere maps onto a member
+        sphere = S.generate_reciprocal_cell(cell, dmin)
+        sphere = sphere[~sg.is_absent(sphere)]
+        asu, isym = sg.hkl_to_asu(sphere)
+        if anomalous:
+            minus = (isym % 2 == 0) & ~sg.is_centric(asu)
+            asu[minus] *= -1
+        assert np.all(np.sort(np.unique(rasu.to_refl_id(asu))) == np.arange(len(Hall)))
+
+
+@pytest.mark.parametrize("anomalous", [[True, True], [True, False], [False, False]])
+@pytest.mark.parametrize("dmin", [[10., 10.], [5., 10.], [5., 5.]])
+def test_double_reciprocal_asu_collection(dmin, anomalous):
+    for cellp, name in CELLS:
+        cell, sg = S.UnitCell(*cellp), S.SpaceGroup.from_name(name)
+        rasus = [ReciprocalASU(cell, sg, d, a) for d, a in zip(dmin, anomalous)]
+        rac = ReciprocalASUCollection(rasus)
+        per_asu = [S.generate_reciprocal_asu(cell, sg, d, a) for d, a in zip(dmin, anomalous)]
+        refl_ids = []
+        for asu_id, h in enumerate(per_asu):
+            refl_id = rac.to_refl_id(asu_id * np.ones((len(h), 1)), h)
+            a_test, h_test = rac.to_asu_id_and_miller_index(refl_id)
+            assert np.all(a_test == asu_id) and np.all(h_test == h)
+            refl_ids.append(refl_id)
+        refl_ids = np.concatenate(refl_ids)
+        assert np.all(refl_ids == np.arange(len(refl_ids)))                  # no gaps, no duplicates
+        assert len(rac.hkls) == sum(len(h) for h in per_asu)
+        assert np.all(rac.centric == np.concatenate([sg.is_centric(h) for h in per_asu]))
+        assert np.all(rac.multiplicity == np.concatenate([sg.epsilon(h) for h in per_asu]))
+        assert rasus[0] is rac[0] and rasus[1] is rac[1]
+        missing = rac.to_refl_id(np.array([[0]]), np.array([[99, 99, 99]]), allow_missing=True)
+        assert missing.tolist() == [-1]
+        with pytest.raises(KeyError):
+            rac.to_refl_id(np.array([[0]]), np.array([[99, 99, 99]]))
+
+
+def test_ngroup_matches_sorted_rank():
+    rng = np.random.default_rng(0)
+    a, b, c = rng.integers(0, 4, 200), rng.integers(-3, 3, 200), rng.integers(0, 2, 200)
+    got = ngroup(a, b, c)
+    keys = sorted(set(zip(a.tolist(), b.tolist(), c.tolist())))
+    want = np.array([keys.index(t) for t in zip(a.tolist(), b.tolist(), c.tolist())])
+    assert np.array_equal(got, want)
+
+
+METADATA_KEYS = ["dHKL", "Hobs", "image_id"]
+GRID = list(itertools.product(["I", None], ["SigI", None], ["BATCH", None], [True, False], [True, False]))
+
+
+@pytest.mark.parametrize("intensity_key,sigma_key,image_key,separate,anomalous", GRID)
+@pytest.mark.parametrize("dmin,isigi,pe", [(0., None, None), (7., 3., ["X", "Y"])])
+def test_mono_formatter(intensity_key, sigma_key, image_key, separate, anomalous, dmin, isigi, pe):
+    ds = [U.load_fixture("pyp_off"), U.load_fixture("pyp_2ms")]
+    f = MonoFormatter(intensity_key, sigma_key, image_key, METADATA_KEYS, separate, anomalous, dmin, isigi, pe, 3)
+    inputs, rac = f(ds)
+    n = inputs[0].shape[0]
+    assert len(inputs) == 6 and n > 0
+    for v in inputs:
+        assert v.ndim == 2 and v.dtype in (np.float32, np.int64) and v.shape[0] == n
+    refl_id = BaseModel.get_refl_id(inputs).reshape(-1)
+    assert refl_id.min() >= 0 and refl_id.max() < len(rac.hkls)
+    assert BaseModel.get_metadata(inputs).shape[1] == 3 + (0 if pe is None else 2 * 2 * 3)
+    file_id = inputs[2].reshape(-1)
+    assert set(np.unique(file_id)) == {0, 1}
+    assert np.all(rac.asu_ids[refl_id] == (file_id if separate else 0))
+    image_id = inputs[1].reshape(-1)
+    assert np.array_equal(np.unique(image_id), np.arange(image_id.max() + 1))
+    if isigi is not None:
+        assert np.all(inputs[4] / inputs[5] >= isigi)
+
+
+def test_mono_formatter_ids_are_the_asu_rows_of_the_file():
+    """refl_id must point at exactly the H,K,L the reference's own writer stored in the file."""
+    raw = U.load_fixture("pyp_off", to_observed=False)
+    f = MonoFormatter(None, None, None, ["dHKL"], False, False)
+    inputs, rac = f([U.load_fixture("pyp_off")])
+    assert np.array_equal(rac.hkls[inputs[0][:, 0]], raw.get_hkls())
+    d = raw.cell.calculate_d_array(raw.get_hkls())
+    z = d ** -2.0
+    assert np.allclose(inputs[3][:, 0], (z - z.mean()) / z.std(), atol=2e-4)
+    assert np.array_equal(inputs[4][:, 0], raw["I"]) and np.array_equal(inputs[5][:, 0], raw["SigI"])
+    assert np.array_equal(inputs[1][:, 0], ngroup(raw["BATCH"]))
+
+
+@pytest.mark.parametrize("lam_min,lam_max", [(None, None), (1.05, 1.15)])
+@pytest.mark.parametrize("separate,anomalous", [(True, True), (False, False)])
+@pytest.mark.parametrize("dmin,isigi,pe", [(None, None, None), (7., 3., ["X", "Y"])])
+def test_laue_formatter(lam_min, lam_max, separate, anomalous, dmin, isigi, pe):
+    ds = [U.load_fixture("pyp_off"), U.load_fixture("pyp_2ms")]
+    f = LaueFormatter("Wavelength", None, None, None, METADATA_KEYS, separate, anomalous, lam_min, lam_max, dmin, isigi, pe, 3)
+    inputs, rac = f(ds)
+    n = inputs[0].shape[0]
+    assert len(inputs) == 8
+    for v in inputs:
+        assert v.ndim == 2 and v.dtype in (np.float32, np.int64) and v.shape[0] == n
+    hid = BaseModel.get_harmonic_id(inputs).reshape(-1)
+    n_spots = hid.max() + 1
+    assert np.array_equal(np.unique(hid), np.arange(n_spots))
+    assert np.all(inputs[4][n_spots:] == 1.0) and np.all(inputs[5][n_spots:] == 1.0)      # padding
+    wl = BaseModel.get_wavelength(inputs).reshape(-1)
+    if lam_min is not None:
+        assert wl.min() >= lam_min and wl.max() <= lam_max
+    # all rows of a spot sit on one image
+    image_id = inputs[1].reshape(-1)
+    assert np.all(np.bincount(hid, weights=image_id) == np.bincount(hid) * image_id[np.unique(hid, return_index=True)[1]])
+
+
+def test_expand_harmonics():
+    """careless/utils/laue.py:9-81: rows = sum over spots of floor(d_0 / dmin); n H_0 = H; lambda_n = lambda_0 / n."""
+    ds = U.load_fixture("pyp_off")
+    ds.compute_dHKL()
+    dmin = 2.0
+    ex = expand_harmonics(ds, dmin, "Wavelength")
+    H = ds.get_hkls()
+    n_obs = np.gcd.reduce(H, axis=1)
+    d0 = ds["dHKL"].astype(np.float64) * n_obs
+    assert len(ex) == int(np.floor(d0 / dmin).sum())
+    H0 = np.stack([ex["H_0"], ex["K_0"], ex["L_0"]], 1)
+    assert np.all(np.gcd.reduce(H0, axis=1) == 1)
+    n = np.gcd.reduce(ex.get_hkls(), axis=1)
+    assert np.array_equal(ex.get_hkls(), n[:, None] * H0)
+    assert np.all(ex["dHKL"] >= np.float32(dmin) * (1 - 1e-6))
+    # every original observation is among the expanded rows with its own wavelength
+    key = lambda h, w: set(zip(map(tuple, h.tolist()), np.round(w.astype(np.float64), 5).tolist()))
+    assert key(H, ds["Wavelength"]) <= key(ex.get_hkls(), ex["Wavelength"])
+
+
+def test_positional_encoding_shape_and_range():
+    x = np.random.default_rng(0).random((50, 2)).astype(np.float32)
+    e = positional_encoding(x, 4)
+    assert e.shape == (50, 16) and np.all(np.abs(e) <= 1.0 + 1e-6)
+
+
+def test_mtz_round_trip(tmp_path):
+    ds = U.load_fixture("pyp_off")
+    ds.hkl_to_asu()
+    path = os.path.join(tmp_path, "rt.mtz")
+    write_mtz(path, ds)
+    back = read_mtz(path, to_observed=False)
+    assert back.keys() == ds.keys()
+    for k in ds.keys():
+        assert np.array_equal(np.asarray(back[k], dtype=np.float32), np.asarray(ds[k], dtype=np.float32)), k
+    assert back.cell.parameters == pytest.approx(ds.cell.parameters)
+    assert [o.triplet() for o in back.spacegroup.sym_ops] == [o.triplet() for o in ds.spacegroup.sym_ops]
+    obs = read_mtz(path)
+    assert np.array_equal(obs.get_hkls(), U.load_fixture("pyp_off").get_hkls())
