@@ -11,16 +11,16 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libcareless_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # enums of include/careless_b200.h
 LIK_NORMAL, LIK_STUDENTT = 0, 1
 PRIOR_WILSON, PRIOR_DOUBLE_WILSON = 0, 1
 BIJ_EXP, BIJ_SOFTPLUS = 0, 1
 ORDER_AUTO, ORDER_REFL, ORDER_SPOT, ORDER_IMAGE, ORDER_NONE = 0, 1, 2, 3, 4
-GROUP_SF_LOC, GROUP_SF_SCALE, GROUP_MLP, GROUP_IMAGE_SCALES, GROUP_DW_R, GROUP_IMAGE_LAYERS = 0, 1, 2, 3, 4, 5
+GROUP_SF_LOC, GROUP_SF_SCALE, GROUP_MLP, GROUP_IMAGE_SCALES, GROUP_DW_R, GROUP_IMAGE_LAYERS, GROUP_LIKELIHOOD = 0, 1, 2, 3, 4, 5, 6
 GROUPS = {"sf_loc_raw": GROUP_SF_LOC, "sf_scale_raw": GROUP_SF_SCALE, "mlp": GROUP_MLP,
-          "image_scales": GROUP_IMAGE_SCALES, "dw_r_logit": GROUP_DW_R, "image_layers": GROUP_IMAGE_LAYERS}
+          "image_scales": GROUP_IMAGE_SCALES, "dw_r_logit": GROUP_DW_R, "image_layers": GROUP_IMAGE_LAYERS, "likelihood": GROUP_LIKELIHOOD}
 
 
 class clb_config(C.Structure):
@@ -35,7 +35,7 @@ class clb_config(C.Structure):
         ("use_kl_weight", C.c_int32), ("kl_weight", C.c_float),
         ("learning_rate", C.c_float), ("beta_1", C.c_float), ("beta_2", C.c_float), ("adam_epsilon", C.c_float),
         ("clipnorm", C.c_float), ("clipvalue", C.c_float), ("global_clipnorm", C.c_float),
-        ("seed", C.c_uint64), ("rank", C.c_int32), ("world_size", C.c_int32), ("image_layers", C.c_int32),
+        ("seed", C.c_uint64), ("rank", C.c_int32), ("world_size", C.c_int32), ("image_layers", C.c_int32), ("refine_uncertainties", C.c_int32),
     ]
 
 

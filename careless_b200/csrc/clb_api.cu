@@ -77,6 +77,8 @@ struct clb_handle {
   bool debug_sync = false;   // CLB_DEBUG_SYNC=1: synchronise + log after every kernel launch
   int order = CLB_ORDER_REFL;
   double ll_const = 0.0;   // per-sample constant log-likelihood of empty Laue slots
+  DevBuf empty_slots;      // Ev11: (I_k) then (sigma_k) of the empty Laue slots
+  int64_t n_empty = 0;
 
   // device state
   DevBuf theta, m, v, grad;
@@ -175,6 +177,7 @@ void build_vars(clb_handle* h) {
   h->gsize[CLB_GROUP_IMAGE_SCALES] = c.image_scales ? std::max(0, c.n_images - 1) : 0;
   h->gsize[CLB_GROUP_DW_R] = (c.prior == CLB_PRIOR_DOUBLE_WILSON && c.optimize_dw_r) ? c.n_asu : 0;
   h->gsize[CLB_GROUP_IMAGE_LAYERS] = (int64_t)c.image_layers * c.n_images * c.mlp_width * (c.mlp_width + 1);
+  h->gsize[CLB_GROUP_LIKELIHOOD] = c.refine_uncertainties ? 3 : 0;
   int64_t off = 0;
   for (int g = 0; g < CLB_N_GROUPS; ++g) { h->goff[g] = off; off += h->gsize[g]; h->gtrain[g] = 1; }
   h->P = off;
@@ -196,6 +199,8 @@ void build_vars(clb_handle* h) {
     add(CLB_GROUP_IMAGE_LAYERS, h->goff[CLB_GROUP_IMAGE_LAYERS] + l * stride, (int64_t)c.n_images * w * w, 1);
     add(CLB_GROUP_IMAGE_LAYERS, h->goff[CLB_GROUP_IMAGE_LAYERS] + l * stride + (int64_t)c.n_images * w * w, (int64_t)c.n_images * w, 1);
   }
+  for (int64_t i = 0; i < h->gsize[CLB_GROUP_LIKELIHOOD]; ++i)    // Sdfac, Sdadd, SdB: three scalar keras variables
+    add(CLB_GROUP_LIKELIHOOD, h->goff[CLB_GROUP_LIKELIHOOD] + i, 1, 1);
   vt.n_vars = n;
 }
 
@@ -223,6 +228,7 @@ struct RowPlan {
   int order = CLB_ORDER_REFL;
   int64_t npad = 0;
   double ll_const = 0.0;              // sum over empty Laue slots of logpdf(0; I_k, sigma_k)
+  std::vector<float> empty;           // (I_k, sigma_k) of the empty Laue slots: first all I, then all sigma (Ev11 needs them on the device)
   std::vector<int32_t> perm;          // sorted position -> original row
   std::vector<int64_t> pos;           // sorted position -> padded row
 };
@@ -274,10 +280,11 @@ int plan_rows(std::string& err, RowPlan& plan, int64_t n, int64_t n_total, int64
   int64_t npad = n;
   if (order == CLB_ORDER_SPOT) {
     clb_config lc{}; lc.likelihood = likelihood; lc.dof = dof;
+    std::vector<float> empty_i, empty_s;
     int64_t p = 0, prev_img = -1;
     for (int64_t k = 0; k < n_keys; ++k) {
       const int64_t len = count[k + 1] - count[k];
-      if (len == 0) { plan.ll_const += lik_logpdf_zero(lc, iobs[k], sig[k]); continue; }
+      if (len == 0) { plan.ll_const += lik_logpdf_zero(lc, iobs[k], sig[k]); empty_i.push_back(iobs[k]); empty_s.push_back(sig[k]); continue; }
       if (len > 32) return bad("spot %lld has %lld harmonics; at most 32 are supported", k, len, 0);
       if (image_tile > 0) {                          // harmonic ids are image-major (formatter.py:617)
         const int64_t img = image_id[plan.perm[count[k]]];
@@ -290,6 +297,8 @@ int plan_rows(std::string& err, RowPlan& plan, int64_t n, int64_t n_total, int64
       p += len;
     }
     npad = p;
+    plan.empty = empty_i;
+    plan.empty.insert(plan.empty.end(), empty_s.begin(), empty_s.end());
   } else if (order == CLB_ORDER_IMAGE && image_tile > 0) {
     int64_t p = 0, prev_img = -1;
     for (int64_t sidx = 0; sidx < n; ++sidx) {
@@ -412,6 +421,8 @@ int clb_create(const clb_config* cfg, clb_handle** out) {
     float* kern = init.data() + h->goff[CLB_GROUP_IMAGE_LAYERS] + l * stride;
     for (int64_t im = 0; im < cfg->n_images; ++im) for (int64_t j = 0; j < w; ++j) kern[(im * w + j) * w + j] = 1.f;
   }
+  for (int64_t i = 0; i < h->gsize[CLB_GROUP_LIKELIHOOD]; ++i)       // softplus^-1(1): TransformedVariable(1., Softplus) (mono.py:42-44)
+    init[h->goff[CLB_GROUP_LIKELIHOOD] + i] = 0.54132485f;
   CREATE_CUDA(cudaMemcpyAsync(h->theta.p, init.data(), pb, cudaMemcpyHostToDevice, h->stream));
   const int big = 0x7fffffff;
   CREATE_CUDA(cudaMemcpyAsync(h->stop_step.p, &big, sizeof(int), cudaMemcpyHostToDevice, h->stream));
@@ -468,6 +479,16 @@ int clb_set_observations(clb_handle* h, int64_t n, int64_t n_total, const int64_
             has_spot ? reinterpret_cast<int32_t*>(hb + o_spot) : nullptr, reinterpret_cast<uint32_t*>(hb + o_oidx),
             reinterpret_cast<float*>(hb + o_meta), reinterpret_cast<float*>(hb + o_iobs), reinterpret_cast<float*>(hb + o_sig));
   h->ll_const = plan.ll_const;
+  h->n_empty = 0;
+  if (c.refine_uncertainties) {      // the empty slots' log-density depends on the error-model parameters: evaluated on the device
+    h->ll_const = 0.0;
+    h->n_empty = (int64_t)plan.empty.size() / 2;
+    if (h->n_empty > 0) {
+      CLB_CUDA(h, h->empty_slots.alloc(sizeof(float) * plan.empty.size()));
+      CLB_CUDA(h, cudaMemcpyAsync(h->empty_slots.p, plan.empty.data(), sizeof(float) * plan.empty.size(), cudaMemcpyHostToDevice, h->stream));
+      CLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    }
+  }
   h->rows_bytes = bytes;
   char* db = h->rows.as<char>();
   h->d_refl = reinterpret_cast<int32_t*>(db + o_refl);
@@ -757,6 +778,17 @@ static int step_begin_impl(clb_handle* h, const float* inj_u, const float* inj_e
     a.lik.lnorm = (c.likelihood == CLB_LIK_STUDENTT)
                       ? (float)(lgamma_d(0.5 * (c.dof + 1.0)) - lgamma_d(0.5 * c.dof) - 0.5 * std::log((double)c.dof * M_PI)) : 0.f;
     a.cl = cl; a.bijector = c.scale_bijector; a.shift = c.scale_shift; a.eps = c.epsilon;
+    a.theta_lik = c.refine_uncertainties ? theta + h->goff[CLB_GROUP_LIKELIHOOD] : nullptr;
+    a.g_lik = (c.refine_uncertainties && h->gtrain[CLB_GROUP_LIKELIHOOD] && !h->eval_mode) ? grad + h->goff[CLB_GROUP_LIKELIHOOD] : nullptr;
+    if (h->n_empty > 0) {
+      const int blocks = (int)std::min<int64_t>((h->n_empty + 255) / 256, 4 * h->n_sms);
+      const float* ei = h->empty_slots.as<float>();
+      if (c.likelihood == CLB_LIK_NORMAL)
+        k_ev11_empty<0><<<blocks, 256, 0, st>>>(ei, ei + h->n_empty, h->n_empty, a.theta_lik, a.g_lik, h->acc.as<double>(), a.lik, cl, (float)S);
+      else
+        k_ev11_empty<1><<<blocks, 256, 0, st>>>(ei, ei + h->n_empty, h->n_empty, a.theta_lik, a.g_lik, h->acc.as<double>(), a.lik, cl, (float)S);
+      CLB_LAUNCHED(h);
+    }
     a.seed = c.seed; a.step = h->step_counter; a.laue = c.laue; a.train_mlp = train_mlp ? 1 : 0;
     if (h->timing) {
       while (h->ev.size() < h->ev_used + 2) { cudaEvent_t e; CLB_CUDA(h, cudaEventCreate(&e)); h->ev.push_back(e); }

@@ -151,6 +151,8 @@ struct ObsArgs {
   float* scale_mean_out; float* scale_std_out;   // (N_total) moments of the scale distribution, original order, or null
   double* acc;
   LikConst lik; float cl;          // likelihood coefficient (1/S or 1/(S*N))
+  // Ev11 error model (likelihoods/mono.py:39-73): raw (pre-softplus) Sdfac, Sdadd, SdB or null; gradient or null
+  const float* theta_lik; float* g_lik;
   int bijector; float shift; float eps;
   uint64_t seed; uint32_t step;
   int laue; int train_mlp;
@@ -446,6 +448,8 @@ __global__ void __launch_bounds__(TC ? tc::kThreads : kObsThreads, TC ? 2 : 1) k
   double* part_rows = a.partials + (size_t)blockIdx.x * PP + (size_t)tid * 4;   // valid for tid < WP*WP/4
   float4* scr = a.scratch + (size_t)blockIdx.x * LT * NC * T;
   double ll_sum = 0.0;
+  float ev_f = 1.f, ev_a = 0.f, ev_b = 0.f;      // Ev11: Sdfac, Sdadd, SdB = softplus(raw)
+  if (a.theta_lik != nullptr) { ev_f = softplusf(a.theta_lik[0]); ev_a = softplusf(a.theta_lik[1]); ev_b = softplusf(a.theta_lik[2]); }
   const int64_t n_tiles = (a.n_rows + T - 1) / T;
 
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -540,6 +544,7 @@ __global__ void __launch_bounds__(TC ? tc::kThreads : kObsThreads, TC ? 2 : 1) k
     const bool img_live = active && img > 0;
     if (a.g_img != nullptr) img_runs = warp_runs(img_live ? img : -1 - lane, lane);
     float dmu = 0.f, drho = 0.f, d_aimg = 0.f;
+    float ev_gf = 0.f, ev_ga = 0.f, ev_gb = 0.f;
     for (int s = 0; s < a.S; ++s) {
       float e = 0.f;
       if (active) e = a.inj_eps ? a.inj_eps[(size_t)s * a.n_rows_total + oi] : obs_normal(a.seed, a.step, (uint32_t)s, oi);
@@ -555,7 +560,13 @@ __global__ void __launch_bounds__(TC ? tc::kThreads : kObsThreads, TC ? 2 : 1) k
         eval = active && spot_runs.tail;   // count each spot once
       }
       float ll = 0.f, g = 0.f;
-      if (active) lik_eval<LIK>(x, iobs, sg, a.lik, ll, g);
+      if (a.theta_lik == nullptr) {
+        if (active) lik_eval<LIK>(x, iobs, sg, a.lik, ll, g);
+      } else if (active) {
+        float gf, ga, gb;
+        ev11_eval<LIK>(x, iobs, sg, ev_f, ev_a, ev_b, a.lik, ll, g, gf, ga, gb);
+        if (eval) { ev_gf += gf; ev_ga += ga; ev_gb += gb; }
+      }
       if (eval) ll_sum += (double)ll;
       const float G = active ? a.cl * g : 0.f;
       const float d_zs = G * zf * zf;
@@ -571,6 +582,14 @@ __global__ void __launch_bounds__(TC ? tc::kThreads : kObsThreads, TC ? 2 : 1) k
     if (a.g_img != nullptr) {
       const float tot = warp_segsum(d_aimg, img_runs, lane);
       if (img_live && img_runs.tail) atomicAdd(&a.g_img[img - 1], tot);
+    }
+    if (a.g_lik != nullptr) {      // d loss / d raw error-model parameters: one atomic per warp and parameter
+      ev_gf = warp_sum(ev_gf); ev_ga = warp_sum(ev_ga); ev_gb = warp_sum(ev_gb);
+      if (lane == 0) {
+        atomicAdd(&a.g_lik[0], a.cl * ev_gf * sigmoidf(a.theta_lik[0]));
+        atomicAdd(&a.g_lik[1], a.cl * ev_ga * sigmoidf(a.theta_lik[1]));
+        atomicAdd(&a.g_lik[2], a.cl * ev_gb * sigmoidf(a.theta_lik[2]));
+      }
     }
     if (!a.train_mlp) continue;
     // ---------------- backward through the MLP ----------------
@@ -670,6 +689,31 @@ __global__ void __launch_bounds__(TC ? tc::kThreads : kObsThreads, TC ? 2 : 1) k
   }
   if constexpr (TC) {
     if (tid < 32) tc::tmem_dealloc(*tc_slot);
+  }
+}
+
+// Ev11 on the empty Laue slots: each contributes logpdf(0; I_k, sigma'(0; sigma_k)) per MC sample, and because sigma'
+// depends on the error-model parameters, also a gradient (the reference differentiates through the padded entries of
+// likelihoods/laue.py:13-35 like through any other).  `mult` = number of MC samples.
+template <int LIK>
+__global__ void __launch_bounds__(256) k_ev11_empty(const float* iobs, const float* sig, int64_t n, const float* theta_lik, float* g_lik,
+                                                    double* acc, LikConst lik, float cl, float mult) {
+  const float f = softplusf(theta_lik[0]), av = softplusf(theta_lik[1]), bv = softplusf(theta_lik[2]);
+  double ll_sum = 0.0;
+  float sgf = 0.f, sga = 0.f, sgb = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float ll, g, gf, ga, gb;
+    ev11_eval<LIK>(0.f, iobs[i], sig[i], f, av, bv, lik, ll, g, gf, ga, gb);
+    ll_sum += (double)ll; sgf += gf; sga += ga; sgb += gb;
+  }
+  ll_sum = warp_sum(ll_sum); sgf = warp_sum(sgf); sga = warp_sum(sga); sgb = warp_sum(sgb);
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&acc[ACC_LL], ll_sum * (double)mult);
+    if (g_lik != nullptr) {
+      atomicAdd(&g_lik[0], cl * mult * sgf * sigmoidf(theta_lik[0]));
+      atomicAdd(&g_lik[1], cl * mult * sga * sigmoidf(theta_lik[1]));
+      atomicAdd(&g_lik[2], cl * mult * sgb * sigmoidf(theta_lik[2]));
+    }
   }
 }
 

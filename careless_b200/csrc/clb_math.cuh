@@ -182,6 +182,25 @@ CLB_DEV void lik_eval(float x, float loc, float scale, const LikConst& c, float&
 CLB_DEV float softplusf(float x) { return (x > 15.0f) ? x + log1pf(expf(-x)) : log1pf(expf(x)); }
 CLB_DEV float sigmoidf(float x) { return 1.0f / (1.0f + expf(-x)); }
 
+// Ev11 error model (likelihoods/mono.py:39-73): the likelihood scale depends on the prediction,
+//   sigma' = Sdfac sqrt(sigma^2 + SdB p + Sdadd p^2),  p = softplus(x)
+// Returns ll, dnll/dx (through the residual AND through sigma') and dnll/d{Sdfac, Sdadd, SdB}.
+template <int LIK>
+CLB_DEV void ev11_eval(float x, float loc, float sigma, float f, float av, float bv, const LikConst& c,
+                       float& ll, float& dnll_dx, float& gf, float& ga, float& gb) {
+  const float p = softplusf(x);
+  const float q = fmaf(sigma, sigma, fmaf(bv, p, av * p * p));
+  const float sq = sqrtf(q);
+  const float sc = f * sq;
+  lik_eval<LIK>(x, loc, sc, c, ll, dnll_dx);
+  const float t = (x - loc) / sc;
+  const float t2 = t * t;
+  const float dsc = (LIK == 0) ? (1.0f - t2) / sc : c.dof * (1.0f - t2) / ((c.dof + t2) * sc);   // dnll/dsigma'
+  const float h = 0.5f * f / sq;
+  dnll_dx += dsc * h * fmaf(2.0f * av, p, bv) * sigmoidf(x);
+  gf = dsc * sq; ga = dsc * h * p * p; gb = dsc * h * p;
+}
+
 // ---------------------------------------------------------------------------------------
 // warp helpers
 // ---------------------------------------------------------------------------------------

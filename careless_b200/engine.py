@@ -25,6 +25,7 @@ class EngineConfig:
     n_images: int = 0
     image_scales: bool = False
     image_layers: int = 0
+    refine_uncertainties: bool = False
     mc_samples: int = 1
     likelihood: str = "normal"
     dof: Optional[float] = None
@@ -59,6 +60,7 @@ class EngineConfig:
         c.n_meta, c.mlp_width, c.mlp_layers = self.n_meta, self.mlp_width, self.mlp_layers
         c.n_images = self.n_images if (self.image_scales or self.image_layers > 0) else 0
         c.image_layers = self.image_layers
+        c.refine_uncertainties = int(self.refine_uncertainties)
         c.image_scales = int(self.image_scales)
         c.mc_samples = self.mc_samples
         c.likelihood = {"normal": L.LIK_NORMAL, "studentt": L.LIK_STUDENTT}[self.likelihood]

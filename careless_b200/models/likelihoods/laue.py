@@ -2,7 +2,7 @@
 summed per spot (harmonic_id) before the mono log-density; done inside the CUDA observation kernel."""
 import numpy as np
 
-from .mono import Likelihood
+from .mono import Ev11Likelihood, Likelihood
 
 
 class LaueBase(Likelihood):
@@ -26,4 +26,18 @@ class StudentTLikelihood(LaueBase):
     kind = "studentt"
 
     def __init__(self, dof):
+        self.dof = float(dof)
+
+
+class NormalEv11Likelihood(LaueBase, Ev11Likelihood):
+    """laue.py:49-56"""
+    kind = "normal"
+
+
+class StudentTEv11Likelihood(LaueBase, Ev11Likelihood):
+    """laue.py:58-65"""
+    kind = "studentt"
+
+    def __init__(self, dof):
+        Ev11Likelihood.__init__(self)
         self.dof = float(dof)

@@ -68,6 +68,7 @@ class VariationalMergingModel(BaseModel):
             n_refl=R, n_meta=n_meta, mlp_width=mlp.width, mlp_layers=mlp.n_layers,
             n_images=(img.max_images if img is not None else (nis.max_images if nis is not None else 0)), image_scales=img is not None,
             image_layers=(len(nis.image_layers) if nis is not None else 0),
+            refine_uncertainties=bool(getattr(self.likelihood, "refine_uncertainties", False)),
             mc_samples=int(self.mc_sample_size), likelihood=self.likelihood.kind, dof=self.likelihood.dof, laue=laue,
             prior="double_wilson" if dw else "wilson", n_asu=(len(prior.r) if dw else 0),
             optimize_dw_r=(prior.optimize_r if dw else False), scale_bijector=mlp.scale_bijector,
@@ -99,6 +100,9 @@ class VariationalMergingModel(BaseModel):
         if isinstance(self.scaling_model, NeuralImageScaler) and self.scaling_model.image_layers:
             eng.set_params("image_layers", self.scaling_model.flat())
             eng.set_trainable("image_layers", self.scaling_model.trainable)
+        if getattr(self.likelihood, "refine_uncertainties", False):
+            eng.set_params("likelihood", self.likelihood.raw)
+            eng.set_trainable("likelihood", self.likelihood.trainable)
         eng.set_trainable("sf_loc_raw", q.trainable)
         eng.set_trainable("sf_scale_raw", q.trainable)
         eng.set_trainable("mlp", self.scaling_model.trainable and mlp.trainable)
@@ -114,6 +118,8 @@ class VariationalMergingModel(BaseModel):
             img._scales = eng.get_params("image_scales")
         if isinstance(self.scaling_model, NeuralImageScaler) and self.scaling_model.image_layers:
             self.scaling_model.from_flat(eng.get_params("image_layers"))
+        if getattr(self.likelihood, "refine_uncertainties", False):
+            self.likelihood.raw = eng.get_params("likelihood").astype(np.float32)
         if isinstance(self.prior, DoubleWilsonPrior) and self.prior.optimize_r:
             self.prior.r = (1.0 / (1.0 + np.exp(-eng.get_params("dw_r_logit")))).astype(np.float32)
 
@@ -146,7 +152,7 @@ class VariationalMergingModel(BaseModel):
                 n = min(chunk, steps - done)
             rows = eng.step(n)            # metrics stay on the device for the whole chunk (no per-step host sync)
             if veng is not None and done % validation_frequency == 0 and rows:
-                for g in ("sf_loc_raw", "sf_scale_raw", "mlp", "image_scales", "dw_r_logit", "image_layers"):
+                for g in ("sf_loc_raw", "sf_scale_raw", "mlp", "image_scales", "dw_r_logit", "image_layers", "likelihood"):
                     if eng.group_size(g) > 0:
                         veng.set_params(g, eng.get_params(g))
                 nll_val = val_scale * veng.eval()["NLL"]
@@ -227,3 +233,9 @@ class VariationalMergingModel(BaseModel):
         if self._engine is not None:
             self._engine.close()
             self._engine = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -48,6 +48,31 @@ class DoubleWilsonPrior(Prior):
                 raise ValueError(f"Supplied --double-wilson-r value {r} outside of allowed range (-1, 1)")
         self.optimize_r = bool(optimize_r)
 
+    @classmethod
+    def from_asu_collection(cls, asu_collection, parents, r_values, reindexing_ops=None, sigma=1., optimize_r=False):
+        """The reference constructor (wilson.py:83-137): parents[i] = j makes ASU j the parent of ASU i; every child
+        reflection (optionally reindexed) is mapped into the parent's ASU and looked up in the collection (-1 = parent
+        absent).  Root ASUs keep their LOCAL ids, as the reference does (never used: roots have no parent term)."""
+        reflids, root = [], []
+        for child, parent in enumerate(parents):
+            child_asu = asu_collection.reciprocal_asus[child]
+            n = len(child_asu.Hall)
+            if parent is None:
+                reflids.append(np.arange(n, dtype=np.int64))
+                root.append(np.ones(n, dtype=bool))
+            else:
+                root.append(np.zeros(n, dtype=bool))
+                parent_asu = asu_collection.reciprocal_asus[parent]
+                h = child_asu.Hall
+                if reindexing_ops is not None:
+                    h = reindexing_ops[child].apply_to_hkl(h)
+                h, _ = parent_asu.spacegroup.hkl_to_asu(h)
+                reflids.append(asu_collection.to_refl_id(np.full((len(h), 1), parent), h, allow_missing=True))
+        out = cls(asu_collection.centric, asu_collection.multiplicity, asu_collection.asu_ids, np.concatenate(reflids),
+                  np.concatenate(root), r_values, sigma=sigma, optimize_r=optimize_r)
+        out.parents = parents
+        return out
+
     @property
     def dw_parent(self):
         """Device encoding: -2 root entry, -1 parent absent, >=0 surrogate index of the parent."""

@@ -19,6 +19,14 @@ class HybridImageScaler(Scaler):
         self.mlp_scaler = mlp_scaler
         self.image_scaler = image_scaler
 
+    def save_weights(self, path):
+        self.mlp_scaler.save_weights(str(path) + "_mlp")
+        np.savez(str(path) + "_image.npz", scales=self.image_scaler._scales)
+
+    def load_weights(self, path):
+        self.mlp_scaler.load_weights(str(path) + "_mlp")
+        self.image_scaler._scales = np.load(str(path) + "_image.npz")["scales"].astype(np.float32)
+
 
 class ImageLayer(Scaler):
     """image.py:66-96: a dense layer whose kernel (units, in) and bias depend on the image; identity / zero init."""
@@ -40,6 +48,14 @@ class NeuralImageScaler(Scaler):
                                               scale_multiplier=scale_multiplier)
         self.max_images = int(max_images)
         self.image_layers = [ImageLayer(mlp_width, max_images) for _ in range(int(image_layers))]
+
+    def save_weights(self, path):
+        self.metadata_scaler.save_weights(str(path) + "_mlp")
+        np.savez(str(path) + "_image_layers.npz", flat=self.flat())
+
+    def load_weights(self, path):
+        self.metadata_scaler.load_weights(str(path) + "_mlp")
+        self.from_flat(np.load(str(path) + "_image_layers.npz")["flat"])
 
     def flat(self):
         return np.concatenate([np.concatenate([l.w.reshape(-1), l.b.reshape(-1)]) for l in self.image_layers]) \

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define CLB_ABI_VERSION 1
+#define CLB_ABI_VERSION 2
 
 typedef struct clb_handle clb_handle;
 
@@ -51,9 +51,10 @@ enum { CLB_ORDER_AUTO = 0, CLB_ORDER_REFL = 1, CLB_ORDER_SPOT = 2, CLB_ORDER_IMA
  *   IMAGE_SCALES      scaling/image.py:21   (n_images-1 values; image 0 is pinned to 1)
  *   DW_R              priors/wilson.py:105-110 (logits of r, one per ASU; --optimize-double-wilson-r)
  *   IMAGE_LAYERS      scaling/image.py:73-88 (--image-layers): per layer kernel (n_images, W, W) as (out, in), bias (n_images, W)
+ *   LIKELIHOOD        likelihoods/mono.py:42-44 (--refine-uncertainties): raw Sdfac, Sdadd, SdB (softplus-transformed, init 1)
  */
 enum { CLB_GROUP_SF_LOC = 0, CLB_GROUP_SF_SCALE = 1, CLB_GROUP_MLP = 2, CLB_GROUP_IMAGE_SCALES = 3,
-       CLB_GROUP_DW_R = 4, CLB_GROUP_IMAGE_LAYERS = 5, CLB_N_GROUPS = 6 };
+       CLB_GROUP_DW_R = 4, CLB_GROUP_IMAGE_LAYERS = 5, CLB_GROUP_LIKELIHOOD = 6, CLB_N_GROUPS = 7 };
 
 /* Everything DataManager.build_model (careless/io/manager.py:380-507) decides, flattened. */
 typedef struct {
@@ -88,6 +89,8 @@ typedef struct {
   uint64_t seed;              /* Philox key for in-kernel draws (--seed, args/tf_options.py:50-54) */
   int32_t rank, world_size;   /* reflection-partitioned data parallelism; 0,1 on one GPU */
   int32_t image_layers;       /* NeuralImageScaler per-image dense layers (--image-layers, args/scaling.py:33-37); needs n_images */
+  int32_t refine_uncertainties; /* Ev11 error model (--refine-uncertainties, likelihoods/mono.py:39-73, laue.py:49-65): group
+                                 CLB_GROUP_LIKELIHOOD holds the raw (pre-softplus) Sdfac, Sdadd, SdB, each initialised to 1 */
 } clb_config;
 
 /* Per-step metrics: the keys of the history dict returned by train_model (variational.py:214-224, 262-268). */

@@ -60,6 +60,7 @@ class ModelConfig:
     image_scales: bool = False          # image.py:9-63 (HybridImageScaler)
     n_images: int = 0
     image_layers: int = 0               # image.py:66-125 (NeuralImageScaler)
+    refine_uncertainties: bool = False  # Ev11 error model, likelihoods/mono.py:39-73, laue.py:49-65
     optimize_dw_r: bool = False         # wilson.py:105-110
     high: float = 1e10                  # surrogate_posteriors.py:105
 
@@ -297,11 +298,21 @@ def laue_convolve(ipred, harmonic_id):
     return out.index_add(1, hid, ipred)
 
 
-def likelihood_log_prob(ipred, data, cfg: ModelConfig):
+def ev11_sigma(x, sig, lik_raw):
+    """mono.py:52-59 corrected_sigiobs: Sdfac sqrt(sigma^2 + SdB softplus(x) + Sdadd softplus(x)^2) with
+    (Sdfac, Sdadd, SdB) = softplus(raw) (TransformedVariable(1., Softplus), mono.py:42-44)."""
+    sdfac, sdadd, sdb = torch.nn.functional.softplus(lik_raw)
+    p = torch.nn.functional.softplus(x)
+    return sdfac * torch.sqrt(sig * sig + sdb * p + sdadd * p * p)
+
+
+def likelihood_log_prob(ipred, data, cfg: ModelConfig, params=None):
     dtype = ipred.dtype
     iobs = torch.as_tensor(np.asarray(data["intensities"]), dtype=dtype)
     sig = torch.as_tensor(np.asarray(data["uncertainties"]), dtype=dtype)
     x = laue_convolve(ipred, data["harmonic_id"]) if cfg.laue else ipred
+    if cfg.refine_uncertainties:
+        sig = ev11_sigma(x, sig, params["likelihood"])
     if cfg.likelihood == "normal":
         return normal_log_prob(x, iobs, sig)
     if cfg.likelihood == "studentt":
@@ -333,7 +344,7 @@ def forward(params, data, prior: PriorData, cfg: ModelConfig, u_f, eps_s):
 
     refl_id = torch.as_tensor(np.asarray(data["refl_id"], dtype=np.int64))
     ipred = z_scale * z_f[:, refl_id] ** 2                                        # :167
-    ll = likelihood_log_prob(ipred, data, cfg)                                    # :169-171
+    ll = likelihood_log_prob(ipred, data, cfg, params)                                    # :169-171
 
     kl_terms = tn_log_prob(z_f, loc, scale, low, high) - prior_log_prob(z_f, params, prior, cfg)  # :123-128
     if cfg.kl_weight is None:                                                     # :172-174
@@ -377,7 +388,8 @@ def adam_apply(params, grads, state, opt: AdamConfig):
     g = {k: torch.where(torch.isfinite(v), v, torch.zeros_like(v)) for k, v in grads.items()}
     if opt.clipnorm is not None:        # per-variable tf.clip_by_norm
         for k in g:
-            n = torch.sqrt((g[k] ** 2).sum())
+            # "likelihood" packs three scalar keras variables (Sdfac, Sdadd, SdB): each is clipped on its own
+            n = torch.abs(g[k]) if k == "likelihood" else torch.sqrt((g[k] ** 2).sum())
             g[k] = g[k] * opt.clipnorm / torch.clamp(n, min=opt.clipnorm)
     if opt.global_clipnorm is not None:  # tf.clip_by_global_norm
         n = torch.sqrt(sum((v ** 2).sum() for v in g.values()))
@@ -440,6 +452,8 @@ def init_params(cfg: ModelConfig, prior: PriorData, dtype=torch.float64, init_sc
         r = np.asarray(prior.r, dtype=np.float64)
         with np.errstate(divide="ignore"):
             p["dw_r_logit"] = torch.as_tensor(np.log(r) - np.log1p(-r), dtype=dtype)
+    if cfg.refine_uncertainties:                                     # mono.py:42-44: softplus^-1(1) three times
+        p["likelihood"] = torch.full((3,), float(np.float32(math.log(math.e - 1.0))), dtype=dtype)
     return p
 
 

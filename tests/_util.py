@@ -32,7 +32,7 @@ def il_flat(params, cfg):
                                            params[f"image_layer.{k}.bias"].detach().numpy().reshape(-1)]) for k in range(cfg.image_layers)])
 
 
-def build(problem, *, mlp_width, mlp_layers, likelihood="normal", dof=None, laue=False, prior="wilson", image_layers=0,
+def build(problem, *, mlp_width, mlp_layers, likelihood="normal", dof=None, laue=False, prior="wilson", image_layers=0, refine_uncertainties=False,
           mc_samples=1, kl_weight=None, scale_bijector="exp", scale_shift=None, image_scales=False,
           optimize_dw_r=False, sigma=1.0, opt=None, seed=1234, eps=1e-7):
     """(oracle cfg, oracle prior, engine) for a synthetic problem dict from careless_b200.synth."""
@@ -42,13 +42,14 @@ def build(problem, *, mlp_width, mlp_layers, likelihood="normal", dof=None, laue
     ocfg = om.ModelConfig(n_refl=R, n_meta=d, mlp_width=mlp_width, mlp_layers=mlp_layers, likelihood=likelihood,
                           dof=dof, laue=laue, prior=prior, mc_samples=mc_samples, kl_weight=kl_weight,
                           scale_bijector=scale_bijector, scale_shift=scale_shift, eps=eps,
-                          image_scales=image_scales, n_images=n_images, optimize_dw_r=optimize_dw_r, image_layers=image_layers)
+                          image_scales=image_scales, n_images=n_images, optimize_dw_r=optimize_dw_r, image_layers=image_layers,
+                          refine_uncertainties=refine_uncertainties)
     oprior = om.PriorData(centric=problem["centric"], multiplicity=problem["multiplicity"], sigma=sigma,
                           reflids=problem.get("reflids"), root=problem.get("root"), asu_ids=problem.get("asu_id"),
                           r=problem.get("r"))
     opt = opt or om.AdamConfig()
     ecfg = EngineConfig(n_refl=R, n_meta=d, mlp_width=mlp_width, mlp_layers=mlp_layers, n_images=n_images,
-                        image_scales=image_scales, image_layers=image_layers, mc_samples=mc_samples, likelihood=likelihood, dof=dof, laue=laue,
+                        image_scales=image_scales, image_layers=image_layers, refine_uncertainties=refine_uncertainties, mc_samples=mc_samples, likelihood=likelihood, dof=dof, laue=laue,
                         prior=prior, n_asu=int(problem.get("n_asu", 0)), optimize_dw_r=optimize_dw_r,
                         scale_bijector=scale_bijector, scale_shift=scale_shift, epsilon=eps, kl_weight=kl_weight,
                         learning_rate=opt.lr, beta_1=opt.beta1, beta_2=opt.beta2, adam_epsilon=opt.eps,
@@ -82,6 +83,8 @@ def push_params(eng, params, ocfg):
         eng.set_params("dw_r_logit", params["dw_r_logit"].numpy())
     if ocfg.image_layers > 0:
         eng.set_params("image_layers", il_flat(params, ocfg))
+    if "likelihood" in params:
+        eng.set_params("likelihood", params["likelihood"].numpy())
 
 
 def pull_params(eng, like, ocfg):
@@ -92,6 +95,8 @@ def pull_params(eng, like, ocfg):
         out["image_scales"] = torch.as_tensor(eng.get_params("image_scales").astype(np.float64))
     if "dw_r_logit" in like:
         out["dw_r_logit"] = torch.as_tensor(eng.get_params("dw_r_logit").astype(np.float64))
+    if "likelihood" in like:
+        out["likelihood"] = torch.as_tensor(eng.get_params("likelihood").astype(np.float64))
     return out
 
 
@@ -103,6 +108,8 @@ def engine_grads(eng, ocfg, like):
         g["image_scales"] = eng.get_grads("image_scales").astype(np.float64)
     if "dw_r_logit" in like:
         g["dw_r_logit"] = eng.get_grads("dw_r_logit").astype(np.float64)
+    if "likelihood" in like:
+        g["likelihood"] = eng.get_grads("likelihood").astype(np.float64)
     if ocfg.image_layers > 0:
         g["image_layers"] = eng.get_grads("image_layers").astype(np.float64)
     return g
@@ -112,7 +119,7 @@ def oracle_grads_grouped(g, ocfg):
     out = {"sf_loc_raw": g["sf_loc_raw"].numpy(), "sf_scale_raw": g["sf_scale_raw"].numpy()}
     if all(n in g for n in mlp_names(ocfg)):
         out["mlp"] = mlp_flat(g, ocfg)
-    for k in ("image_scales", "dw_r_logit"):
+    for k in ("image_scales", "dw_r_logit", "likelihood"):
         if k in g:
             out[k] = g[k].numpy()
     if ocfg.image_layers > 0 and "image_layer.0.kernel" in g:

@@ -145,6 +145,40 @@ def test_image_layers(width, laue):
                   likelihood="studentt", dof=6.0)
 
 
+@pytest.mark.parametrize("laue,likelihood,width", [(False, "normal", 8), (False, "studentt", 32), (True, "normal", 12), (True, "studentt", 32)])
+def test_ev11_error_model(laue, likelihood, width):
+    """--refine-uncertainties (likelihoods/mono.py:39-73, laue.py:49-65): sigma' depends on the prediction and on three
+    trainable scalars; the empty Laue slots contribute to their gradient too."""
+    p = synth.make_laue(5000, 600, d=3, n_images=15, seed=21) if laue else synth.make_mono(5000, 600, d=3, n_images=15, seed=21)
+    _compare_step(p, f"ev11-{likelihood}-W{width}{'-laue' if laue else ''}", mlp_width=width, mlp_layers=3, laue=laue,
+                  likelihood=likelihood, dof=6.0 if likelihood == "studentt" else None, refine_uncertainties=True,
+                  mc_samples=2 if laue else 1)
+
+
+def test_ev11_trajectory():
+    p = synth.make_laue(3000, 300, d=3, n_images=9, seed=22)
+    opt = om.AdamConfig(lr=1e-2, clipnorm=5.0)
+    rng = np.random.default_rng(5)
+    ocfg, oprior, eng = U.build(p, mlp_width=8, mlp_layers=3, laue=True, likelihood="studentt", dof=8.0, refine_uncertainties=True, opt=opt)
+    try:
+        params = U.perturbed_params(ocfg, oprior, rng, amount=0.05)
+        U.push_params(eng, params, ocfg)
+        n = 5
+        u, e = _draws(rng, 1, ocfg.n_refl, len(p["refl_id"]), n)
+        hist = eng.step(n, u_f=u, eps_s=e)
+        oparams, ohist, _ = om.train(params, p, oprior, ocfg, opt, [(u[i], e[i]) for i in range(n)])
+        for i in range(n):
+            for k in ("loss", "NLL", "F KLDiv", "Grad Norm"):
+                assert abs(hist[i][k] - ohist[i][k]) <= 2e-4 * abs(ohist[i][k]) + 1e-6, (i, k, hist[i], ohist[i])
+        got = U.pull_params(eng, params, ocfg)
+        errs = {k: U.rel_err(got[k].numpy(), oparams[k].numpy()) for k in got}
+        print("\n[ev11-adam] " + "  ".join(f"{k}={v:.2e}" for k, v in errs.items()))
+        assert max(errs.values()) <= 2e-4, errs
+        assert not np.allclose(got["likelihood"].numpy(), params["likelihood"].numpy())
+    finally:
+        eng.close()
+
+
 def test_frozen_scaler():
     p = synth.make_mono(2000, 300, d=3, n_images=5, seed=10)
     _compare_step(p, "frozen-mlp", frozen=("mlp",), mlp_width=8, mlp_layers=3)
