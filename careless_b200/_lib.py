@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libcareless_b200.so")
+LIB_PATH = os.environ.get("CLB_LIB_PATH") or os.path.join(HERE, "libcareless_b200.so")   # CLB_LIB_PATH: instrumented debug builds (tools/)
 ABI_VERSION = 2
 
 # enums of include/careless_b200.h

@@ -1009,3 +1009,13 @@ int clb_step(clb_handle* h, int32_t n_steps, const float* inj_u_f, const float* 
 }
 
 }  // extern "C"
+
+#ifdef CLB_PHASE_TIMING
+// Debug build only (tools/phase_times.py): read and clear the per-phase cycle sums of k_obs.
+extern "C" int clb_debug_phases(unsigned long long* out32) {
+  unsigned long long zero[32] = {0};
+  if (cudaMemcpyFromSymbol(out32, clb::g_phase, sizeof zero) != cudaSuccess) return -1;
+  if (cudaMemcpyToSymbol(clb::g_phase, zero, sizeof zero) != cudaSuccess) return -1;
+  return 0;
+}
+#endif

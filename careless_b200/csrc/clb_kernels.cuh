@@ -14,6 +14,18 @@ constexpr int kObsThreads = 256;     // observations per CTA tile (one per threa
 constexpr int kMaxVars = 2 * kMaxLayers + 8;
 
 // scalar accumulators (double) of one step
+// Optional per-phase cycle accounting of k_obs (tools/phase_times.py builds with -DCLB_PHASE_TIMING): thread 0 of every
+// CTA adds the cycles since its previous mark to g_phase[i].  Compiled out of the product library.
+#ifdef CLB_PHASE_TIMING
+__device__ unsigned long long g_phase[32];
+__shared__ long long s_phase_last;
+#define CLB_PH(i) do { if (threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd(&g_phase[i], (unsigned long long)(t_ - s_phase_last)); s_phase_last = t_; } } while (0)
+#define CLB_PH_START() do { if (threadIdx.x == 0) s_phase_last = clock64(); } while (0)
+#else
+#define CLB_PH(i) do { } while (0)
+#define CLB_PH_START() do { } while (0)
+#endif
+
 enum { ACC_LOGQ_MINUS_LOGP = 0, ACC_LL = 1, ACC_SUMSQ_RAW = 2, ACC_SUMSQ_FILT = 3, ACC_NONFINITE = 4, ACC_COUNT = 8 };
 
 // ---------------------------------------------------------------------------------------
@@ -322,11 +334,17 @@ __device__ __forceinline__ void tc_layer_backward(tc::Ctx& tcx, float (&dp)[32],
       pr[h][1] = __ldcg(reinterpret_cast<const double2*>(part + 512 * h) + 1);
     }
   }
+  CLB_PH(5);
   bias_partial<32>(dp, bias_part, tid);
+  CLB_PH(6);
   tc::issue_backward(tcx, dp, ain, w, need_dx);
+  CLB_PH(7);
   if (need_dx) tc::collect(tcx, dp);
+  CLB_PH(8);
   tc::collect_dw(tcx);
+  CLB_PH(9);
   __syncthreads();
+  CLB_PH(10);
   {
     const int pj = (tid & 63) >> 3, pi = tid & 7;
 #pragma unroll
@@ -355,7 +373,9 @@ __device__ __forceinline__ void tc_layer_backward(tc::Ctx& tcx, float (&dp)[32],
       else if (il_gb != nullptr && tid < il_w) atomicAdd(&il_gb[tid], sum);
     }
   }
+  CLB_PH(11);
   __syncthreads();      // the stage aliases the operand image of the next layer
+  CLB_PH(12);
 }
 
 // Padded per-CTA partial layout: [NL][WP*WP] kernel sums in patch order -- element (i, j) of layer k at
@@ -452,6 +472,7 @@ __global__ void __launch_bounds__(TC ? tc::kThreads : kObsThreads, TC ? 2 : 1) k
   if (a.theta_lik != nullptr) { ev_f = softplusf(a.theta_lik[0]); ev_a = softplusf(a.theta_lik[1]); ev_b = softplusf(a.theta_lik[2]); }
   const int64_t n_tiles = (a.n_rows + T - 1) / T;
 
+  CLB_PH_START();
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t row = tile * T + tid;
     const bool inb = row < a.n_rows;
@@ -488,11 +509,14 @@ __global__ void __launch_bounds__(TC ? tc::kThreads : kObsThreads, TC ? 2 : 1) k
       const float* bk = (k >= L) ? bimg + (size_t)(k - L) * WP : bsm + (size_t)k * WP;
       float o[WP];
       if constexpr (TC) {
+        CLB_PH(0);
         tc::issue<false>(tcx, h, wreg);
+        CLB_PH(1);
         // prefetch the next pass's weights while the tensor cores work: next forward layer, or the first backward layer
         if (k + 1 < LT) tc::load_w<false>(wsrc(k + 1), tid, wreg);
         else if (a.train_mlp && LT > 1) tc::load_w<true>(wsrc(LT - 1), tid, wreg);
         tc::collect(tcx, o);
+        CLB_PH(2);
 #pragma unroll
         for (int j = 0; j < WP; ++j) o[j] += bk[j];
       } else {
@@ -515,6 +539,7 @@ __global__ void __launch_bounds__(TC ? tc::kThreads : kObsThreads, TC ? 2 : 1) k
         for (int c = 0; c < NC; ++c) scr[((size_t)k * NC + c) * T + tid] = make_float4(h[4 * c], h[4 * c + 1], h[4 * c + 2], h[4 * c + 3]);
       }
     }
+    CLB_PH(3);
     float out0, out1;
     {
       out0 = bsm[L * WP]; out1 = bsm[L * WP + 1];
@@ -591,6 +616,7 @@ __global__ void __launch_bounds__(TC ? tc::kThreads : kObsThreads, TC ? 2 : 1) k
         atomicAdd(&a.g_lik[2], a.cl * ev_gb * sigmoidf(a.theta_lik[2]));
       }
     }
+    CLB_PH(4);
     if (!a.train_mlp) continue;
     // ---------------- backward through the MLP ----------------
     float dp[WP], nxt[WP];

@@ -138,7 +138,7 @@ __device__ __forceinline__ void split32(const float (&x)[32], uint32_t (&hi)[32]
   for (int k = 0; k < 32; ++k) {
     const float h = tf32_rna(x[k]);
     hi[k] = __float_as_uint(h);
-    lo[k] = __float_as_uint(tf32_rna(x[k] - h));
+    lo[k] = __float_as_uint(x[k] - h);      // exact; the MMA ignores the low 13 bits (measured: tools/tc_probe mode 5)
   }
 }
 
@@ -191,8 +191,8 @@ __device__ __forceinline__ void build_weight_image(Ctx& c, const float (&w)[8]) 
     const uint32_t off = kq * kLBO + (n >> 3) * kSBO + (n & 7) * 16;
     float4 hi, lo;
     hi.x = tf32_rna(w[4 * h]); hi.y = tf32_rna(w[4 * h + 1]); hi.z = tf32_rna(w[4 * h + 2]); hi.w = tf32_rna(w[4 * h + 3]);
-    lo.x = tf32_rna(w[4 * h] - hi.x); lo.y = tf32_rna(w[4 * h + 1] - hi.y);
-    lo.z = tf32_rna(w[4 * h + 2] - hi.z); lo.w = tf32_rna(w[4 * h + 3] - hi.w);
+    lo.x = w[4 * h] - hi.x; lo.y = w[4 * h + 1] - hi.y;
+    lo.z = w[4 * h + 2] - hi.z; lo.w = w[4 * h + 3] - hi.w;
     *reinterpret_cast<float4*>(c.img_hi + off) = hi;
     *reinterpret_cast<float4*>(c.img_lo + off) = lo;
   }

@@ -58,6 +58,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
                "@P1 bra DONE;\n\tbra WAIT_LOOP;\n\tDONE:\n\t}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
+// operand preparation variants:
+//  0: 1xTF32, hi = rna(x)                      1: 3xTF32, hi = rna(x), lo = rna(x - hi)   (5 ops / value)
+//  2: 1xTF32, raw FP32 bits handed to the MMA   3: 1xTF32, hi = x & 0xFFFFE000 (explicit truncation)
+//  4: 3xTF32, hi = raw x, lo = x - trunc(x) raw (2 ops)   5: 3xTF32, hi = rna(x), lo = x - hi raw (3 ops)
+__device__ __forceinline__ void split_mode(float x, int mode, float& hi, float& lo) {
+  const float tr = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+  switch (mode) {
+    case 0: case 1: hi = tf32_rna(x); lo = tf32_rna(x - hi); break;
+    case 2: hi = x; lo = 0.f; break;
+    case 3: hi = tr; lo = 0.f; break;
+    case 4: hi = x; lo = x - tr; break;
+    default: hi = tf32_rna(x); lo = x - hi; break;
+  }
+}
+
 constexpr int kCols = 128;   // TMEM columns: D [0,32)  A_hi [32,64)  A_lo [64,96)
 
 __global__ void __launch_bounds__(128, 1) probe(const float* A, const float* W, float* D, int mode, int iters, long long* cycles) {
@@ -71,7 +86,8 @@ __global__ void __launch_bounds__(128, 1) probe(const float* A, const float* W, 
   for (int idx = tid; idx < 1024; idx += 128) {
     const int n = idx / 32, k = idx % 32;
     const float w = W[k * 32 + n];
-    const float hi = tf32_rna(w), lo = tf32_rna(w - hi);
+    float hi, lo;
+    split_mode(w, mode, hi, lo);
     *reinterpret_cast<float*>(reinterpret_cast<char*>(Bhi) + b_off_kmajor(n, k)) = hi;
     *reinterpret_cast<float*>(reinterpret_cast<char*>(Blo) + b_off_kmajor(n, k)) = lo;
   }
@@ -102,9 +118,10 @@ __global__ void __launch_bounds__(128, 1) probe(const float* A, const float* W, 
     uint32_t hi[32], lo[32];
 #pragma unroll
     for (int k = 0; k < 32; ++k) {
-      const float h = tf32_rna(a[k]);
+      float h, l;
+      split_mode(a[k], mode, h, l);
       hi[k] = __float_as_uint(h);
-      lo[k] = __float_as_uint(tf32_rna(a[k] - h));
+      lo[k] = __float_as_uint(l);
     }
     TMEM_ST32(t_ahi, hi);
     TMEM_ST32(t_alo, lo);
@@ -114,7 +131,7 @@ __global__ void __launch_bounds__(128, 1) probe(const float* A, const float* W, 
     if (tid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       uint32_t acc = 0;
-      const int nparts = (mode == 0) ? 1 : 3;
+      const int nparts = (mode == 0 || mode == 2 || mode == 3) ? 1 : 3;
       for (int part = 0; part < nparts; ++part) {
         const uint32_t ta = (part == 2) ? (tbase + 64) : (tbase + 32);       // A_lo for the third product
         const uint64_t db = (part == 1) ? dlo : dhi;                         // W_lo for the second product
@@ -153,21 +170,30 @@ int main() {
   CK(cudaMalloc(&dA, A.size() * 4)); CK(cudaMalloc(&dW, W.size() * 4)); CK(cudaMalloc(&dD, D.size() * 4)); CK(cudaMalloc(&dC, 8));
   CK(cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dW, W.data(), W.size() * 4, cudaMemcpyHostToDevice));
-  for (int mode = 0; mode < 2; ++mode) {
+  std::vector<float> Dm[6];
+  for (int mode = 0; mode < 6; ++mode) {
     probe<<<1, 128>>>(dA, dW, dD, mode, 1, dC);
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost));
-    double maxerr = 0, maxref = 0;
+    Dm[mode] = D;
+    double maxerr = 0, maxref = 0, sumsq = 0;
     for (int m = 0; m < 128; ++m)
       for (int n = 0; n < 32; ++n) {
         double ref = 0;
         for (int k = 0; k < 32; ++k) ref += (double)A[m * 32 + k] * (double)W[k * 32 + n];
         maxerr = fmax(maxerr, fabs(ref - D[m * 32 + n])); maxref = fmax(maxref, fabs(ref));
+        sumsq += (ref - D[m * 32 + n]) * (ref - D[m * 32 + n]);
       }
-    printf("mode %d (%s): max abs err %.3e (max |ref| %.3f)  D[0][0..3] = %f %f %f %f\n", mode, mode ? "3xTF32" : "1xTF32", maxerr, maxref,
+    printf("mode %d: max abs err %.3e  rms err %.3e (max |ref| %.3f)  D[0][0..3] = %f %f %f %f\n", mode, maxerr, sqrt(sumsq / (128 * 32)), maxref,
            D[0], D[1], D[2], D[3]);
   }
-  for (int mode = 0; mode < 2; ++mode) {
+  {
+    int diff23 = 0, diff20 = 0;
+    for (size_t i = 0; i < D.size(); ++i) { diff23 += Dm[2][i] != Dm[3][i]; diff20 += Dm[2][i] != Dm[0][i]; }
+    printf("raw operands vs explicit truncation: %d of %zu outputs differ (0 => the MMA ignores the low 13 bits); raw vs rna: %d differ\n",
+           diff23, D.size(), diff20);
+  }
+  for (int mode = 0; mode < 6; ++mode) {
     long long c = 0;
     probe<<<1, 128>>>(dA, dW, dD, mode, 1000, dC);
     CK(cudaDeviceSynchronize());
