@@ -74,6 +74,7 @@ struct clb_handle {
   bool have_obs = false, have_prior = false, in_step = false;
   bool eval_mode = false;    // clb_eval: forward only (no gradients, no Adam)
   bool use_tc = false;       // tensor-core (tcgen05) path of k_obs: padded width 32, unless CLB_NO_TC=1
+  bool use_tc2 = false;      // ... with two threads per observation row (k_obs_tc2), unless CLB_TC_ONE_THREAD_PER_ROW=1
   bool debug_sync = false;   // CLB_DEBUG_SYNC=1: synchronise + log after every kernel launch
   int order = CLB_ORDER_REFL;
   double ll_const = 0.0;   // per-sample constant log-likelihood of empty Laue slots
@@ -137,8 +138,16 @@ template <int WP, int LIK, bool TC> cudaError_t launch_obs(clb_handle* h, const 
   return cudaGetLastError();
 }
 
+template <int LIK> cudaError_t launch_obs_tc2(clb_handle* h, const ObsArgs& a) {
+  cudaError_t e = cudaFuncSetAttribute(k_obs_tc2<LIK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_obs);
+  if (e != cudaSuccess) return e;
+  k_obs_tc2<LIK><<<h->grid_obs, tc::kThreads2, h->smem_obs, h->stream>>>(a);
+  return cudaGetLastError();
+}
+
 cudaError_t dispatch_obs(clb_handle* h, const ObsArgs& a) {
   const int lik = h->cfg.likelihood;
+  if (h->use_tc2) return lik ? launch_obs_tc2<1>(h, a) : launch_obs_tc2<0>(h, a);
   switch (h->WP) {
     case 8:  return lik ? launch_obs<8, 1, false>(h, a) : launch_obs<8, 0, false>(h, a);
     case 16: return lik ? launch_obs<16, 1, false>(h, a) : launch_obs<16, 0, false>(h, a);
@@ -386,12 +395,14 @@ int clb_create(const clb_config* cfg, clb_handle** out) {
   build_vars(h);
   h->NL = h->lay.n_layers;
   { const char* no_tc = getenv("CLB_NO_TC"); h->use_tc = (WP == 32) && (cfg->mlp_layers + cfg->image_layers) > 0 && !(no_tc && no_tc[0] == '1'); }
-  h->obs_threads = h->use_tc ? tc::kThreads : kObsThreads;
+  { const char* one = getenv("CLB_TC_ONE_THREAD_PER_ROW"); h->use_tc2 = h->use_tc && !(one && one[0] == '1'); }
+  h->obs_threads = h->use_tc ? tc::kThreads : kObsThreads;      // = observation rows per CTA tile
   switch (WP) {
     case 8: h->smem_obs = ObsSmem<8>::bytes(h->NL, false, cfg->image_layers); break;
     case 16: h->smem_obs = ObsSmem<16>::bytes(h->NL, false, cfg->image_layers); break;
     default: h->smem_obs = ObsSmem<32>::bytes(h->NL, h->use_tc, cfg->image_layers); break;
   }
+  if (h->use_tc2) h->smem_obs = ObsSmem2::bytes(h->NL, cfg->image_layers);
   if (h->smem_obs > (size_t)prop.sharedMemPerBlockOptin) {
     fail(h, CLB_ERR_INVALID, "scale MLP (%d layers x padded width %d) needs %zu B of shared memory; the device offers %zu",
          cfg->mlp_layers, WP, h->smem_obs, (size_t)prop.sharedMemPerBlockOptin);

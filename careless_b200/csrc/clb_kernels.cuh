@@ -386,6 +386,82 @@ __host__ __device__ inline int partial_elem(int i, int j, int WP) {
 }
 __host__ __device__ inline int partial_row_size(int n_layers, int WP) { return n_layers * (WP * WP + WP); }
 
+// Everything between the scale network's two outputs and their gradients for one observation row: the scale sample,
+// the gather of z_f, the (Laue: per-spot) likelihood, dL/dz_f reduced over runs of equal refl_id with one atomic per
+// run, image-scale and error-model gradients.  All 32 lanes of the warp must call it (warp-level scans inside).
+template <int LIK>
+__device__ __forceinline__ void obs_epilogue(const ObsArgs& a, int64_t row, bool inb, bool active, int refl, int lane,
+                                             float out0, float out1, float ev_f, float ev_a, float ev_b,
+                                             double& ll_sum, float& dmu, float& drho) {
+  float sig_s, dsig;
+  if (a.bijector == 0) { dsig = expf(out1); sig_s = dsig + a.eps; }
+  else { sig_s = softplusf(out1) + a.eps; dsig = sigmoidf(out1); }
+  const int img = (a.image != nullptr && inb) ? a.image[row] : 0;
+  const float aimg = (a.theta_img != nullptr && img > 0) ? a.theta_img[img - 1] : 1.0f;
+  const uint32_t oi = inb ? a.oidx[row] : 0u;
+  const float iobs = inb ? a.iobs[row] : 0.f;
+  const float sg = inb ? a.sig[row] : 1.f;
+  if (a.scale_mean_out != nullptr && active) {     // variational.py:67-69: scale_dist.mean() / .stddev()
+    a.scale_mean_out[oi] = aimg * (out0 + a.shift);
+    a.scale_std_out[oi] = fabsf(aimg) * sig_s;
+  }
+  // runs of equal keys inside the warp (same for every MC sample)
+  const WarpRuns refl_runs = warp_runs(active ? refl : -1 - lane, lane);
+  WarpRuns spot_runs = refl_runs, img_runs = refl_runs;
+  if (a.laue) spot_runs = warp_runs(inb ? a.spot[row] : -1, lane);   // padding rows carry spot -1
+  const bool img_live = active && img > 0;
+  if (a.g_img != nullptr) img_runs = warp_runs(img_live ? img : -1 - lane, lane);
+  float d_aimg = 0.f;
+  dmu = 0.f; drho = 0.f;
+  float ev_gf = 0.f, ev_ga = 0.f, ev_gb = 0.f;
+  for (int s = 0; s < a.S; ++s) {
+    float e = 0.f;
+    if (active) e = a.inj_eps ? a.inj_eps[(size_t)s * a.n_rows_total + oi] : obs_normal(a.seed, a.step, (uint32_t)s, oi);
+    const float base = fmaf(sig_s, e, out0) + a.shift;
+    const float zs = aimg * base;
+    const float zf = active ? __ldg(&a.z[(size_t)s * a.R + refl]) : 0.f;
+    const float ip = zs * zf * zf;
+    if (a.ipred_out != nullptr && active) a.ipred_out[(size_t)s * a.n_rows_total + oi] = ip;
+    float x = ip;
+    bool eval = active;
+    if (a.laue) {           // harmonic segment-sum within the warp (spots never straddle a warp)
+      x = warp_segtotal(active ? ip : 0.f, spot_runs, lane);
+      eval = active && spot_runs.tail;   // count each spot once
+    }
+    float ll = 0.f, g = 0.f;
+    if (a.theta_lik == nullptr) {
+      if (active) lik_eval<LIK>(x, iobs, sg, a.lik, ll, g);
+    } else if (active) {
+      float gf, ga, gb;
+      ev11_eval<LIK>(x, iobs, sg, ev_f, ev_a, ev_b, a.lik, ll, g, gf, ga, gb);
+      if (eval) { ev_gf += gf; ev_ga += ga; ev_gb += gb; }
+    }
+    if (eval) ll_sum += (double)ll;
+    const float G = active ? a.cl * g : 0.f;
+    const float d_zs = G * zf * zf;
+    const float d_zf = G * zs * 2.0f * zf;
+    // segmented reduction of dL/dz_f over runs of equal refl_id, one atomic per run
+    const float tot = warp_segsum(d_zf, refl_runs, lane);
+    if (active && refl_runs.tail) atomicAdd(&a.gz[(size_t)s * a.R + refl], tot);
+    const float d_base = aimg * d_zs;
+    d_aimg += base * d_zs;
+    dmu += d_base;
+    drho += d_base * e * dsig;
+  }
+  if (a.g_img != nullptr) {
+    const float tot = warp_segsum(d_aimg, img_runs, lane);
+    if (img_live && img_runs.tail) atomicAdd(&a.g_img[img - 1], tot);
+  }
+  if (a.g_lik != nullptr) {      // d loss / d raw error-model parameters: one atomic per warp and parameter
+    ev_gf = warp_sum(ev_gf); ev_ga = warp_sum(ev_ga); ev_gb = warp_sum(ev_gb);
+    if (lane == 0) {
+      atomicAdd(&a.g_lik[0], a.cl * ev_gf * sigmoidf(a.theta_lik[0]));
+      atomicAdd(&a.g_lik[1], a.cl * ev_ga * sigmoidf(a.theta_lik[1]));
+      atomicAdd(&a.g_lik[2], a.cl * ev_gb * sigmoidf(a.theta_lik[2]));
+    }
+  }
+}
+
 // TC = true (WP == 32 only): the forward and dX products of the hidden layers run on the tensor cores
 // (tcgen05.mma kind::tf32, 3xTF32 error-compensated, operands/accumulators in tensor memory; clb_tc.cuh);
 // TC = false: everything on the FP32 FMA pipe.
@@ -550,72 +626,8 @@ __global__ void __launch_bounds__(TC ? tc::kThreads : kObsThreads, TC ? 2 : 1) k
       }
     }
     // ---------------- scale sample, gather, likelihood ----------------
-    float sig_s, dsig;
-    if (a.bijector == 0) { dsig = expf(out1); sig_s = dsig + a.eps; }
-    else { sig_s = softplusf(out1) + a.eps; dsig = sigmoidf(out1); }
-    const int img = (a.image != nullptr && inb) ? a.image[row] : 0;
-    const float aimg = (a.theta_img != nullptr && img > 0) ? a.theta_img[img - 1] : 1.0f;
-    const uint32_t oi = inb ? a.oidx[row] : 0u;
-    const float iobs = inb ? a.iobs[row] : 0.f;
-    const float sg = inb ? a.sig[row] : 1.f;
-    if (a.scale_mean_out != nullptr && active) {     // variational.py:67-69: scale_dist.mean() / .stddev()
-      a.scale_mean_out[oi] = aimg * (out0 + a.shift);
-      a.scale_std_out[oi] = fabsf(aimg) * sig_s;
-    }
-    // runs of equal keys inside the warp (same for every MC sample)
-    const WarpRuns refl_runs = warp_runs(active ? refl : -1 - lane, lane);
-    WarpRuns spot_runs = refl_runs, img_runs = refl_runs;
-    if (a.laue) spot_runs = warp_runs(inb ? a.spot[row] : -1, lane);   // padding rows carry spot -1
-    const bool img_live = active && img > 0;
-    if (a.g_img != nullptr) img_runs = warp_runs(img_live ? img : -1 - lane, lane);
-    float dmu = 0.f, drho = 0.f, d_aimg = 0.f;
-    float ev_gf = 0.f, ev_ga = 0.f, ev_gb = 0.f;
-    for (int s = 0; s < a.S; ++s) {
-      float e = 0.f;
-      if (active) e = a.inj_eps ? a.inj_eps[(size_t)s * a.n_rows_total + oi] : obs_normal(a.seed, a.step, (uint32_t)s, oi);
-      const float base = fmaf(sig_s, e, out0) + a.shift;
-      const float zs = aimg * base;
-      const float zf = active ? __ldg(&a.z[(size_t)s * a.R + refl]) : 0.f;
-      const float ip = zs * zf * zf;
-      if (a.ipred_out != nullptr && active) a.ipred_out[(size_t)s * a.n_rows_total + oi] = ip;
-      float x = ip;
-      bool eval = active;
-      if (a.laue) {           // harmonic segment-sum within the warp (spots never straddle a warp)
-        x = warp_segtotal(active ? ip : 0.f, spot_runs, lane);
-        eval = active && spot_runs.tail;   // count each spot once
-      }
-      float ll = 0.f, g = 0.f;
-      if (a.theta_lik == nullptr) {
-        if (active) lik_eval<LIK>(x, iobs, sg, a.lik, ll, g);
-      } else if (active) {
-        float gf, ga, gb;
-        ev11_eval<LIK>(x, iobs, sg, ev_f, ev_a, ev_b, a.lik, ll, g, gf, ga, gb);
-        if (eval) { ev_gf += gf; ev_ga += ga; ev_gb += gb; }
-      }
-      if (eval) ll_sum += (double)ll;
-      const float G = active ? a.cl * g : 0.f;
-      const float d_zs = G * zf * zf;
-      const float d_zf = G * zs * 2.0f * zf;
-      // segmented reduction of dL/dz_f over runs of equal refl_id, one atomic per run
-      const float tot = warp_segsum(d_zf, refl_runs, lane);
-      if (active && refl_runs.tail) atomicAdd(&a.gz[(size_t)s * a.R + refl], tot);
-      const float d_base = aimg * d_zs;
-      d_aimg += base * d_zs;
-      dmu += d_base;
-      drho += d_base * e * dsig;
-    }
-    if (a.g_img != nullptr) {
-      const float tot = warp_segsum(d_aimg, img_runs, lane);
-      if (img_live && img_runs.tail) atomicAdd(&a.g_img[img - 1], tot);
-    }
-    if (a.g_lik != nullptr) {      // d loss / d raw error-model parameters: one atomic per warp and parameter
-      ev_gf = warp_sum(ev_gf); ev_ga = warp_sum(ev_ga); ev_gb = warp_sum(ev_gb);
-      if (lane == 0) {
-        atomicAdd(&a.g_lik[0], a.cl * ev_gf * sigmoidf(a.theta_lik[0]));
-        atomicAdd(&a.g_lik[1], a.cl * ev_ga * sigmoidf(a.theta_lik[1]));
-        atomicAdd(&a.g_lik[2], a.cl * ev_gb * sigmoidf(a.theta_lik[2]));
-      }
-    }
+    float dmu, drho;
+    obs_epilogue<LIK>(a, row, inb, active, refl, lane, out0, out1, ev_f, ev_a, ev_b, ll_sum, dmu, drho);
     CLB_PH(4);
     if (!a.train_mlp) continue;
     // ---------------- backward through the MLP ----------------
@@ -716,6 +728,282 @@ __global__ void __launch_bounds__(TC ? tc::kThreads : kObsThreads, TC ? 2 : 1) k
   if constexpr (TC) {
     if (tid < 32) tc::tmem_dealloc(*tc_slot);
   }
+}
+
+
+// ---------------------------------------------------------------------------------------
+// k_obs_tc2: the tensor-core observation kernel with TWO THREADS PER ROW (padded width 32).
+// Same math, same shared / tensor-memory images and the same global layouts (scratch, FP64 partials) as
+// k_obs<32, LIK, true>; the 128 rows of a tile are shared by 256 threads: thread (row = tid % 128, hf = tid / 128)
+// carries features [16 hf, 16 hf + 16) of its row through the chain, so every per-row phase (operand split, tensor-
+// memory and shared-memory image stores, bias / LeakyReLU, scratch traffic) is half as long per thread and an SM runs
+// 16 warps (two CTAs) instead of 8.  The head and the likelihood epilogue run in the hf = 0 threads.
+// ---------------------------------------------------------------------------------------
+struct ObsSmem2 {
+  static size_t bytes(int n_layers, int n_img_layers) {
+    return 2 * (size_t)tc::kDwImgBytes + sizeof(float) * (64 + 2 * (size_t)n_layers * 32 + (size_t)n_img_layers * (1024 + 32) + 8 * 16)
+           + 64 * sizeof(double) + 2 * (size_t)tc::kImgBytes + 64 + 4 * 128 * sizeof(float) + 128;
+  }
+};
+
+// One layer's backward on the tensor cores, two threads per row (see tc_layer_backward).
+__device__ __forceinline__ void tc_layer_backward2(tc::Ctx& tcx, float (&dp)[16], const float (&ain)[16], const float (&w)[4],
+                                                   bool need_dx, float* bias_part, float* dbacc_k, double* part, int tid,
+                                                   float* il_gk = nullptr, float* il_gb = nullptr, int il_w = 0) {
+  const bool to_image = il_w > 0;
+  double2 pr0 = make_double2(0.0, 0.0), pr1 = pr0;
+#ifndef CLB_ABL_PART
+  if (!to_image) {
+    pr0 = __ldcg(reinterpret_cast<const double2*>(part));
+    pr1 = __ldcg(reinterpret_cast<const double2*>(part) + 1);
+  }
+#endif
+  CLB_PH(5);
+  bias_partial<16>(dp, bias_part, tid);          // bias_part[warp][16]: warps 0-3 columns 0-15, warps 4-7 columns 16-31
+  CLB_PH(6);
+  tc::issue_backward2(tcx, dp, ain, w, need_dx);
+  CLB_PH(7);
+  if (need_dx) tc::collect2(tcx, dp);
+  CLB_PH(8);
+  tc::collect_dw2(tcx);
+  CLB_PH(9);
+  __syncthreads();
+  CLB_PH(10);
+  {
+    // float4 output o4 = tid = r*64 + pj*8 + pi holds dW[i = pi + 8 r][j = 4 pj .. 4 pj + 3]
+    const int r = tid >> 6, pj = (tid & 63) >> 3, pi = tid & 7;
+    const float* st = reinterpret_cast<const float*>(tcx.dw_a) + (size_t)(pi + 8 * r) * tc::kStageStride + 4 * pj;
+    const float4 t0 = *reinterpret_cast<const float4*>(st);
+    const float4 t1 = *reinterpret_cast<const float4*>(st + (size_t)32 * tc::kStageStride);
+    if (!to_image) {
+#ifdef CLB_ABL_PART
+      if (t0.x + t1.x == 1.2345e30f) __stcg(reinterpret_cast<double2*>(part), make_double2(pr0.x + (double)(t0.y + t1.y), pr1.y + (double)(t0.z + t1.w)));
+#else
+      __stcg(reinterpret_cast<double2*>(part), make_double2(pr0.x + (double)(t0.x + t1.x), pr0.y + (double)(t0.y + t1.y)));
+      __stcg(reinterpret_cast<double2*>(part) + 1, make_double2(pr1.x + (double)(t0.z + t1.z), pr1.y + (double)(t0.w + t1.w)));
+#endif
+    } else if (il_gk != nullptr) {
+      const int i = pi + 8 * r;
+      const float tv[4] = {t0.x + t1.x, t0.y + t1.y, t0.z + t1.z, t0.w + t1.w};
+      if (i < il_w) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { const int j = 4 * pj + c; if (j < il_w) atomicAdd(&il_gk[j * il_w + i], tv[c]); }
+      }
+    }
+    if (tid < 32) {
+      const int hfc = tid >> 4, cc = tid & 15;
+      float sum = 0.f;
+#pragma unroll
+      for (int w2 = 0; w2 < 4; ++w2) sum += bias_part[(4 * hfc + w2) * 16 + cc];
+      if (!to_image) dbacc_k[tid] += sum;
+      else if (il_gb != nullptr && tid < il_w) atomicAdd(&il_gb[tid], sum);
+    }
+  }
+  CLB_PH(11);
+  __syncthreads();      // the stage aliases the operand image of the next layer
+  CLB_PH(12);
+}
+
+template <int LIK>
+__global__ void __launch_bounds__(tc::kThreads2, 2) k_obs_tc2(ObsArgs a) {
+  constexpr int WP = 32, TR = tc::kThreads, T = tc::kThreads2, NC = WP / 4, HW = 16;   // TR rows per tile, T threads
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  const int NL = a.lay.n_layers, L = NL - 1, K = a.n_img_layers, LT = L + K;
+  unsigned char* sp = smem_raw;
+  char* tc_dwa = reinterpret_cast<char*>(sp);
+  char* tc_dwb = tc_dwa + tc::kDwImgBytes;
+  sp += 2 * tc::kDwImgBytes;
+  float* Whead = reinterpret_cast<float*>(sp);              // [32][2]
+  float* bsm = Whead + 64;                                  // [NL][32]
+  float* dbacc = bsm + (size_t)NL * WP;                     // [NL][32]
+  float* Wimg = dbacc + (size_t)NL * WP;                    // [K][32][32] this tile's image-layer kernels as [in][out]
+  float* bimg = Wimg + (size_t)K * WP * WP;                 // [K][32]
+  float* bias_part = bimg + (size_t)K * WP;                 // [8 warps][16]
+  double* red = reinterpret_cast<double*>(bias_part + 8 * 16);
+  char* tc_img = reinterpret_cast<char*>(red + 64);
+  uint64_t* tc_bar = reinterpret_cast<uint64_t*>(tc_img + 2 * tc::kImgBytes);
+  uint32_t* tc_slot = reinterpret_cast<uint32_t*>(tc_bar + 2);
+  float2* xch = reinterpret_cast<float2*>(tc_slot + 4);     // [2][128]: head partial sums of hf = 1, then (dmu, drho)
+
+  const int tid = threadIdx.x, lane = tid & 31, rrow = tid & (TR - 1), hf = tid >> 7;
+  tc::Ctx tcx{};
+  if (tid == 0) { tc::mbar_init(tc::smem_u32(tc_bar), 1); tc::mbar_init(tc::smem_u32(tc_bar + 1), 1); }
+  if (tid < 32) tc::tmem_alloc(tc::smem_u32(tc_slot));
+  tc::fence_before();
+  for (int idx = tid; idx < WP * 2; idx += T) {
+    const int i = idx / 2, j = idx % 2;
+    Whead[idx] = (i < a.lay.in_dim[L] && j < a.lay.out_dim[L]) ? a.theta_mlp[a.lay.koff[L] + i * a.lay.out_dim[L] + j] : 0.f;
+  }
+  for (int idx = tid; idx < NL * WP; idx += T) {
+    const int k = idx / WP, j = idx % WP;
+    bsm[idx] = (j < a.lay.out_dim[k]) ? a.theta_mlp[a.lay.boff[k] + j] : 0.f;
+    dbacc[idx] = 0.f;
+  }
+  __syncthreads();
+  {
+    tc::fence_after();
+    const uint32_t tbase = *tc_slot;
+    const int warp = tid >> 5;
+    tcx.row_addr = tbase + ((uint32_t)(32 * (warp & 3)) << 16);
+    tcx.mbar = tc::smem_u32(tc_bar); tcx.parity = 0;
+    tcx.img_hi = tc_img; tcx.img_lo = tc_img + tc::kImgBytes;
+    tcx.desc_hi = tc::make_desc(tc::smem_u32(tcx.img_hi)); tcx.desc_lo = tc::make_desc(tc::smem_u32(tcx.img_lo));
+    tcx.tid = tid; tcx.base = tbase;
+    tcx.mbar_dw = tc::smem_u32(tc_bar + 1); tcx.parity_dw = 0;
+    tcx.dw_a = tc_dwa; tcx.dw_b = tc_dwb;
+    tcx.desc_dwa = tc::make_desc_mn(tc::smem_u32(tc_dwa)); tcx.desc_dwb = tc::make_desc_mn(tc::smem_u32(tc_dwb));
+    tcx.row = rrow; tcx.hf = hf; tcx.col = (uint32_t)(HW * hf);
+  }
+  const int PP = partial_row_size(NL, WP);
+  double* part_rows = a.partials + (size_t)blockIdx.x * PP + (size_t)tid * 4;    // every thread owns 4 consecutive doubles per layer
+  float4* scr = a.scratch + (size_t)blockIdx.x * LT * NC * TR;
+  double ll_sum = 0.0;
+  float ev_f = 1.f, ev_a = 0.f, ev_b = 0.f;
+  if (a.theta_lik != nullptr) { ev_f = softplusf(a.theta_lik[0]); ev_a = softplusf(a.theta_lik[1]); ev_b = softplusf(a.theta_lik[2]); }
+  const int64_t n_tiles = (a.n_rows + TR - 1) / TR;
+  auto wsrc = [&](int k) -> const float* { return (k >= L) ? Wimg + (size_t)(k - L) * WP * WP : a.wpack + (size_t)k * 1024; };
+
+  CLB_PH_START();
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t row = tile * TR + rrow;
+    const bool inb = row < a.n_rows;
+    const int refl = inb ? a.refl[row] : -1;
+    const bool active = refl >= 0;
+    const int timg = (K > 0) ? a.image[tile * TR] : 0;
+    if (K > 0) {
+      __syncthreads();
+      const int w = a.il_width;
+      const size_t lstride = (size_t)a.il_n_images * w * (w + 1);
+      for (int idx = tid; idx < K * WP * WP; idx += T) {
+        const int l = idx / (WP * WP), i = (idx / WP) % WP, j = idx % WP;
+        Wimg[idx] = (i < w && j < w) ? a.theta_il[l * lstride + ((size_t)timg * w + j) * w + i] : 0.f;
+      }
+      for (int idx = tid; idx < K * WP; idx += T) {
+        const int l = idx / WP, j = idx % WP;
+        bimg[idx] = (j < w) ? a.theta_il[l * lstride + (size_t)a.il_n_images * w * w + (size_t)timg * w + j] : 0.f;
+      }
+      __syncthreads();
+    }
+    // ---------------- forward: my 16 features ----------------
+    float h[HW];
+#pragma unroll
+    for (int i = 0; i < HW; ++i) { const int f = HW * hf + i; h[i] = (inb && f < a.d) ? a.meta[(size_t)f * a.n_rows + row] : 0.f; }
+    float wreg[4];
+    if (LT > 0) tc::load_w2<false>(wsrc(0), tid, wreg);
+    for (int k = 0; k < LT; ++k) {
+      const float* bk = ((k >= L) ? bimg + (size_t)(k - L) * WP : bsm + (size_t)k * WP) + HW * hf;
+      float o[HW];
+      CLB_PH(0);
+      tc::issue2<false>(tcx, h, wreg);
+      CLB_PH(1);
+      if (k + 1 < LT) tc::load_w2<false>(wsrc(k + 1), tid, wreg);
+      else if (a.train_mlp && LT > 1) tc::load_w2<true>(wsrc(LT - 1), tid, wreg);
+      tc::collect2(tcx, o);
+      CLB_PH(2);
+#pragma unroll
+      for (int j = 0; j < HW; ++j) { const float v = o[j] + bk[j]; h[j] = fmaxf(v, kLeak * v); }
+#ifndef CLB_ABL_SCR
+      if (a.train_mlp) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) scr[((size_t)k * NC + 4 * hf + c) * TR + rrow] = make_float4(h[4 * c], h[4 * c + 1], h[4 * c + 2], h[4 * c + 3]);
+      }
+#endif
+    }
+    CLB_PH(3);
+    // ---------------- head: partial dot products of both halves, epilogue in the hf = 0 threads ----------------
+    float out0 = 0.f, out1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < HW; ++i) {
+      const float2 w = *reinterpret_cast<const float2*>(&Whead[(HW * hf + i) * 2]);
+      out0 = fmaf(h[i], w.x, out0); out1 = fmaf(h[i], w.y, out1);
+    }
+    if (hf == 1) xch[rrow] = make_float2(out0, out1);
+    __syncthreads();
+    float dmu = 0.f, drho = 0.f;
+    if (hf == 0) {
+      const float2 o1 = xch[rrow];
+      out0 += o1.x + bsm[L * WP]; out1 += o1.y + bsm[L * WP + 1];
+      obs_epilogue<LIK>(a, row, inb, active, refl, lane, out0, out1, ev_f, ev_a, ev_b, ll_sum, dmu, drho);
+      xch[TR + rrow] = make_float2(dmu, drho);
+    }
+    CLB_PH(4);
+    if (!a.train_mlp) { __syncthreads(); continue; }
+    __syncthreads();
+    { const float2 g = xch[TR + rrow]; dmu = g.x; drho = g.y; }
+    // ---------------- backward ----------------
+    float dp[HW], nxt[HW];
+    auto load_act = [&](float (&dst)[HW], int k) {           // my half of a_k, the input of chain layer k
+      if (k > 0) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+#ifdef CLB_ABL_SCR
+          const float4 v = make_float4(dmu + c, drho, dmu - c, drho + k);
+#else
+          const float4 v = __ldcg(&scr[((size_t)(k - 1) * NC + 4 * hf + c) * TR + rrow]);
+#endif
+          dst[4 * c] = v.x; dst[4 * c + 1] = v.y; dst[4 * c + 2] = v.z; dst[4 * c + 3] = v.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < HW; ++i) { const int f = HW * hf + i; dst[i] = (inb && f < a.d) ? a.meta[(size_t)f * a.n_rows + row] : 0.f; }
+      }
+    };
+    if (LT > 0) load_act(nxt, LT - 1);
+#pragma unroll
+    for (int j = 0; j < HW; ++j) dp[j] = 0.f;
+    if (hf == 0) { dp[0] = dmu; dp[1] = drho; }
+    // head: dW_out = a_L^T [dmu, drho]
+    tc_layer_backward2(tcx, dp, h, wreg, false, bias_part, dbacc + L * WP, part_rows + (size_t)L * WP * WP, tid);
+    unsigned mask = 0u;
+#pragma unroll
+    for (int j = 0; j < HW; ++j) mask |= (h[j] > 0.f ? 1u : 0u) << j;
+#pragma unroll
+    for (int i = 0; i < HW; ++i) {
+      const float2 w = *reinterpret_cast<const float2*>(&Whead[(HW * hf + i) * 2]);
+      dp[i] = w.x * dmu + w.y * drho;
+    }
+    for (int k = LT - 1; k >= 0; --k) {
+      const bool is_il = k >= L;
+      float* il_gk = nullptr; float* il_gb = nullptr;
+      if (is_il && a.g_il != nullptr) {
+        const int w = a.il_width;
+        const size_t lstride = (size_t)a.il_n_images * w * (w + 1);
+        il_gk = a.g_il + (size_t)(k - L) * lstride + (size_t)timg * w * w;
+        il_gb = a.g_il + (size_t)(k - L) * lstride + (size_t)a.il_n_images * w * w + (size_t)timg * w;
+      }
+      const int il_w = is_il ? a.il_width : 0;
+      float* dbk = dbacc + (size_t)(is_il ? L : k) * WP;
+      double* partk = part_rows + (size_t)(is_il ? L : k) * WP * WP;
+#pragma unroll
+      for (int j = 0; j < HW; ++j) dp[j] = ((mask >> j) & 1u) ? dp[j] : kLeak * dp[j];
+      float ain[HW];
+      mask = 0u;
+#pragma unroll
+      for (int i = 0; i < HW; ++i) { ain[i] = nxt[i]; mask |= (ain[i] > 0.f ? 1u : 0u) << i; }
+      if (k > 0) load_act(nxt, k - 1);
+      float wcur[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) wcur[q] = wreg[q];
+      if (k > 1) tc::load_w2<true>(wsrc(k - 1), tid, wreg);
+      tc_layer_backward2(tcx, dp, ain, wcur, k > 0, bias_part, dbk, partk, tid, il_gk, il_gb, il_w);
+    }
+  }
+  // ---- flush: bias gradients and the log-likelihood sum ----
+  __syncthreads();
+  if (a.train_mlp) {
+    for (int idx = tid; idx < NL * WP; idx += T)
+      a.partials[(size_t)blockIdx.x * PP + (size_t)NL * WP * WP + idx] += (double)dbacc[idx];
+  }
+  ll_sum = warp_sum(ll_sum);
+  if (lane == 0) red[tid >> 5] = ll_sum;
+  tc::fence_before();
+  __syncthreads();
+  if (tid == 0) {
+    double t = 0.0;
+    for (int i = 0; i < T / 32; ++i) t += red[i];
+    atomicAdd(&a.acc[ACC_LL], t);
+  }
+  if (tid < 32) tc::tmem_dealloc(*tc_slot);
 }
 
 // Ev11 on the empty Laue slots: each contributes logpdf(0; I_k, sigma'(0; sigma_k)) per MC sample, and because sigma'

@@ -131,6 +131,8 @@ struct Ctx {
   char* dw_a; char* dw_b;              // MN-major operand images (kDwImgBytes each); dw_a doubles as the reduction stage
   uint64_t desc_dwa, desc_dwb;
   uint32_t base;                       // tensor-memory base address
+  // two-threads-per-row kernels (k_obs_tc2): this thread's tile row, feature half and its column offset (16 hf)
+  int row, hf; uint32_t col;
 };
 
 __device__ __forceinline__ void split32(const float (&x)[32], uint32_t (&hi)[32], uint32_t (&lo)[32]) {
@@ -209,6 +211,7 @@ __device__ __forceinline__ void issue_chain_mmas(Ctx& c) {
     const uint32_t d = base + kColD;
     const uint32_t bar = uniform32(c.mbar);
     if (elect_one()) {
+#ifndef CLB_ABL_CHAIN
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks)
         mma_tf32_ts(d, base + kColAhi + 8u * (uint32_t)ks, blo + (uint64_t)((2u * kLBO * (uint32_t)ks) >> 4), ks > 0 ? 1u : 0u);
@@ -218,6 +221,7 @@ __device__ __forceinline__ void issue_chain_mmas(Ctx& c) {
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks)
         mma_tf32_ts(d, base + kColAhi + 8u * (uint32_t)ks, bhi + (uint64_t)((2u * kLBO * (uint32_t)ks) >> 4), 1u);
+#endif
       commit(bar);
     }
     __syncwarp();
@@ -314,6 +318,163 @@ __device__ __forceinline__ void collect(Ctx& c, float (&y)[32]) {
   wait_ld();
 #pragma unroll
   for (int k = 0; k < 32; ++k) y[k] = __uint_as_float(v[k]);
+}
+
+
+// ---------------------------------------------------------------------------------------
+// Two threads per observation row (k_obs_tc2): 256-thread CTAs, thread (row = tid % 128, hf = tid / 128) owns
+// features [16 hf, 16 hf + 16) of its row.  Warps w and w + 4 share the tensor-memory lanes 32 (w % 4) .. + 31 and use
+// different columns.  Twice the warps per SM for the same shared / tensor memory, half the serial work per thread.
+// ---------------------------------------------------------------------------------------
+constexpr int kThreads2 = 256;
+#define CLB_TMEM_ST16(taddr, v) asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" \
+  :: "r"(taddr), "r"(v[0]),"r"(v[1]),"r"(v[2]),"r"(v[3]),"r"(v[4]),"r"(v[5]),"r"(v[6]),"r"(v[7]),"r"(v[8]),"r"(v[9]),"r"(v[10]),"r"(v[11]),"r"(v[12]),"r"(v[13]),"r"(v[14]),"r"(v[15]) : "memory")
+#define CLB_TMEM_LD16(taddr, v) asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];" \
+  : "=r"(v[0]),"=r"(v[1]),"=r"(v[2]),"=r"(v[3]),"=r"(v[4]),"=r"(v[5]),"=r"(v[6]),"=r"(v[7]),"=r"(v[8]),"=r"(v[9]),"=r"(v[10]),"=r"(v[11]),"=r"(v[12]),"=r"(v[13]),"=r"(v[14]),"=r"(v[15]) \
+  : "r"(taddr) : "memory")
+
+__device__ __forceinline__ void split16(const float (&x)[16], uint32_t (&hi)[16], uint32_t (&lo)[16]) {
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const float h = tf32_rna(x[k]);
+    hi[k] = __float_as_uint(h);
+    lo[k] = __float_as_uint(x[k] - h);
+  }
+}
+
+// This thread's 16 features (32-byte chunks 2 hf and 2 hf + 1) of row k of an MN-major operand image.
+__device__ __forceinline__ void dw_store_half(char* img, int k, int hf, const uint32_t (&hi)[16], const uint32_t (&lo)[16]) {
+#ifdef CLB_ABL_STS
+  if (hi[0] == 0x7fc01234u && lo[3] == 0x7fc04321u) *reinterpret_cast<uint32_t*>(img) = hi[1] ^ lo[2] ^ hi[15] ^ lo[15] ^ hi[8] ^ lo[8];
+  return;
+#endif
+  const int r = k & 3;
+  char* row = img + (size_t)(k >> 2) * kDwSBO + r * 128;
+#pragma unroll
+  for (int cc = 0; cc < 2; ++cc) {
+    char* p = row + (((2 * hf + cc) ^ r) * 32);
+    *reinterpret_cast<uint4*>(p) = make_uint4(hi[8 * cc], hi[8 * cc + 1], hi[8 * cc + 2], hi[8 * cc + 3]);
+    *reinterpret_cast<uint4*>(p + 16) = make_uint4(hi[8 * cc + 4], hi[8 * cc + 5], hi[8 * cc + 6], hi[8 * cc + 7]);
+    *reinterpret_cast<uint4*>(p + kDwLBO) = make_uint4(lo[8 * cc], lo[8 * cc + 1], lo[8 * cc + 2], lo[8 * cc + 3]);
+    *reinterpret_cast<uint4*>(p + kDwLBO + 16) = make_uint4(lo[8 * cc + 4], lo[8 * cc + 5], lo[8 * cc + 6], lo[8 * cc + 7]);
+  }
+}
+
+// The 4 weights this thread contributes to the B operand image of one layer (256 threads x 4 = 32 x 32):
+//   forward  (B[n][k] = W[k][n]): thread (n = tid % 32, kq = tid / 32) gathers k = 4 kq .. 4 kq + 3;
+//   backward (B[n][k] = W[n][k]): thread (kq = tid % 8, n = tid / 8) copies k = 4 kq .. 4 kq + 3.
+template <bool BWD>
+__device__ __forceinline__ void load_w2(const float* Wg, int tid, float (&w)[4]) {
+  if (!BWD) {
+    const int n = tid & 31, kq = tid >> 5;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) w[i] = Wg[(4 * kq + i) * 32 + n];
+  } else {
+    const int kq = tid & 7, n = tid >> 3;
+    const float4 v = *reinterpret_cast<const float4*>(Wg + n * 32 + 4 * kq);
+    w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+  }
+}
+
+template <bool BWD>
+__device__ __forceinline__ void build_weight_image2(Ctx& c, const float (&w)[4]) {
+  int n, kq;
+  if (!BWD) { n = c.tid & 31; kq = c.tid >> 5; }
+  else { kq = c.tid & 7; n = c.tid >> 3; }
+  const uint32_t off = kq * kLBO + (n >> 3) * kSBO + (n & 7) * 16;
+  float4 hi, lo;
+  hi.x = tf32_rna(w[0]); hi.y = tf32_rna(w[1]); hi.z = tf32_rna(w[2]); hi.w = tf32_rna(w[3]);
+  lo.x = w[0] - hi.x; lo.y = w[1] - hi.y; lo.z = w[2] - hi.z; lo.w = w[3] - hi.w;
+  *reinterpret_cast<float4*>(c.img_hi + off) = hi;
+  *reinterpret_cast<float4*>(c.img_lo + off) = lo;
+}
+
+template <bool BWD>
+__device__ __forceinline__ void issue2(Ctx& c, const float (&x)[16], const float (&w)[4]) {
+  {
+    uint32_t hi[16], lo[16];
+    split16(x, hi, lo);
+    CLB_TMEM_ST16(c.row_addr + kColAhi + c.col, hi);
+    CLB_TMEM_ST16(c.row_addr + kColAlo + c.col, lo);
+  }
+  build_weight_image2<BWD>(c, w);
+  wait_st();
+  fence_async_smem();
+  fence_before();
+  __syncthreads();
+  issue_chain_mmas(c);
+}
+
+__device__ __forceinline__ void collect2(Ctx& c, float (&y)[16]) {
+  mbar_wait(c.mbar, c.parity);
+  c.parity ^= 1u;
+  fence_after();
+  uint32_t v[16];
+  CLB_TMEM_LD16(c.row_addr + kColD + c.col, v);
+  wait_ld();
+#pragma unroll
+  for (int k = 0; k < 16; ++k) y[k] = __uint_as_float(v[k]);
+}
+
+// Backward of one layer (see issue_backward): the dW issuer is warp 7, the chain issuer warp 0.
+__device__ __forceinline__ void issue_backward2(Ctx& c, const float (&dp)[16], const float (&ain)[16], const float (&w)[4], bool need_dx) {
+  {
+    uint32_t hi[16], lo[16];
+    split16(dp, hi, lo);
+    if (need_dx) {
+      CLB_TMEM_ST16(c.row_addr + kColAhi + c.col, hi);
+      CLB_TMEM_ST16(c.row_addr + kColAlo + c.col, lo);
+    }
+    dw_store_half(c.dw_b, c.row, c.hf, hi, lo);
+    split16(ain, hi, lo);
+    dw_store_half(c.dw_a, c.row, c.hf, hi, lo);
+  }
+  if (need_dx) build_weight_image2<true>(c, w);
+  wait_st();
+  fence_async_smem();
+  fence_before();
+  __syncthreads();
+  if (need_dx) issue_chain_mmas(c);
+  const uint32_t warp = uniform32((uint32_t)c.tid >> 5);
+  if (warp == 7u) {
+    fence_after();
+    const uint32_t d = uniform32(c.base) + kColDw;
+    const uint64_t a0 = uniform64(c.desc_dwa), b0 = uniform64(c.desc_dwb);
+    const uint32_t bar = uniform32(c.mbar_dw);
+    if (elect_one()) {
+#ifndef CLB_ABL_DW
+#pragma unroll
+      for (int ks = 0; ks < kThreads / 8; ++ks)
+        mma_tf32_ss(d, a0 + (uint64_t)((2u * kDwSBO * (uint32_t)ks) >> 4), b0 + (uint64_t)((2u * kDwSBO * (uint32_t)ks) >> 4), kIdescDw, ks > 0 ? 1u : 0u);
+#endif
+      commit(bar);
+    }
+    __syncwarp();
+  }
+}
+
+// dW rows live at lanes (r % 16) + 32 (r / 16): in every warp the lanes < 16 hold row r = 16 (warp % 4) + lane; the
+// thread folds the delta-hi and delta-lo column blocks of ITS 16 columns and parks them in the stage (aliases dw_a).
+__device__ __forceinline__ void collect_dw2(Ctx& c) {
+  mbar_wait(c.mbar_dw, c.parity_dw);
+  c.parity_dw ^= 1u;
+  fence_after();
+  const int q = (c.tid >> 5) & 3, lane = c.tid & 31;
+  const uint32_t addr = c.row_addr + kColDw + c.col;
+  uint32_t v0[16], v1[16];
+  CLB_TMEM_LD16(addr, v0);
+  CLB_TMEM_LD16(addr + 32, v1);
+  wait_ld();
+  if (lane < 16) {
+    const int r = 16 * q + lane;
+    float* dst = reinterpret_cast<float*>(c.dw_a) + ((size_t)(r >> 5) * 32 + (r & 31)) * kStageStride + 16 * c.hf;
+#pragma unroll
+    for (int qq = 0; qq < 4; ++qq)
+      *reinterpret_cast<float4*>(dst + 4 * qq) = make_float4(__uint_as_float(v0[4 * qq]) + __uint_as_float(v1[4 * qq]),
+                                                             __uint_as_float(v0[4 * qq + 1]) + __uint_as_float(v1[4 * qq + 1]),
+                                                             __uint_as_float(v0[4 * qq + 2]) + __uint_as_float(v1[4 * qq + 2]),
+                                                             __uint_as_float(v0[4 * qq + 3]) + __uint_as_float(v1[4 * qq + 3]));
+  }
 }
 
 }  // namespace tc
