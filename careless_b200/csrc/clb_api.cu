@@ -90,7 +90,7 @@ struct clb_handle {
   size_t rows_bytes = 0;
   int32_t *d_refl = nullptr, *d_image = nullptr, *d_spot = nullptr; uint32_t* d_oidx = nullptr;
   float *d_meta = nullptr, *d_iobs = nullptr, *d_sig = nullptr;
-  DevBuf partials, scratch, wpack;
+  DevBuf partials, scratch, wpack, wimg;
   int obs_threads = kObsThreads;   // rows per CTA tile: 256 (FP32 kernels) or 128 (tensor-core kernels, 2 CTAs per SM)
   DevBuf acc, var_sums, red, metrics, var_scale, adam_alpha, stop_step;
   DevBuf inj_u, inj_eps, ipred, scale_mom, results;
@@ -517,6 +517,11 @@ int clb_set_observations(clb_handle* h, int64_t n, int64_t n_total, const int64_
   CLB_CUDA(h, h->partials.alloc(sizeof(double) * (size_t)h->grid_obs * h->KS * partial_row_size(h->NL, h->WP)));
   CLB_CUDA(h, h->scratch.alloc(sizeof(float4) * (size_t)h->grid_obs * std::max(1, c.mlp_layers + c.image_layers) * (h->WP / 4) * h->obs_threads));
   if (h->use_tc) CLB_CUDA(h, h->wpack.alloc(sizeof(float) * (size_t)std::max(1, c.mlp_layers) * 1024));
+  if (h->use_tc2) {     // [L][fwd, bwd][hi, lo][kImgBytes]; the padding bytes of the images stay zero
+    const size_t nb = (size_t)std::max(1, c.mlp_layers) * 4 * tc::kImgBytes;
+    CLB_CUDA(h, h->wimg.alloc(nb));
+    CLB_CUDA(h, cudaMemsetAsync(h->wimg.p, 0, nb, h->stream));
+  }
   h->have_obs = true;
   return clb_upload_observations(h);
 }
@@ -767,12 +772,14 @@ static int step_begin_impl(clb_handle* h, const float* inj_u, const float* inj_e
     a.theta_mlp = theta + h->goff[CLB_GROUP_MLP];
     a.theta_img = c.image_scales ? theta + h->goff[CLB_GROUP_IMAGE_SCALES] : nullptr;
     a.wpack = h->use_tc ? h->wpack.as<float>() : nullptr;
+    a.wimg = h->use_tc2 ? h->wimg.as<float>() : nullptr;
     a.n_img_layers = c.image_layers; a.il_width = c.mlp_width; a.il_n_images = c.n_images;
     a.theta_il = c.image_layers > 0 ? theta + h->goff[CLB_GROUP_IMAGE_LAYERS] : nullptr;
     a.g_il = (c.image_layers > 0 && h->gtrain[CLB_GROUP_IMAGE_LAYERS] && !h->eval_mode) ? grad + h->goff[CLB_GROUP_IMAGE_LAYERS] : nullptr;
     if (h->use_tc) {
       if (c.mlp_layers > 0) {
-        k_pack_weights<<<(c.mlp_layers * 1024 + 255) / 256, 256, 0, st>>>(a.theta_mlp, h->lay, h->wpack.as<float>());
+        if (h->use_tc2) k_pack_images<<<(c.mlp_layers * 2048 + 255) / 256, 256, 0, st>>>(a.theta_mlp, h->lay, h->wimg.as<float>());
+        else k_pack_weights<<<(c.mlp_layers * 1024 + 255) / 256, 256, 0, st>>>(a.theta_mlp, h->lay, h->wpack.as<float>());
         CLB_LAUNCHED(h);
       }
     }

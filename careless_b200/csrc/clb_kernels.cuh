@@ -150,6 +150,7 @@ struct ObsArgs {
   // model
   const float* theta_mlp; const float* theta_img;   // image scales (n_img-1) or null
   const float* wpack;              // [L][32][32] zero-padded FP32 copy of the hidden-layer kernels (TC kernels)
+  const float* wimg;               // [L][fwd, bwd][hi, lo][kImgBytes] ready-made B operand images (k_obs_tc2, fetched by TMA)
   // image layers (scaling/image.py:66-125): per layer a kernel [n_img][W][W] (out, in) and a bias [n_img][W]
   int n_img_layers; int il_width; int il_n_images;
   const float* theta_il; float* g_il;   // parameter group and its gradient (null: frozen / eval)
@@ -742,13 +743,14 @@ __global__ void __launch_bounds__(TC ? tc::kThreads : kObsThreads, TC ? 2 : 1) k
 struct ObsSmem2 {
   static size_t bytes(int n_layers, int n_img_layers) {
     return 2 * (size_t)tc::kDwImgBytes + sizeof(float) * (64 + 2 * (size_t)n_layers * 32 + (size_t)n_img_layers * (1024 + 32) + 8 * 16)
-           + 64 * sizeof(double) + 2 * (size_t)tc::kImgBytes + 64 + 4 * 128 * sizeof(float) + 128;
+           + 64 * sizeof(double) + 4 * (size_t)tc::kImgBytes + 64 + 4 * 128 * sizeof(float) + 128;
   }
 };
 
 // One layer's backward on the tensor cores, two threads per row (see tc_layer_backward).
-__device__ __forceinline__ void tc_layer_backward2(tc::Ctx& tcx, float (&dp)[16], const float (&ain)[16], const float (&w)[4],
-                                                   bool need_dx, float* bias_part, float* dbacc_k, double* part, int tid,
+__device__ __forceinline__ void tc_layer_backward2(tc::Ctx& tcx, float (&dp)[16], const float (&ain)[16], bool need_dx,
+                                                   const float* build_from, char* img_base, const float* next_img,
+                                                   float* bias_part, float* dbacc_k, double* part, int tid,
                                                    float* il_gk = nullptr, float* il_gb = nullptr, int il_w = 0) {
   const bool to_image = il_w > 0;
   double2 pr0 = make_double2(0.0, 0.0), pr1 = pr0;
@@ -761,7 +763,7 @@ __device__ __forceinline__ void tc_layer_backward2(tc::Ctx& tcx, float (&dp)[16]
   CLB_PH(5);
   bias_partial<16>(dp, bias_part, tid);          // bias_part[warp][16]: warps 0-3 columns 0-15, warps 4-7 columns 16-31
   CLB_PH(6);
-  tc::issue_backward2(tcx, dp, ain, w, need_dx);
+  tc::issue_backward3(tcx, dp, ain, need_dx, build_from, img_base, next_img);
   CLB_PH(7);
   if (need_dx) tc::collect2(tcx, dp);
   CLB_PH(8);
@@ -820,14 +822,17 @@ __global__ void __launch_bounds__(tc::kThreads2, 2) k_obs_tc2(ObsArgs a) {
   float* bimg = Wimg + (size_t)K * WP * WP;                 // [K][32]
   float* bias_part = bimg + (size_t)K * WP;                 // [8 warps][16]
   double* red = reinterpret_cast<double*>(bias_part + 8 * 16);
-  char* tc_img = reinterpret_cast<char*>(red + 64);
-  uint64_t* tc_bar = reinterpret_cast<uint64_t*>(tc_img + 2 * tc::kImgBytes);
-  uint32_t* tc_slot = reinterpret_cast<uint32_t*>(tc_bar + 2);
+  char* tc_img = reinterpret_cast<char*>(red + 64);         // [2 buffers][hi, lo][kImgBytes] chain B operand images
+  uint64_t* tc_bar = reinterpret_cast<uint64_t*>(tc_img + 4 * tc::kImgBytes);   // [0] chain, [1] dW, [2..3] image buffers
+  uint32_t* tc_slot = reinterpret_cast<uint32_t*>(tc_bar + 4);
   float2* xch = reinterpret_cast<float2*>(tc_slot + 4);     // [2][128]: head partial sums of hf = 1, then (dmu, drho)
 
   const int tid = threadIdx.x, lane = tid & 31, rrow = tid & (TR - 1), hf = tid >> 7;
   tc::Ctx tcx{};
-  if (tid == 0) { tc::mbar_init(tc::smem_u32(tc_bar), 1); tc::mbar_init(tc::smem_u32(tc_bar + 1), 1); }
+  if (tid == 0) {
+    tc::mbar_init(tc::smem_u32(tc_bar), 1); tc::mbar_init(tc::smem_u32(tc_bar + 1), 1);
+    tc::mbar_init(tc::smem_u32(tc_bar + 2), 1); tc::mbar_init(tc::smem_u32(tc_bar + 3), 1);
+  }
   if (tid < 32) tc::tmem_alloc(tc::smem_u32(tc_slot));
   tc::fence_before();
   for (int idx = tid; idx < WP * 2; idx += T) {
@@ -853,7 +858,18 @@ __global__ void __launch_bounds__(tc::kThreads2, 2) k_obs_tc2(ObsArgs a) {
     tcx.dw_a = tc_dwa; tcx.dw_b = tc_dwb;
     tcx.desc_dwa = tc::make_desc_mn(tc::smem_u32(tc_dwa)); tcx.desc_dwb = tc::make_desc_mn(tc::smem_u32(tc_dwb));
     tcx.row = rrow; tcx.hf = hf; tcx.col = (uint32_t)(HW * hf);
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      tcx.wimg[b] = tc::smem_u32(tc_img + (size_t)b * 2 * tc::kImgBytes);
+      tcx.wdesc_hi[b] = tc::make_desc(tcx.wimg[b]); tcx.wdesc_lo[b] = tc::make_desc(tcx.wimg[b] + tc::kImgBytes);
+      tcx.wbar[b] = tc::smem_u32(tc_bar + 2 + b);
+    }
+    tcx.pass = 0; tcx.wphase = 0;
   }
+  // ready-made images of hidden layer k in global memory: dir 0 = forward (B[n][k] = W[k][n]), 1 = backward; null for
+  // image layers, whose per-tile kernels are turned into images by the threads themselves
+  constexpr size_t IMGF = tc::kImgBytes / 4;
+  auto gimg = [&](int k, int dir) -> const float* { return (k < L) ? a.wimg + ((size_t)(k * 2 + dir) * 2) * IMGF : nullptr; };
   const int PP = partial_row_size(NL, WP);
   double* part_rows = a.partials + (size_t)blockIdx.x * PP + (size_t)tid * 4;    // every thread owns 4 consecutive doubles per layer
   float4* scr = a.scratch + (size_t)blockIdx.x * LT * NC * TR;
@@ -863,8 +879,11 @@ __global__ void __launch_bounds__(tc::kThreads2, 2) k_obs_tc2(ObsArgs a) {
   const int64_t n_tiles = (a.n_rows + TR - 1) / TR;
   auto wsrc = [&](int k) -> const float* { return (k >= L) ? Wimg + (size_t)(k - L) * WP * WP : a.wpack + (size_t)k * 1024; };
 
+  // the first pass's images (forward, layer 0) start travelling now
+  if (tid == 0 && LT > 0 && blockIdx.x < n_tiles && gimg(0, 0) != nullptr) tc::tma_fetch_image(tcx.wimg[0], gimg(0, 0), tcx.wbar[0]);
   CLB_PH_START();
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const bool more_tiles = tile + gridDim.x < n_tiles;
     const int64_t row = tile * TR + rrow;
     const bool inb = row < a.n_rows;
     const int refl = inb ? a.refl[row] : -1;
@@ -888,16 +907,14 @@ __global__ void __launch_bounds__(tc::kThreads2, 2) k_obs_tc2(ObsArgs a) {
     float h[HW];
 #pragma unroll
     for (int i = 0; i < HW; ++i) { const int f = HW * hf + i; h[i] = (inb && f < a.d) ? a.meta[(size_t)f * a.n_rows + row] : 0.f; }
-    float wreg[4];
-    if (LT > 0) tc::load_w2<false>(wsrc(0), tid, wreg);
     for (int k = 0; k < LT; ++k) {
       const float* bk = ((k >= L) ? bimg + (size_t)(k - L) * WP : bsm + (size_t)k * WP) + HW * hf;
       float o[HW];
       CLB_PH(0);
-      tc::issue2<false>(tcx, h, wreg);
+      // the pass after this one: next forward layer, else the first dX pass, else the next tile's first layer
+      const float* next = (k + 1 < LT) ? gimg(k + 1, 0) : (a.train_mlp && LT > 1) ? gimg(LT - 1, 1) : (more_tiles ? gimg(0, 0) : nullptr);
+      tc::issue3(tcx, h, (k >= L) ? wsrc(k) : nullptr, tc_img, next);
       CLB_PH(1);
-      if (k + 1 < LT) tc::load_w2<false>(wsrc(k + 1), tid, wreg);
-      else if (a.train_mlp && LT > 1) tc::load_w2<true>(wsrc(LT - 1), tid, wreg);
       tc::collect2(tcx, o);
       CLB_PH(2);
 #pragma unroll
@@ -953,7 +970,7 @@ __global__ void __launch_bounds__(tc::kThreads2, 2) k_obs_tc2(ObsArgs a) {
     for (int j = 0; j < HW; ++j) dp[j] = 0.f;
     if (hf == 0) { dp[0] = dmu; dp[1] = drho; }
     // head: dW_out = a_L^T [dmu, drho]
-    tc_layer_backward2(tcx, dp, h, wreg, false, bias_part, dbacc + L * WP, part_rows + (size_t)L * WP * WP, tid);
+    tc_layer_backward2(tcx, dp, h, false, nullptr, tc_img, nullptr, bias_part, dbacc + L * WP, part_rows + (size_t)L * WP * WP, tid);
     unsigned mask = 0u;
 #pragma unroll
     for (int j = 0; j < HW; ++j) mask |= (h[j] > 0.f ? 1u : 0u) << j;
@@ -981,11 +998,9 @@ __global__ void __launch_bounds__(tc::kThreads2, 2) k_obs_tc2(ObsArgs a) {
 #pragma unroll
       for (int i = 0; i < HW; ++i) { ain[i] = nxt[i]; mask |= (ain[i] > 0.f ? 1u : 0u) << i; }
       if (k > 0) load_act(nxt, k - 1);
-      float wcur[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) wcur[q] = wreg[q];
-      if (k > 1) tc::load_w2<true>(wsrc(k - 1), tid, wreg);
-      tc_layer_backward2(tcx, dp, ain, wcur, k > 0, bias_part, dbk, partk, tid, il_gk, il_gb, il_w);
+      // the pass after this layer's dX: the next layer's dX (k - 1 >= 1), else the next tile's first forward layer
+      const float* next = (k > 1) ? gimg(k - 1, 1) : (more_tiles ? gimg(0, 0) : nullptr);
+      tc_layer_backward2(tcx, dp, ain, k > 0, (k >= L) ? wsrc(k) : nullptr, tc_img, next, bias_part, dbk, partk, tid, il_gk, il_gb, il_w);
     }
   }
   // ---- flush: bias gradients and the log-likelihood sum ----
@@ -1071,6 +1086,24 @@ __global__ void __launch_bounds__(256) k_pack_weights(const float* theta_mlp, Ml
   if (idx >= L * 1024) return;
   const int k = idx >> 10, i = (idx >> 5) & 31, j = idx & 31;
   wpack[idx] = (i < lay.in_dim[k] && j < lay.out_dim[k]) ? theta_mlp[lay.koff[k] + i * lay.out_dim[k] + j] : 0.f;
+}
+
+// Ready-made B operand images of every hidden layer for k_obs_tc2 (fetched by TMA): per layer [fwd, bwd][hi, lo] in
+// the canonical K-major no-swizzle UMMA layout with the padded LBO of clb_tc.cuh; forward B[n][k] = W[k][n] (n = out,
+// k = in), backward B[n][k] = W[n][k] (n = in, k = out).  hi = tf32(w), lo = w - hi.
+__global__ void __launch_bounds__(256) k_pack_images(const float* theta_mlp, MlpLayout lay, float* wimg) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int L = lay.n_layers - 1;
+  if (idx >= L * 2 * 1024) return;
+  const int layer = idx >> 11, dir = (idx >> 10) & 1, n = (idx >> 5) & 31, k = idx & 31;
+  const int i = dir ? n : k, j = dir ? k : n;          // W[i = in][j = out]
+  const float w = (i < lay.in_dim[layer] && j < lay.out_dim[layer]) ? theta_mlp[lay.koff[layer] + i * lay.out_dim[layer] + j] : 0.f;
+  const float hi = tc::tf32_rna(w);
+  const size_t IMGF = tc::kImgBytes / 4;
+  float* base = wimg + ((size_t)(layer * 2 + dir) * 2) * IMGF;
+  const uint32_t off = ((k >> 2) * tc::kLBO + (n >> 3) * tc::kSBO + (n & 7) * 16 + (k & 3) * 4) / 4;
+  base[off] = hi;
+  base[IMGF + off] = w - hi;
 }
 
 // Sum the per-CTA partial weight gradients (padded layout, see partial_row_size) into the flat keras-order

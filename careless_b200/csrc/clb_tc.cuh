@@ -133,6 +133,10 @@ struct Ctx {
   uint32_t base;                       // tensor-memory base address
   // two-threads-per-row kernels (k_obs_tc2): this thread's tile row, feature half and its column offset (16 hf)
   int row, hf; uint32_t col;
+  // weight images delivered by TMA (k_obs_tc2): two shared-memory buffers [hi | lo], their descriptors and barriers
+  uint64_t wdesc_hi[2], wdesc_lo[2];
+  uint32_t wimg[2], wbar[2];
+  uint32_t pass, wphase;               // chain passes started so far (buffer = pass & 1); phase bit of each buffer's barrier
 };
 
 __device__ __forceinline__ void split32(const float (&x)[32], uint32_t (&hi)[32], uint32_t (&lo)[32]) {
@@ -342,21 +346,38 @@ __device__ __forceinline__ void split16(const float (&x)[16], uint32_t (&hi)[16]
   }
 }
 
+// Swap the two 4-value blocks of each 8-value chunk when sw != 0 (two selects per pair of values).
+__device__ __forceinline__ void swap_blocks(uint32_t (&v)[16], int sw) {
+#pragma unroll
+  for (int cc = 0; cc < 2; ++cc) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t x = v[8 * cc + i], y = v[8 * cc + 4 + i];
+      v[8 * cc + i] = sw ? y : x;
+      v[8 * cc + 4 + i] = sw ? x : y;
+    }
+  }
+}
+
 // This thread's 16 features (32-byte chunks 2 hf and 2 hf + 1) of row k of an MN-major operand image.
-__device__ __forceinline__ void dw_store_half(char* img, int k, int hf, const uint32_t (&hi)[16], const uint32_t (&lo)[16]) {
+__device__ __forceinline__ void dw_store_half(char* img, int k, int hf, const uint32_t (&hi)[16], const uint32_t (&lo)[16], int sw) {
 #ifdef CLB_ABL_STS
   if (hi[0] == 0x7fc01234u && lo[3] == 0x7fc04321u) *reinterpret_cast<uint32_t*>(img) = hi[1] ^ lo[2] ^ hi[15] ^ lo[15] ^ hi[8] ^ lo[8];
   return;
 #endif
   const int r = k & 3;
-  char* row = img + (size_t)(k >> 2) * kDwSBO + r * 128;
+  // sw = 1 (lanes with (lane >> 2) odd): the caller passes the two 16-byte blocks of every chunk SWAPPED in the register
+  // arrays and they are stored to the swapped halves, so that one instruction's 32 lanes cover both halves of the
+  // chunks: 4 wavefronts per STS.128 instead of 8.
+  char* row = img + (size_t)(k >> 2) * kDwSBO + r * 128 + 16 * sw;
+  const int odd = 16 - 32 * sw;
 #pragma unroll
   for (int cc = 0; cc < 2; ++cc) {
     char* p = row + (((2 * hf + cc) ^ r) * 32);
     *reinterpret_cast<uint4*>(p) = make_uint4(hi[8 * cc], hi[8 * cc + 1], hi[8 * cc + 2], hi[8 * cc + 3]);
-    *reinterpret_cast<uint4*>(p + 16) = make_uint4(hi[8 * cc + 4], hi[8 * cc + 5], hi[8 * cc + 6], hi[8 * cc + 7]);
+    *reinterpret_cast<uint4*>(p + odd) = make_uint4(hi[8 * cc + 4], hi[8 * cc + 5], hi[8 * cc + 6], hi[8 * cc + 7]);
     *reinterpret_cast<uint4*>(p + kDwLBO) = make_uint4(lo[8 * cc], lo[8 * cc + 1], lo[8 * cc + 2], lo[8 * cc + 3]);
-    *reinterpret_cast<uint4*>(p + kDwLBO + 16) = make_uint4(lo[8 * cc + 4], lo[8 * cc + 5], lo[8 * cc + 6], lo[8 * cc + 7]);
+    *reinterpret_cast<uint4*>(p + kDwLBO + odd) = make_uint4(lo[8 * cc + 4], lo[8 * cc + 5], lo[8 * cc + 6], lo[8 * cc + 7]);
   }
 }
 
@@ -425,9 +446,27 @@ __device__ __forceinline__ void issue_backward2(Ctx& c, const float (&dp)[16], c
       CLB_TMEM_ST16(c.row_addr + kColAhi + c.col, hi);
       CLB_TMEM_ST16(c.row_addr + kColAlo + c.col, lo);
     }
-    dw_store_half(c.dw_b, c.row, c.hf, hi, lo);
-    split16(ain, hi, lo);
-    dw_store_half(c.dw_a, c.row, c.hf, hi, lo);
+    const int sw = (c.row >> 2) & 1;       // conflict-free image stores: see dw_store_half
+#ifndef CLB_EXPERIMENT_SWZ
+    swap_blocks(hi, sw); swap_blocks(lo, sw);
+#endif
+    dw_store_half(c.dw_b, c.row, c.hf, hi, lo, sw);
+    {
+      uint32_t a2[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) a2[k] = __float_as_uint(ain[k]);
+#ifndef CLB_EXPERIMENT_SWZ
+      swap_blocks(a2, sw);
+#endif
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const float x = __uint_as_float(a2[k]);
+        const float h = tf32_rna(x);
+        hi[k] = __float_as_uint(h);
+        lo[k] = __float_as_uint(x - h);
+      }
+    }
+    dw_store_half(c.dw_a, c.row, c.hf, hi, lo, sw);
   }
   if (need_dx) build_weight_image2<true>(c, w);
   wait_st();
@@ -474,6 +513,142 @@ __device__ __forceinline__ void collect_dw2(Ctx& c) {
                                                              __uint_as_float(v0[4 * qq + 1]) + __uint_as_float(v1[4 * qq + 1]),
                                                              __uint_as_float(v0[4 * qq + 2]) + __uint_as_float(v1[4 * qq + 2]),
                                                              __uint_as_float(v0[4 * qq + 3]) + __uint_as_float(v1[4 * qq + 3]));
+  }
+}
+
+
+// ---- weight images by TMA --------------------------------------------------------------------------------------
+// The hi / lo B-operand images of every hidden layer (both orientations) are prepared once per step in global memory
+// in their final shared-memory byte layout (k_pack_images); a pass copies its two images (4224 B each) with
+// cp.async.bulk into the buffer (pass & 1) while the previous pass is still computing.  No thread builds images, no
+// register staging, no generic-proxy stores: the MMA issuer alone waits for the copy.
+__device__ __forceinline__ void tma_fetch_image(uint32_t dst_smem, const float* src_hi_lo, uint32_t bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(2u * kImgBytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(dst_smem), "l"(src_hi_lo), "r"(2u * kImgBytes), "r"(bar) : "memory");
+}
+
+// Issue one chain pass from buffer b; `tma` = the image came by TMA (wait for it), `next` = global image of the next
+// pass to prefetch into the other buffer (or null).  Called by all threads after the pass's __syncthreads().
+__device__ __forceinline__ void issue_chain_mmas2(Ctx& c, bool tma, const float* next) {
+  const uint32_t b = c.pass & 1u;
+  const uint32_t warp = uniform32((uint32_t)c.tid >> 5);
+  if (warp == 0u) {
+    fence_after();
+    const uint32_t base = uniform32(c.base);
+    const uint64_t bhi = uniform64(b ? c.wdesc_hi[1] : c.wdesc_hi[0]), blo = uniform64(b ? c.wdesc_lo[1] : c.wdesc_lo[0]);
+    const uint32_t d = base + kColD;
+    const uint32_t bar = uniform32(c.mbar);
+    const uint32_t wb = uniform32(b ? c.wbar[1] : c.wbar[0]), wph = uniform32((c.wphase >> b) & 1u);
+    const uint32_t nb = uniform32(b ? c.wbar[0] : c.wbar[1]), ndst = uniform32(b ? c.wimg[0] : c.wimg[1]);
+    if (elect_one()) {
+      if (tma) mbar_wait(wb, wph);
+#ifndef CLB_ABL_CHAIN
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)
+        mma_tf32_ts(d, base + kColAhi + 8u * (uint32_t)ks, blo + (uint64_t)((2u * kLBO * (uint32_t)ks) >> 4), ks > 0 ? 1u : 0u);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)
+        mma_tf32_ts(d, base + kColAlo + 8u * (uint32_t)ks, bhi + (uint64_t)((2u * kLBO * (uint32_t)ks) >> 4), 1u);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)
+        mma_tf32_ts(d, base + kColAhi + 8u * (uint32_t)ks, bhi + (uint64_t)((2u * kLBO * (uint32_t)ks) >> 4), 1u);
+#endif
+      commit(bar);
+      if (next != nullptr) tma_fetch_image(ndst, next, nb);
+    }
+    __syncwarp();
+  }
+  if (tma) c.wphase ^= (1u << b);
+  c.pass += 1u;
+}
+
+// Build the images of this pass in buffer (pass & 1) from FP32 weights `Wg` (image layers: the tile's kernels in
+// shared memory).  All threads; the caller's fence + __syncthreads() publish them.
+template <bool BWD>
+__device__ __forceinline__ void build_weight_image3(Ctx& c, const float* Wg, char* img_base) {
+  float w[4];
+  load_w2<BWD>(Wg, c.tid, w);
+  int n, kq;
+  if (!BWD) { n = c.tid & 31; kq = c.tid >> 5; }
+  else { kq = c.tid & 7; n = c.tid >> 3; }
+  const uint32_t off = kq * kLBO + (n >> 3) * kSBO + (n & 7) * 16;
+  float4 hi, lo;
+  hi.x = tf32_rna(w[0]); hi.y = tf32_rna(w[1]); hi.z = tf32_rna(w[2]); hi.w = tf32_rna(w[3]);
+  lo.x = w[0] - hi.x; lo.y = w[1] - hi.y; lo.z = w[2] - hi.z; lo.w = w[3] - hi.w;
+  char* dst = img_base + (size_t)(c.pass & 1u) * 2 * kImgBytes;
+  *reinterpret_cast<float4*>(dst + off) = hi;
+  *reinterpret_cast<float4*>(dst + kImgBytes + off) = lo;
+}
+
+// Forward pass of one layer.  build_from == nullptr: the layer's images were prefetched by TMA.
+__device__ __forceinline__ void issue3(Ctx& c, const float (&x)[16], const float* build_from, char* img_base, const float* next) {
+  {
+    uint32_t hi[16], lo[16];
+    split16(x, hi, lo);
+    CLB_TMEM_ST16(c.row_addr + kColAhi + c.col, hi);
+    CLB_TMEM_ST16(c.row_addr + kColAlo + c.col, lo);
+  }
+  if (build_from != nullptr) { build_weight_image3<false>(c, build_from, img_base); fence_async_smem(); }
+  wait_st();
+  fence_before();
+  __syncthreads();
+  issue_chain_mmas2(c, build_from == nullptr, next);
+}
+
+// Backward of one layer: dX chain (if need_dx) and dW.
+__device__ __forceinline__ void issue_backward3(Ctx& c, const float (&dp)[16], const float (&ain)[16], bool need_dx,
+                                                const float* build_from, char* img_base, const float* next) {
+  {
+    uint32_t hi[16], lo[16];
+    split16(dp, hi, lo);
+    if (need_dx) {
+      CLB_TMEM_ST16(c.row_addr + kColAhi + c.col, hi);
+      CLB_TMEM_ST16(c.row_addr + kColAlo + c.col, lo);
+    }
+    const int sw = (c.row >> 2) & 1;       // conflict-free image stores: see dw_store_half
+#ifndef CLB_EXPERIMENT_SWZ
+    swap_blocks(hi, sw); swap_blocks(lo, sw);
+#endif
+    dw_store_half(c.dw_b, c.row, c.hf, hi, lo, sw);
+    {
+      uint32_t a2[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) a2[k] = __float_as_uint(ain[k]);
+#ifndef CLB_EXPERIMENT_SWZ
+      swap_blocks(a2, sw);
+#endif
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const float x = __uint_as_float(a2[k]);
+        const float h = tf32_rna(x);
+        hi[k] = __float_as_uint(h);
+        lo[k] = __float_as_uint(x - h);
+      }
+    }
+    dw_store_half(c.dw_a, c.row, c.hf, hi, lo, sw);
+  }
+  if (need_dx && build_from != nullptr) build_weight_image3<true>(c, build_from, img_base);
+  wait_st();
+  fence_async_smem();
+  fence_before();
+  __syncthreads();
+  if (need_dx) issue_chain_mmas2(c, build_from == nullptr, next);
+  const uint32_t warp = uniform32((uint32_t)c.tid >> 5);
+  if (warp == 7u) {
+    fence_after();
+    const uint32_t d = uniform32(c.base) + kColDw;
+    const uint64_t a0 = uniform64(c.desc_dwa), b0 = uniform64(c.desc_dwb);
+    const uint32_t bar = uniform32(c.mbar_dw);
+    if (elect_one()) {
+#ifndef CLB_ABL_DW
+#pragma unroll
+      for (int ks = 0; ks < kThreads / 8; ++ks)
+        mma_tf32_ss(d, a0 + (uint64_t)((2u * kDwSBO * (uint32_t)ks) >> 4), b0 + (uint64_t)((2u * kDwSBO * (uint32_t)ks) >> 4), kIdescDw, ks > 0 ? 1u : 0u);
+#endif
+      commit(bar);
+    }
+    __syncwarp();
   }
 }
 
