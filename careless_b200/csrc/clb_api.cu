@@ -32,6 +32,7 @@ struct DevBuf {
     if (e == cudaSuccess) bytes = n;
     return e;
   }
+  void free() { if (p) { cudaFree(p); p = nullptr; bytes = 0; } }
   template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
@@ -88,6 +89,14 @@ struct clb_handle {
   DevBuf rows;             // one allocation holding all row arrays
   PinBuf rows_host;        // pinned mirror (for re-upload)
   size_t rows_bytes = 0;
+  // double-buffered input pipeline (clb_prefetch_observations): the next step's rows travel on a copy stream into the
+  // other buffer while the current step computes; step_begin switches buffers once the copy has landed
+  DevBuf rows_alt;
+  size_t row_off[7] = {0, 0, 0, 0, 0, 0, 0};   // refl, image, spot, oidx, meta, iobs, sig
+  bool has_img_rows = false, has_spot_rows = false, pending_swap = false, alt_used = false;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_copy_done = nullptr, ev_rows_free[2] = {nullptr, nullptr};   // [b]: the last kernel reading buffer b is done
+  int cur_rows = 0;          // which of the two events belongs to the buffer `rows` currently points to
   int32_t *d_refl = nullptr, *d_image = nullptr, *d_spot = nullptr; uint32_t* d_oidx = nullptr;
   float *d_meta = nullptr, *d_iobs = nullptr, *d_sig = nullptr;
   DevBuf partials, scratch, wpack, wimg;
@@ -106,6 +115,9 @@ struct clb_handle {
 
   ~clb_handle() {
     for (auto e : ev) cudaEventDestroy(e);
+    if (ev_copy_done) cudaEventDestroy(ev_copy_done);
+    for (auto e : ev_rows_free) if (e) cudaEventDestroy(e);
+    if (copy_stream) cudaStreamDestroy(copy_stream);
     if (own_stream && stream) cudaStreamDestroy(stream);
   }
 };
@@ -456,6 +468,16 @@ int clb_synchronize(clb_handle* h) {
   return CLB_OK;
 }
 
+static void point_rows(clb_handle* h, char* db) {
+  h->d_refl = reinterpret_cast<int32_t*>(db + h->row_off[0]);
+  h->d_image = h->has_img_rows ? reinterpret_cast<int32_t*>(db + h->row_off[1]) : nullptr;
+  h->d_spot = h->has_spot_rows ? reinterpret_cast<int32_t*>(db + h->row_off[2]) : nullptr;
+  h->d_oidx = reinterpret_cast<uint32_t*>(db + h->row_off[3]);
+  h->d_meta = reinterpret_cast<float*>(db + h->row_off[4]);
+  h->d_iobs = reinterpret_cast<float*>(db + h->row_off[5]);
+  h->d_sig = reinterpret_cast<float*>(db + h->row_off[6]);
+}
+
 int clb_set_observations(clb_handle* h, int64_t n, int64_t n_total, const int64_t* refl_id, const int64_t* image_id,
                          const float* metadata, const float* iobs, const float* sig,
                          const int64_t* harmonic_id, const int64_t* obs_index, int32_t order) {
@@ -501,14 +523,12 @@ int clb_set_observations(clb_handle* h, int64_t n, int64_t n_total, const int64_
     }
   }
   h->rows_bytes = bytes;
-  char* db = h->rows.as<char>();
-  h->d_refl = reinterpret_cast<int32_t*>(db + o_refl);
-  h->d_image = has_img ? reinterpret_cast<int32_t*>(db + o_img) : nullptr;
-  h->d_spot = has_spot ? reinterpret_cast<int32_t*>(db + o_spot) : nullptr;
-  h->d_oidx = reinterpret_cast<uint32_t*>(db + o_oidx);
-  h->d_meta = reinterpret_cast<float*>(db + o_meta);
-  h->d_iobs = reinterpret_cast<float*>(db + o_iobs);
-  h->d_sig = reinterpret_cast<float*>(db + o_sig);
+  h->row_off[0] = o_refl; h->row_off[1] = o_img; h->row_off[2] = o_spot; h->row_off[3] = o_oidx;
+  h->row_off[4] = o_meta; h->row_off[5] = o_iobs; h->row_off[6] = o_sig;
+  h->has_img_rows = has_img; h->has_spot_rows = has_spot;
+  if (h->pending_swap || h->alt_used) { CLB_CUDA(h, cudaStreamSynchronize(h->copy_stream)); h->pending_swap = false; h->alt_used = false; }
+  h->rows_alt.free();
+  point_rows(h, h->rows.as<char>());
   h->n_rows_raw = n; h->n_rows = npad; h->n_rows_total = n_total; h->order = plan.order;
 
   // ---- launch geometry + per-CTA buffers of the observation kernel ----
@@ -545,6 +565,28 @@ int clb_prepare_rows(int64_t n, int64_t n_refl, int32_t n_meta, int32_t n_images
   if (!refl_out || !oidx_out || !meta_out || !iobs_out || !sig_out) return fail(nullptr, CLB_ERR_INVALID, "clb_prepare_rows: null output");
   fill_rows(plan, n, n_meta, refl_id, image_id, metadata, iobs, sig, harmonic_id, obs_index,
             refl_out, image_id ? image_out : nullptr, laue ? spot_out : nullptr, oidx_out, meta_out, iobs_out, sig_out);
+  return CLB_OK;
+}
+
+// Start the host -> device copy of the prepared rows into the OTHER device buffer on a copy stream and return at once;
+// the next clb_step / clb_step_begin / clb_eval waits for the copy (device side) and switches to that buffer.  With one
+// call per step this is a prefetching input pipeline: step t computes while the rows of step t + 1 arrive.
+int clb_prefetch_observations(clb_handle* h) {
+  if (!h || !h->have_obs) return fail(h, CLB_ERR_STATE, "clb_prefetch_observations before clb_set_observations");
+  if (h->pending_swap) return fail(h, CLB_ERR_STATE, "clb_prefetch_observations: the previous prefetch has not been consumed by a step yet");
+  CLB_CUDA(h, cudaSetDevice(h->cfg.device));
+  if (!h->copy_stream) {
+    CLB_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    CLB_CUDA(h, cudaEventCreateWithFlags(&h->ev_copy_done, cudaEventDisableTiming));
+    CLB_CUDA(h, cudaEventCreateWithFlags(&h->ev_rows_free[0], cudaEventDisableTiming));
+    CLB_CUDA(h, cudaEventCreateWithFlags(&h->ev_rows_free[1], cudaEventDisableTiming));
+  }
+  if (!h->rows_alt.p) CLB_CUDA(h, h->rows_alt.alloc(h->rows_bytes));
+  // the target buffer was last read by the step before the current one; wait until that step's kernels are done
+  if (h->alt_used) CLB_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->ev_rows_free[h->cur_rows ^ 1], 0));
+  CLB_CUDA(h, cudaMemcpyAsync(h->rows_alt.p, h->rows_host.p, h->rows_bytes, cudaMemcpyHostToDevice, h->copy_stream));
+  CLB_CUDA(h, cudaEventRecord(h->ev_copy_done, h->copy_stream));
+  h->pending_swap = true;
   return CLB_OK;
 }
 
@@ -708,6 +750,12 @@ static int step_begin_impl(clb_handle* h, const float* inj_u, const float* inj_e
   if (!h->have_obs || !h->have_prior) return fail(h, CLB_ERR_STATE, "clb_step before clb_set_observations / clb_set_prior");
   CLB_CUDA(h, cudaSetDevice(c.device));
   cudaStream_t st = h->stream;
+  if (h->pending_swap) {        // the prefetched rows become this step's input once their copy has landed
+    CLB_CUDA(h, cudaStreamWaitEvent(st, h->ev_copy_done, 0));
+    std::swap(h->rows.p, h->rows_alt.p); std::swap(h->rows.bytes, h->rows_alt.bytes);
+    point_rows(h, h->rows.as<char>());
+    h->pending_swap = false; h->alt_used = true; h->cur_rows ^= 1;
+  }
   const int64_t R = h->R; const int S = h->S;
   float* theta = h->theta.as<float>();
   float* grad = h->grad.as<float>();
@@ -813,6 +861,7 @@ static int step_begin_impl(clb_handle* h, const float* inj_u, const float* inj_e
       CLB_CUDA(h, cudaEventRecord(h->ev[h->ev_used], st));
     }
     CLB_CUDA(h, dispatch_obs(h, a)); h->obs_launches++; CLB_LAUNCHED(h);
+    if (h->copy_stream) CLB_CUDA(h, cudaEventRecord(h->ev_rows_free[h->cur_rows], st));   // the row buffer of this step may be refilled after this point
     if (h->timing) { CLB_CUDA(h, cudaEventRecord(h->ev[h->ev_used + 1], st)); h->ev_used += 2; }
   }
   if (train_mlp) {

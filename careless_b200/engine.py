@@ -135,6 +135,10 @@ class Engine:
     def upload_observations(self):
         self._check(self.lib.clb_upload_observations(self._h))
 
+    def prefetch_observations(self):
+        """Asynchronous copy of the prepared rows into the second device buffer; the next step switches to it."""
+        self._check(self.lib.clb_prefetch_observations(self._h))
+
     def set_prior(self, centric, multiplicity, sigma=None, dw_parent=None, asu_id=None, r=None,
                   refl_index=None, init_scale=1.0):
         R = self.cfg.n_refl

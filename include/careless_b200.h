@@ -137,6 +137,12 @@ int clb_prepare_rows(int64_t n_rows, int64_t n_refl, int32_t n_meta, int32_t n_i
 /* Re-upload of the already prepared (pinned) device-layout rows: the host->device copy of
  * one step's inputs, used by the end-to-end measurement. */
 int clb_upload_observations(clb_handle* h);
+/* Input pipeline: start copying the prepared rows into the handle's SECOND device buffer on a copy stream and return;
+ * the next clb_step / clb_step_begin / clb_eval waits for that copy on the device and switches buffers.  Called once
+ * per step after the step's kernels have been launched (clb_step_begin ... clb_step_end without metrics), the copy of
+ * step t+1's inputs overlaps the compute of step t (the tf.data prefetch a keras fit() loop would do; the reference's
+ * train_model keeps its single batch resident, careless.py:61-70). */
+int clb_prefetch_observations(clb_handle* h);
 
 /* Replaces: WilsonPrior / DoubleWilsonPrior construction (priors/wilson.py:29-49, 82-138) and
  * the surrogate initialisation of manager.py:432-436.  centric (R) uint8, multiplicity (R),

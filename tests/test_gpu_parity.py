@@ -263,3 +263,34 @@ def test_errors_are_reported():
             eng.set_observations(np.array([11]), None, np.zeros((1, 2)), np.ones(1), np.ones(1))   # refl_id out of range
     finally:
         eng.close()
+
+
+def test_prefetched_rows_give_identical_steps():
+    """clb_prefetch_observations: the double-buffered input pipeline changes nothing but where the rows live."""
+    p = synth.make_mono(20000, 1500, d=4, n_images=13, seed=31)
+    hists, params = [], []
+    for mode in ("resident", "prefetch"):
+        _, _, eng = U.build(p, mlp_width=32, mlp_layers=4, likelihood="studentt", dof=8.0, image_scales=True, seed=77)
+        try:
+            if mode == "resident":
+                hist = eng.step(5)
+            else:
+                hist = []
+                eng.upload_observations()
+                for i in range(5):
+                    eng.step_begin(); eng.step_norms()
+                    if i + 1 < 5:
+                        eng.prefetch_observations()
+                    hist.append(eng.step_end(True))
+                with pytest.raises(Exception):       # a second prefetch before a step consumed the first one is refused
+                    eng.prefetch_observations(); eng.prefetch_observations()
+                eng.step(1)
+            hists.append(hist[:5])
+            params.append(eng.get_params("mlp").copy())
+        finally:
+            eng.close()
+    for a, b in zip(*hists):          # same rows, same Philox draws; float atomics make the last bits run-dependent
+        for k in a:
+            assert abs(a[k] - b[k]) <= 1e-6 * abs(a[k]), (k, a, b)
+    assert not np.array_equal(params[0], params[1])      # the prefetch engine took one more step ...
+    assert np.all(np.isfinite(params[1]))
