@@ -285,9 +285,13 @@ def run_ours(args):
         fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12
         tf32_peak = peaks["bf16_tflops"] / 2.0            # dense TF32 runs at half the bf16 rate on the same tensor pipe
         executed = tflops * (3 + 3 + 4) / 3.0              # 3xTF32 forward + dX, 4-product dW: tensor-pipe FLOPs actually issued
-        roofline = {"kernel": "k_obs<32,studentt,TC> (scale MLP fwd+bwd on tcgen05/TMEM, 3xTF32; likelihood; segmented dL/dz_f reduction)",
+        # DRAM bytes of one k_obs_tc2 launch at the default workload, from the committed ncu --set full capture
+        # (profiles/r01_k_obs_tc2_ncu_full10M.txt: dram__bytes_read.sum 24.19 GB + dram__bytes_write.sum 38.30 GB)
+        traffic = 6.249e10 if (N, R) == (10_000_000, 500_000) else None
+        roofline = {"kernel": "k_obs_tc2<studentt> (scale MLP fwd+bwd on tcgen05/TMEM, 3xTF32, two threads per row; likelihood; segmented dL/dz_f reduction)",
                     "bound": "tensor", "achieved": tflops, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                    "frac": tflops / peaks["bf16_tflops"], "traffic": None, "peak_source": peaks["source"] + " bf16 cuBLAS burst",
+                    "frac": tflops / peaks["bf16_tflops"], "traffic": traffic, "traffic_unit": "bytes per launch (dram read + write, ncu)",
+                    "peak_source": peaks["source"] + " bf16 cuBLAS burst",
                     "note": "achieved = ALGORITHMIC FP32 FLOPs (N x 118080) / kernel time; the kernel multiplies in TF32 (half the bf16 rate) "
                             "and issues 3.33x the algorithmic FLOPs for FP32-level accuracy (error-compensated 3xTF32), so frac <= 0.15 by construction",
                     "tensor_tf32": {"achieved_executed": executed, "peak": tf32_peak, "frac_executed": executed / tf32_peak,

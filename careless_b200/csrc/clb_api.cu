@@ -536,6 +536,26 @@ int clb_set_observations(clb_handle* h, int64_t n, int64_t n_total, const int64_
   h->grid_obs = (int)std::min<int64_t>(n_tiles, (int64_t)h->n_sms * (h->use_tc ? 2 : 1));
   CLB_CUDA(h, h->partials.alloc(sizeof(double) * (size_t)h->grid_obs * h->KS * partial_row_size(h->NL, h->WP)));
   CLB_CUDA(h, h->scratch.alloc(sizeof(float4) * (size_t)h->grid_obs * std::max(1, c.mlp_layers + c.image_layers) * (h->WP / 4) * h->obs_threads));
+  {
+    // Keep the per-CTA FP64 weight-gradient partials (read-modify-written once per tile and layer) resident in L2: the
+    // activation scratch streams through the same cache and would otherwise evict them (12 GB of extra DRAM writes
+    // per 10 M observations).  CLB_NO_L2_PERSIST=1 switches the policy window off.
+    const char* off = getenv("CLB_NO_L2_PERSIST");
+    int max_persist = 0, max_window = 0;
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, c.device);
+    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, c.device);
+    if (!(off && off[0] == '1') && max_persist > 0 && max_window > 0 && h->partials.bytes > 0) {
+      const size_t want = std::min<size_t>(h->partials.bytes, (size_t)max_persist);
+      cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+      cudaStreamAttrValue attr{};
+      attr.accessPolicyWindow.base_ptr = h->partials.p;
+      attr.accessPolicyWindow.num_bytes = std::min<size_t>(h->partials.bytes, (size_t)max_window);
+      attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)want / (double)attr.accessPolicyWindow.num_bytes);
+      attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+      if (cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
+    }
+  }
   if (h->use_tc) CLB_CUDA(h, h->wpack.alloc(sizeof(float) * (size_t)std::max(1, c.mlp_layers) * 1024));
   if (h->use_tc2) {     // [L][fwd, bwd][hi, lo][kImgBytes]; the padding bytes of the images stay zero
     const size_t nb = (size_t)std::max(1, c.mlp_layers) * 4 * tc::kImgBytes;
