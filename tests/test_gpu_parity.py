@@ -294,3 +294,30 @@ def test_prefetched_rows_give_identical_steps():
             assert abs(a[k] - b[k]) <= 1e-6 * abs(a[k]), (k, a, b)
     assert not np.array_equal(params[0], params[1])      # the prefetch engine took one more step ...
     assert np.all(np.isfinite(params[1]))
+
+
+@pytest.mark.parametrize("layers", [1, 2])
+def test_tensor_core_kernel_short_chains(layers):
+    """Width 32 with one / two hidden layers: the chain has no (one) dX pass, the TMA image prefetch wraps to the next tile."""
+    p = synth.make_mono(7000, 800, d=5, n_images=10, seed=41)
+    _compare_step(p, f"tc-short-L{layers}", mlp_width=32, mlp_layers=layers, likelihood="studentt", dof=5.0, mc_samples=2)
+
+
+def test_tensor_core_kernel_frozen_and_eval():
+    """Width 32: frozen scale model (forward-only chain, surrogate gradients still exact) and clb_eval."""
+    p = synth.make_mono(6000, 700, d=4, n_images=8, seed=42)
+    _compare_step(p, "tc-frozen", frozen=("mlp",), mlp_width=32, mlp_layers=3)
+    rng = np.random.default_rng(9)
+    ocfg, oprior, eng = U.build(p, mlp_width=32, mlp_layers=3)
+    try:
+        params = U.perturbed_params(ocfg, oprior, rng)
+        U.push_params(eng, params, ocfg)
+        u, e = _draws(rng, 1, ocfg.n_refl, len(p["refl_id"]))
+        before = eng.get_params("mlp").copy()
+        m = eng.eval(u_f=u, eps_s=e)
+        metrics, _, _ = om.loss_and_grads(params, p, oprior, ocfg, u[0], e[0])
+        for k in ("loss", "NLL", "F KLDiv"):
+            assert abs(m[k] - metrics[k]) <= 1e-5 * abs(metrics[k]), (k, m, metrics)
+        assert np.array_equal(before, eng.get_params("mlp"))
+    finally:
+        eng.close()
