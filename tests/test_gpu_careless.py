@@ -101,3 +101,27 @@ def test_run_careless_outputs(tmp_path, mode, flags):
     if flags.get("optimize_double_wilson_r"):
         assert run["model"].prior.r[0] == 0.0 and run["model"].prior.r[1] != np.float32(0.9)
     run["model"].close()
+
+
+def test_command_line_entry_point(tmp_path):
+    """`python -m careless_b200.careless mono ...` on MTZ files written to disk (argparse + read_mtz + the whole flow)."""
+    from careless_b200.careless import main
+    from careless_b200.io.mtz import write_mtz
+    files = []
+    for name in ("pyp_off", "pyp_2ms"):
+        ds = U.load_fixture(name)
+        ds.hkl_to_asu()                       # unmerged MTZ convention: ASU indices + M/ISYM, as the reference's fixtures
+        path = os.path.join(tmp_path, name + ".mtz")
+        write_mtz(path, ds)
+        files.append(path)
+    out = os.path.join(tmp_path, "cli")
+    main(["mono", "--iterations", "8", "--mlp-layers", "2", "--disable-progress-bar", "--separate-files", "--studentt-likelihood-dof", "8",
+          "--mc-samples", "2", "dHKL,Hobs,Kobs,Lobs,X,Y", files[0], files[1], out])
+    for i in range(2):
+        merged = read_mtz(out + f"_{i}.mtz")
+        assert len(merged) > 50 and np.all(np.isfinite(merged["F"])) and np.all(merged["SigF"] > 0)
+    lines = open(out + "_history.csv").read().strip().splitlines()
+    assert lines[0].split(",")[:3] == ["step", "loss", "NLL"] and len(lines) == 9
+    main(["poly", "--iterations", "4", "--mlp-layers", "2", "--disable-progress-bar", "-w", "Wavelength", "dHKL,Wavelength",
+          files[0], out + "_laue"])
+    assert len(read_mtz(out + "_laue_0.mtz")) > 50
