@@ -856,6 +856,7 @@ static int step_begin_impl(clb_handle* h, const float* inj_u, const float* inj_e
     a.inj_eps = d_inj_eps;
     a.g_img = (c.image_scales && h->gtrain[CLB_GROUP_IMAGE_SCALES] && !h->eval_mode) ? grad + h->goff[CLB_GROUP_IMAGE_SCALES] : nullptr;
     a.partials = h->partials.as<double>(); a.scratch = h->scratch.as<float4>();
+    a.partials32 = h->partials.as<float>();
     a.ipred_out = h->want_ipred ? h->ipred.as<float>() : nullptr;
     a.scale_mean_out = h->want_scale_moments ? h->scale_mom.as<float>() : nullptr;
     a.scale_std_out = h->want_scale_moments ? h->scale_mom.as<float>() + h->n_rows_total : nullptr;
@@ -886,7 +887,8 @@ static int step_begin_impl(clb_handle* h, const float* inj_u, const float* inj_e
   }
   if (train_mlp) {
     const int np = h->lay.n_params;
-    k_reduce_partials<<<(np + 255) / 256, 256, 0, st>>>(h->partials.as<double>(), h->grid_obs * h->KS, h->lay, h->WP, grad + h->goff[CLB_GROUP_MLP]);
+    if (h->use_tc2) k_reduce_partials32<<<(np + 255) / 256, 256, 0, st>>>(h->partials.as<float>(), h->grid_obs, h->lay, grad + h->goff[CLB_GROUP_MLP]);
+    else k_reduce_partials<<<(np + 255) / 256, 256, 0, st>>>(h->partials.as<double>(), h->grid_obs * h->KS, h->lay, h->WP, grad + h->goff[CLB_GROUP_MLP]);
     CLB_LAUNCHED(h);
   }
   if (!h->eval_mode) {

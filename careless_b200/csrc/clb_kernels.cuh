@@ -159,6 +159,7 @@ struct ObsArgs {
   const float* inj_eps;            // (S, N_total) or null
   float* g_img;                    // gradient of image scales or null
   double* partials;                // [grid*KS][n_params], FP64 so that the cross-tile accumulation adds no FP32 rounding
+  float* partials32;               // k_obs_tc2: the same memory as [grid][n_layers][32*32 + 32] FP32, accumulated with vector REDs
   float4* scratch;                 // [grid][L][WP/4][T]
   float* ipred_out;                // (S, N_total) original order, or null
   float* scale_mean_out; float* scale_std_out;   // (N_total) moments of the scale distribution, original order, or null
@@ -742,68 +743,50 @@ __global__ void __launch_bounds__(TC ? tc::kThreads : kObsThreads, TC ? 2 : 1) k
 // ---------------------------------------------------------------------------------------
 struct ObsSmem2 {
   static size_t bytes(int n_layers, int n_img_layers) {
-    return 2 * (size_t)tc::kDwImgBytes + sizeof(float) * (64 + 2 * (size_t)n_layers * 32 + (size_t)n_img_layers * (1024 + 32) + 8 * 16)
+    return 2 * (size_t)tc::kDwImgBytes + sizeof(float) * (64 + (size_t)n_layers * 32 + (size_t)n_img_layers * (1024 + 32))
            + 64 * sizeof(double) + 4 * (size_t)tc::kImgBytes + 64 + 4 * 128 * sizeof(float) + 128;
   }
 };
 
-// One layer's backward on the tensor cores, two threads per row (see tc_layer_backward).
+// Column sums of the warp's 32 rows of a 16-column block (recursive halving, 16 shuffles); the even lanes then add
+// their column (lane >> 1) to dst[col] with one RED each.
+__device__ __forceinline__ void bias_red16(const float (&dp)[16], float* dst, int lane, int limit) {
+  float v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = dp[j];
+#pragma unroll
+  for (int st = 0; st < 4; ++st) {
+    const int bit = 16 >> st, half = 16 >> (st + 1);
+    const bool up = (lane & bit) != 0;
+#pragma unroll
+    for (int j = 0; j < half; ++j) {
+      const float send = up ? v[j] : v[j + half];
+      const float recv = __shfl_xor_sync(0xffffffffu, send, bit);
+      v[j] = (up ? v[j + half] : v[j]) + recv;
+    }
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+  const int col = lane >> 1;
+  if ((lane & 1) == 0 && dst != nullptr && col < limit) atomicAdd(&dst[col], v[0]);
+}
+
+// One layer's backward on the tensor cores, two threads per row: dW_k = a_k^T dp_k and, when need_dx, dp <- dp_k W_k^T.
+// The tile's dW leaves tensor memory straight into the CTA's private FP32 partial in L2 (vector REDs, no staging, no
+// barrier); `wk` / `bk` = kernel [32][32] and bias [32] slots of this layer in that partial, or the image's gradient
+// slots (il_w > 0: kernel stored (out, in), width il_w).
 __device__ __forceinline__ void tc_layer_backward2(tc::Ctx& tcx, float (&dp)[16], const float (&ain)[16], bool need_dx,
                                                    const float* build_from, char* img_base, const float* next_img,
-                                                   float* bias_part, float* dbacc_k, double* part, int tid,
-                                                   float* il_gk = nullptr, float* il_gb = nullptr, int il_w = 0) {
-  const bool to_image = il_w > 0;
-  double2 pr0 = make_double2(0.0, 0.0), pr1 = pr0;
-#ifndef CLB_ABL_PART
-  if (!to_image) {
-    pr0 = __ldcg(reinterpret_cast<const double2*>(part));
-    pr1 = __ldcg(reinterpret_cast<const double2*>(part) + 1);
-  }
-#endif
+                                                   float* wk, float* bk, int il_w) {
+  const int lane = tcx.tid & 31;
   CLB_PH(5);
-  bias_partial<16>(dp, bias_part, tid);          // bias_part[warp][16]: warps 0-3 columns 0-15, warps 4-7 columns 16-31
+  bias_red16(dp, bk != nullptr ? bk + 16 * tcx.hf : nullptr, lane, il_w > 0 ? il_w - 16 * tcx.hf : 16);
   CLB_PH(6);
   tc::issue_backward3(tcx, dp, ain, need_dx, build_from, img_base, next_img);
   CLB_PH(7);
   if (need_dx) tc::collect2(tcx, dp);
   CLB_PH(8);
-  tc::collect_dw2(tcx);
+  tc::collect_dw_red(tcx, wk, il_w);
   CLB_PH(9);
-  __syncthreads();
-  CLB_PH(10);
-  {
-    // float4 output o4 = tid = r*64 + pj*8 + pi holds dW[i = pi + 8 r][j = 4 pj .. 4 pj + 3]
-    const int r = tid >> 6, pj = (tid & 63) >> 3, pi = tid & 7;
-    const float* st = reinterpret_cast<const float*>(tcx.dw_a) + (size_t)(pi + 8 * r) * tc::kStageStride + 4 * pj;
-    const float4 t0 = *reinterpret_cast<const float4*>(st);
-    const float4 t1 = *reinterpret_cast<const float4*>(st + (size_t)32 * tc::kStageStride);
-    if (!to_image) {
-#ifdef CLB_ABL_PART
-      if (t0.x + t1.x == 1.2345e30f) __stcg(reinterpret_cast<double2*>(part), make_double2(pr0.x + (double)(t0.y + t1.y), pr1.y + (double)(t0.z + t1.w)));
-#else
-      __stcg(reinterpret_cast<double2*>(part), make_double2(pr0.x + (double)(t0.x + t1.x), pr0.y + (double)(t0.y + t1.y)));
-      __stcg(reinterpret_cast<double2*>(part) + 1, make_double2(pr1.x + (double)(t0.z + t1.z), pr1.y + (double)(t0.w + t1.w)));
-#endif
-    } else if (il_gk != nullptr) {
-      const int i = pi + 8 * r;
-      const float tv[4] = {t0.x + t1.x, t0.y + t1.y, t0.z + t1.z, t0.w + t1.w};
-      if (i < il_w) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) { const int j = 4 * pj + c; if (j < il_w) atomicAdd(&il_gk[j * il_w + i], tv[c]); }
-      }
-    }
-    if (tid < 32) {
-      const int hfc = tid >> 4, cc = tid & 15;
-      float sum = 0.f;
-#pragma unroll
-      for (int w2 = 0; w2 < 4; ++w2) sum += bias_part[(4 * hfc + w2) * 16 + cc];
-      if (!to_image) dbacc_k[tid] += sum;
-      else if (il_gb != nullptr && tid < il_w) atomicAdd(&il_gb[tid], sum);
-    }
-  }
-  CLB_PH(11);
-  __syncthreads();      // the stage aliases the operand image of the next layer
-  CLB_PH(12);
 }
 
 template <int LIK>
@@ -817,11 +800,9 @@ __global__ void __launch_bounds__(tc::kThreads2, 2) k_obs_tc2(ObsArgs a) {
   sp += 2 * tc::kDwImgBytes;
   float* Whead = reinterpret_cast<float*>(sp);              // [32][2]
   float* bsm = Whead + 64;                                  // [NL][32]
-  float* dbacc = bsm + (size_t)NL * WP;                     // [NL][32]
-  float* Wimg = dbacc + (size_t)NL * WP;                    // [K][32][32] this tile's image-layer kernels as [in][out]
+  float* Wimg = bsm + (size_t)NL * WP;                      // [K][32][32] this tile's image-layer kernels as [in][out]
   float* bimg = Wimg + (size_t)K * WP * WP;                 // [K][32]
-  float* bias_part = bimg + (size_t)K * WP;                 // [8 warps][16]
-  double* red = reinterpret_cast<double*>(bias_part + 8 * 16);
+  double* red = reinterpret_cast<double*>(bimg + (size_t)K * WP);
   char* tc_img = reinterpret_cast<char*>(red + 64);         // [2 buffers][hi, lo][kImgBytes] chain B operand images
   uint64_t* tc_bar = reinterpret_cast<uint64_t*>(tc_img + 4 * tc::kImgBytes);   // [0] chain, [1] dW, [2..3] image buffers
   uint32_t* tc_slot = reinterpret_cast<uint32_t*>(tc_bar + 4);
@@ -842,7 +823,6 @@ __global__ void __launch_bounds__(tc::kThreads2, 2) k_obs_tc2(ObsArgs a) {
   for (int idx = tid; idx < NL * WP; idx += T) {
     const int k = idx / WP, j = idx % WP;
     bsm[idx] = (j < a.lay.out_dim[k]) ? a.theta_mlp[a.lay.boff[k] + j] : 0.f;
-    dbacc[idx] = 0.f;
   }
   __syncthreads();
   {
@@ -870,8 +850,8 @@ __global__ void __launch_bounds__(tc::kThreads2, 2) k_obs_tc2(ObsArgs a) {
   // image layers, whose per-tile kernels are turned into images by the threads themselves
   constexpr size_t IMGF = tc::kImgBytes / 4;
   auto gimg = [&](int k, int dir) -> const float* { return (k < L) ? a.wimg + ((size_t)(k * 2 + dir) * 2) * IMGF : nullptr; };
-  const int PP = partial_row_size(NL, WP);
-  double* part_rows = a.partials + (size_t)blockIdx.x * PP + (size_t)tid * 4;    // every thread owns 4 consecutive doubles per layer
+  constexpr int PSLOT = WP * WP + WP;                        // one layer of the CTA's FP32 partial: kernel [32][32], bias [32]
+  float* part32 = a.partials32 + (size_t)blockIdx.x * NL * PSLOT;
   float4* scr = a.scratch + (size_t)blockIdx.x * LT * NC * TR;
   double ll_sum = 0.0;
   float ev_f = 1.f, ev_a = 0.f, ev_b = 0.f;
@@ -970,7 +950,7 @@ __global__ void __launch_bounds__(tc::kThreads2, 2) k_obs_tc2(ObsArgs a) {
     for (int j = 0; j < HW; ++j) dp[j] = 0.f;
     if (hf == 0) { dp[0] = dmu; dp[1] = drho; }
     // head: dW_out = a_L^T [dmu, drho]
-    tc_layer_backward2(tcx, dp, h, false, nullptr, tc_img, nullptr, bias_part, dbacc + L * WP, part_rows + (size_t)L * WP * WP, tid);
+    tc_layer_backward2(tcx, dp, h, false, nullptr, tc_img, nullptr, part32 + (size_t)L * PSLOT, part32 + (size_t)L * PSLOT + WP * WP, 0);
     unsigned mask = 0u;
 #pragma unroll
     for (int j = 0; j < HW; ++j) mask |= (h[j] > 0.f ? 1u : 0u) << j;
@@ -989,8 +969,8 @@ __global__ void __launch_bounds__(tc::kThreads2, 2) k_obs_tc2(ObsArgs a) {
         il_gb = a.g_il + (size_t)(k - L) * lstride + (size_t)a.il_n_images * w * w + (size_t)timg * w;
       }
       const int il_w = is_il ? a.il_width : 0;
-      float* dbk = dbacc + (size_t)(is_il ? L : k) * WP;
-      double* partk = part_rows + (size_t)(is_il ? L : k) * WP * WP;
+      float* wk = is_il ? il_gk : part32 + (size_t)k * PSLOT;
+      float* bk2 = is_il ? il_gb : part32 + (size_t)k * PSLOT + WP * WP;
 #pragma unroll
       for (int j = 0; j < HW; ++j) dp[j] = ((mask >> j) & 1u) ? dp[j] : kLeak * dp[j];
       float ain[HW];
@@ -1000,15 +980,11 @@ __global__ void __launch_bounds__(tc::kThreads2, 2) k_obs_tc2(ObsArgs a) {
       if (k > 0) load_act(nxt, k - 1);
       // the pass after this layer's dX: the next layer's dX (k - 1 >= 1), else the next tile's first forward layer
       const float* next = (k > 1) ? gimg(k - 1, 1) : (more_tiles ? gimg(0, 0) : nullptr);
-      tc_layer_backward2(tcx, dp, ain, k > 0, (k >= L) ? wsrc(k) : nullptr, tc_img, next, bias_part, dbk, partk, tid, il_gk, il_gb, il_w);
+      tc_layer_backward2(tcx, dp, ain, k > 0, (k >= L) ? wsrc(k) : nullptr, tc_img, next, wk, bk2, il_w);
     }
   }
-  // ---- flush: bias gradients and the log-likelihood sum ----
+  // ---- flush: the log-likelihood sum ----
   __syncthreads();
-  if (a.train_mlp) {
-    for (int idx = tid; idx < NL * WP; idx += T)
-      a.partials[(size_t)blockIdx.x * PP + (size_t)NL * WP * WP + idx] += (double)dbacc[idx];
-  }
   ll_sum = warp_sum(ll_sum);
   if (lane == 0) red[tid >> 5] = ll_sum;
   tc::fence_before();
@@ -1104,6 +1080,27 @@ __global__ void __launch_bounds__(256) k_pack_images(const float* theta_mlp, Mlp
   const uint32_t off = ((k >> 2) * tc::kLBO + (n >> 3) * tc::kSBO + (n & 7) * 16 + (k & 3) * 4) / 4;
   base[off] = hi;
   base[IMGF + off] = w - hi;
+}
+
+// k_obs_tc2's partials: [rows][n_layers][32*32 + 32] FP32 (kernel [in][out] padded to 32 x 32, then the bias), summed over
+// the CTAs in FP64 in a fixed order.
+__global__ void __launch_bounds__(256) k_reduce_partials32(const float* partials, int rows, MlpLayout lay, float* grad) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= lay.n_params) return;
+  const int PSLOT = 32 * 32 + 32, PP = lay.n_layers * PSLOT;
+  int src = -1;
+  for (int k = 0; k < lay.n_layers; ++k) {
+    const int nk = lay.in_dim[k] * lay.out_dim[k];
+    if (p >= lay.koff[k] && p < lay.koff[k] + nk) {
+      const int i = (p - lay.koff[k]) / lay.out_dim[k], j = (p - lay.koff[k]) % lay.out_dim[k];
+      src = k * PSLOT + i * 32 + j;
+      break;
+    }
+    if (p >= lay.boff[k] && p < lay.boff[k] + lay.out_dim[k]) { src = k * PSLOT + 1024 + (p - lay.boff[k]); break; }
+  }
+  double acc = 0.0;
+  if (src >= 0) for (int r = 0; r < rows; ++r) acc += (double)partials[(size_t)r * PP + src];
+  grad[p] = (float)acc;
 }
 
 // Sum the per-CTA partial weight gradients (padded layout, see partial_row_size) into the flat keras-order

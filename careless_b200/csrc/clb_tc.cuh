@@ -517,6 +517,37 @@ __device__ __forceinline__ void collect_dw2(Ctx& c) {
 }
 
 
+// dW rows live at lanes (r % 16) + 32 (r / 16): in every warp the lanes < 16 hold row r = 16 (warp % 4) + lane, i.e.
+// feature i = r % 32 (rows 0..31 from a_hi, 32..63 from a_lo).  The thread folds the delta-hi and delta-lo column blocks of
+// ITS 16 columns and adds them to wk[i][16 hf ..] with four 16-byte REDs (il_w > 0: an image layer's kernel, stored
+// (out, in) with width il_w, scalar REDs).  When this returns the dW MMAs are complete: the operand images and the
+// accumulator may be reused after the next __syncthreads().
+__device__ __forceinline__ void collect_dw_red(Ctx& c, float* wk, int il_w) {
+  mbar_wait(c.mbar_dw, c.parity_dw);
+  c.parity_dw ^= 1u;
+  fence_after();
+  const int q = (c.tid >> 5) & 3, lane = c.tid & 31;
+  const uint32_t addr = c.row_addr + kColDw + c.col;
+  uint32_t v0[16], v1[16];
+  CLB_TMEM_LD16(addr, v0);
+  CLB_TMEM_LD16(addr + 32, v1);
+  wait_ld();
+  if (lane < 16 && wk != nullptr) {
+    const int i = (16 * q + lane) & 31;
+    float f[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) f[k] = __uint_as_float(v0[k]) + __uint_as_float(v1[k]);
+    if (il_w == 0) {
+      float4* dst = reinterpret_cast<float4*>(wk + i * 32 + 16 * c.hf);
+#pragma unroll
+      for (int qq = 0; qq < 4; ++qq) atomicAdd(dst + qq, make_float4(f[4 * qq], f[4 * qq + 1], f[4 * qq + 2], f[4 * qq + 3]));
+    } else if (i < il_w) {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) { const int j = 16 * c.hf + k; if (j < il_w) atomicAdd(&wk[j * il_w + i], f[k]); }
+    }
+  }
+}
+
 // ---- weight images by TMA --------------------------------------------------------------------------------------
 // The hi / lo B-operand images of every hidden layer (both orientations) are prepared once per step in global memory
 // in their final shared-memory byte layout (k_pack_images); a pass copies its two images (4224 B each) with
