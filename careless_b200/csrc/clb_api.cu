@@ -150,16 +150,19 @@ template <int WP, int LIK, bool TC> cudaError_t launch_obs(clb_handle* h, const 
   return cudaGetLastError();
 }
 
-template <int LIK> cudaError_t launch_obs_tc2(clb_handle* h, const ObsArgs& a) {
-  cudaError_t e = cudaFuncSetAttribute(k_obs_tc2<LIK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_obs);
+template <int LIK, bool IL> cudaError_t launch_obs_tc2(clb_handle* h, const ObsArgs& a) {
+  cudaError_t e = cudaFuncSetAttribute(k_obs_tc2<LIK, IL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_obs);
   if (e != cudaSuccess) return e;
-  k_obs_tc2<LIK><<<h->grid_obs, tc::kThreads2, h->smem_obs, h->stream>>>(a);
+  k_obs_tc2<LIK, IL><<<h->grid_obs, tc::kThreads2, h->smem_obs, h->stream>>>(a);
   return cudaGetLastError();
 }
 
 cudaError_t dispatch_obs(clb_handle* h, const ObsArgs& a) {
   const int lik = h->cfg.likelihood;
-  if (h->use_tc2) return lik ? launch_obs_tc2<1>(h, a) : launch_obs_tc2<0>(h, a);
+  if (h->use_tc2) {
+    if (h->cfg.image_layers > 0) return lik ? launch_obs_tc2<1, true>(h, a) : launch_obs_tc2<0, true>(h, a);
+    return lik ? launch_obs_tc2<1, false>(h, a) : launch_obs_tc2<0, false>(h, a);
+  }
   switch (h->WP) {
     case 8:  return lik ? launch_obs<8, 1, false>(h, a) : launch_obs<8, 0, false>(h, a);
     case 16: return lik ? launch_obs<16, 1, false>(h, a) : launch_obs<16, 0, false>(h, a);

@@ -789,11 +789,12 @@ __device__ __forceinline__ void tc_layer_backward2(tc::Ctx& tcx, float (&dp)[16]
   CLB_PH(9);
 }
 
-template <int LIK>
+// IL = the model has image layers (their code is compiled out otherwise)
+template <int LIK, bool IL>
 __global__ void __launch_bounds__(tc::kThreads2, 2) k_obs_tc2(ObsArgs a) {
   constexpr int WP = 32, TR = tc::kThreads, T = tc::kThreads2, NC = WP / 4, HW = 16;   // TR rows per tile, T threads
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  const int NL = a.lay.n_layers, L = NL - 1, K = a.n_img_layers, LT = L + K;
+  const int NL = a.lay.n_layers, L = NL - 1, K = IL ? a.n_img_layers : 0, LT = L + K;
   unsigned char* sp = smem_raw;
   char* tc_dwa = reinterpret_cast<char*>(sp);
   char* tc_dwb = tc_dwa + tc::kDwImgBytes;
@@ -849,7 +850,7 @@ __global__ void __launch_bounds__(tc::kThreads2, 2) k_obs_tc2(ObsArgs a) {
   // ready-made images of hidden layer k in global memory: dir 0 = forward (B[n][k] = W[k][n]), 1 = backward; null for
   // image layers, whose per-tile kernels are turned into images by the threads themselves
   constexpr size_t IMGF = tc::kImgBytes / 4;
-  auto gimg = [&](int k, int dir) -> const float* { return (k < L) ? a.wimg + ((size_t)(k * 2 + dir) * 2) * IMGF : nullptr; };
+  auto gimg = [&](int k, int dir) -> const float* { return (!IL || k < L) ? a.wimg + ((size_t)(k * 2 + dir) * 2) * IMGF : nullptr; };
   constexpr int PSLOT = WP * WP + WP;                        // one layer of the CTA's FP32 partial: kernel [32][32], bias [32]
   float* part32 = a.partials32 + (size_t)blockIdx.x * NL * PSLOT;
   float4* scr = a.scratch + (size_t)blockIdx.x * LT * NC * TR;
@@ -868,8 +869,8 @@ __global__ void __launch_bounds__(tc::kThreads2, 2) k_obs_tc2(ObsArgs a) {
     const bool inb = row < a.n_rows;
     const int refl = inb ? a.refl[row] : -1;
     const bool active = refl >= 0;
-    const int timg = (K > 0) ? a.image[tile * TR] : 0;
-    if (K > 0) {
+    const int timg = (IL && K > 0) ? a.image[tile * TR] : 0;
+    if (IL && K > 0) {
       __syncthreads();
       const int w = a.il_width;
       const size_t lstride = (size_t)a.il_n_images * w * (w + 1);
@@ -888,12 +889,12 @@ __global__ void __launch_bounds__(tc::kThreads2, 2) k_obs_tc2(ObsArgs a) {
 #pragma unroll
     for (int i = 0; i < HW; ++i) { const int f = HW * hf + i; h[i] = (inb && f < a.d) ? a.meta[(size_t)f * a.n_rows + row] : 0.f; }
     for (int k = 0; k < LT; ++k) {
-      const float* bk = ((k >= L) ? bimg + (size_t)(k - L) * WP : bsm + (size_t)k * WP) + HW * hf;
+      const float* bk = ((IL && k >= L) ? bimg + (size_t)(k - L) * WP : bsm + (size_t)k * WP) + HW * hf;
       float o[HW];
       CLB_PH(0);
       // the pass after this one: next forward layer, else the first dX pass, else the next tile's first layer
       const float* next = (k + 1 < LT) ? gimg(k + 1, 0) : (a.train_mlp && LT > 1) ? gimg(LT - 1, 1) : (more_tiles ? gimg(0, 0) : nullptr);
-      tc::issue3(tcx, h, (k >= L) ? wsrc(k) : nullptr, tc_img, next);
+      tc::issue3(tcx, h, (IL && k >= L) ? wsrc(k) : nullptr, tc_img, next);
       CLB_PH(1);
       tc::collect2(tcx, o);
       CLB_PH(2);
@@ -960,7 +961,7 @@ __global__ void __launch_bounds__(tc::kThreads2, 2) k_obs_tc2(ObsArgs a) {
       dp[i] = w.x * dmu + w.y * drho;
     }
     for (int k = LT - 1; k >= 0; --k) {
-      const bool is_il = k >= L;
+      const bool is_il = IL && k >= L;
       float* il_gk = nullptr; float* il_gb = nullptr;
       if (is_il && a.g_il != nullptr) {
         const int w = a.il_width;
@@ -980,7 +981,7 @@ __global__ void __launch_bounds__(tc::kThreads2, 2) k_obs_tc2(ObsArgs a) {
       if (k > 0) load_act(nxt, k - 1);
       // the pass after this layer's dX: the next layer's dX (k - 1 >= 1), else the next tile's first forward layer
       const float* next = (k > 1) ? gimg(k - 1, 1) : (more_tiles ? gimg(0, 0) : nullptr);
-      tc_layer_backward2(tcx, dp, ain, k > 0, (k >= L) ? wsrc(k) : nullptr, tc_img, next, wk, bk2, il_w);
+      tc_layer_backward2(tcx, dp, ain, k > 0, is_il ? wsrc(k) : nullptr, tc_img, next, wk, bk2, il_w);
     }
   }
   // ---- flush: the log-likelihood sum ----
