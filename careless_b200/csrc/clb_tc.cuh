@@ -337,12 +337,15 @@ constexpr int kThreads2 = 256;
   : "=r"(v[0]),"=r"(v[1]),"=r"(v[2]),"=r"(v[3]),"=r"(v[4]),"=r"(v[5]),"=r"(v[6]),"=r"(v[7]),"=r"(v[8]),"=r"(v[9]),"=r"(v[10]),"=r"(v[11]),"=r"(v[12]),"=r"(v[13]),"=r"(v[14]),"=r"(v[15]) \
   : "r"(taddr) : "memory")
 
+// TF32 split with two instructions per value: the MMA reads only the upper 19 bits of an operand (tools/tc_probe: raw
+// FP32 bits and explicitly truncated bits give bit-identical products), so the hi part is x itself and
+// lo = x - trunc(x) (exact).  3xTF32 with truncated parts is 1.4e-6 rms relative per product against 7e-7 with
+// rounded hi parts (tc_probe modes 4 / 5).
 __device__ __forceinline__ void split16(const float (&x)[16], uint32_t (&hi)[16], uint32_t (&lo)[16]) {
 #pragma unroll
   for (int k = 0; k < 16; ++k) {
-    const float h = tf32_rna(x[k]);
-    hi[k] = __float_as_uint(h);
-    lo[k] = __float_as_uint(x[k] - h);
+    hi[k] = __float_as_uint(x[k]);
+    lo[k] = __float_as_uint(x[k] - __uint_as_float(hi[k] & 0xFFFFE000u));
   }
 }
 
@@ -460,10 +463,8 @@ __device__ __forceinline__ void issue_backward2(Ctx& c, const float (&dp)[16], c
 #endif
 #pragma unroll
       for (int k = 0; k < 16; ++k) {
-        const float x = __uint_as_float(a2[k]);
-        const float h = tf32_rna(x);
-        hi[k] = __float_as_uint(h);
-        lo[k] = __float_as_uint(x - h);
+        hi[k] = a2[k];
+        lo[k] = __float_as_uint(__uint_as_float(a2[k]) - __uint_as_float(a2[k] & 0xFFFFE000u));
       }
     }
     dw_store_half(c.dw_a, c.row, c.hf, hi, lo, sw);
@@ -651,10 +652,8 @@ __device__ __forceinline__ void issue_backward3(Ctx& c, const float (&dp)[16], c
 #endif
 #pragma unroll
       for (int k = 0; k < 16; ++k) {
-        const float x = __uint_as_float(a2[k]);
-        const float h = tf32_rna(x);
-        hi[k] = __float_as_uint(h);
-        lo[k] = __float_as_uint(x - h);
+        hi[k] = a2[k];
+        lo[k] = __float_as_uint(__uint_as_float(a2[k]) - __uint_as_float(a2[k] & 0xFFFFE000u));
       }
     }
     dw_store_half(c.dw_a, c.row, c.hf, hi, lo, sw);
