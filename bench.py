@@ -286,8 +286,8 @@ def run_ours(args):
         tf32_peak = peaks["bf16_tflops"] / 2.0            # dense TF32 runs at half the bf16 rate on the same tensor pipe
         executed = tflops * (3 + 3 + 4) / 3.0              # 3xTF32 forward + dX, 4-product dW: tensor-pipe FLOPs actually issued
         # DRAM bytes of one k_obs_tc2 launch at the default workload, from the committed ncu --set full capture
-        # (profiles/r01_k_obs_tc2_ncu_full10M.txt: dram__bytes_read.sum 24.19 GB + dram__bytes_write.sum 38.30 GB)
-        traffic = 6.249e10 if (N, R) == (10_000_000, 500_000) else None
+        # (profiles/r01_k_obs_tc2_ncu_full10M.txt: dram__bytes_read.sum 10.27 GB + dram__bytes_write.sum 25.00 GB)
+        traffic = 3.527e10 if (N, R) == (10_000_000, 500_000) else None
         roofline = {"kernel": "k_obs_tc2<studentt> (scale MLP fwd+bwd on tcgen05/TMEM, 3xTF32, two threads per row; likelihood; segmented dL/dz_f reduction)",
                     "bound": "tensor", "achieved": tflops, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                     "frac": tflops / peaks["bf16_tflops"], "traffic": traffic, "traffic_unit": "bytes per launch (dram read + write, ncu)",
