@@ -321,3 +321,11 @@ def test_tensor_core_kernel_frozen_and_eval():
         assert np.array_equal(before, eng.get_params("mlp"))
     finally:
         eng.close()
+
+
+@pytest.mark.parametrize("env", ["CLB_TC_ONE_THREAD_PER_ROW", "CLB_NO_TC"])
+def test_width32_fallback_kernels(env, monkeypatch):
+    """The previous tensor-core generation (one thread per row) and the FP32-FMA kernel at width 32 stay correct."""
+    monkeypatch.setenv(env, "1")
+    p = synth.make_laue(6000, 700, d=4, n_images=12, seed=51)
+    _compare_step(p, f"w32-{env}", mlp_width=32, mlp_layers=4, laue=True, likelihood="studentt", dof=7.0, image_scales=True)
