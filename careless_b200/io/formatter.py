@@ -161,7 +161,10 @@ class DataFormatter:
         def load(filename):
             if filename.endswith(".mtz"):
                 return read_mtz(filename)
-            raise ValueError(f"{filename}: only .mtz input is supported by careless_b200 (CrystFEL .stream parsing is not built)")
+            if filename.endswith(".stream"):
+                from .crystfel import read_crystfel
+                return read_crystfel(filename)
+            raise ValueError(f"{filename}: expected a .mtz or .stream file")
         return self(load(f) for f in files)
 
     def _metadata(self, data):

@@ -33,6 +33,11 @@ class DataManager:
     def from_mtz_files(cls, filenames, formatter):
         return cls.from_datasets((read_mtz(i) for i in filenames), formatter)
 
+    @classmethod
+    def from_stream_files(cls, filenames, formatter):
+        from .crystfel import read_crystfel
+        return cls.from_datasets((read_crystfel(i) for i in filenames), formatter)
+
     # ---- priors -------------------------------------------------------------------
     @staticmethod
     def wilson_sigma(b, dHKL):

@@ -265,7 +265,10 @@ class SpaceGroup:
     @classmethod
     def from_name(cls, name):
         key = " ".join(str(name).split())
-        key = key if key in _SOHNCKE else _SHORT.get(key.replace(" ", ""), _SHORT.get(key))
+        if key.isdigit():      # ITA number (gemmi.SpaceGroup("19")), reference setting
+            key = next((k for k, (num, _) in _SOHNCKE.items() if num == int(key)), None)
+        else:
+            key = key if key in _SOHNCKE else _SHORT.get(key.replace(" ", ""), _SHORT.get(key))
         if key is None:
             raise ValueError(f"unknown space group {name!r} (the 65 Sohncke groups are tabulated, reference settings)")
         number, hall = _SOHNCKE[key]

@@ -168,3 +168,31 @@ def load_fixture(name, to_observed=True):
         ds.set_hkls(sg.hkl_to_observed(ds.get_hkls(), ds["M/ISYM"]))
         del ds.columns["M/ISYM"]
     return ds
+
+
+def write_stream(path, crystals):
+    """A minimal CrystFEL 2.3 stream: `crystals` = list of dicts(cell=(a,b,c nm, al,be,ga), hkl=(n,3) int, I, SigI, fs, ss)."""
+    with open(path, "w") as f:
+        f.write("CrystFEL stream format 2.3\nGenerated by tests\n----- Begin unit cell -----\n----- End unit cell -----\n")
+        for n, c in enumerate(crystals):
+            f.write("----- Begin chunk -----\nImage filename: synthetic_%d.h5\nImage serial number: %d\nhit = 1\n" % (n, n + 1))
+            f.write("Peaks from peak search\n  fs/px   ss/px (1/d)/nm^-1   Intensity  Panel\n 624.00  259.50       3.55       74.18   p0\nEnd of peak list\n")
+            f.write("--- Begin crystal\nCell parameters %.5f %.5f %.5f nm, %.5f %.5f %.5f deg\n" % tuple(c["cell"]))
+            f.write("lattice_type = tetragonal\ncentering = P\nnum_reflections = %d\nReflections measured after indexing\n" % len(c["hkl"]))
+            f.write("   h    k    l          I   sigma(I)       peak background  fs/px  ss/px panel\n")
+            for (h, k, l), i, s, x, y in zip(c["hkl"], c["I"], c["SigI"], c["fs"], c["ss"]):
+                f.write("%4d %4d %4d %10.2f %10.2f %10.2f %10.2f %6.1f %6.1f p0\n" % (h, k, l, i, s, 10.0, 1.0, x, y))
+            f.write("End of reflections\n--- End crystal\n----- End chunk -----\n")
+
+
+def synthetic_stream(path, n_crystals=6, n_refl=180, seed=0):
+    rng = np.random.default_rng(seed)
+    crystals = []
+    for _ in range(n_crystals):
+        hkl = rng.integers(-12, 13, size=(n_refl, 3))
+        hkl = hkl[np.any(hkl != 0, axis=1)]
+        i = rng.gamma(2.0, 50.0, size=len(hkl))
+        crystals.append(dict(cell=(7.9 + 0.01 * rng.standard_normal(), 7.9, 3.8, 90.0, 90.0, 90.0), hkl=hkl, I=i,
+                             SigI=5.0 + 0.1 * np.sqrt(i), fs=rng.uniform(0, 1400, len(hkl)), ss=rng.uniform(0, 1400, len(hkl))))
+    write_stream(path, crystals)
+    return crystals

@@ -125,3 +125,16 @@ def test_command_line_entry_point(tmp_path):
     main(["poly", "--iterations", "4", "--mlp-layers", "2", "--disable-progress-bar", "-w", "Wavelength", "dHKL,Wavelength",
           files[0], out + "_laue"])
     assert len(read_mtz(out + "_laue_0.mtz")) > 50
+
+
+def test_crystfel_stream_entry_point(tmp_path):
+    """tests/test_cli.py:112-119: `careless mono --spacegroups=1 dHKL,image_id file.stream out`; poly refuses streams."""
+    from careless_b200.careless import main
+    path = os.path.join(tmp_path, "synthetic.stream")
+    U.synthetic_stream(path, n_crystals=6, n_refl=150, seed=5)
+    out = os.path.join(tmp_path, "sfx")
+    main(["mono", "--iterations", "10", "--mlp-layers", "2", "--disable-progress-bar", "--spacegroups=1", "dHKL,image_id", path, out])
+    merged = read_mtz(out + "_0.mtz")
+    assert len(merged) > 100 and np.all(np.isfinite(merged["F"])) and merged.spacegroup.name == "P 1"
+    with pytest.raises(ValueError):
+        main(["poly", "--iterations", "2", "--disable-progress-bar", "--spacegroups=1", "dHKL,image_id", path, out + "_p"])

@@ -245,3 +245,35 @@ def test_mtz_round_trip(tmp_path):
     assert [o.triplet() for o in back.spacegroup.sym_ops] == [o.triplet() for o in ds.spacegroup.sym_ops]
     obs = read_mtz(path)
     assert np.array_equal(obs.get_hkls(), U.load_fixture("pyp_off").get_hkls())
+
+
+def test_crystfel_stream_reader(tmp_path):
+    """rs.read_crystfel as careless uses it (tests/test_cli.py:112-119): observed indices, I / SigI, crystal number as BATCH."""
+    from careless_b200.io.crystfel import read_crystfel
+    path = os.path.join(tmp_path, "synthetic.stream")
+    crystals = U.synthetic_stream(path, n_crystals=4, n_refl=50, seed=3)
+    ds = read_crystfel(path)
+    hkl = np.concatenate([c["hkl"] for c in crystals])
+    assert np.array_equal(ds.get_hkls(), hkl)
+    assert np.allclose(ds["I"], np.concatenate([c["I"] for c in crystals]), atol=5e-3)
+    assert np.array_equal(ds["BATCH"], np.concatenate([np.full(len(c["hkl"]), i) for i, c in enumerate(crystals)]))
+    assert ds.dtypes["BATCH"] == "B" and ds.dtypes["I"] == "J" and ds.dtypes["SigI"] == "Q" and not ds.merged
+    assert ds.cell.a == pytest.approx(10 * np.mean([c["cell"][0] for c in crystals]), abs=1e-3) and ds.spacegroup is None
+    f = MonoFormatter(None, None, None, ["dHKL", "image_id"], False, False, spacegroups=["1"])
+    inputs, rac = f.format_files([path])
+    assert inputs[0].shape[0] == len(hkl) and inputs[1].max() == 3
+    with pytest.raises(ValueError):
+        MonoFormatter(None, None, None, ["dHKL"], False, False).format_files([path])       # a stream has no space group
+    with pytest.raises(ValueError):
+        LaueFormatter("Wavelength", None, None, None, ["dHKL"], False, False).format_files([path])
+    ref = "/root/reference/tests/data/crystfel.stream"
+    if os.path.exists(ref):          # the reference's own fixture (build container only)
+        real = read_crystfel(ref)
+        assert len(real) == 618 and real["BATCH"].max() == 2 and real.cell.c == pytest.approx(38.76, abs=0.01)
+
+
+def test_spacegroup_by_number():
+    assert S.SpaceGroup.from_name("1").name == "P 1" and S.SpaceGroup.from_name("96").name == "P 43 21 2"
+    assert S.SpaceGroup.from_name("P212121").number == 19
+    with pytest.raises(ValueError):
+        S.SpaceGroup.from_name("P -1")
