@@ -329,3 +329,35 @@ def test_width32_fallback_kernels(env, monkeypatch):
     monkeypatch.setenv(env, "1")
     p = synth.make_laue(6000, 700, d=4, n_images=12, seed=51)
     _compare_step(p, f"w32-{env}", mlp_width=32, mlp_layers=4, laue=True, likelihood="studentt", dof=7.0, image_scales=True)
+
+
+@pytest.mark.parametrize("name", ["mono_t_w32", "laue_n_w10_hybrid", "dw_w8"])
+def test_engine_matches_committed_golden_vectors(name):
+    """The CUDA engine against tests/golden/oracle_vectors.npz (float64 oracle outputs committed with their generator):
+    first-step ELBO terms and gradients, loss history and surrogate parameters after three Adam steps, Philox draws."""
+    import importlib.util, os
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_oracle_vectors", os.path.join(here, "golden", "make_oracle_vectors.py"))
+    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+    gold = np.load(os.path.join(here, "golden", "oracle_vectors.npz"))
+    case = mod.CASES[name]
+    p = mod.problem(case["gen"])
+    kw = dict(case["cfg"])
+    ocfg, oprior, eng = U.build(p, opt=om.AdamConfig(lr=1e-2), seed=mod.SEED, **kw)
+    try:
+        hist = eng.step(1)
+        m = gold[f"{name}/metrics"]
+        for i, k in enumerate(("loss", "NLL", "F KLDiv", "Grad Norm")):
+            assert abs(hist[0][k] - m[i]) <= 1e-4 * abs(m[i]), (k, hist[0][k], m[i])
+        for grp, key in (("sf_loc_raw", "sf_loc_raw"), ("sf_scale_raw", "sf_scale_raw")):
+            g = eng.get_grads(grp).astype(np.float64)
+            assert abs(np.linalg.norm(g) - gold[f"{name}/grad_norm/{key}"][0]) <= 1e-4 * gold[f"{name}/grad_norm/{key}"][0]
+            head = gold[f"{name}/grad_head/{key}"]
+            assert np.max(np.abs(g[:8] - head)) <= 2e-4 * (np.max(np.abs(head)) + 1e-12)
+        hist += eng.step(2)
+        lh = gold[f"{name}/loss_history"]
+        assert np.allclose([h["loss"] for h in hist], lh, rtol=2e-4)
+        final = eng.get_params("sf_loc_raw").astype(np.float64)
+        assert U.rel_err(final, gold[f"{name}/sf_loc_raw_final"]) <= 2e-4
+    finally:
+        eng.close()

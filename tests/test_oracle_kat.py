@@ -202,3 +202,16 @@ def test_uniform_grid_is_exact_in_float32_and_never_hits_the_ends():
     # the oracle sampler clamps injected draws like the kernel does
     z = om.tn_sample(T([1.0]), T([0.5]), T([0.0]), T([1e10]), T([[1.0], [0.0]]))
     assert np.all(np.isfinite(z.numpy()))
+
+
+def test_oracle_reproduces_committed_golden_vectors():
+    """tests/golden/oracle_vectors.npz (made by make_oracle_vectors.py): the checker itself must not drift."""
+    import importlib.util, os
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_oracle_vectors", os.path.join(here, "golden", "make_oracle_vectors.py"))
+    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+    gold = np.load(os.path.join(here, "golden", "oracle_vectors.npz"))
+    for name in mod.CASES:
+        now = mod.run_case(name)
+        for k, v in now.items():
+            assert np.allclose(v, gold[k], rtol=1e-9, atol=1e-12), k
