@@ -776,13 +776,19 @@ __device__ __forceinline__ void bias_red16(const float (&dp)[16], float* dst, in
 // slots (il_w > 0: kernel stored (out, in), width il_w).
 __device__ __forceinline__ void tc_layer_backward2(tc::Ctx& tcx, float (&dp)[16], const float (&ain)[16], bool need_dx,
                                                    const float* build_from, char* img_base, const float* next_img,
-                                                   float* wk, float* bk, int il_w) {
+                                                   float* wk, float* bk, int il_w, unsigned& mask_out) {
   const int lane = tcx.tid & 31;
   CLB_PH(5);
-  bias_red16(dp, bk != nullptr ? bk + 16 * tcx.hf : nullptr, lane, il_w > 0 ? il_w - 16 * tcx.hf : 16);
-  CLB_PH(6);
   tc::issue_backward3(tcx, dp, ain, need_dx, build_from, img_base, next_img);
   CLB_PH(7);
+  // everything that does not feed the tensor cores runs while they work: the sign mask of a_k (leaky' of the layer
+  // below) and the bias gradient (column sums of dp)
+  unsigned mask = 0u;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) mask |= (ain[i] > 0.f ? 1u : 0u) << i;
+  mask_out = mask;
+  bias_red16(dp, bk != nullptr ? bk + 16 * tcx.hf : nullptr, lane, il_w > 0 ? il_w - 16 * tcx.hf : 16);
+  CLB_PH(6);
   if (need_dx) tc::collect2(tcx, dp);
   CLB_PH(8);
   tc::collect_dw_red(tcx, wk, il_w);
@@ -951,10 +957,8 @@ __global__ void __launch_bounds__(tc::kThreads2, 2) k_obs_tc2(ObsArgs a) {
     for (int j = 0; j < HW; ++j) dp[j] = 0.f;
     if (hf == 0) { dp[0] = dmu; dp[1] = drho; }
     // head: dW_out = a_L^T [dmu, drho]
-    tc_layer_backward2(tcx, dp, h, false, nullptr, tc_img, nullptr, part32 + (size_t)L * PSLOT, part32 + (size_t)L * PSLOT + WP * WP, 0);
-    unsigned mask = 0u;
-#pragma unroll
-    for (int j = 0; j < HW; ++j) mask |= (h[j] > 0.f ? 1u : 0u) << j;
+    unsigned mask = 0u;                  // sign bits of the layer input just processed: leaky'(pre-activation) of the layer below
+    tc_layer_backward2(tcx, dp, h, false, nullptr, tc_img, nullptr, part32 + (size_t)L * PSLOT, part32 + (size_t)L * PSLOT + WP * WP, 0, mask);
 #pragma unroll
     for (int i = 0; i < HW; ++i) {
       const float2 w = *reinterpret_cast<const float2*>(&Whead[(HW * hf + i) * 2]);
@@ -975,13 +979,12 @@ __global__ void __launch_bounds__(tc::kThreads2, 2) k_obs_tc2(ObsArgs a) {
 #pragma unroll
       for (int j = 0; j < HW; ++j) dp[j] = ((mask >> j) & 1u) ? dp[j] : kLeak * dp[j];
       float ain[HW];
-      mask = 0u;
 #pragma unroll
-      for (int i = 0; i < HW; ++i) { ain[i] = nxt[i]; mask |= (ain[i] > 0.f ? 1u : 0u) << i; }
+      for (int i = 0; i < HW; ++i) ain[i] = nxt[i];
       if (k > 0) load_act(nxt, k - 1);
       // the pass after this layer's dX: the next layer's dX (k - 1 >= 1), else the next tile's first forward layer
       const float* next = (k > 1) ? gimg(k - 1, 1) : (more_tiles ? gimg(0, 0) : nullptr);
-      tc_layer_backward2(tcx, dp, ain, k > 0, is_il ? wsrc(k) : nullptr, tc_img, next, wk, bk2, il_w);
+      tc_layer_backward2(tcx, dp, ain, k > 0, is_il ? wsrc(k) : nullptr, tc_img, next, wk, bk2, il_w, mask);
     }
   }
   // ---- flush: the log-likelihood sum ----
