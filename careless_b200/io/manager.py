@@ -178,81 +178,75 @@ class DataManager:
         return self.split_mono_data_by_mask(test_idx)
 
     # ---- model factory ------------------------------------------------------------------
+    def _prior_from(self, opt):
+        """Wilson prior, or the DoubleWilson prior when --double-wilson-parents is given (manager.py:405-429)."""
+        if opt.parents is None:
+            return self.get_wilson_prior(opt.wilson_prior_b)
+        parents = [None if tok == "None" else int(tok) for tok in opt.parents.split(",")]
+        r_values = [float(tok) for tok in opt.dwr.split(",")]
+        bad = [r for r in r_values if not (-1. < r < 1.)]
+        if bad:
+            raise ValueError(f"Supplied --double-wilson-r value {bad[0]} outside of allowed range (-1, 1)")
+        for r in r_values:
+            if r < 0:
+                warnings.warn(f"Supplied --double-wilson-r value {r} is negative")
+        ops = None
+        if opt.reindexing_ops is not None:
+            ops = [parse_triplet(_hkl_to_xyz(tok)) for tok in opt.reindexing_ops.split(";")]
+        return DoubleWilsonPrior.from_asu_collection(self.asu_collection, parents, r_values, ops,
+                                                     sigma=self.get_wilson_sigma(opt.wilson_prior_b),
+                                                     optimize_r=opt.optimize_double_wilson_r)
+
+    def _likelihood_from(self, opt):
+        """Normal / Student-t, mono / Laue, plain / Ev11 (manager.py:392-403, 438-444)."""
+        if opt.type not in ("mono", "poly"):
+            raise ValueError(f"unknown mode {opt.type!r}")
+        if opt.type == "poly":
+            from ..models.likelihoods import laue as family
+        else:
+            from ..models.likelihoods import mono as family
+        suffix = "Ev11Likelihood" if opt.refine_uncertainties else "Likelihood"
+        dof = opt.studentt_likelihood_dof
+        return getattr(family, "Normal" + suffix)() if dof is None else getattr(family, "StudentT" + suffix)(dof)
+
+    def _scaler_from(self, opt):
+        """MLP (+ image scales | image layers) scale model (manager.py:446-490)."""
+        from ..models.scaling.image import HybridImageScaler, ImageScaler, NeuralImageScaler
+        from ..models.scaling.nn import MLPScaler
+        bijector = opt.scale_bijector.lower()
+        if bijector not in ("exp", "softplus"):
+            raise ValueError(f"Unsupported scale bijector type, {opt.scale_bijector}")
+        # softplus models work in units of the intensity spread (additive shift of the scale distribution)
+        shift = float(BaseModel.get_intensities(self.inputs).std()) if bijector == "softplus" else None
+        width = opt.mlp_width if opt.mlp_width is not None else BaseModel.get_metadata(self.inputs).shape[-1]
+        n_images = int(np.max(BaseModel.get_image_id(self.inputs))) + 1
+        common = dict(epsilon=opt.epsilon, scale_bijector=bijector, scale_multiplier=shift)
+        if opt.image_layers > 0:
+            return NeuralImageScaler(opt.image_layers, n_images, opt.mlp_layers, width, **common)
+        mlp = MLPScaler(opt.mlp_layers, width, **common)
+        return HybridImageScaler(mlp, ImageScaler(n_images)) if opt.use_image_scales else mlp
+
     def build_model(self, parser=None, surrogate_posterior=None, prior=None, likelihood=None, scaling_model=None, mc_sample_size=None):
         """The model `parser` describes (manager.py:380-507); any of the four parts can be overridden."""
         from ..models.merging.surrogate_posteriors import TruncatedNormal
         from ..models.merging.variational import VariationalMergingModel
-        from ..models.scaling.image import HybridImageScaler, ImageScaler, NeuralImageScaler
-        from ..models.scaling.nn import MLPScaler
         from ..optimizers import Adam
-        parser = parser if parser is not None else self.parser
-        if parser is None:
+        opt = self.parser if parser is None else parser
+        if opt is None:
             raise ValueError("No parser supplied, but self.parser is unset")
-        if parser.type == "poly":
-            from ..models.likelihoods import laue as lik
-        elif parser.type == "mono":
-            from ..models.likelihoods import mono as lik
-        else:
-            raise ValueError(f"unknown mode {parser.type!r}")
-        if parser.refine_uncertainties:
-            NormalLikelihood, StudentTLikelihood = lik.NormalEv11Likelihood, lik.StudentTEv11Likelihood
-        else:
-            NormalLikelihood, StudentTLikelihood = lik.NormalLikelihood, lik.StudentTLikelihood
-
-        parents, r_values = parser.parents, parser.dwr
-        if prior is None and parents is None:
-            prior = self.get_wilson_prior(parser.wilson_prior_b)
-        elif prior is None:
-            parents = [None if i == "None" else int(i) for i in parents.split(",")]
-            r_values = [float(i) for i in r_values.split(",")]
-            for r in r_values:
-                if (r >= 1.) or (r <= -1.):
-                    raise ValueError(f"Supplied --double-wilson-r value {r} outside of allowed range (-1, 1)")
-                if r < 0:
-                    warnings.warn(f"Supplied --double-wilson-r value {r} is negative")
-            sigma = self.get_wilson_sigma(parser.wilson_prior_b)
-            reindexing_ops = parser.reindexing_ops
-            if reindexing_ops is not None:
-                reindexing_ops = [parse_triplet(_hkl_to_xyz(i)) for i in reindexing_ops.split(";")]
-            prior = DoubleWilsonPrior.from_asu_collection(self.asu_collection, parents, r_values, reindexing_ops, sigma=sigma,
-                                                          optimize_r=parser.optimize_double_wilson_r)
-
-        loc, scale = prior.mean(), prior.stddev()
-        scale = scale * parser.structure_factor_init_scale
-        low = (1e-32 * ~self.asu_collection.centric).astype("float32")
+        likelihood = likelihood if likelihood is not None else self._likelihood_from(opt)
+        prior = prior if prior is not None else self._prior_from(opt)
         if surrogate_posterior is None:
-            surrogate_posterior = TruncatedNormal.from_loc_and_scale(loc, scale, low, scale_shift=parser.epsilon)
-        if likelihood is None:
-            dof = parser.studentt_likelihood_dof
-            likelihood = NormalLikelihood() if dof is None else StudentTLikelihood(dof)
-        if scaling_model is None:
-            mlp_width = parser.mlp_width
-            if mlp_width is None:
-                mlp_width = BaseModel.get_metadata(self.inputs).shape[-1]
-            bij = parser.scale_bijector.lower()
-            if bij == "softplus":
-                istd = float(BaseModel.get_intensities(self.inputs).std())
-            elif bij == "exp":
-                istd = None
-            else:
-                raise ValueError(f"Unsupported scale bijector type, {parser.scale_bijector}")
-            if parser.image_layers > 0:
-                n_images = int(np.max(BaseModel.get_image_id(self.inputs))) + 1
-                scaling_model = NeuralImageScaler(parser.image_layers, n_images, parser.mlp_layers, mlp_width, epsilon=parser.epsilon,
-                                                  scale_bijector=bij, scale_multiplier=istd)
-            else:
-                mlp_scaler = MLPScaler(parser.mlp_layers, mlp_width, epsilon=parser.epsilon, scale_bijector=bij, scale_multiplier=istd)
-                if parser.use_image_scales:
-                    n_images = int(np.max(BaseModel.get_image_id(self.inputs))) + 1
-                    scaling_model = HybridImageScaler(mlp_scaler, ImageScaler(n_images))
-                else:
-                    scaling_model = mlp_scaler
+            # start at the prior's moments; acentric reflections are kept off zero (manager.py:431-436)
+            lower = np.where(self.asu_collection.centric, 0., 1e-32).astype("float32")
+            surrogate_posterior = TruncatedNormal.from_loc_and_scale(prior.mean(), prior.stddev() * opt.structure_factor_init_scale,
+                                                                     lower, scale_shift=opt.epsilon)
+        scaling_model = scaling_model if scaling_model is not None else self._scaler_from(opt)
         model = VariationalMergingModel(surrogate_posterior, prior, likelihood, scaling_model,
-                                        parser.mc_samples if mc_sample_size is None else mc_sample_size, kl_weight=parser.kl_weight)
-        model.seed = getattr(parser, "seed", 1234)
-        model.device = getattr(parser, "gpu_id", 0)
-        model.compile(Adam(parser.learning_rate, parser.beta_1, parser.beta_2, clipnorm=parser.clipnorm, clipvalue=parser.clipvalue,
-                           global_clipnorm=parser.global_clipnorm))
+                                        opt.mc_samples if mc_sample_size is None else mc_sample_size, kl_weight=opt.kl_weight)
+        model.seed, model.device = getattr(opt, "seed", 1234), getattr(opt, "gpu_id", 0)
+        model.compile(Adam(opt.learning_rate, opt.beta_1, opt.beta_2, clipnorm=opt.clipnorm, clipvalue=opt.clipvalue,
+                           global_clipnorm=opt.global_clipnorm))
         return model
 
 

@@ -1,61 +1,52 @@
-"""Input-tuple schema shared by every model part (mirror of careless/models/base.py:22-121, numpy arrays)."""
+"""Input-tuple schema shared by every model part.
+
+careless passes its data around as one tuple of 2-D arrays whose positions are fixed by `BaseModel.input_index`
+(careless/models/base.py:22-31) and read through `BaseModel.get_<column>(inputs)` static accessors (:84-121); a tuple
+that reaches the `harmonic_id` slot is Laue data (:39-46).  Same names and error behaviour here, on numpy arrays;
+the accessors are generated from the column list instead of being written out one by one.
+"""
 import numpy as np
+
+COLUMNS = ("refl_id", "image_id", "file_id", "metadata", "intensities", "uncertainties", "wavelength", "harmonic_id")
 
 
 class BaseModel:
-    input_index = {
-        'refl_id': 0,
-        'image_id': 1,
-        'file_id': 2,
-        'metadata': 3,
-        'intensities': 4,
-        'uncertainties': 5,
-        'wavelength': 6,
-        'harmonic_id': 7,
-    }
-
-    @staticmethod
-    def is_laue(inputs) -> bool:
-        return len(inputs) >= BaseModel.get_index_by_name('harmonic_id') + 1
-
-    @staticmethod
-    def get_name_by_index(index):
-        for k, v in BaseModel.input_index.items():
-            if v == index:
-                return k
-        raise ValueError(f"index, {index}, not a valid index. Valid indices are {BaseModel.input_index.values()}.")
+    input_index = {name: position for position, name in enumerate(COLUMNS)}
 
     @staticmethod
     def get_index_by_name(name):
-        if name not in BaseModel.input_index:
-            raise ValueError(f"name, {name}, not a valid key. Valid keys are {BaseModel.input_index.keys()}.")
-        return BaseModel.input_index[name]
+        try:
+            return BaseModel.input_index[name]
+        except KeyError:
+            raise ValueError(f"name, {name}, not a valid key. Valid keys are {BaseModel.input_index.keys()}.") from None
+
+    @staticmethod
+    def get_name_by_index(index):
+        if isinstance(index, (int, np.integer)) and 0 <= index < len(COLUMNS):
+            return COLUMNS[index]
+        raise ValueError(f"index, {index}, not a valid index. Valid indices are {BaseModel.input_index.values()}.")
+
+    @staticmethod
+    def is_laue(inputs) -> bool:
+        return len(inputs) > BaseModel.input_index["harmonic_id"]
 
     @staticmethod
     def get_input_by_name(inputs, name):
-        idx = BaseModel.get_index_by_name(name)
-        try:
-            datum = inputs[idx]
-        except Exception:
+        position = BaseModel.get_index_by_name(name)
+        if position >= len(inputs):
             raise ValueError(f"Attempting to gather {name} data from input tensors with length {len(inputs)} failed.")
-        datum = np.asarray(datum)
-        if datum.ndim > 1 and datum.shape[0] == 1:
-            datum = np.squeeze(datum, axis=0)
-        return datum
+        column = np.asarray(inputs[position])
+        # a leading batch axis of size one (a keras `fit` leftover, base.py:79-80) is dropped
+        return column[0] if (column.ndim > 1 and column.shape[0] == 1) else column
 
-    @staticmethod
-    def get_refl_id(inputs): return BaseModel.get_input_by_name(inputs, 'refl_id')
-    @staticmethod
-    def get_file_id(inputs): return BaseModel.get_input_by_name(inputs, 'file_id')
-    @staticmethod
-    def get_image_id(inputs): return BaseModel.get_input_by_name(inputs, 'image_id')
-    @staticmethod
-    def get_metadata(inputs): return BaseModel.get_input_by_name(inputs, 'metadata')
-    @staticmethod
-    def get_intensities(inputs): return BaseModel.get_input_by_name(inputs, 'intensities')
-    @staticmethod
-    def get_uncertainties(inputs): return BaseModel.get_input_by_name(inputs, 'uncertainties')
-    @staticmethod
-    def get_wavelength(inputs): return BaseModel.get_input_by_name(inputs, 'wavelength')
-    @staticmethod
-    def get_harmonic_id(inputs): return BaseModel.get_input_by_name(inputs, 'harmonic_id')
+
+def _accessor(name):
+    def get(inputs):
+        return BaseModel.get_input_by_name(inputs, name)
+    get.__name__ = f"get_{name}"
+    get.__doc__ = f"The `{name}` column of an input tuple."
+    return staticmethod(get)
+
+
+for _name in COLUMNS:
+    setattr(BaseModel, f"get_{_name}", _accessor(_name))
