@@ -99,7 +99,8 @@ struct clb_handle {
   int cur_rows = 0;          // which of the two events belongs to the buffer `rows` currently points to
   int32_t *d_refl = nullptr, *d_image = nullptr, *d_spot = nullptr; uint32_t* d_oidx = nullptr;
   float *d_meta = nullptr, *d_iobs = nullptr, *d_sig = nullptr;
-  DevBuf partials, scratch, wpack, wimg;
+  DevBuf partials, wpack, wimg;     // partials: [weight-gradient partials | activation scratch]
+  size_t partial_bytes = 0; float4* scratch_ptr = nullptr;
   int obs_threads = kObsThreads;   // rows per CTA tile: 256 (FP32 kernels) or 128 (tensor-core kernels, 2 CTAs per SM)
   DevBuf acc, var_sums, red, metrics, var_scale, adam_alpha, stop_step;
   DevBuf inj_u, inj_eps, ipred, scale_mom, results;
@@ -537,23 +538,31 @@ int clb_set_observations(clb_handle* h, int64_t n, int64_t n_total, const int64_
   // ---- launch geometry + per-CTA buffers of the observation kernel ----
   const int64_t n_tiles = (npad + h->obs_threads - 1) / h->obs_threads;
   h->grid_obs = (int)std::min<int64_t>(n_tiles, (int64_t)h->n_sms * (h->use_tc ? 2 : 1));
-  CLB_CUDA(h, h->partials.alloc(sizeof(double) * (size_t)h->grid_obs * h->KS * partial_row_size(h->NL, h->WP)));
-  CLB_CUDA(h, h->scratch.alloc(sizeof(float4) * (size_t)h->grid_obs * std::max(1, c.mlp_layers + c.image_layers) * (h->WP / 4) * h->obs_threads));
   {
-    // Keep the per-CTA FP64 weight-gradient partials (read-modify-written once per tile and layer) resident in L2: the
-    // activation scratch streams through the same cache and would otherwise evict them (12 GB of extra DRAM writes
-    // per 10 M observations).  CLB_NO_L2_PERSIST=1 switches the policy window off.
-    const char* off = getenv("CLB_NO_L2_PERSIST");
+    // One allocation [weight-gradient partials | activation scratch] so that a single L2 access-policy window can cover
+    // both: the partials are read-modify-written once per tile and layer and must not be evicted by the scratch
+    // streaming through the same cache; whatever persisting capacity is left keeps the most recently written
+    // activations on chip until the backward pass reads them.  CLB_L2_WINDOW=0 no window, 1 partials only, 2 both.
+    const size_t pbytes = h->use_tc2 ? sizeof(float) * (size_t)h->grid_obs * h->NL * (32 * 32 + 32)
+                                     : sizeof(double) * (size_t)h->grid_obs * h->KS * partial_row_size(h->NL, h->WP);
+    const size_t pb = (pbytes + 255) & ~(size_t)255;
+    const size_t sbytes = sizeof(float4) * (size_t)h->grid_obs * std::max(1, c.mlp_layers + c.image_layers) * (h->WP / 4) * h->obs_threads;
+    CLB_CUDA(h, h->partials.alloc(pb + sbytes));
+    h->partial_bytes = pbytes;
+    h->scratch_ptr = reinterpret_cast<float4*>(h->partials.as<char>() + pb);
+    const char* mode_s = getenv("CLB_L2_WINDOW");
+    const int mode = mode_s ? atoi(mode_s) : 1;
     int max_persist = 0, max_window = 0;
     cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, c.device);
     cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, c.device);
-    if (!(off && off[0] == '1') && max_persist > 0 && max_window > 0 && h->partials.bytes > 0) {
-      const size_t want = std::min<size_t>(h->partials.bytes, (size_t)max_persist);
+    if (mode > 0 && max_persist > 0 && max_window > 0) {
+      const size_t span = std::min<size_t>(mode >= 2 ? pb + sbytes : pb, (size_t)max_window);
+      const size_t want = std::min<size_t>(span, (size_t)max_persist);
       cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
       cudaStreamAttrValue attr{};
       attr.accessPolicyWindow.base_ptr = h->partials.p;
-      attr.accessPolicyWindow.num_bytes = std::min<size_t>(h->partials.bytes, (size_t)max_window);
-      attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)want / (double)attr.accessPolicyWindow.num_bytes);
+      attr.accessPolicyWindow.num_bytes = span;
+      attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)want / (double)span);
       attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
       attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
       if (cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
@@ -807,7 +816,7 @@ static int step_begin_impl(clb_handle* h, const float* inj_u, const float* inj_e
   // gradients of the replicated groups are accumulated with atomics / overwritten by the reduction
   if (h->P > 2 * R) CLB_CUDA(h, cudaMemsetAsync(grad + 2 * R, 0, sizeof(float) * (h->P - 2 * R), st));
   const bool train_mlp = h->gtrain[CLB_GROUP_MLP] != 0 && !h->eval_mode;
-  if (train_mlp) CLB_CUDA(h, cudaMemsetAsync(h->partials.p, 0, sizeof(double) * (size_t)h->grid_obs * h->KS * partial_row_size(h->NL, h->WP), st));
+  if (train_mlp) CLB_CUDA(h, cudaMemsetAsync(h->partials.p, 0, h->partial_bytes, st));
 
   const bool dw = c.prior == CLB_PRIOR_DOUBLE_WILSON;
   {
@@ -858,7 +867,7 @@ static int step_begin_impl(clb_handle* h, const float* inj_u, const float* inj_e
     a.z = h->z.as<float>(); a.gz = h->gz.as<float>(); a.R = R; a.S = S;
     a.inj_eps = d_inj_eps;
     a.g_img = (c.image_scales && h->gtrain[CLB_GROUP_IMAGE_SCALES] && !h->eval_mode) ? grad + h->goff[CLB_GROUP_IMAGE_SCALES] : nullptr;
-    a.partials = h->partials.as<double>(); a.scratch = h->scratch.as<float4>();
+    a.partials = h->partials.as<double>(); a.scratch = h->scratch_ptr;
     a.partials32 = h->partials.as<float>();
     a.ipred_out = h->want_ipred ? h->ipred.as<float>() : nullptr;
     a.scale_mean_out = h->want_scale_moments ? h->scale_mom.as<float>() : nullptr;
