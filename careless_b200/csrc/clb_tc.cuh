@@ -400,35 +400,6 @@ __device__ __forceinline__ void load_w2(const float* Wg, int tid, float (&w)[4])
   }
 }
 
-template <bool BWD>
-__device__ __forceinline__ void build_weight_image2(Ctx& c, const float (&w)[4]) {
-  int n, kq;
-  if (!BWD) { n = c.tid & 31; kq = c.tid >> 5; }
-  else { kq = c.tid & 7; n = c.tid >> 3; }
-  const uint32_t off = kq * kLBO + (n >> 3) * kSBO + (n & 7) * 16;
-  float4 hi, lo;
-  hi.x = tf32_rna(w[0]); hi.y = tf32_rna(w[1]); hi.z = tf32_rna(w[2]); hi.w = tf32_rna(w[3]);
-  lo.x = w[0] - hi.x; lo.y = w[1] - hi.y; lo.z = w[2] - hi.z; lo.w = w[3] - hi.w;
-  *reinterpret_cast<float4*>(c.img_hi + off) = hi;
-  *reinterpret_cast<float4*>(c.img_lo + off) = lo;
-}
-
-template <bool BWD>
-__device__ __forceinline__ void issue2(Ctx& c, const float (&x)[16], const float (&w)[4]) {
-  {
-    uint32_t hi[16], lo[16];
-    split16(x, hi, lo);
-    CLB_TMEM_ST16(c.row_addr + kColAhi + c.col, hi);
-    CLB_TMEM_ST16(c.row_addr + kColAlo + c.col, lo);
-  }
-  build_weight_image2<BWD>(c, w);
-  wait_st();
-  fence_async_smem();
-  fence_before();
-  __syncthreads();
-  issue_chain_mmas(c);
-}
-
 __device__ __forceinline__ void collect2(Ctx& c, float (&y)[16]) {
   mbar_wait(c.mbar, c.parity);
   c.parity ^= 1u;
@@ -439,84 +410,6 @@ __device__ __forceinline__ void collect2(Ctx& c, float (&y)[16]) {
 #pragma unroll
   for (int k = 0; k < 16; ++k) y[k] = __uint_as_float(v[k]);
 }
-
-// Backward of one layer (see issue_backward): the dW issuer is warp 7, the chain issuer warp 0.
-__device__ __forceinline__ void issue_backward2(Ctx& c, const float (&dp)[16], const float (&ain)[16], const float (&w)[4], bool need_dx) {
-  {
-    uint32_t hi[16], lo[16];
-    split16(dp, hi, lo);
-    if (need_dx) {
-      CLB_TMEM_ST16(c.row_addr + kColAhi + c.col, hi);
-      CLB_TMEM_ST16(c.row_addr + kColAlo + c.col, lo);
-    }
-    const int sw = (c.row >> 2) & 1;       // conflict-free image stores: see dw_store_half
-#ifndef CLB_EXPERIMENT_SWZ
-    swap_blocks(hi, sw); swap_blocks(lo, sw);
-#endif
-    dw_store_half(c.dw_b, c.row, c.hf, hi, lo, sw);
-    {
-      uint32_t a2[16];
-#pragma unroll
-      for (int k = 0; k < 16; ++k) a2[k] = __float_as_uint(ain[k]);
-#ifndef CLB_EXPERIMENT_SWZ
-      swap_blocks(a2, sw);
-#endif
-#pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        hi[k] = a2[k];
-        lo[k] = __float_as_uint(__uint_as_float(a2[k]) - __uint_as_float(a2[k] & 0xFFFFE000u));
-      }
-    }
-    dw_store_half(c.dw_a, c.row, c.hf, hi, lo, sw);
-  }
-  if (need_dx) build_weight_image2<true>(c, w);
-  wait_st();
-  fence_async_smem();
-  fence_before();
-  __syncthreads();
-  if (need_dx) issue_chain_mmas(c);
-  const uint32_t warp = uniform32((uint32_t)c.tid >> 5);
-  if (warp == 7u) {
-    fence_after();
-    const uint32_t d = uniform32(c.base) + kColDw;
-    const uint64_t a0 = uniform64(c.desc_dwa), b0 = uniform64(c.desc_dwb);
-    const uint32_t bar = uniform32(c.mbar_dw);
-    if (elect_one()) {
-#ifndef CLB_ABL_DW
-#pragma unroll
-      for (int ks = 0; ks < kThreads / 8; ++ks)
-        mma_tf32_ss(d, a0 + (uint64_t)((2u * kDwSBO * (uint32_t)ks) >> 4), b0 + (uint64_t)((2u * kDwSBO * (uint32_t)ks) >> 4), kIdescDw, ks > 0 ? 1u : 0u);
-#endif
-      commit(bar);
-    }
-    __syncwarp();
-  }
-}
-
-// dW rows live at lanes (r % 16) + 32 (r / 16): in every warp the lanes < 16 hold row r = 16 (warp % 4) + lane; the
-// thread folds the delta-hi and delta-lo column blocks of ITS 16 columns and parks them in the stage (aliases dw_a).
-__device__ __forceinline__ void collect_dw2(Ctx& c) {
-  mbar_wait(c.mbar_dw, c.parity_dw);
-  c.parity_dw ^= 1u;
-  fence_after();
-  const int q = (c.tid >> 5) & 3, lane = c.tid & 31;
-  const uint32_t addr = c.row_addr + kColDw + c.col;
-  uint32_t v0[16], v1[16];
-  CLB_TMEM_LD16(addr, v0);
-  CLB_TMEM_LD16(addr + 32, v1);
-  wait_ld();
-  if (lane < 16) {
-    const int r = 16 * q + lane;
-    float* dst = reinterpret_cast<float*>(c.dw_a) + ((size_t)(r >> 5) * 32 + (r & 31)) * kStageStride + 16 * c.hf;
-#pragma unroll
-    for (int qq = 0; qq < 4; ++qq)
-      *reinterpret_cast<float4*>(dst + 4 * qq) = make_float4(__uint_as_float(v0[4 * qq]) + __uint_as_float(v1[4 * qq]),
-                                                             __uint_as_float(v0[4 * qq + 1]) + __uint_as_float(v1[4 * qq + 1]),
-                                                             __uint_as_float(v0[4 * qq + 2]) + __uint_as_float(v1[4 * qq + 2]),
-                                                             __uint_as_float(v0[4 * qq + 3]) + __uint_as_float(v1[4 * qq + 3]));
-  }
-}
-
 
 // dW rows live at lanes (r % 16) + 32 (r / 16): in every warp the lanes < 16 hold row r = 16 (warp % 4) + lane, i.e.
 // feature i = r % 32 (rows 0..31 from a_hi, 32..63 from a_lo).  The thread folds the delta-hi and delta-lo column blocks of
@@ -639,17 +532,13 @@ __device__ __forceinline__ void issue_backward3(Ctx& c, const float (&dp)[16], c
       CLB_TMEM_ST16(c.row_addr + kColAlo + c.col, lo);
     }
     const int sw = (c.row >> 2) & 1;       // conflict-free image stores: see dw_store_half
-#ifndef CLB_EXPERIMENT_SWZ
     swap_blocks(hi, sw); swap_blocks(lo, sw);
-#endif
     dw_store_half(c.dw_b, c.row, c.hf, hi, lo, sw);
     {
       uint32_t a2[16];
 #pragma unroll
       for (int k = 0; k < 16; ++k) a2[k] = __float_as_uint(ain[k]);
-#ifndef CLB_EXPERIMENT_SWZ
       swap_blocks(a2, sw);
-#endif
 #pragma unroll
       for (int k = 0; k < 16; ++k) {
         hi[k] = a2[k];
