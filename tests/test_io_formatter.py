@@ -277,3 +277,66 @@ def test_spacegroup_by_number():
     assert S.SpaceGroup.from_name("P212121").number == 19
     with pytest.raises(ValueError):
         S.SpaceGroup.from_name("P -1")
+
+
+# ---- property tests (hypothesis) --------------------------------------------------------------------------------
+from hypothesis import given, settings, strategies as st
+
+
+@settings(max_examples=40, deadline=None)
+@given(st.sampled_from(sorted(S._SOHNCKE)), st.integers(0, 2 ** 31 - 1))
+def test_asu_mapping_properties(name, seed):
+    """For any tabulated group and any reflections: the image is in the wedge, the stored operation maps back to the
+    observation, mapping is idempotent, and symmetry mates (Friedel mates included) share one ASU reflection."""
+    sg = S.SpaceGroup.from_name(name)
+    rng = np.random.default_rng(seed)
+    hkl = rng.integers(-15, 16, size=(64, 3))
+    hkl = hkl[np.any(hkl != 0, axis=1)]
+    asu, isym = sg.hkl_to_asu(hkl)
+    assert sg.in_asu(asu).all()
+    assert np.array_equal(sg.hkl_to_observed(asu, isym), hkl)
+    again, isym2 = sg.hkl_to_asu(asu)
+    assert np.array_equal(again, asu)
+    op = sg.sym_ops[int(rng.integers(len(sg.sym_ops)))]
+    sign = int(rng.choice([-1, 1]))
+    mates, _ = sg.hkl_to_asu(sign * op.apply_to_hkl(hkl))
+    assert np.array_equal(mates, asu)
+    # Friedel mates of acentric reflections are told apart by the parity of M/ISYM
+    mates_minus, isym_minus = sg.hkl_to_asu(-hkl)
+    acentric = ~sg.is_centric(hkl)
+    assert np.all((isym_minus[acentric] % 2) != (isym[acentric] % 2))
+
+
+@settings(max_examples=25, deadline=None)
+@given(n=st.integers(1, 400), n_extra=st.integers(1, 6), seed=st.integers(0, 2 ** 31 - 1))
+def test_mtz_round_trip_property(n, n_extra, seed):
+    import tempfile
+    rng = np.random.default_rng(seed)
+    sg = S.SpaceGroup.from_name(sorted(S._SOHNCKE)[seed % len(S._SOHNCKE)])
+    cell = S.UnitCell(40. + seed % 7, 50., 60. + seed % 11, 90., 90., 90.)
+    from careless_b200.io.mtz import DataSet
+    cols = {"H": rng.integers(-30, 31, n).astype(np.int32), "K": rng.integers(-30, 31, n).astype(np.int32),
+            "L": rng.integers(1, 31, n).astype(np.int32)}
+    types = {"H": "H", "K": "H", "L": "H"}
+    for j in range(n_extra):
+        cols[f"C{j}"] = rng.standard_normal(n).astype(np.float32) * 10.0 ** rng.integers(-3, 6)
+        types[f"C{j}"] = "R"
+    ds = DataSet(cols, types, cell, sg, merged=True)
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "p.mtz")
+        write_mtz(path, ds)
+        back = read_mtz(path)
+    assert back.keys() == ds.keys() and len(back) == n
+    for k in cols:
+        assert np.array_equal(np.asarray(back[k], dtype=np.float32), cols[k].astype(np.float32)), k
+    assert back.spacegroup.laue == sg.laue and len(back.spacegroup.sym_ops) == len(sg.sym_ops)
+    assert len(back.spacegroup.cen_ops) == len(sg.cen_ops)
+
+
+@settings(max_examples=50, deadline=None)
+@given(st.lists(st.tuples(st.integers(0, 5), st.integers(-3, 3)), min_size=1, max_size=60))
+def test_ngroup_property(pairs):
+    a = np.array([p[0] for p in pairs]); b = np.array([p[1] for p in pairs])
+    g = ngroup(a, b)
+    uniq = sorted(set(pairs))
+    assert np.array_equal(g, np.array([uniq.index(p) for p in pairs]))
