@@ -76,6 +76,7 @@ struct clb_handle {
   bool eval_mode = false;    // clb_eval: forward only (no gradients, no Adam)
   bool use_tc = false;       // tensor-core (tcgen05) path of k_obs: padded width 32, unless CLB_NO_TC=1
   bool use_tc2 = false;      // ... with two threads per observation row (k_obs_tc2), unless CLB_TC_ONE_THREAD_PER_ROW=1
+  bool use_tc16 = false;     // narrow MLPs (padded width <= 16, no image layers) on the tensor cores (k_obs_tc16): CLB_TC16=1
   bool debug_sync = false;   // CLB_DEBUG_SYNC=1: synchronise + log after every kernel launch
   int order = CLB_ORDER_REFL;
   double ll_const = 0.0;   // per-sample constant log-likelihood of empty Laue slots
@@ -160,6 +161,13 @@ template <int LIK, bool IL> cudaError_t launch_obs_tc2(clb_handle* h, const ObsA
 
 cudaError_t dispatch_obs(clb_handle* h, const ObsArgs& a) {
   const int lik = h->cfg.likelihood;
+  if (h->use_tc16) {
+    auto kern = lik ? k_obs_tc16<1> : k_obs_tc16<0>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_obs);
+    if (e != cudaSuccess) return e;
+    kern<<<h->grid_obs, tc16::kRows, h->smem_obs, h->stream>>>(a);
+    return cudaGetLastError();
+  }
   if (h->use_tc2) {
     if (h->cfg.image_layers > 0) return lik ? launch_obs_tc2<1, true>(h, a) : launch_obs_tc2<0, true>(h, a);
     return lik ? launch_obs_tc2<1, false>(h, a) : launch_obs_tc2<0, false>(h, a);
@@ -412,13 +420,16 @@ int clb_create(const clb_config* cfg, clb_handle** out) {
   h->NL = h->lay.n_layers;
   { const char* no_tc = getenv("CLB_NO_TC"); h->use_tc = (WP == 32) && (cfg->mlp_layers + cfg->image_layers) > 0 && !(no_tc && no_tc[0] == '1'); }
   { const char* one = getenv("CLB_TC_ONE_THREAD_PER_ROW"); h->use_tc2 = h->use_tc && !(one && one[0] == '1'); }
-  h->obs_threads = h->use_tc ? tc::kThreads : kObsThreads;      // = observation rows per CTA tile
+  { const char* t16 = getenv("CLB_TC16");
+    h->use_tc16 = (WP <= 16) && cfg->mlp_layers > 0 && cfg->image_layers == 0 && cfg->n_meta <= 16 && (t16 && t16[0] == '1'); }
+  h->obs_threads = (h->use_tc || h->use_tc16) ? tc::kThreads : kObsThreads;      // = observation rows per CTA tile
   switch (WP) {
     case 8: h->smem_obs = ObsSmem<8>::bytes(h->NL, false, cfg->image_layers); break;
     case 16: h->smem_obs = ObsSmem<16>::bytes(h->NL, false, cfg->image_layers); break;
     default: h->smem_obs = ObsSmem<32>::bytes(h->NL, h->use_tc, cfg->image_layers); break;
   }
   if (h->use_tc2) h->smem_obs = ObsSmem2::bytes(h->NL, cfg->image_layers);
+  if (h->use_tc16) h->smem_obs = ObsSmem16::bytes(h->NL);
   if (h->smem_obs > (size_t)prop.sharedMemPerBlockOptin) {
     fail(h, CLB_ERR_INVALID, "scale MLP (%d layers x padded width %d) needs %zu B of shared memory; the device offers %zu",
          cfg->mlp_layers, WP, h->smem_obs, (size_t)prop.sharedMemPerBlockOptin);
@@ -537,16 +548,17 @@ int clb_set_observations(clb_handle* h, int64_t n, int64_t n_total, const int64_
 
   // ---- launch geometry + per-CTA buffers of the observation kernel ----
   const int64_t n_tiles = (npad + h->obs_threads - 1) / h->obs_threads;
-  h->grid_obs = (int)std::min<int64_t>(n_tiles, (int64_t)h->n_sms * (h->use_tc ? 2 : 1));
+  h->grid_obs = (int)std::min<int64_t>(n_tiles, (int64_t)h->n_sms * (h->use_tc16 ? 4 : h->use_tc ? 2 : 1));
   {
     // One allocation [weight-gradient partials | activation scratch] so that a single L2 access-policy window can cover
     // both: the partials are read-modify-written once per tile and layer and must not be evicted by the scratch
     // streaming through the same cache; whatever persisting capacity is left keeps the most recently written
     // activations on chip until the backward pass reads them.  CLB_L2_WINDOW=0 no window, 1 partials only, 2 both.
-    const size_t pbytes = h->use_tc2 ? sizeof(float) * (size_t)h->grid_obs * h->NL * (32 * 32 + 32)
-                                     : sizeof(double) * (size_t)h->grid_obs * h->KS * partial_row_size(h->NL, h->WP);
+    const size_t pbytes = h->use_tc16 ? sizeof(float) * (size_t)h->grid_obs * h->NL * tc16::PSLOT16
+                          : h->use_tc2 ? sizeof(float) * (size_t)h->grid_obs * h->NL * (32 * 32 + 32)
+                                       : sizeof(double) * (size_t)h->grid_obs * h->KS * partial_row_size(h->NL, h->WP);
     const size_t pb = (pbytes + 255) & ~(size_t)255;
-    const size_t sbytes = sizeof(float4) * (size_t)h->grid_obs * std::max(1, c.mlp_layers + c.image_layers) * (h->WP / 4) * h->obs_threads;
+    const size_t sbytes = sizeof(float4) * (size_t)h->grid_obs * std::max(1, c.mlp_layers + c.image_layers) * ((h->use_tc16 ? 16 : h->WP) / 4) * h->obs_threads;
     CLB_CUDA(h, h->partials.alloc(pb + sbytes));
     h->partial_bytes = pbytes;
     h->scratch_ptr = reinterpret_cast<float4*>(h->partials.as<char>() + pb);
@@ -569,8 +581,8 @@ int clb_set_observations(clb_handle* h, int64_t n, int64_t n_total, const int64_
     }
   }
   if (h->use_tc) CLB_CUDA(h, h->wpack.alloc(sizeof(float) * (size_t)std::max(1, c.mlp_layers) * 1024));
-  if (h->use_tc2) {     // [L][fwd, bwd][hi, lo][kImgBytes]; the padding bytes of the images stay zero
-    const size_t nb = (size_t)std::max(1, c.mlp_layers) * 4 * tc::kImgBytes;
+  if (h->use_tc2 || h->use_tc16) {     // [L][fwd, bwd][hi, lo][image bytes]; the padding bytes of the images stay zero
+    const size_t nb = (size_t)std::max(1, c.mlp_layers) * 4 * (h->use_tc16 ? tc16::kImg16 : tc::kImgBytes);
     CLB_CUDA(h, h->wimg.alloc(nb));
     CLB_CUDA(h, cudaMemsetAsync(h->wimg.p, 0, nb, h->stream));
   }
@@ -852,7 +864,11 @@ static int step_begin_impl(clb_handle* h, const float* inj_u, const float* inj_e
     a.theta_mlp = theta + h->goff[CLB_GROUP_MLP];
     a.theta_img = c.image_scales ? theta + h->goff[CLB_GROUP_IMAGE_SCALES] : nullptr;
     a.wpack = h->use_tc ? h->wpack.as<float>() : nullptr;
-    a.wimg = h->use_tc2 ? h->wimg.as<float>() : nullptr;
+    a.wimg = (h->use_tc2 || h->use_tc16) ? h->wimg.as<float>() : nullptr;
+    if (h->use_tc16 && c.mlp_layers > 0) {
+      k_pack_images16<<<(c.mlp_layers * 512 + 255) / 256, 256, 0, st>>>(a.theta_mlp, h->lay, h->wimg.as<float>());
+      CLB_LAUNCHED(h);
+    }
     a.n_img_layers = c.image_layers; a.il_width = c.mlp_width; a.il_n_images = c.n_images;
     a.theta_il = c.image_layers > 0 ? theta + h->goff[CLB_GROUP_IMAGE_LAYERS] : nullptr;
     a.g_il = (c.image_layers > 0 && h->gtrain[CLB_GROUP_IMAGE_LAYERS] && !h->eval_mode) ? grad + h->goff[CLB_GROUP_IMAGE_LAYERS] : nullptr;
@@ -899,7 +915,8 @@ static int step_begin_impl(clb_handle* h, const float* inj_u, const float* inj_e
   }
   if (train_mlp) {
     const int np = h->lay.n_params;
-    if (h->use_tc2) k_reduce_partials32<<<(np + 255) / 256, 256, 0, st>>>(h->partials.as<float>(), h->grid_obs, h->lay, grad + h->goff[CLB_GROUP_MLP]);
+    if (h->use_tc16) k_reduce_partials16<<<(np + 255) / 256, 256, 0, st>>>(h->partials.as<float>(), h->grid_obs, h->lay, grad + h->goff[CLB_GROUP_MLP]);
+    else if (h->use_tc2) k_reduce_partials32<<<(np + 255) / 256, 256, 0, st>>>(h->partials.as<float>(), h->grid_obs, h->lay, grad + h->goff[CLB_GROUP_MLP]);
     else k_reduce_partials<<<(np + 255) / 256, 256, 0, st>>>(h->partials.as<double>(), h->grid_obs * h->KS, h->lay, h->WP, grad + h->goff[CLB_GROUP_MLP]);
     CLB_LAUNCHED(h);
   }

@@ -1275,3 +1275,5 @@ __global__ void __launch_bounds__(256) k_adam(float* theta, float* m, float* v, 
 }
 
 }  // namespace clb
+
+#include "clb_tc16.cuh"

@@ -1,0 +1,402 @@
+// clb_tc16.cuh -- tensor-core observation kernel for NARROW scale MLPs (padded width 16: the careless CLI default
+// --mlp-width 10 lives here).  Same algorithm, same global layouts and the same epilogue as k_obs_tc2 (clb_kernels.cuh);
+// what changes is the tiling: one thread per observation row carries all 16 features, a CTA is 128 threads / 128 rows,
+// FOUR CTAs share an SM (128 tensor-memory columns, ~37 KB of shared memory, <= 128 registers each).
+//   chain pass   : D[128 x 16] += A[128 x 16] (tensor memory, hi | lo) x B[16 x 16] (shared, K-major no-swizzle images by
+//                  TMA); kind::tf32, K = 8 per instruction -> 2 k-steps x 3 products = 6 tcgen05.mma per pass;
+//   dW product   : one 128-byte row per observation holds [x_hi (16) | x_lo (16)], so the MN-major SWIZZLE_128B_BASE32B
+//                  image of `a` IS [a_hi | a_lo] (one 32-element MN group) and likewise for delta-p:
+//                  D_dw[64 x 32] = [a_hi | a_lo | (junk group)]^T [dp_hi | dp_lo], 16 tcgen05.mma (M = 64, N = 32, K = 8);
+//                  rows 0..15 (a_hi) sit in lanes 0..15 of warp 0, rows 16..31 (a_lo) in lanes 0..15 of warp 1; each folds
+//                  its two 16-column blocks and REDs them into the CTA's FP32 partial.
+// Included by clb_kernels.cuh (needs ObsArgs, obs_epilogue, bias_red16).
+#pragma once
+
+namespace clb {
+namespace tc16 {
+
+using namespace tc;
+
+constexpr int kRows = 128;                         // rows (= threads) per CTA tile
+constexpr uint32_t kLBO16 = 272;                   // bytes between K-adjacent core matrices of the 16 x 16 weight image
+constexpr uint32_t kImg16 = 4 * kLBO16;            // one 16 x 16 tf32 operand image (1088 B)
+constexpr uint32_t kCols16 = 128;                  // tensor-memory columns per CTA (four CTAs per SM)
+constexpr uint32_t kA_hi = 0, kA_lo = 16, kD = 32, kDdw = 64;
+constexpr uint32_t kDwImg16 = kRows * 128;         // one MN-major operand image: 128 rows x 128 B
+constexpr uint32_t kIdesc16 = (1u << 4) | (2u << 7) | (2u << 10) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr uint32_t kIdescDw16 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((32u >> 3) << 17) | ((64u >> 4) << 24);
+constexpr int PSLOT16 = 16 * 16 + 16;              // one layer of the CTA's FP32 partial
+
+__device__ __forceinline__ uint64_t make_desc16(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((kLBO16 >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((kSBO >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
+}
+// MN-major 128B/32B-base swizzle; LBO (distance to the second MN group, whose rows of D are never read) = one image
+__device__ __forceinline__ uint64_t make_desc_mn16(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((kDwImg16 >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((kDwSBO >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) | ((uint64_t)1 << 61);
+}
+__device__ __forceinline__ void mma16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n"
+               :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(kIdesc16), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc16(uint32_t slot_smem) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(slot_smem), "r"(kCols16) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc16(uint32_t tbase) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tbase), "r"(kCols16) : "memory");
+}
+__device__ __forceinline__ void tma_fetch16(uint32_t dst_smem, const float* src_hi_lo, uint32_t bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(2u * kImg16) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(dst_smem), "l"(src_hi_lo), "r"(2u * kImg16), "r"(bar) : "memory");
+}
+
+// Rounded-hi split (3 instructions per value, 7e-7 rms per product against 1.4e-6 for the truncating split16): the chain
+// passes of the narrow kernel use it -- 20 layers of width 10 are conditioning-limited in FP32 and the parity criterion
+// (3 x the FP32 noise floor of the oracle) leaves no room for the cheaper split there; the dW operands keep split16.
+__device__ __forceinline__ void split16_rna(const float (&x)[16], uint32_t (&hi)[16], uint32_t (&lo)[16]) {
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const float h = tf32_rna(x[k]);
+    hi[k] = __float_as_uint(h);
+    lo[k] = __float_as_uint(x[k] - h);
+  }
+}
+
+struct Ctx16 {
+  uint32_t row_addr, base;            // tensor memory: this thread's lane, the CTA's base
+  uint32_t mbar, parity;              // chain barrier
+  uint32_t mbar_dw, parity_dw;        // dW barrier
+  uint32_t wimg0, wimg1, wbar0, wbar1;   // weight image buffers [hi | lo] and their TMA barriers
+  uint32_t pass, wphase;
+  char* dw_a; char* dw_b;
+  uint32_t dwa_s, dwb_s;              // shared addresses of the operand images
+  int tid;
+};
+
+// One row of an MN-major operand image: chunks 0, 1 = hi[0..7], hi[8..15], chunks 2, 3 = lo[0..7], lo[8..15]; with sw = 1
+// the caller passes the two 4-value blocks of every chunk swapped and they land in the swapped halves (conflict-free).
+__device__ __forceinline__ void dw_store_row16(char* img, int k, const uint32_t (&hi)[16], const uint32_t (&lo)[16], int sw) {
+  const int r = k & 3;
+  char* row = img + (size_t)(k >> 2) * kDwSBO + r * 128 + 16 * sw;
+  const int odd = 16 - 32 * sw;
+#pragma unroll
+  for (int cc = 0; cc < 2; ++cc) {
+    char* p = row + ((cc ^ r) * 32);
+    char* q = row + (((2 + cc) ^ r) * 32);
+    *reinterpret_cast<uint4*>(p) = make_uint4(hi[8 * cc], hi[8 * cc + 1], hi[8 * cc + 2], hi[8 * cc + 3]);
+    *reinterpret_cast<uint4*>(p + odd) = make_uint4(hi[8 * cc + 4], hi[8 * cc + 5], hi[8 * cc + 6], hi[8 * cc + 7]);
+    *reinterpret_cast<uint4*>(q) = make_uint4(lo[8 * cc], lo[8 * cc + 1], lo[8 * cc + 2], lo[8 * cc + 3]);
+    *reinterpret_cast<uint4*>(q + odd) = make_uint4(lo[8 * cc + 4], lo[8 * cc + 5], lo[8 * cc + 6], lo[8 * cc + 7]);
+  }
+}
+
+// All threads, after the pass's __syncthreads(): warp 0 waits for the layer's images and issues the six MMAs.
+__device__ __forceinline__ void issue_chain16(Ctx16& c, const float* next) {
+  const uint32_t b = c.pass & 1u;
+  const uint32_t warp = uniform32((uint32_t)c.tid >> 5);
+  if (warp == 0u) {
+    fence_after();
+    const uint32_t base = uniform32(c.base);
+    const uint32_t img = uniform32(b ? c.wimg1 : c.wimg0);
+    const uint64_t bhi = make_desc16(img), blo = make_desc16(img + kImg16);
+    const uint32_t d = base + kD;
+    const uint32_t bar = uniform32(c.mbar);
+    const uint32_t wb = uniform32(b ? c.wbar1 : c.wbar0), wph = uniform32((c.wphase >> b) & 1u);
+    const uint32_t nb = uniform32(b ? c.wbar0 : c.wbar1), ndst = uniform32(b ? c.wimg0 : c.wimg1);
+    if (elect_one()) {
+      mbar_wait(wb, wph);
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks)
+        mma16_ts(d, base + kA_hi + 8u * (uint32_t)ks, blo + (uint64_t)((2u * kLBO16 * (uint32_t)ks) >> 4), ks > 0 ? 1u : 0u);
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks)
+        mma16_ts(d, base + kA_lo + 8u * (uint32_t)ks, bhi + (uint64_t)((2u * kLBO16 * (uint32_t)ks) >> 4), 1u);
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks)
+        mma16_ts(d, base + kA_hi + 8u * (uint32_t)ks, bhi + (uint64_t)((2u * kLBO16 * (uint32_t)ks) >> 4), 1u);
+      commit(bar);
+      if (next != nullptr) tma_fetch16(ndst, next, nb);
+    }
+    __syncwarp();
+  }
+  c.wphase ^= (1u << b);
+  c.pass += 1u;
+}
+
+__device__ __forceinline__ void issue_fwd16(Ctx16& c, const float (&x)[16], const float* next) {
+  {
+    uint32_t hi[16], lo[16];
+    split16_rna(x, hi, lo);
+    CLB_TMEM_ST16(c.row_addr + kA_hi, hi);
+    CLB_TMEM_ST16(c.row_addr + kA_lo, lo);
+  }
+  wait_st();
+  fence_before();
+  __syncthreads();
+  issue_chain16(c, next);
+}
+
+__device__ __forceinline__ void collect16(Ctx16& c, float (&y)[16]) {
+  mbar_wait(c.mbar, c.parity);
+  c.parity ^= 1u;
+  fence_after();
+  uint32_t v[16];
+  CLB_TMEM_LD16(c.row_addr + kD, v);
+  wait_ld();
+#pragma unroll
+  for (int k = 0; k < 16; ++k) y[k] = __uint_as_float(v[k]);
+}
+
+__device__ __forceinline__ void issue_bwd16(Ctx16& c, const float (&dp)[16], const float (&ain)[16], bool need_dx, const float* next) {
+  {
+    uint32_t hi[16], lo[16];
+    split16_rna(dp, hi, lo);
+    if (need_dx) {
+      CLB_TMEM_ST16(c.row_addr + kA_hi, hi);
+      CLB_TMEM_ST16(c.row_addr + kA_lo, lo);
+    }
+    const int sw = (c.tid >> 2) & 1;
+    swap_blocks(hi, sw); swap_blocks(lo, sw);
+    dw_store_row16(c.dw_b, c.tid, hi, lo, sw);
+    uint32_t a2[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) a2[k] = __float_as_uint(ain[k]);
+    swap_blocks(a2, sw);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      hi[k] = a2[k];
+      lo[k] = __float_as_uint(__uint_as_float(a2[k]) - __uint_as_float(a2[k] & 0xFFFFE000u));
+    }
+    dw_store_row16(c.dw_a, c.tid, hi, lo, sw);
+  }
+  wait_st();
+  fence_async_smem();
+  fence_before();
+  __syncthreads();
+  if (need_dx) issue_chain16(c, next);
+  const uint32_t warp = uniform32((uint32_t)c.tid >> 5);
+  if (warp == 3u) {
+    fence_after();
+    const uint32_t d = uniform32(c.base) + kDdw;
+    const uint64_t a0 = make_desc_mn16(uniform32(c.dwa_s)), b0 = make_desc_mn16(uniform32(c.dwb_s));
+    const uint32_t bar = uniform32(c.mbar_dw);
+    if (elect_one()) {
+#pragma unroll
+      for (int ks = 0; ks < kRows / 8; ++ks)
+        mma_tf32_ss(d, a0 + (uint64_t)((2u * kDwSBO * (uint32_t)ks) >> 4), b0 + (uint64_t)((2u * kDwSBO * (uint32_t)ks) >> 4), kIdescDw16, ks > 0 ? 1u : 0u);
+      commit(bar);
+    }
+    __syncwarp();
+  }
+}
+
+// D_dw rows 0..15 (a_hi) = lanes 0..15 of warp 0, rows 16..31 (a_lo) = lanes 0..15 of warp 1; 32 columns [.dp_hi | .dp_lo].
+__device__ __forceinline__ void collect_dw16(Ctx16& c, float* wk) {
+  mbar_wait(c.mbar_dw, c.parity_dw);
+  c.parity_dw ^= 1u;
+  fence_after();
+  const int warp = c.tid >> 5, lane = c.tid & 31;
+  if (warp < 2) {
+    uint32_t v[32];
+    CLB_TMEM_LD32(c.row_addr + kDdw, v);
+    wait_ld();
+    if (lane < 16 && wk != nullptr) {
+      float4* dst = reinterpret_cast<float4*>(wk + lane * 16);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        atomicAdd(dst + q, make_float4(__uint_as_float(v[4 * q]) + __uint_as_float(v[16 + 4 * q]),
+                                       __uint_as_float(v[4 * q + 1]) + __uint_as_float(v[16 + 4 * q + 1]),
+                                       __uint_as_float(v[4 * q + 2]) + __uint_as_float(v[16 + 4 * q + 2]),
+                                       __uint_as_float(v[4 * q + 3]) + __uint_as_float(v[16 + 4 * q + 3])));
+    }
+  }
+}
+
+}  // namespace tc16
+
+struct ObsSmem16 {
+  static size_t bytes(int n_layers) {
+    return 2 * (size_t)tc16::kDwImg16 + 4 * (size_t)tc16::kImg16 + 64 + sizeof(float) * (32 + (size_t)n_layers * 16) + 64 * sizeof(double) + 128;
+  }
+};
+
+template <int LIK>
+__global__ void __launch_bounds__(tc16::kRows, 4) k_obs_tc16(ObsArgs a) {
+  using namespace tc16;
+  constexpr int WP = 16, TR = kRows, T = kRows, NC = 4;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  const int NL = a.lay.n_layers, L = NL - 1, LT = L;
+  char* dw_a = reinterpret_cast<char*>(smem_raw);
+  char* dw_b = dw_a + kDwImg16;
+  char* w_img = dw_b + kDwImg16;                                     // [2 buffers][hi, lo][kImg16]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(w_img + 4 * kImg16);  // [0] chain, [1] dW, [2..3] image buffers
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bars + 4);
+  float* Whead = reinterpret_cast<float*>(slot + 8);                 // [16][2]
+  float* bsm = Whead + 32;                                           // [NL][16]
+  double* red = reinterpret_cast<double*>(bsm + (size_t)NL * WP + ((NL * WP) & 1));
+
+  const int tid = threadIdx.x, lane = tid & 31;
+  if (tid == 0) { for (int i = 0; i < 4; ++i) tc::mbar_init(tc::smem_u32(bars + i), 1); }
+  if (tid < 32) tmem_alloc16(tc::smem_u32(slot));
+  tc::fence_before();
+  for (int idx = tid; idx < WP * 2; idx += T) {
+    const int i = idx / 2, j = idx % 2;
+    Whead[idx] = (i < a.lay.in_dim[L] && j < a.lay.out_dim[L]) ? a.theta_mlp[a.lay.koff[L] + i * a.lay.out_dim[L] + j] : 0.f;
+  }
+  for (int idx = tid; idx < NL * WP; idx += T) {
+    const int k = idx / WP, j = idx % WP;
+    bsm[idx] = (j < a.lay.out_dim[k]) ? a.theta_mlp[a.lay.boff[k] + j] : 0.f;
+  }
+  __syncthreads();
+  Ctx16 c{};
+  {
+    tc::fence_after();
+    c.base = *slot;
+    c.row_addr = c.base + ((uint32_t)(32 * (tid >> 5)) << 16);
+    c.mbar = tc::smem_u32(bars); c.mbar_dw = tc::smem_u32(bars + 1);
+    c.wbar0 = tc::smem_u32(bars + 2); c.wbar1 = tc::smem_u32(bars + 3);
+    c.wimg0 = tc::smem_u32(w_img); c.wimg1 = tc::smem_u32(w_img + 2 * kImg16);
+    c.dw_a = dw_a; c.dw_b = dw_b; c.dwa_s = tc::smem_u32(dw_a); c.dwb_s = tc::smem_u32(dw_b);
+    c.tid = tid;
+  }
+  constexpr size_t IMGF = kImg16 / 4;
+  auto gimg = [&](int k, int dir) -> const float* { return a.wimg + ((size_t)(k * 2 + dir) * 2) * IMGF; };
+  float* part32 = a.partials32 + (size_t)blockIdx.x * NL * PSLOT16;
+  float4* scr = a.scratch + (size_t)blockIdx.x * LT * NC * TR;
+  double ll_sum = 0.0;
+  float ev_f = 1.f, ev_a = 0.f, ev_b = 0.f;
+  if (a.theta_lik != nullptr) { ev_f = softplusf(a.theta_lik[0]); ev_a = softplusf(a.theta_lik[1]); ev_b = softplusf(a.theta_lik[2]); }
+  const int64_t n_tiles = (a.n_rows + TR - 1) / TR;
+  if (tid == 0 && LT > 0 && blockIdx.x < n_tiles) tma_fetch16(c.wimg0, gimg(0, 0), c.wbar0);
+
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const bool more_tiles = tile + gridDim.x < n_tiles;
+    const int64_t row = tile * TR + tid;
+    const bool inb = row < a.n_rows;
+    const int refl = inb ? a.refl[row] : -1;
+    const bool active = refl >= 0;
+    // ---------------- forward ----------------
+    float h[WP];
+#pragma unroll
+    for (int i = 0; i < WP; ++i) h[i] = (inb && i < a.d) ? a.meta[(size_t)i * a.n_rows + row] : 0.f;
+    for (int k = 0; k < LT; ++k) {
+      const float* bk = bsm + (size_t)k * WP;
+      const float* next = (k + 1 < LT) ? gimg(k + 1, 0) : (a.train_mlp && LT > 1) ? gimg(LT - 1, 1) : (more_tiles ? gimg(0, 0) : nullptr);
+      issue_fwd16(c, h, next);
+      float o[WP];
+      collect16(c, o);
+#pragma unroll
+      for (int j = 0; j < WP; ++j) { const float v = o[j] + bk[j]; h[j] = fmaxf(v, kLeak * v); }
+      if (a.train_mlp) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) scr[((size_t)k * NC + q) * TR + tid] = make_float4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
+      }
+    }
+    float out0 = bsm[L * WP], out1 = bsm[L * WP + 1];
+#pragma unroll
+    for (int i = 0; i < WP; ++i) {
+      const float2 w = *reinterpret_cast<const float2*>(&Whead[i * 2]);
+      out0 = fmaf(h[i], w.x, out0); out1 = fmaf(h[i], w.y, out1);
+    }
+    float dmu, drho;
+    obs_epilogue<LIK>(a, row, inb, active, refl, lane, out0, out1, ev_f, ev_a, ev_b, ll_sum, dmu, drho);
+    if (!a.train_mlp) continue;
+    // ---------------- backward ----------------
+    float dp[WP], nxt[WP];
+    auto load_act = [&](float (&dst)[WP], int k) {
+      if (k > 0) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 v = __ldcg(&scr[((size_t)(k - 1) * NC + q) * TR + tid]);
+          dst[4 * q] = v.x; dst[4 * q + 1] = v.y; dst[4 * q + 2] = v.z; dst[4 * q + 3] = v.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < WP; ++i) dst[i] = (inb && i < a.d) ? a.meta[(size_t)i * a.n_rows + row] : 0.f;
+      }
+    };
+    auto layer_backward = [&](const float (&ain)[WP], bool need_dx, const float* next, float* wk, unsigned& mask_out) {
+      issue_bwd16(c, dp, ain, need_dx, next);
+      unsigned m = 0u;
+#pragma unroll
+      for (int i = 0; i < WP; ++i) m |= (ain[i] > 0.f ? 1u : 0u) << i;
+      mask_out = m;
+      bias_red16(dp, wk + WP * WP, lane, 16);
+      if (need_dx) collect16(c, dp);
+      collect_dw16(c, wk);
+    };
+    if (LT > 0) load_act(nxt, LT - 1);
+#pragma unroll
+    for (int j = 0; j < WP; ++j) dp[j] = 0.f;
+    dp[0] = dmu; dp[1] = drho;
+    unsigned mask = 0u;
+    layer_backward(h, false, nullptr, part32 + (size_t)L * PSLOT16, mask);     // head: dW_out = a_L^T [dmu, drho]
+#pragma unroll
+    for (int i = 0; i < WP; ++i) {
+      const float2 w = *reinterpret_cast<const float2*>(&Whead[i * 2]);
+      dp[i] = w.x * dmu + w.y * drho;
+    }
+    for (int k = LT - 1; k >= 0; --k) {
+#pragma unroll
+      for (int j = 0; j < WP; ++j) dp[j] = ((mask >> j) & 1u) ? dp[j] : kLeak * dp[j];
+      float ain[WP];
+#pragma unroll
+      for (int i = 0; i < WP; ++i) ain[i] = nxt[i];
+      if (k > 0) load_act(nxt, k - 1);
+      const float* next = (k > 1) ? gimg(k - 1, 1) : (more_tiles ? gimg(0, 0) : nullptr);
+      layer_backward(ain, k > 0, next, part32 + (size_t)k * PSLOT16, mask);
+    }
+  }
+  __syncthreads();
+  ll_sum = warp_sum(ll_sum);
+  if (lane == 0) red[tid >> 5] = ll_sum;
+  tc::fence_before();
+  __syncthreads();
+  if (tid == 0) {
+    double t = 0.0;
+    for (int i = 0; i < T / 32; ++i) t += red[i];
+    atomicAdd(&a.acc[ACC_LL], t);
+  }
+  if (tid < 32) tmem_dealloc16(*slot);
+}
+
+// Ready-made 16 x 16 B operand images of every hidden layer for k_obs_tc16: per layer [fwd, bwd][hi, lo][kImg16].
+__global__ void __launch_bounds__(256) k_pack_images16(const float* theta_mlp, MlpLayout lay, float* wimg) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int L = lay.n_layers - 1;
+  if (idx >= L * 2 * 256) return;
+  const int layer = idx >> 9, dir = (idx >> 8) & 1, n = (idx >> 4) & 15, k = idx & 15;
+  const int i = dir ? n : k, j = dir ? k : n;          // W[i = in][j = out]
+  const float w = (i < lay.in_dim[layer] && j < lay.out_dim[layer]) ? theta_mlp[lay.koff[layer] + i * lay.out_dim[layer] + j] : 0.f;
+  const float hi = tc::tf32_rna(w);
+  const size_t IMGF = tc16::kImg16 / 4;
+  float* base = wimg + ((size_t)(layer * 2 + dir) * 2) * IMGF;
+  const uint32_t off = ((k >> 2) * tc16::kLBO16 + (n >> 3) * tc::kSBO + (n & 7) * 16 + (k & 3) * 4) / 4;
+  base[off] = hi;
+  base[IMGF + off] = w - hi;
+}
+
+__global__ void __launch_bounds__(256) k_reduce_partials16(const float* partials, int rows, MlpLayout lay, float* grad) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= lay.n_params) return;
+  const int PSLOT = tc16::PSLOT16, PP = lay.n_layers * PSLOT;
+  int src = -1;
+  for (int k = 0; k < lay.n_layers; ++k) {
+    const int nk = lay.in_dim[k] * lay.out_dim[k];
+    if (p >= lay.koff[k] && p < lay.koff[k] + nk) {
+      const int i = (p - lay.koff[k]) / lay.out_dim[k], j = (p - lay.koff[k]) % lay.out_dim[k];
+      src = k * PSLOT + i * 16 + j;
+      break;
+    }
+    if (p >= lay.boff[k] && p < lay.boff[k] + lay.out_dim[k]) { src = k * PSLOT + 256 + (p - lay.boff[k]); break; }
+  }
+  double acc = 0.0;
+  if (src >= 0) for (int r = 0; r < rows; ++r) acc += (double)partials[(size_t)r * PP + src];
+  grad[p] = (float)acc;
+}
+
+}  // namespace clb

