@@ -1,7 +1,7 @@
 // clb_kernels.cuh -- CUDA kernels of the ELBO gradient + Adam step (sm_100a).
 //
-// Step = k_refl_sample -> [k_dw_prior] -> k_obs -> k_reduce_partials -> k_refl_backward
-//        -> k_var_sumsq -> (all-reduce) -> k_finalize -> k_adam
+// Step = k_refl_sample -> [k_dw_prior] -> [k_pack_images] -> k_obs_tc2 | k_obs | k_obs_tc16 -> k_reduce_partials*
+//        -> k_refl_backward -> (all-reduce) -> k_var_sumsq -> k_pack_scalars -> (all-reduce) -> k_finalize -> k_adam
 // See DESIGN.md for the data layout and the roofline of each kernel.
 #pragma once
 #include "clb_math.cuh"

@@ -1,17 +1,17 @@
-// clb_tc.cuh -- tcgen05 / TMEM building blocks for the scale-MLP products of k_obs (sm_100a only).
+// clb_tc.cuh -- tcgen05 / TMEM building blocks for the scale-MLP products of the observation kernels (sm_100a only).
 //
-// One "pass" multiplies the CTA's 256x32 activation (or delta) tile by one 32x32 weight matrix on the
-// 5th-generation tensor cores, error-compensated 3xTF32 so that the result keeps FP32 accuracy:
-//     X W  ~=  X_hi W_hi + X_hi W_lo + X_lo W_hi          (X_hi = tf32(X), X_lo = tf32(X - X_hi), same for W)
-// * A operand (X): one row per thread, written to TENSOR MEMORY with tcgen05.st (lane = row) -- no layout puzzle;
-// * B operand (W): built per pass in shared memory in the canonical K-major / no-swizzle UMMA layout
-//   (8x16-byte core matrices, LBO = 528 B between K-adjacent core matrices, SBO = 128 B between 8-row groups);
-// * D (FP32 accumulators): tensor memory, read back one row per thread with tcgen05.ld.
-// A CTA is 128 threads = one M=128 tile (thread = row = tensor-memory lane); two CTAs share an SM so that one
-// CTA's st -> barrier -> mma -> commit -> wait -> ld latencies hide behind the other's work.  Each of the three
-// products has its own accumulator columns and its own issuing warp (several warps issue concurrently, one
-// thread alone only manages a tcgen05.mma every ~60 cycles -- tools/tc_rate.cu): a pass is 3 issuers x 4
-// k-steps (K = 8 per tf32 instruction); the dW product is issued by the fourth warp.
+// One "pass" multiplies the CTA's 128 x 32 activation (or delta) tile by one 32 x 32 weight matrix on the
+// 5th-generation tensor cores, error-compensated 3xTF32 so that the result keeps FP32-level accuracy:
+//     X W  ~=  X_hi W_lo + X_lo W_hi + X_hi W_hi          (hi = the upper 19 bits the MMA reads, lo = the exact rest)
+// * A operand (X): written to TENSOR MEMORY with tcgen05.st (lane = row) -- no layout puzzle;
+// * B operand (W): shared-memory images in the canonical K-major / no-swizzle UMMA layout (8 x 16-byte core matrices,
+//   LBO = 528 B between K-adjacent core matrices, SBO = 128 B between 8-row groups); k_obs_tc2 receives them ready-made
+//   by TMA (cp.async.bulk + mbarrier), the older k_obs<32, LIK, true> builds them per pass;
+// * D (FP32 accumulators): tensor memory, one accumulator region for all three products (12 MMAs, K = 8 each, issued
+//   back to back by ONE elected lane with warp-uniform operands), read back with tcgen05.ld;
+// * dW = A^T dP: both operands from shared memory in the MN-major SWIZZLE_128B_BASE32B layout, M = N = 64.
+// First half of the file: helpers shared by all kernels and the one-thread-per-row generation (k_obs<32, LIK, true>,
+// 128-thread CTAs); second half: two threads per row (k_obs_tc2, 256-thread CTAs).  clb_tc16.cuh: narrow models.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
