@@ -76,7 +76,7 @@ struct clb_handle {
   bool eval_mode = false;    // clb_eval: forward only (no gradients, no Adam)
   bool use_tc = false;       // tensor-core (tcgen05) path of k_obs: padded width 32, unless CLB_NO_TC=1
   bool use_tc2 = false;      // ... with two threads per observation row (k_obs_tc2), unless CLB_TC_ONE_THREAD_PER_ROW=1
-  bool use_tc16 = false;     // narrow MLPs (padded width <= 16, no image layers) on the tensor cores (k_obs_tc16): CLB_TC16=1
+  bool use_tc16 = false;     // narrow MLPs (padded width <= 16, no image layers) on the tensor cores (k_obs_tc16), unless CLB_TC16=0
   bool debug_sync = false;   // CLB_DEBUG_SYNC=1: synchronise + log after every kernel launch
   int order = CLB_ORDER_REFL;
   double ll_const = 0.0;   // per-sample constant log-likelihood of empty Laue slots
@@ -420,8 +420,9 @@ int clb_create(const clb_config* cfg, clb_handle** out) {
   h->NL = h->lay.n_layers;
   { const char* no_tc = getenv("CLB_NO_TC"); h->use_tc = (WP == 32) && (cfg->mlp_layers + cfg->image_layers) > 0 && !(no_tc && no_tc[0] == '1'); }
   { const char* one = getenv("CLB_TC_ONE_THREAD_PER_ROW"); h->use_tc2 = h->use_tc && !(one && one[0] == '1'); }
-  { const char* t16 = getenv("CLB_TC16");
-    h->use_tc16 = (WP <= 16) && cfg->mlp_layers > 0 && cfg->image_layers == 0 && cfg->n_meta <= 16 && (t16 && t16[0] == '1'); }
+  { const char* t16 = getenv("CLB_TC16"); const char* no_tc = getenv("CLB_NO_TC");
+    h->use_tc16 = (WP <= 16) && cfg->mlp_layers > 0 && cfg->image_layers == 0 && cfg->n_meta <= 16 &&
+                  !(t16 && t16[0] == '0') && !(no_tc && no_tc[0] == '1'); }
   h->obs_threads = (h->use_tc || h->use_tc16) ? tc::kThreads : kObsThreads;      // = observation rows per CTA tile
   switch (WP) {
     case 8: h->smem_obs = ObsSmem<8>::bytes(h->NL, false, cfg->image_layers); break;
@@ -582,7 +583,7 @@ int clb_set_observations(clb_handle* h, int64_t n, int64_t n_total, const int64_
   }
   if (h->use_tc) CLB_CUDA(h, h->wpack.alloc(sizeof(float) * (size_t)std::max(1, c.mlp_layers) * 1024));
   if (h->use_tc2 || h->use_tc16) {     // [L][fwd, bwd][hi, lo][image bytes]; the padding bytes of the images stay zero
-    const size_t nb = (size_t)std::max(1, c.mlp_layers) * 4 * (h->use_tc16 ? tc16::kImg16 : tc::kImgBytes);
+    const size_t nb = (size_t)std::max(1, c.mlp_layers) * (h->use_tc16 ? 6 * (size_t)tc16::kImg16 : 4 * (size_t)tc::kImgBytes);
     CLB_CUDA(h, h->wimg.alloc(nb));
     CLB_CUDA(h, cudaMemsetAsync(h->wimg.p, 0, nb, h->stream));
   }

@@ -21,7 +21,7 @@ constexpr int kRows = 128;                         // rows (= threads) per CTA t
 constexpr uint32_t kLBO16 = 272;                   // bytes between K-adjacent core matrices of the 16 x 16 weight image
 constexpr uint32_t kImg16 = 4 * kLBO16;            // one 16 x 16 tf32 operand image (1088 B)
 constexpr uint32_t kCols16 = 128;                  // tensor-memory columns per CTA (four CTAs per SM)
-constexpr uint32_t kA_hi = 0, kA_lo = 16, kD = 32, kDdw = 64;
+constexpr uint32_t kA_hi = 0, kA_mid = 16, kA_lo = 32, kD = 48, kDdw = 64;   // forward: three-way split of X (hi, mid, lo)
 constexpr uint32_t kDwImg16 = kRows * 128;         // one MN-major operand image: 128 rows x 128 B
 constexpr uint32_t kIdesc16 = (1u << 4) | (2u << 7) | (2u << 10) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
 constexpr uint32_t kIdescDw16 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((32u >> 3) << 17) | ((64u >> 4) << 24);
@@ -48,10 +48,26 @@ __device__ __forceinline__ void tmem_alloc16(uint32_t slot_smem) {
 __device__ __forceinline__ void tmem_dealloc16(uint32_t tbase) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tbase), "r"(kCols16) : "memory");
 }
-__device__ __forceinline__ void tma_fetch16(uint32_t dst_smem, const float* src_hi_lo, uint32_t bar) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(2u * kImg16) : "memory");
+// images of one (layer, direction) in global memory: [hi, mid, lo][kImg16]; a forward pass fetches all three, a backward
+// pass the first two... the backward images are stored as [hi, lo, unused]
+__device__ __forceinline__ void tma_fetch16(uint32_t dst_smem, const float* src, uint32_t n_images, uint32_t bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(n_images * kImg16) : "memory");
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               :: "r"(dst_smem), "l"(src_hi_lo), "r"(2u * kImg16), "r"(bar) : "memory");
+               :: "r"(dst_smem), "l"(src), "r"(n_images * kImg16), "r"(bar) : "memory");
+}
+
+// Three-way TF32 split for the FORWARD chain: hi = tf32(x), mid = tf32(x - hi), lo = the exact rest.  With the six
+// products hi.lo, lo.hi, mid.mid, hi.mid, mid.hi, hi.hi the layer output is exact to ~2^-24 like an FP32 FMA chain:
+// the surrogate gradients depend on the forward pass only (through the predicted intensity), and 20 narrow layers are
+// conditioning-limited in FP32, so this is where 3xTF32 (2^-21) is not enough.
+__device__ __forceinline__ void split16_3(const float (&x)[16], uint32_t (&hi)[16], uint32_t (&mid)[16], uint32_t (&lo)[16]) {
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const float h = tf32_rna(x[k]);
+    const float r = x[k] - h;
+    const float m = tf32_rna(r);
+    hi[k] = __float_as_uint(h); mid[k] = __float_as_uint(m); lo[k] = __float_as_uint(r - m);
+  }
 }
 
 // Rounded-hi split (3 instructions per value, 7e-7 rms per product against 1.4e-6 for the truncating split16): the chain
@@ -94,32 +110,35 @@ __device__ __forceinline__ void dw_store_row16(char* img, int k, const uint32_t 
   }
 }
 
-// All threads, after the pass's __syncthreads(): warp 0 waits for the layer's images and issues the six MMAs.
-__device__ __forceinline__ void issue_chain16(Ctx16& c, const float* next) {
+// All threads, after the pass's __syncthreads(): warp 0 waits for the layer's images and issues the MMAs: six products of
+// the three-way split in a forward pass (12 MMAs), three products of the two-way split in a dX pass (6 MMAs).
+// `next` / `next_n`: global images of the next pass and how many of them to prefetch.
+__device__ __forceinline__ void issue_chain16(Ctx16& c, bool fwd, const float* next, uint32_t next_n) {
   const uint32_t b = c.pass & 1u;
   const uint32_t warp = uniform32((uint32_t)c.tid >> 5);
   if (warp == 0u) {
     fence_after();
     const uint32_t base = uniform32(c.base);
     const uint32_t img = uniform32(b ? c.wimg1 : c.wimg0);
-    const uint64_t bhi = make_desc16(img), blo = make_desc16(img + kImg16);
+    const uint64_t w0 = make_desc16(img), w1 = make_desc16(img + kImg16), w2 = make_desc16(img + 2 * kImg16);
     const uint32_t d = base + kD;
     const uint32_t bar = uniform32(c.mbar);
     const uint32_t wb = uniform32(b ? c.wbar1 : c.wbar0), wph = uniform32((c.wphase >> b) & 1u);
     const uint32_t nb = uniform32(b ? c.wbar0 : c.wbar1), ndst = uniform32(b ? c.wimg0 : c.wimg1);
     if (elect_one()) {
       mbar_wait(wb, wph);
-#pragma unroll
-      for (int ks = 0; ks < 2; ++ks)
-        mma16_ts(d, base + kA_hi + 8u * (uint32_t)ks, blo + (uint64_t)((2u * kLBO16 * (uint32_t)ks) >> 4), ks > 0 ? 1u : 0u);
-#pragma unroll
-      for (int ks = 0; ks < 2; ++ks)
-        mma16_ts(d, base + kA_lo + 8u * (uint32_t)ks, bhi + (uint64_t)((2u * kLBO16 * (uint32_t)ks) >> 4), 1u);
-#pragma unroll
-      for (int ks = 0; ks < 2; ++ks)
-        mma16_ts(d, base + kA_hi + 8u * (uint32_t)ks, bhi + (uint64_t)((2u * kLBO16 * (uint32_t)ks) >> 4), 1u);
+#define CLB_MMA16(acol, wdesc, first) \
+      mma16_ts(d, base + (acol), (wdesc), (first) ? 0u : 1u); \
+      mma16_ts(d, base + (acol) + 8u, (wdesc) + (uint64_t)((2u * kLBO16) >> 4), 1u)
+      if (fwd) {          // images [hi, mid, lo]
+        CLB_MMA16(kA_hi, w2, true);  CLB_MMA16(kA_lo, w0, false); CLB_MMA16(kA_mid, w1, false);
+        CLB_MMA16(kA_hi, w1, false); CLB_MMA16(kA_mid, w0, false); CLB_MMA16(kA_hi, w0, false);
+      } else {            // images [hi, lo]; delta-p as (hi at kA_hi, lo at kA_lo)
+        CLB_MMA16(kA_hi, w1, true);  CLB_MMA16(kA_lo, w0, false); CLB_MMA16(kA_hi, w0, false);
+      }
+#undef CLB_MMA16
       commit(bar);
-      if (next != nullptr) tma_fetch16(ndst, next, nb);
+      if (next != nullptr) tma_fetch16(ndst, next, next_n, nb);
     }
     __syncwarp();
   }
@@ -127,17 +146,18 @@ __device__ __forceinline__ void issue_chain16(Ctx16& c, const float* next) {
   c.pass += 1u;
 }
 
-__device__ __forceinline__ void issue_fwd16(Ctx16& c, const float (&x)[16], const float* next) {
+__device__ __forceinline__ void issue_fwd16(Ctx16& c, const float (&x)[16], const float* next, uint32_t next_n) {
   {
-    uint32_t hi[16], lo[16];
-    split16_rna(x, hi, lo);
+    uint32_t hi[16], mid[16], lo[16];
+    split16_3(x, hi, mid, lo);
     CLB_TMEM_ST16(c.row_addr + kA_hi, hi);
+    CLB_TMEM_ST16(c.row_addr + kA_mid, mid);
     CLB_TMEM_ST16(c.row_addr + kA_lo, lo);
   }
   wait_st();
   fence_before();
   __syncthreads();
-  issue_chain16(c, next);
+  issue_chain16(c, true, next, next_n);
 }
 
 __device__ __forceinline__ void collect16(Ctx16& c, float (&y)[16]) {
@@ -151,7 +171,7 @@ __device__ __forceinline__ void collect16(Ctx16& c, float (&y)[16]) {
   for (int k = 0; k < 16; ++k) y[k] = __uint_as_float(v[k]);
 }
 
-__device__ __forceinline__ void issue_bwd16(Ctx16& c, const float (&dp)[16], const float (&ain)[16], bool need_dx, const float* next) {
+__device__ __forceinline__ void issue_bwd16(Ctx16& c, const float (&dp)[16], const float (&ain)[16], bool need_dx, const float* next, uint32_t next_n) {
   {
     uint32_t hi[16], lo[16];
     split16_rna(dp, hi, lo);
@@ -177,7 +197,7 @@ __device__ __forceinline__ void issue_bwd16(Ctx16& c, const float (&dp)[16], con
   fence_async_smem();
   fence_before();
   __syncthreads();
-  if (need_dx) issue_chain16(c, next);
+  if (need_dx) issue_chain16(c, false, next, next_n);
   const uint32_t warp = uniform32((uint32_t)c.tid >> 5);
   if (warp == 3u) {
     fence_after();
@@ -220,7 +240,7 @@ __device__ __forceinline__ void collect_dw16(Ctx16& c, float* wk) {
 
 struct ObsSmem16 {
   static size_t bytes(int n_layers) {
-    return 2 * (size_t)tc16::kDwImg16 + 4 * (size_t)tc16::kImg16 + 64 + sizeof(float) * (32 + (size_t)n_layers * 16) + 64 * sizeof(double) + 128;
+    return 2 * (size_t)tc16::kDwImg16 + 6 * (size_t)tc16::kImg16 + 64 + sizeof(float) * (32 + (size_t)n_layers * 16) + 64 * sizeof(double) + 128;
   }
 };
 
@@ -232,8 +252,8 @@ __global__ void __launch_bounds__(tc16::kRows, 4) k_obs_tc16(ObsArgs a) {
   const int NL = a.lay.n_layers, L = NL - 1, LT = L;
   char* dw_a = reinterpret_cast<char*>(smem_raw);
   char* dw_b = dw_a + kDwImg16;
-  char* w_img = dw_b + kDwImg16;                                     // [2 buffers][hi, lo][kImg16]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(w_img + 4 * kImg16);  // [0] chain, [1] dW, [2..3] image buffers
+  char* w_img = dw_b + kDwImg16;                                     // [2 buffers][hi, mid, lo][kImg16]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(w_img + 6 * kImg16);  // [0] chain, [1] dW, [2..3] image buffers
   uint32_t* slot = reinterpret_cast<uint32_t*>(bars + 4);
   float* Whead = reinterpret_cast<float*>(slot + 8);                 // [16][2]
   float* bsm = Whead + 32;                                           // [NL][16]
@@ -259,19 +279,19 @@ __global__ void __launch_bounds__(tc16::kRows, 4) k_obs_tc16(ObsArgs a) {
     c.row_addr = c.base + ((uint32_t)(32 * (tid >> 5)) << 16);
     c.mbar = tc::smem_u32(bars); c.mbar_dw = tc::smem_u32(bars + 1);
     c.wbar0 = tc::smem_u32(bars + 2); c.wbar1 = tc::smem_u32(bars + 3);
-    c.wimg0 = tc::smem_u32(w_img); c.wimg1 = tc::smem_u32(w_img + 2 * kImg16);
+    c.wimg0 = tc::smem_u32(w_img); c.wimg1 = tc::smem_u32(w_img + 3 * kImg16);
     c.dw_a = dw_a; c.dw_b = dw_b; c.dwa_s = tc::smem_u32(dw_a); c.dwb_s = tc::smem_u32(dw_b);
     c.tid = tid;
   }
   constexpr size_t IMGF = kImg16 / 4;
-  auto gimg = [&](int k, int dir) -> const float* { return a.wimg + ((size_t)(k * 2 + dir) * 2) * IMGF; };
+  auto gimg = [&](int k, int dir) -> const float* { return a.wimg + ((size_t)(k * 2 + dir) * 3) * IMGF; };   // [hi, mid, lo] / [hi, lo, -]
   float* part32 = a.partials32 + (size_t)blockIdx.x * NL * PSLOT16;
   float4* scr = a.scratch + (size_t)blockIdx.x * LT * NC * TR;
   double ll_sum = 0.0;
   float ev_f = 1.f, ev_a = 0.f, ev_b = 0.f;
   if (a.theta_lik != nullptr) { ev_f = softplusf(a.theta_lik[0]); ev_a = softplusf(a.theta_lik[1]); ev_b = softplusf(a.theta_lik[2]); }
   const int64_t n_tiles = (a.n_rows + TR - 1) / TR;
-  if (tid == 0 && LT > 0 && blockIdx.x < n_tiles) tma_fetch16(c.wimg0, gimg(0, 0), c.wbar0);
+  if (tid == 0 && LT > 0 && blockIdx.x < n_tiles) tma_fetch16(c.wimg0, gimg(0, 0), 3u, c.wbar0);
 
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const bool more_tiles = tile + gridDim.x < n_tiles;
@@ -285,8 +305,9 @@ __global__ void __launch_bounds__(tc16::kRows, 4) k_obs_tc16(ObsArgs a) {
     for (int i = 0; i < WP; ++i) h[i] = (inb && i < a.d) ? a.meta[(size_t)i * a.n_rows + row] : 0.f;
     for (int k = 0; k < LT; ++k) {
       const float* bk = bsm + (size_t)k * WP;
-      const float* next = (k + 1 < LT) ? gimg(k + 1, 0) : (a.train_mlp && LT > 1) ? gimg(LT - 1, 1) : (more_tiles ? gimg(0, 0) : nullptr);
-      issue_fwd16(c, h, next);
+      const bool next_bwd = !(k + 1 < LT) && a.train_mlp && LT > 1;
+      const float* next = (k + 1 < LT) ? gimg(k + 1, 0) : next_bwd ? gimg(LT - 1, 1) : (more_tiles ? gimg(0, 0) : nullptr);
+      issue_fwd16(c, h, next, next_bwd ? 2u : 3u);
       float o[WP];
       collect16(c, o);
 #pragma unroll
@@ -319,8 +340,8 @@ __global__ void __launch_bounds__(tc16::kRows, 4) k_obs_tc16(ObsArgs a) {
         for (int i = 0; i < WP; ++i) dst[i] = (inb && i < a.d) ? a.meta[(size_t)i * a.n_rows + row] : 0.f;
       }
     };
-    auto layer_backward = [&](const float (&ain)[WP], bool need_dx, const float* next, float* wk, unsigned& mask_out) {
-      issue_bwd16(c, dp, ain, need_dx, next);
+    auto layer_backward = [&](const float (&ain)[WP], bool need_dx, const float* next, uint32_t next_n, float* wk, unsigned& mask_out) {
+      issue_bwd16(c, dp, ain, need_dx, next, next_n);
       unsigned m = 0u;
 #pragma unroll
       for (int i = 0; i < WP; ++i) m |= (ain[i] > 0.f ? 1u : 0u) << i;
@@ -334,7 +355,7 @@ __global__ void __launch_bounds__(tc16::kRows, 4) k_obs_tc16(ObsArgs a) {
     for (int j = 0; j < WP; ++j) dp[j] = 0.f;
     dp[0] = dmu; dp[1] = drho;
     unsigned mask = 0u;
-    layer_backward(h, false, nullptr, part32 + (size_t)L * PSLOT16, mask);     // head: dW_out = a_L^T [dmu, drho]
+    layer_backward(h, false, nullptr, 0u, part32 + (size_t)L * PSLOT16, mask);     // head: dW_out = a_L^T [dmu, drho]
 #pragma unroll
     for (int i = 0; i < WP; ++i) {
       const float2 w = *reinterpret_cast<const float2*>(&Whead[i * 2]);
@@ -348,7 +369,7 @@ __global__ void __launch_bounds__(tc16::kRows, 4) k_obs_tc16(ObsArgs a) {
       for (int i = 0; i < WP; ++i) ain[i] = nxt[i];
       if (k > 0) load_act(nxt, k - 1);
       const float* next = (k > 1) ? gimg(k - 1, 1) : (more_tiles ? gimg(0, 0) : nullptr);
-      layer_backward(ain, k > 0, next, part32 + (size_t)k * PSLOT16, mask);
+      layer_backward(ain, k > 0, next, (k > 1) ? 2u : 3u, part32 + (size_t)k * PSLOT16, mask);
     }
   }
   __syncthreads();
@@ -373,11 +394,14 @@ __global__ void __launch_bounds__(256) k_pack_images16(const float* theta_mlp, M
   const int i = dir ? n : k, j = dir ? k : n;          // W[i = in][j = out]
   const float w = (i < lay.in_dim[layer] && j < lay.out_dim[layer]) ? theta_mlp[lay.koff[layer] + i * lay.out_dim[layer] + j] : 0.f;
   const float hi = tc::tf32_rna(w);
+  const float r = w - hi;
+  const float mid = tc::tf32_rna(r);
   const size_t IMGF = tc16::kImg16 / 4;
-  float* base = wimg + ((size_t)(layer * 2 + dir) * 2) * IMGF;
+  float* base = wimg + ((size_t)(layer * 2 + dir) * 3) * IMGF;
   const uint32_t off = ((k >> 2) * tc16::kLBO16 + (n >> 3) * tc::kSBO + (n & 7) * 16 + (k & 3) * 4) / 4;
   base[off] = hi;
-  base[IMGF + off] = w - hi;
+  if (dir == 0) { base[IMGF + off] = mid; base[2 * IMGF + off] = r - mid; }     // forward: [hi, mid, lo]
+  else base[IMGF + off] = r;                                                     // backward: [hi, lo]
 }
 
 __global__ void __launch_bounds__(256) k_reduce_partials16(const float* partials, int rows, MlpLayout lay, float* grad) {
