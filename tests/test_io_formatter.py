@@ -340,3 +340,32 @@ def test_ngroup_property(pairs):
     g = ngroup(a, b)
     uniq = sorted(set(pairs))
     assert np.array_equal(g, np.array([uniq.index(p) for p in pairs]))
+
+
+def test_command_line_options_match_the_reference_defaults():
+    """careless/args/*.py: option names, destinations and defaults (the values DataManager.build_model reads)."""
+    from careless_b200.careless import build_argparser, default_parser, make_formatter
+    ns = build_argparser().parse_args(["mono", "dHKL,image_id", "a.mtz", "b.mtz", "out/base"])
+    expect = dict(type="mono", mc_samples=1, epsilon=1e-7, iterations=10000, learning_rate=0.001, beta_1=0.9, beta_2=0.99,
+                  mlp_layers=20, mlp_width=10, image_layers=0, use_image_scales=True, scale_bijector="exp", kl_weight=None,
+                  studentt_likelihood_dof=None, refine_uncertainties=False, standardize_metadata=True, seed=1234,
+                  validation_frequency=10, half_dataset_repeats=1, structure_factor_init_scale=1.0, anomalous=False,
+                  separate_files=False, positional_encoding_frequencies=4, reflection_files=["a.mtz", "b.mtz"], output_base="out/base")
+    for k, v in expect.items():
+        assert getattr(ns, k) == v, k
+    d = default_parser("mono")
+    for k in expect:
+        if k not in ("reflection_files", "output_base"):
+            assert getattr(d, k) == getattr(ns, k), k
+    ns = build_argparser().parse_args(["poly", "--disable-image-scales", "--disable-metadata-standardization", "-l", "0.95", "1.2",
+                                       "--studentt-likelihood-dof", "16", "--double-wilson-parents", "None,0", "--double-wilson-r", "0.,0.99",
+                                       "--separate-files", "-d", "2.0", "-c", "1.5", "dHKL,Wavelength", "a.mtz", "b.mtz", "o"])
+    assert ns.use_image_scales is False and ns.standardize_metadata is False and ns.wavelength_range == [0.95, 1.2]
+    assert ns.parents == "None,0" and ns.dwr == "0.,0.99" and ns.dmin == 2.0 and ns.isigi_cutoff == 1.5
+    f = make_formatter(ns)
+    assert type(f).__name__ == "LaueFormatter" and f.lam_min == 0.95 and f.lam_max == 1.2 and f.standardize is False
+    with pytest.raises(TypeError):
+        default_parser("mono", not_an_option=1)
+    with pytest.raises(ValueError):
+        ns.spacegroups = "P 1,P 1,P 1"
+        make_formatter(ns)
