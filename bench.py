@@ -1,21 +1,30 @@
 #!/usr/bin/env python
 """bench.py -- reflection observations/sec through the ELBO gradient + Adam step.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--obs N] [--refl R]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--config mono|laue|dw|stills] [--obs N] [--refl R] [--scaling weak|strong]
 
-Workload at every N: BASELINE.json configs[1] per GPU ("synthetic mono: 10M observations, 500k unique
-reflections, StudentTLikelihood, MLPScaler width 32 x 20 layers"; d=5 metadata columns), i.e. weak
-scaling: each rank owns its own 500k reflections and their 10M observations; the scale-MLP gradients
-and the scalar ELBO terms are all-reduced over NCCL every step.
+Default workload (the one the driver runs at N = 1, 2, 4, 8): BASELINE.json configs[1] PER GPU ("synthetic mono: 10M
+observations, 500k unique reflections, StudentTLikelihood, MLPScaler width 32 x 20 layers"; d = 5), weak scaling.
+--config selects the other BASELINE configs (parity-test shapes; `stills` = configs[4], 200 M observations / 2 M
+reflections / 100 k images, MLP 10 x 20 + 2 per-image layers, STRONG scaling: the job is fixed and split over the ranks).
 
-One "step" = one full-batch ELBO gradient + Adam step over the resident observations.
-* value  : obs/s with the inputs resident in HBM (K steps, CUDA events on the launch stream, max over ranks)
+At every N the global problem's integer structure (refl_id / image_id / harmonic_id / DoubleWilson parents) is drawn
+identically on every rank and goes through the product's partitioner (careless_b200.parallel: reflection_groups ->
+assign_ranks -> shard, balanced by observation count); each rank then attaches metadata and intensities to ITS rows.
+The per-step exchange is inside the library (clb_comm_init: one grouped NCCL all-reduce of {replicated gradients f32 |
+scalars f64} per step on the step's stream) -- there is no Python between the steps of the timed region.
+
+One "step" = one full-batch ELBO gradient + Adam step over the rank's resident observations.
+* value  : obs/s, inputs resident in HBM (K steps in ONE clb_step call, CUDA events on the launch stream, max over ranks)
 * e2e    : obs/s through the C-ABI with HOST buffers: every step's prepared rows are copied from pinned host memory
            (K copies for K steps, all inside the timed region; from the second step on the copy of step t+1 runs on a
            copy stream while step t computes: clb_prefetch_observations), the step runs and its metrics are read back.
-* roofline: the dominant kernel (k_obs), timed live with CUDA events inside the same K steps.
-* cpu_baseline / --impl reference: the float32 torch-CPU restatement of the reference graph (oracle/,
-  "port": TensorFlow is not installable here) on a bounded sample of the same workload.
+* roofline: the dominant kernel (the observation kernel), timed live with CUDA events inside the same K steps;
+           `traffic` comes from profiles/traffic.json, which tools/ncu_traffic.py regenerates from an ncu capture.
+* cpu_baseline / --impl reference: the reference's CPU path on the box's host cores -- the real TensorFlow careless model
+  when tensorflow + tensorflow_probability + tf_keras import (kind "reference"), else the float32 torch-CPU restatement
+  (oracle/, kind "port") -- on a bounded SUBSAMPLE of the same workload, which the line's config states.
 """
 import argparse
 import json
@@ -33,17 +42,31 @@ sys.path.insert(0, ROOT)
 
 METRIC = "reflection observations/sec through ELBO grad+Adam step"
 UNIT = "obs/s"
-D_META, WIDTH, LAYERS, DOF = 5, 32, 20, 12.0
+D_META = 5
+
+# BASELINE.json configs[1..4] (SURVEY.md 8(d) restatement): global sizes, model, default scaling mode
+CONFIGS = {
+    "mono":   dict(index=1, obs=10_000_000, refl=500_000, width=32, layers=20, image_layers=0, likelihood="studentt", dof=12.0,
+                   n_images=5000, scaling="weak", label="synthetic mono"),
+    "laue":   dict(index=2, obs=20_000_000, refl=1_000_000, width=32, layers=20, image_layers=0, likelihood="normal", dof=None,
+                   n_images=10000, scaling="strong", label="synthetic Laue (harmonic segment-sum)"),
+    "dw":     dict(index=3, obs=40_000_000, refl=2_000_000, width=32, layers=20, image_layers=0, likelihood="normal", dof=None,
+                   n_images=2500, scaling="strong", label="4-dataset DoubleWilson merge"),
+    "stills": dict(index=4, obs=200_000_000, refl=2_000_000, width=10, layers=20, image_layers=2, likelihood="normal", dof=None,
+                   n_images=100_000, scaling="strong", label="serial-crystallography stills, per-image scale layers"),
+}
 
 
-def flops_per_obs(d=D_META, w=WIDTH, layers=LAYERS):
-    """forward + backward (dX, dW) of the scale MLP = 6 (dW + (L-1)W^2 + 2W)."""
-    return 6 * (d * w + (layers - 1) * w * w + 2 * w)
+def flops_per_obs(d, w, layers, image_layers=0):
+    """forward + backward (dX, dW) of the scale MLP = 6 (dW + (L-1)W^2 + 2W) (+ 6 W(W+1) per image layer)."""
+    return 6 * (d * w + (layers - 1) * w * w + 2 * w) + 6 * image_layers * w * (w + 1)
 
 
-def bytes_per_step(n_obs, n_refl, d=D_META):
-    """compulsory HBM bytes of the non-MLP stages: N(16+4d) + 72R (no image ids here: -4)."""
-    return n_obs * (12 + 4 * d + 4) + n_refl * 72
+def bytes_per_step(n_obs, n_refl, d, image_ids=False, laue_spots=0):
+    """compulsory HBM bytes of the non-MLP stages: N(16+4d) + 72R (-4 N without image ids; Laue: 32 B/row + 8 B/spot)."""
+    if laue_spots:
+        return n_obs * 32 + laue_spots * 8 + n_refl * 72
+    return n_obs * (12 + 4 * d + (4 if image_ids else 0)) + n_refl * 72
 
 
 def load_peaks():
@@ -53,6 +76,19 @@ def load_peaks():
         return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"], "bf16_tflops_sustained": p.get("bf16_tflops_sustained"),
                 "source": "measured"}
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+def load_traffic(kernel, key):
+    """DRAM bytes per launch of `kernel` on workload `key` from profiles/traffic.json (written by tools/ncu_traffic.py from
+    an `ncu --set full` capture of this very command); None when no capture of that workload has been committed."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        for e in json.load(open(path)):
+            if e.get("workload") == key and kernel.split("<")[0] == e.get("kernel", "?"):
+                return e
+    except Exception:
+        pass
+    return None
 
 
 class ClockSampler:
@@ -103,16 +139,79 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------
-# reference arm / cpu baseline: float32 torch-CPU restatement of the reference graph
+# reference arm / cpu baseline
 # ----------------------------------------------------------------------------------------
-def cpu_reference(budget_s, n_obs, n_refl, steps=None, warmup=1):
+def _tf_reference_available():
+    try:
+        import tensorflow  # noqa: F401
+        import tensorflow_probability  # noqa: F401
+        import tf_keras  # noqa: F401
+        return True
+    except Exception:
+        return False
+
+
+def _tf_reference(c, n_obs, n_refl, steps, warmup):
+    """The UNMODIFIED reference model (baseline/_ref = `pip install --no-deps --target baseline/_ref /root/reference`) on
+    TensorFlow CPU: VariationalMergingModel.train_model (variational.py:226-275), all host threads."""
+    import importlib
+    import types
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref, "careless")):
+        raise RuntimeError("baseline/_ref/careless is missing")
+    sys.path.insert(0, ref)
+    if importlib.util.find_spec("reciprocalspaceship") is None:       # imported by priors/wilson.py, unused by WilsonPrior
+        sys.modules["reciprocalspaceship"] = types.ModuleType("reciprocalspaceship")
+    import tensorflow as tf
+    import tf_keras as tfk
+    tf.config.set_visible_devices([], "GPU")
+    from careless.models.likelihoods.mono import NormalLikelihood, StudentTLikelihood
+    from careless.models.merging.surrogate_posteriors import TruncatedNormal
+    from careless.models.merging.variational import VariationalMergingModel
+    from careless.models.priors.wilson import WilsonPrior
+    from careless.models.scaling.nn import MLPScaler
+    from careless_b200 import synth
+    p = synth.make_mono(n_obs, n_refl, d=D_META, n_images=max(2, n_obs // 2000), seed=1234)
+    prior = WilsonPrior(p["centric"], p["multiplicity"])
+    loc, scale = prior.mean(), prior.stddev()
+    low = (1e-32 * (~p["centric"])).astype("float32")
+    q = TruncatedNormal.from_loc_and_scale(loc, scale, low)
+    lik = StudentTLikelihood(c["dof"]) if c["likelihood"] == "studentt" else NormalLikelihood()
+    from tensorflow_probability import bijectors as tfb
+    scaler = MLPScaler(c["layers"], c["width"], scale_bijector=tfb.Chain([tfb.Shift(1e-7), tfb.Exp()]))     # io/manager.py:457-463 (CLI default)
+    model = VariationalMergingModel(q, prior, lik, scaler, 1)
+    model.compile(tfk.optimizers.Adam(1e-3, 0.9, 0.99))
+    col = lambda a, t: np.asarray(a).reshape(-1, 1).astype(t)
+    data = (col(p["refl_id"], "int64"), col(p["image_id"], "int64"), col(p["file_id"], "int64"), p["metadata"].astype("float32"),
+            col(p["intensities"], "float32"), col(p["uncertainties"], "float32"))
+    data = tuple(tf.convert_to_tensor(x) for x in data)
+    model.train_model(data, max(1, warmup), progress=False)
+    t0 = time.perf_counter()
+    model.train_model(data, steps, progress=False)
+    el = time.perf_counter() - t0
+    return el, f"tensorflow {tf.__version__} CPU, unmodified careless train_model"
+
+
+def cpu_reference(c, budget_s, n_obs, n_refl, steps=None, warmup=1):
+    """Reference CPU path on a SUBSAMPLE (n_obs / n_refl, same obs-per-reflection ratio and the same model) of config `c`."""
+    cores = os.cpu_count() or 1
+    if _tf_reference_available():
+        try:
+            k = steps or 3
+            el, how = _tf_reference(c, n_obs, n_refl, k, warmup)
+            return {"value": n_obs * k / el, "unit": UNIT, "cores": cores, "kind": "reference",
+                    "sample": f"{k} steps x {n_obs} obs / {n_refl} reflections SUBSAMPLE of the config ({how}, {el:.1f} s)",
+                    "ms_per_step": 1e3 * el / k, "n_obs": n_obs, "n_refl": n_refl, "steps": k}
+        except Exception as e:      # fall through to the port, saying why
+            why = f"{type(e).__name__}: {e}"[:160]
+    else:
+        why = "tensorflow / tensorflow_probability / tf_keras not importable"
     import torch
     from careless_b200 import synth
     from oracle import model as om
-    cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     p = synth.make_mono(n_obs, n_refl, d=D_META, n_images=max(2, n_obs // 2000), seed=1234)
-    cfg = om.ModelConfig(n_refl=n_refl, n_meta=D_META, mlp_width=WIDTH, mlp_layers=LAYERS, likelihood="studentt", dof=DOF)
+    cfg = om.ModelConfig(n_refl=n_refl, n_meta=D_META, mlp_width=c["width"], mlp_layers=c["layers"], likelihood=c["likelihood"], dof=c["dof"])
     prior = om.PriorData(p["centric"], p["multiplicity"])
     params = om.init_params(cfg, prior, dtype=torch.float32)
     state = om.adam_init(params)
@@ -136,45 +235,84 @@ def cpu_reference(budget_s, n_obs, n_refl, steps=None, warmup=1):
             break
     el = time.perf_counter() - t0
     return {"value": n_obs * done / el, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{done} steps x {n_obs} obs / {n_refl} reflections of the same config (float32 torch {torch.__version__} CPU restatement, "
-                      f"{el:.1f} s)", "ms_per_step": 1e3 * el / done}
+            "sample": f"{done} steps x {n_obs} obs / {n_refl} reflections SUBSAMPLE of the config (float32 torch {torch.__version__} CPU "
+                      f"restatement of the reference graph, {el:.1f} s; real reference not used: {why})",
+            "ms_per_step": 1e3 * el / done, "n_obs": n_obs, "n_refl": n_refl, "steps": done}
 
 
-def run_reference(args):
+def run_reference(args, c):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_obs, n_refl = 500_000, 25_000
-    steps = max(1, min(args.steps, 6))
-    r = cpu_reference(20.0, n_obs, n_refl, steps=steps, warmup=min(args.warmup, 1))
-    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-            "warmup": min(args.warmup, 1), "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, 1), "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+    # bounded sample: 1 M observations (cost is linear in N; 10 M would need ~26 GB of autograd activations and minutes per step)
+    n_obs, n_refl = 1_000_000, max(1000, int(1_000_000 * c["refl"] / c["obs"]))
+    steps = max(1, min(args.steps, 5))
+    warm = min(max(args.warmup, 0), 1)
+    r = cpu_reference(c, 20.0, n_obs, n_refl, steps=steps, warmup=warm)
+    cfg = workload_config(args, c, 1, c["obs"], c["refl"])
+    cfg["reference_sample"] = {"obs": n_obs, "refl": n_refl, "steps": r["steps"],
+                               "note": "the reference arm ran this SUBSAMPLE of the workload, not the full configuration; obs/s is linear in N"}
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": r["steps"],
+            "warmup": warm, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": c["scaling"],
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, world):
-    return {"workload": f"BASELINE configs[1] per GPU: synthetic mono, {args.obs} obs, {args.refl} unique reflections, "
-                        f"StudentT(dof={DOF:g}), MLPScaler {WIDTH}x{LAYERS}, d={D_META}, WilsonPrior, 1 MC sample",
-            "obs_per_gpu": args.obs, "refl_per_gpu": args.refl, "world_size": world,
-            "l2_note": "inputs per step (>= 360 MB/GPU) exceed the 126 MB L2, no flush needed",
-            "parallelism": f"reflection-partitioned dp{world}" if world > 1 else "single GPU"}
+def workload_config(args, c, world, n_obs_global, n_refl_global):
+    il = f" + {c['image_layers']} per-image layers ({c['n_images']} images)" if c["image_layers"] else ""
+    lik = f"StudentT(dof={c['dof']:g})" if c["likelihood"] == "studentt" else "Normal"
+    per = " per GPU" if c["scaling"] == "weak" else ""
+    return {"workload": f"BASELINE configs[{c['index']}]{per}: {c['label']}, {c['obs']} obs, {c['refl']} unique reflections, "
+                        f"{lik}, MLPScaler {c['width']}x{c['layers']}{il}, d={D_META}, "
+                        f"{'DoubleWilson' if args.config == 'dw' else 'Wilson'}Prior, 1 MC sample",
+            "config_name": args.config, "obs_global": n_obs_global, "refl_global": n_refl_global, "world_size": world,
+            "l2_note": "inputs per step (>= 32 B x obs per GPU, >= 320 MB) exceed the 126 MB L2, no flush needed",
+            "parallelism": (f"reflection-partitioned dp{world} (careless_b200.parallel partitioner, in-library NCCL exchange)"
+                            if world > 1 else "single GPU")}
 
 
 # ----------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------
-class _DevView:
-    def __init__(self, ptr, n, typestr):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+def build_problem(args, c, rank, world):
+    """Global integer structure (same on every rank) -> partition -> this rank's rows with payload.  Returns
+    (local inputs, local tables, extras) ready for Engine.set_observations / set_prior."""
+    from careless_b200 import parallel, synth
+    t0 = time.perf_counter()
+    mult = world if c["scaling"] == "weak" else 1
+    N, R = args.obs * mult, args.refl * mult
+    name = args.config
+    if name == "mono":
+        ids = synth.ids_mono(N, R, seed=1234)
+    elif name == "stills":
+        ids = synth.ids_stills(N, R, c["n_images"], seed=1234)
+    elif name == "laue":
+        ids = synth.ids_laue(N, R, c["n_images"], seed=1234)
+    else:
+        ids = synth.ids_double_wilson(N // 4, R // 4, 4, c["n_images"], seed=1234)
+    tables = synth.global_tables(R, seed=1234, n_datasets=4 if name == "dw" else 1)
+    if name == "dw":
+        tables.update(dw_parent=ids["dw_parent"], asu_id=ids["asu_id"])
+    t_ids = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    ranks = parallel.partition(R, ids["refl_id"], world, harmonic_id=ids.get("harmonic_id"), dw_parent=tables.get("dw_parent"))
+    inputs = {k: ids.get(k) for k in ("refl_id", "image_id", "harmonic_id")}
+    li, lt = parallel.shard(inputs, tables, ranks, rank, laue=(name == "laue"))
+    t_part = time.perf_counter() - t0
+    f_rows = tables["f_true"][lt["refl_index"]][li["refl_id"]]
+    li = synth.attach_payload(li, f_rows, d=D_META, seed=1234 + 17 * rank, laue=(name == "laue"))
+    counts = np.bincount(ranks, weights=np.bincount(ids["refl_id"], minlength=R), minlength=world)
+    extras = {"N": N, "R": R, "obs_per_rank": [int(x) for x in counts], "refl_per_rank": [int(x) for x in np.bincount(ranks, minlength=world)],
+              "t_ids_s": t_ids, "t_partition_s": t_part, "r": ids.get("r"), "n_spots_local": int(li["harmonic_id"].max()) + 1 if name == "laue" else 0}
+    return li, lt, extras
 
 
-def run_ours(args):
+def run_ours(args, c):
     import torch
     import torch.distributed as dist
-    from careless_b200 import synth
+    from careless_b200 import parallel
     from careless_b200.engine import Engine, EngineConfig
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -185,46 +323,44 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    stream = torch.cuda.Stream(device=local)      # a real (non-legacy) stream shared by the engine, NCCL and the events
+    stream = torch.cuda.Stream(device=local)      # a real (non-legacy) stream shared by the engine, its NCCL exchange and the events
     torch.cuda.set_stream(stream)
+    name = args.config
 
-    N, R = args.obs, args.refl
-    p = synth.make_mono(N, R, d=D_META, n_images=5000, seed=1234 + rank)
-    cfg = EngineConfig(n_refl=R, n_refl_total=R * world, n_meta=D_META, mlp_width=WIDTH, mlp_layers=LAYERS,
-                       likelihood="studentt", dof=DOF, seed=1234, device=local, stream=stream.cuda_stream,
-                       rank=rank, world_size=world)
+    li, lt, ex = build_problem(args, c, rank, world)
+    N_glob, R_glob = ex["N"], ex["R"]
+    n_loc, r_loc = len(li["refl_id"]), len(lt["refl_index"])
+    use_img = c["image_layers"] > 0
+    cfg = EngineConfig(n_refl=r_loc, n_refl_total=R_glob, n_meta=D_META, mlp_width=c["width"], mlp_layers=c["layers"],
+                       likelihood=c["likelihood"], dof=c["dof"], laue=(name == "laue"),
+                       n_images=c["n_images"] if use_img else 0, image_layers=c["image_layers"],
+                       prior="double_wilson" if name == "dw" else "wilson", n_asu=4 if name == "dw" else 0,
+                       seed=1234, device=local, stream=stream.cuda_stream, rank=rank, world_size=world)
     eng = Engine(cfg)
     t_prep = time.perf_counter()
-    eng.set_observations(p["refl_id"], None, p["metadata"], p["intensities"], p["uncertainties"],
-                         obs_index=np.arange(N, dtype=np.int64) + rank * N, n_rows_total=N * world)
-    eng.set_prior(p["centric"], p["multiplicity"], refl_index=np.arange(R, dtype=np.int64) + rank * R)
+    eng.set_observations(li["refl_id"], li.get("image_id") if use_img else None, li["metadata"], li["intensities"], li["uncertainties"],
+                         harmonic_id=li.get("harmonic_id"), obs_index=li["obs_index"], n_rows_total=N_glob)
+    eng.set_prior(lt["centric"], lt["multiplicity"], None, dw_parent=lt.get("dw_parent"), asu_id=lt.get("asu_id"), r=ex["r"],
+                  refl_index=lt["refl_index"])
     eng.synchronize()
     t_prep = time.perf_counter() - t_prep
-
-    if world > 1:
-        pf, nf, pd, nd = eng.reduce_buffers()
-        gbuf = torch.as_tensor(_DevView(pf, nf, "<f4"), device=f"cuda:{local}")
-        sbuf = torch.as_tensor(_DevView(pd, nd, "<f8"), device=f"cuda:{local}")
-
-    def step(want_metrics=False):
-        if world == 1:
-            return eng.step(1)[0] if want_metrics else (eng.step_begin(), eng.step_norms(), eng.step_end(False))
-        eng.step_begin()
-        dist.all_reduce(gbuf)
-        eng.step_norms()
-        dist.all_reduce(sbuf)
-        return eng.step_end(want_metrics)
+    if world > 1:        # library-side communicator: rank 0's id travels over the (already initialised) process group
+        idt = torch.zeros(128, dtype=torch.uint8, device=f"cuda:{local}")
+        if rank == 0:
+            from careless_b200 import _lib
+            idt = torch.frombuffer(bytearray(_lib.comm_unique_id()), dtype=torch.uint8).to(f"cuda:{local}")
+        dist.broadcast(idt, src=0)
+        eng.init_comm(bytes(idt.cpu().numpy().tobytes()))
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step()
+    eng.step(max(args.warmup, 3))
     barrier()
 
-    # ---- timed region 1: resident inputs ----
+    # ---- timed region 1: resident inputs, K steps in one library call (no host code between the steps) ----
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -232,84 +368,92 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record(stream)
-    for _ in range(args.steps):
-        step()
+    hist = eng.step(args.steps)
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
     kt = eng.kernel_times()
     eng.reset_timers(False)
-    last = step(True)
+    last = hist[-1]
     clocks = sampler.stop() if rank == 0 else None
-    if not all(math.isfinite(v) for v in last.values()):
+    if len(hist) != args.steps or not all(math.isfinite(v) for v in last.values()):
         raise SystemExit(f"bench.py: the step produced non-finite metrics {last}: timing such a run would be meaningless")
 
     # ---- timed region 2: end to end through the C-ABI with host buffers ----
-    h2d = 0
     barrier()
     t0 = time.perf_counter()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record(stream)
     eng.upload_observations()              # pinned host -> device copy of the first step's inputs (exposed)
     for i in range(args.steps):
-        # the step's kernels are queued first, then the NEXT step's inputs start travelling on the copy stream
-        # (second device buffer, clb_prefetch_observations), then this step's metrics are read back (4 doubles)
+        # the step's kernels (and its exchange) are queued first, then the NEXT step's inputs start travelling on the copy
+        # stream (second device buffer, clb_prefetch_observations), then this step's metrics are read back (4 doubles)
         eng.step_begin()
-        if world > 1:
-            dist.all_reduce(gbuf)
         eng.step_norms()
-        if world > 1:
-            dist.all_reduce(sbuf)
         if i + 1 < args.steps:
             eng.prefetch_observations()
-        m = eng.step_end(True)
+        eng.step_end(True)
     e3.record(stream)
     barrier()
     ms_e2e = max(e2.elapsed_time(e3), 1e3 * (time.perf_counter() - t0))
-    h2d = N * (4 + 4 + 4 * D_META + 4 + 4)
+    row_bytes = 4 + 4 + 4 * D_META + 4 + 4 + (4 if use_img else 0) + (4 if name == "laue" else 0)
+    h2d = n_loc * row_bytes
+    obs_ms = kt["obs_kernel_ms"]
     if world > 1:
-        t = torch.tensor([ms, ms_e2e, kt["obs_kernel_ms"]], device=f"cuda:{local}", dtype=torch.float64)
+        t = torch.tensor([ms, ms_e2e, obs_ms], device=f"cuda:{local}", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e2e, obs_ms = [float(x) for x in t.tolist()]
-    else:
-        obs_ms = kt["obs_kernel_ms"]
+        t = torch.tensor([float(h2d)], device=f"cuda:{local}", dtype=torch.float64)
+        dist.all_reduce(t)
+        h2d = int(t.item())
 
     if rank == 0:
         peaks = load_peaks()
         ms_step = ms / args.steps
-        value = N * world * args.steps / (ms * 1e-3)
+        value = N_glob * args.steps / (ms * 1e-3)
         launches_per_step = kt["total_launches"] / max(1, args.steps)
         obs_avg_ms = obs_ms / max(1, kt["obs_kernel_launches"])
-        tflops = N * flops_per_obs() / (obs_avg_ms * 1e-3) / 1e12
-        hbm_gbs = bytes_per_step(N, R) / (obs_avg_ms * 1e-3) / 1e9
+        n_max = max(ex["obs_per_rank"])                    # the launch that sets the step time processes the largest shard
+        fpo = flops_per_obs(D_META, c["width"], c["layers"], c["image_layers"])
+        tflops = n_max * fpo / (obs_avg_ms * 1e-3) / 1e12
+        alg_bytes = bytes_per_step(n_max, max(ex["refl_per_rank"]), D_META, image_ids=use_img, laue_spots=ex["n_spots_local"])
+        hbm_gbs = alg_bytes / (obs_avg_ms * 1e-3) / 1e9
         fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12
-        tf32_peak = peaks["bf16_tflops"] / 2.0            # dense TF32 runs at half the bf16 rate on the same tensor pipe
-        executed = tflops * (3 + 3 + 4) / 3.0              # 3xTF32 forward + dX, 4-product dW: tensor-pipe FLOPs actually issued
-        # DRAM bytes of one k_obs_tc2 launch at the default workload, from the committed ncu --set full capture
-        # (profiles/r01_k_obs_tc2_ncu_full10M.txt: dram__bytes_read.sum 10.27 GB + dram__bytes_write.sum 25.00 GB)
-        traffic = 3.527e10 if (N, R) == (10_000_000, 500_000) else None
-        roofline = {"kernel": "k_obs_tc2<studentt> (scale MLP fwd+bwd on tcgen05/TMEM, 3xTF32, two threads per row; likelihood; segmented dL/dz_f reduction)",
+        tf32 = measured_tf32_peak(peaks)
+        wide = c["width"] > 16
+        # tensor-pipe FLOPs actually issued per algorithmic FLOP: W=32 3xTF32 forward + dX, 4-product dW; W<=16: 6-product forward
+        executed = tflops * ((3 + 3 + 4) / 3.0 if wide else (6 + 3 + 4) / 3.0) * ((32.0 if wide else 16.0) / c["width"]) ** 2
+        kern = ("k_obs_tc2" if wide else "k_obs_tc16") + ("<IL>" if use_img else "")
+        wkey = f"{name}:{n_max}:{c['width']}x{c['layers']}"
+        tr = load_traffic(kern, wkey) or (load_traffic(kern, f"{name}:{args.obs}:{c['width']}x{c['layers']}") if world == 1 else None)
+        roofline = {"kernel": f"{kern} (scale MLP fwd+bwd on tcgen05/TMEM; likelihood; segmented dL/dz_f reduction)",
                     "bound": "tensor", "achieved": tflops, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                    "frac": tflops / peaks["bf16_tflops"], "traffic": traffic, "traffic_unit": "bytes per launch (dram read + write, ncu)",
+                    "frac": tflops / peaks["bf16_tflops"],
+                    "traffic": tr["dram_bytes_per_launch"] if tr else None, "traffic_unit": "bytes per launch (dram read + write, ncu --set full)",
+                    "traffic_source": (tr.get("source") if tr else "no committed ncu capture of this workload"),
                     "peak_source": peaks["source"] + " bf16 cuBLAS burst",
-                    "note": "achieved = ALGORITHMIC FP32 FLOPs (N x 118080) / kernel time; the kernel multiplies in TF32 (half the bf16 rate) "
-                            "and issues 3.33x the algorithmic FLOPs for FP32-level accuracy (error-compensated 3xTF32), so frac <= 0.15 by construction",
-                    "tensor_tf32": {"achieved_executed": executed, "peak": tf32_peak, "frac_executed": executed / tf32_peak,
-                                    "peak_source": "measured bf16 / 2"},
+                    "note": "achieved = ALGORITHMIC FP32 FLOPs (obs x flops_per_obs) / kernel time; the kernel multiplies in TF32 (half the bf16 rate) "
+                            "and issues >= 3.33x the algorithmic FLOPs for FP32-level accuracy (error-compensated 3xTF32) on tiles padded to "
+                            "width 32 / 16, so frac <= 0.15 by construction",
+                    "tensor_tf32": {"achieved_executed": executed, "peak": tf32["peak"], "frac_executed": executed / tf32["peak"],
+                                    "peak_source": tf32["source"]},
                     "fp32_fma_equivalent": {"achieved": tflops, "peak": fp32_peak, "frac": tflops / fp32_peak,
                                             "peak_source": "computed 148x128x2x1.965GHz (what an FP32-FMA kernel could at most reach)"},
                     "hbm": {"achieved": hbm_gbs, "peak": peaks["hbm_gbs"], "frac": hbm_gbs / peaks["hbm_gbs"], "unit": "GB/s",
-                            "algorithmic_bytes_per_step": bytes_per_step(N, R)},
-                    "kernel_ms": obs_avg_ms, "kernel_share_of_step": obs_avg_ms / ms_step,
-                    "flops_per_obs": flops_per_obs()}
+                            "algorithmic_bytes_per_step": alg_bytes},
+                    "kernel_ms": obs_avg_ms, "kernel_share_of_step": obs_avg_ms / ms_step, "flops_per_obs": fpo}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            cpu = cpu_reference(12.0, 250_000, 12_500)
+            cpu = cpu_reference(c, 12.0, 250_000, max(500, int(250_000 * c["refl"] / c["obs"])))
             cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        cfgd = workload_config(args, c, world, N_glob, R_glob)
+        cfgd["partition"] = {"obs_per_rank": ex["obs_per_rank"], "refl_per_rank": ex["refl_per_rank"],
+                             "imbalance": max(ex["obs_per_rank"]) / (sum(ex["obs_per_rank"]) / world),
+                             "ids_s": ex["t_ids_s"], "partition_and_shard_s": ex["t_partition_s"]}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic", "config": workload_config(args, world),
-                "e2e": {"value": N * world * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d * world,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": c["scaling"], "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": cfgd,
+                "e2e": {"value": N_glob * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": 32 * world, "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": int(round(launches_per_step * args.steps)), "launches_per_step": launches_per_step,
                 "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
@@ -320,20 +464,43 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def measured_tf32_peak(peaks):
+    """Dense TF32 tcgen05 peak: profiles/tf32_peak.json (tools/tc_rate.cu run on the B200, kind::tf32 M=128 N=256 back to back)
+    when committed, else half the measured bf16 cuBLAS rate (same tensor pipe, half the K per instruction)."""
+    path = os.path.join(ROOT, "profiles", "tf32_peak.json")
+    try:
+        p = json.load(open(path))
+        return {"peak": float(p["tf32_tflops"]), "source": p.get("source", "profiles/tf32_peak.json")}
+    except Exception:
+        return {"peak": peaks["bf16_tflops"] / 2.0, "source": "measured bf16 / 2 (no TF32 probe committed)"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--obs", type=int, default=10_000_000)
-    ap.add_argument("--refl", type=int, default=500_000)
+    ap.add_argument("--config", default="mono", choices=sorted(CONFIGS))
+    ap.add_argument("--obs", type=int, default=None, help="observations (per GPU for weak scaling, total for strong)")
+    ap.add_argument("--refl", type=int, default=None)
+    ap.add_argument("--scaling", default=None, choices=["weak", "strong"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    c = dict(CONFIGS[args.config])
+    if args.scaling:
+        c["scaling"] = args.scaling
+    if args.obs is None:
+        args.obs = c["obs"]
+    if args.refl is None:
+        args.refl = c["refl"]
+    if args.obs != c["obs"] or args.refl != c["refl"]:
+        c["n_images"] = max(2, int(c["n_images"] * args.obs / c["obs"]))
+        c["obs"], c["refl"] = args.obs, args.refl
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args, c)
     else:
-        run_ours(args)
+        run_ours(args, c)
 
 
 if __name__ == "__main__":

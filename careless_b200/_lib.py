@@ -11,7 +11,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CLB_LIB_PATH") or os.path.join(HERE, "libcareless_b200.so")   # CLB_LIB_PATH: instrumented debug builds (tools/)
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # enums of include/careless_b200.h
 LIK_NORMAL, LIK_STUDENTT = 0, 1
@@ -74,6 +74,8 @@ SYMBOLS = {
     "clb_step_norms": (C.c_int, [_H]),
     "clb_step_end": (C.c_int, [_H, C.POINTER(clb_metrics)]),
     "clb_reduce_buffers": (C.c_int, [_H, C.POINTER(C.c_void_p), _I64, C.POINTER(C.c_void_p), _I64]),
+    "clb_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "clb_comm_init": (C.c_int, [_H, C.c_void_p]),
     "clb_get_samples": (C.c_int, [_H, C.c_void_p, C.c_int64]),
     "clb_enable_ipred": (C.c_int, [_H, C.c_int32]),
     "clb_get_ipred": (C.c_int, [_H, C.c_void_p, C.c_int64]),
@@ -121,3 +123,10 @@ def check(rc, handle=None):
     if rc != 0:
         msg = load().clb_last_error(handle)
         raise ClbError(rc, msg.decode() if msg else "unknown error")
+
+
+def comm_unique_id() -> bytes:
+    """128-byte id of a new library-side communicator (rank 0 calls this and hands the bytes to the other ranks)."""
+    buf = (C.c_uint8 * 128)()
+    check(load().clb_comm_unique_id(buf))
+    return bytes(buf)

@@ -132,8 +132,19 @@ def _concat_rows(a, b):
 
 def run_careless(parser, datasets=None):
     """careless.py:11-139.  `datasets` (already loaded DataSet objects) may replace `parser.reflection_files`."""
+    from . import parallel
     from .io.manager import DataManager
-    from .io.mtz import write_mtz
+    from .io.mtz import write_mtz as _write_mtz
+
+    # `torchrun --nproc-per-node N -m careless_b200.careless ...`: every process formats the same inputs (the splits below
+    # draw from the same seeded generator), trains its share of the reflections on its own GPU and takes part in the
+    # gathers; only rank 0 writes the output files.
+    ctx = parallel.context()
+    chief = ctx.rank == 0
+
+    def write_mtz(path, ds):
+        if chief:
+            _write_mtz(path, ds)
 
     np.random.seed(parser.seed)
     df = make_formatter(parser)
@@ -162,13 +173,14 @@ def run_careless(parser, datasets=None):
     for i, ds in enumerate(results):
         write_mtz(out + f"_{i}.mtz", ds)
     keys = list(history.keys())
-    with open(out + "_history.csv", "w", newline="") as f:
-        w = csv.writer(f)
-        w.writerow(["step"] + keys)
-        for step in range(len(history[keys[0]]) if keys else 0):
-            w.writerow([step] + [history[k][step] for k in keys])
-    model.surrogate_posterior.save_weights(out + "_structure_factor")
-    model.scaling_model.save_weights(out + "_scale")
+    if chief:
+        with open(out + "_history.csv", "w", newline="") as f:
+            w = csv.writer(f)
+            w.writerow(["step"] + keys)
+            for step in range(len(history[keys[0]]) if keys else 0):
+                w.writerow([step] + [history[k][step] for k in keys])
+        model.surrogate_posterior.save_weights(out + "_structure_factor")
+        model.scaling_model.save_weights(out + "_scale")
 
     if test is not None:
         pairs = zip(dm.get_predictions(model, train, test_value=0), dm.get_predictions(model, test, test_value=1))
@@ -194,6 +206,7 @@ def run_careless(parser, datasets=None):
                 hmodel.close()
         for file_id, ds in enumerate(xval):
             write_mtz(out + f"_xval_{file_id}.mtz", ds)
+    ctx.barrier()
     return {"model": model, "data_manager": dm, "history": history, "results": results, "train": train, "test": test, "xval": xval}
 
 

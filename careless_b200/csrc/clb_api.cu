@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <dlfcn.h>
 #include <string>
 #include <vector>
 
@@ -50,6 +51,46 @@ struct PinBuf {
   template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+// ---- NCCL, bound at run time (dlopen) -----------------------------------------------------------------------------
+// The library has no link-time dependency on NCCL: a single-GPU user (and the CPU-side build check) never needs it, and a
+// process that has already loaded an NCCL (torch bundles its own libnccl.so.2) gets THAT copy back from dlopen instead of
+// a second one.  Only the few entry points of the step's exchange are bound; types follow nccl.h (2.x ABI).
+struct NcclUniqueId { char internal[128]; };
+typedef struct ncclComm* NcclComm;
+enum { kNcclSum = 0, kNcclFloat32 = 7, kNcclFloat64 = 8 };
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(NcclUniqueId*) = nullptr;
+  int (*CommInitRank)(NcclComm*, int, NcclUniqueId, int) = nullptr;
+  int (*CommDestroy)(NcclComm) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  std::string err;
+  bool load() {
+    if (lib) return true;
+    const char* names[] = {getenv("CLB_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+      if (!n || !n[0]) continue;
+      lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (lib) break;
+    }
+    if (!lib) { err = std::string("cannot load NCCL (libnccl.so.2): ") + (dlerror() ? dlerror() : "?"); return false; }
+    auto sym = [&](const char* n) { void* p = dlsym(lib, n); if (!p) err = std::string("NCCL symbol missing: ") + n; return p; };
+    GetUniqueId = reinterpret_cast<decltype(GetUniqueId)>(sym("ncclGetUniqueId"));
+    CommInitRank = reinterpret_cast<decltype(CommInitRank)>(sym("ncclCommInitRank"));
+    CommDestroy = reinterpret_cast<decltype(CommDestroy)>(sym("ncclCommDestroy"));
+    AllReduce = reinterpret_cast<decltype(AllReduce)>(sym("ncclAllReduce"));
+    GroupStart = reinterpret_cast<decltype(GroupStart)>(sym("ncclGroupStart"));
+    GroupEnd = reinterpret_cast<decltype(GroupEnd)>(sym("ncclGroupEnd"));
+    GetErrorString = reinterpret_cast<decltype(GetErrorString)>(sym("ncclGetErrorString"));
+    if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllReduce || !GroupStart || !GroupEnd || !GetErrorString) { lib = nullptr; return false; }
+    return true;
+  }
+};
+NcclApi g_nccl;
+
 }  // namespace
 
 struct clb_handle {
@@ -76,7 +117,8 @@ struct clb_handle {
   bool eval_mode = false;    // clb_eval: forward only (no gradients, no Adam)
   bool use_tc = false;       // tensor-core (tcgen05) path of k_obs: padded width 32, unless CLB_NO_TC=1
   bool use_tc2 = false;      // ... with two threads per observation row (k_obs_tc2), unless CLB_TC_ONE_THREAD_PER_ROW=1
-  bool use_tc16 = false;     // narrow MLPs (padded width <= 16, no image layers) on the tensor cores (k_obs_tc16), unless CLB_TC16=0
+  bool use_tc16 = false;     // narrow MLPs (padded width <= 16, with or without image layers) on the tensor cores (k_obs_tc16), unless CLB_TC16=0
+  bool discard_scratch = true;   // consumed activation-scratch lines are discarded from L2 (no DRAM write-back), unless CLB_DISCARD=0
   bool debug_sync = false;   // CLB_DEBUG_SYNC=1: synchronise + log after every kernel launch
   int order = CLB_ORDER_REFL;
   double ll_const = 0.0;   // per-sample constant log-likelihood of empty Laue slots
@@ -115,7 +157,12 @@ struct clb_handle {
   size_t ev_used = 0;
   double obs_ms = 0.0; int64_t obs_launches = 0, total_launches = 0;
 
+  // in-library exchange step (clb_comm_init): one grouped NCCL all-reduce per step on the handle's stream
+  NcclComm comm = nullptr;
+  int64_t exchanges = 0;
+
   ~clb_handle() {
+    if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
     for (auto e : ev) cudaEventDestroy(e);
     if (ev_copy_done) cudaEventDestroy(ev_copy_done);
     for (auto e : ev_rows_free) if (e) cudaEventDestroy(e);
@@ -162,7 +209,8 @@ template <int LIK, bool IL> cudaError_t launch_obs_tc2(clb_handle* h, const ObsA
 cudaError_t dispatch_obs(clb_handle* h, const ObsArgs& a) {
   const int lik = h->cfg.likelihood;
   if (h->use_tc16) {
-    auto kern = lik ? k_obs_tc16<1> : k_obs_tc16<0>;
+    const bool il = h->cfg.image_layers > 0;
+    auto kern = il ? (lik ? k_obs_tc16<1, true> : k_obs_tc16<0, true>) : (lik ? k_obs_tc16<1, false> : k_obs_tc16<0, false>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_obs);
     if (e != cudaSuccess) return e;
     kern<<<h->grid_obs, tc16::kRows, h->smem_obs, h->stream>>>(a);
@@ -408,6 +456,7 @@ int clb_create(const clb_config* cfg, clb_handle** out) {
   if (h->cfg.n_refl_total <= 0) h->cfg.n_refl_total = h->cfg.n_refl;
   if (h->cfg.world_size <= 0) { h->cfg.world_size = 1; h->cfg.rank = 0; }
   { const char* dbg = getenv("CLB_DEBUG_SYNC"); h->debug_sync = dbg && dbg[0] == '1'; }
+  { const char* dis = getenv("CLB_DISCARD"); h->discard_scratch = !(dis && dis[0] == '0'); }
   h->R = cfg->n_refl; h->S = cfg->mc_samples; h->WP = WP; h->KS = 1;
   auto bail = [&](int code) { g_create_error = h->err; delete h; return code; };
 #define CREATE_CUDA(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { fail(h, CLB_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); return bail(CLB_ERR_CUDA); } } while (0)
@@ -421,7 +470,7 @@ int clb_create(const clb_config* cfg, clb_handle** out) {
   { const char* no_tc = getenv("CLB_NO_TC"); h->use_tc = (WP == 32) && (cfg->mlp_layers + cfg->image_layers) > 0 && !(no_tc && no_tc[0] == '1'); }
   { const char* one = getenv("CLB_TC_ONE_THREAD_PER_ROW"); h->use_tc2 = h->use_tc && !(one && one[0] == '1'); }
   { const char* t16 = getenv("CLB_TC16"); const char* no_tc = getenv("CLB_NO_TC");
-    h->use_tc16 = (WP <= 16) && cfg->mlp_layers > 0 && cfg->image_layers == 0 && cfg->n_meta <= 16 &&
+    h->use_tc16 = (WP <= 16) && cfg->mlp_layers > 0 && cfg->n_meta <= 16 &&
                   !(t16 && t16[0] == '0') && !(no_tc && no_tc[0] == '1'); }
   h->obs_threads = (h->use_tc || h->use_tc16) ? tc::kThreads : kObsThreads;      // = observation rows per CTA tile
   switch (WP) {
@@ -430,7 +479,7 @@ int clb_create(const clb_config* cfg, clb_handle** out) {
     default: h->smem_obs = ObsSmem<32>::bytes(h->NL, h->use_tc, cfg->image_layers); break;
   }
   if (h->use_tc2) h->smem_obs = ObsSmem2::bytes(h->NL, cfg->image_layers);
-  if (h->use_tc16) h->smem_obs = ObsSmem16::bytes(h->NL);
+  if (h->use_tc16) h->smem_obs = ObsSmem16::bytes(h->NL, cfg->image_layers);
   if (h->smem_obs > (size_t)prop.sharedMemPerBlockOptin) {
     fail(h, CLB_ERR_INVALID, "scale MLP (%d layers x padded width %d) needs %zu B of shared memory; the device offers %zu",
          cfg->mlp_layers, WP, h->smem_obs, (size_t)prop.sharedMemPerBlockOptin);
@@ -906,6 +955,7 @@ static int step_begin_impl(clb_handle* h, const float* inj_u, const float* inj_e
       CLB_LAUNCHED(h);
     }
     a.seed = c.seed; a.step = h->step_counter; a.laue = c.laue; a.train_mlp = train_mlp ? 1 : 0;
+    a.discard_scratch = h->discard_scratch ? 1 : 0;
     if (h->timing) {
       while (h->ev.size() < h->ev_used + 2) { cudaEvent_t e; CLB_CUDA(h, cudaEventCreate(&e)); h->ev.push_back(e); }
       CLB_CUDA(h, cudaEventRecord(h->ev[h->ev_used], st));
@@ -943,10 +993,36 @@ static int step_norms_impl(clb_handle* h) {
   int64_t maxsz = 1;
   for (int v = 0; v < h->vt.n_vars; ++v) maxsz = std::max(maxsz, h->vt.size[v]);
   const int chunks = (int)std::min<int64_t>((maxsz + 256 * 8 - 1) / (256 * 8), 4 * h->n_sms);
-  k_var_sumsq<<<dim3(std::max(chunks, 1), h->vt.n_vars), 256, 0, st>>>(h->grad.as<float>(), h->vt, h->var_sums.as<double>());
+  const dim3 grid(std::max(chunks, 1), h->vt.n_vars);
+  if (h->comm == nullptr) {
+    k_var_sumsq<<<grid, 256, 0, st>>>(h->grad.as<float>(), h->vt, h->var_sums.as<double>(), 0);
+    CLB_LAUNCHED(h);
+    k_pack_scalars<<<1, 128, 0, st>>>(h->acc.as<double>(), h->var_sums.as<double>(), h->vt, h->red.as<double>(), h->cfg.rank,
+                                    (double)h->S * h->ll_const, 0);
+    CLB_LAUNCHED(h);
+    return CLB_OK;
+  }
+  // In-library exchange (clb_comm_init): everything that is rank-local -- sum(log q - log p), sum(ll), the sums of squares of
+  // the surrogate gradients -- is known BEFORE the replicated gradients are reduced, so the float32 gradient buffer and the
+  // float64 scalar buffer travel in ONE grouped NCCL all-reduce on the step's stream; the replicated variables' norms are
+  // then taken from the reduced gradient, identically on every rank.
+  k_var_sumsq<<<grid, 256, 0, st>>>(h->grad.as<float>(), h->vt, h->var_sums.as<double>(), 1);
   CLB_LAUNCHED(h);
   k_pack_scalars<<<1, 128, 0, st>>>(h->acc.as<double>(), h->var_sums.as<double>(), h->vt, h->red.as<double>(), h->cfg.rank,
-                                  (double)h->S * h->ll_const);
+                                  (double)h->S * h->ll_const, 1);
+  CLB_LAUNCHED(h);
+  {
+    const int64_t nf = h->P - 2 * h->R, nd = 2 + 2 * h->vt.n_vars;
+    float* gf = h->grad.as<float>() + 2 * h->R;
+    int rc = g_nccl.GroupStart();
+    if (rc == 0 && nf > 0) rc = g_nccl.AllReduce(gf, gf, (size_t)nf, kNcclFloat32, kNcclSum, h->comm, st);
+    if (rc == 0) rc = g_nccl.AllReduce(h->red.p, h->red.p, (size_t)nd, kNcclFloat64, kNcclSum, h->comm, st);
+    const int rc2 = g_nccl.GroupEnd();
+    if (rc == 0) rc = rc2;
+    if (rc != 0) return fail(h, CLB_ERR_CUDA, "NCCL all-reduce failed: %s", g_nccl.GetErrorString(rc));
+    h->exchanges++;
+  }
+  k_var_sumsq<<<grid, 256, 0, st>>>(h->grad.as<float>(), h->vt, h->red.as<double>() + 2, 2);
   CLB_LAUNCHED(h);
   return CLB_OK;
 }
@@ -984,7 +1060,7 @@ static int step_end_impl(clb_handle* h, double* d_metrics) {
 // draws and no update (keras test_on_batch at variational.py:257-260).  grad_norm is reported as 0.
 int clb_eval(clb_handle* h, const float* inj_u_f, const float* inj_eps_s, clb_metrics* out) {
   if (!h) return CLB_ERR_INVALID;
-  if (h->cfg.world_size > 1) return fail(h, CLB_ERR_STATE, "clb_eval is single-GPU");
+  if (h->cfg.world_size > 1 && h->comm == nullptr) return fail(h, CLB_ERR_STATE, "clb_eval with world_size > 1 needs clb_comm_init");
   int rc = ensure_metrics(h, 1); if (rc) return rc;
   h->eval_mode = true;
   rc = step_begin_impl(h, inj_u_f, inj_eps_s);
@@ -993,8 +1069,12 @@ int clb_eval(clb_handle* h, const float* inj_u_f, const float* inj_eps_s, clb_me
   cudaStream_t st = h->stream;
   CLB_CUDA(h, cudaMemsetAsync(h->var_sums.p, 0, sizeof(double) * 2 * kMaxVars, st));
   k_pack_scalars<<<1, 128, 0, st>>>(h->acc.as<double>(), h->var_sums.as<double>(), h->vt, h->red.as<double>(), h->cfg.rank,
-                                    (double)h->S * h->ll_const);
+                                    (double)h->S * h->ll_const, 0);
   CLB_LAUNCHED(h);
+  if (h->comm != nullptr) {      // the scalar ELBO terms of all ranks
+    const int rc = g_nccl.AllReduce(h->red.p, h->red.p, (size_t)2, kNcclFloat64, kNcclSum, h->comm, st);
+    if (rc != 0) return fail(h, CLB_ERR_CUDA, "NCCL all-reduce failed: %s", g_nccl.GetErrorString(rc));
+  }
   const clb_config& c = h->cfg;
   FinalizeArgs f{};
   f.acc = h->acc.as<double>(); f.red = h->red.as<double>(); f.vt = h->vt; f.vt.n_vars = 0;
@@ -1061,6 +1141,30 @@ int clb_get_results(clb_handle* h, float* F, float* SigF, float* I, float* SigI,
   return CLB_OK;
 }
 
+// ---- in-library exchange step ----
+int clb_comm_unique_id(uint8_t* id128) {
+  if (!id128) return fail(nullptr, CLB_ERR_INVALID, "clb_comm_unique_id: null argument");
+  if (!g_nccl.load()) return fail(nullptr, CLB_ERR_STATE, "%s", g_nccl.err.c_str());
+  NcclUniqueId id;
+  const int rc = g_nccl.GetUniqueId(&id);
+  if (rc != 0) return fail(nullptr, CLB_ERR_CUDA, "ncclGetUniqueId failed: %s", g_nccl.GetErrorString(rc));
+  memcpy(id128, id.internal, sizeof id.internal);
+  return CLB_OK;
+}
+
+int clb_comm_init(clb_handle* h, const uint8_t* id128) {
+  if (!h || !id128) return fail(h, CLB_ERR_INVALID, "clb_comm_init: null argument");
+  if (h->cfg.world_size <= 1) return fail(h, CLB_ERR_INVALID, "clb_comm_init: the handle was created with world_size %d", h->cfg.world_size);
+  if (h->comm) return fail(h, CLB_ERR_STATE, "clb_comm_init: communicator already initialised");
+  if (!g_nccl.load()) return fail(h, CLB_ERR_STATE, "%s", g_nccl.err.c_str());
+  CLB_CUDA(h, cudaSetDevice(h->cfg.device));
+  NcclUniqueId id;
+  memcpy(id.internal, id128, sizeof id.internal);
+  const int rc = g_nccl.CommInitRank(&h->comm, h->cfg.world_size, id, h->cfg.rank);
+  if (rc != 0) { h->comm = nullptr; return fail(h, CLB_ERR_CUDA, "ncclCommInitRank failed: %s", g_nccl.GetErrorString(rc)); }
+  return CLB_OK;
+}
+
 int clb_step_begin(clb_handle* h, const float* inj_u_f, const float* inj_eps_s) {
   if (!h) return CLB_ERR_INVALID;
   return step_begin_impl(h, inj_u_f, inj_eps_s);
@@ -1096,7 +1200,8 @@ int clb_reduce_buffers(clb_handle* h, void** gf, int64_t* nf, void** sd, int64_t
 int clb_step(clb_handle* h, int32_t n_steps, const float* inj_u_f, const float* inj_eps_s,
              clb_metrics* out, int32_t* steps_done) {
   if (!h || n_steps <= 0) return fail(h, CLB_ERR_INVALID, "clb_step: n_steps must be positive");
-  if (h->cfg.world_size > 1) return fail(h, CLB_ERR_STATE, "clb_step is single-GPU; with world_size > 1 drive clb_step_begin/_norms/_end around the all-reduces");
+  if (h->cfg.world_size > 1 && h->comm == nullptr)
+    return fail(h, CLB_ERR_STATE, "clb_step with world_size > 1 needs clb_comm_init (or drive clb_step_begin/_norms/_end around your own all-reduces)");
   int rc = ensure_metrics(h, n_steps); if (rc) return rc;
   {
     const int big = 0x7fffffff;   // a new train_model call starts with a clean early-stop state

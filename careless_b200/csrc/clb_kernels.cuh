@@ -170,7 +170,16 @@ struct ObsArgs {
   int bijector; float shift; float eps;
   uint64_t seed; uint32_t step;
   int laue; int train_mlp;
+  int discard_scratch;             // 1: drop the activation scratch lines from L2 once the backward pass has consumed them (discard.global.L2)
 };
+
+// The activation scratch is written in the forward pass and read exactly once in the backward pass.  Without help every
+// line is written back to DRAM when it is evicted (2.5 KB per observation and step); `discard.global.L2` tells the L2 that
+// a line's contents are dead, so a line that is still resident when its reader is done never costs DRAM bandwidth.
+// One lane per 128-byte line (8 consecutive rows x 16 B) issues it AFTER the warp has consumed the loaded registers.
+__device__ __forceinline__ void discard_line(const void* p) {
+  asm volatile("discard.global.L2 [%0], 128;" :: "l"(p) : "memory");
+}
 
 template <int WP> struct ObsSmem {
   static constexpr int T = kObsThreads;
@@ -776,10 +785,15 @@ __device__ __forceinline__ void bias_red16(const float (&dp)[16], float* dst, in
 // slots (il_w > 0: kernel stored (out, in), width il_w).
 __device__ __forceinline__ void tc_layer_backward2(tc::Ctx& tcx, float (&dp)[16], const float (&ain)[16], bool need_dx,
                                                    const float* build_from, char* img_base, const float* next_img,
-                                                   float* wk, float* bk, int il_w, unsigned& mask_out) {
+                                                   float* wk, float* bk, int il_w, unsigned& mask_out, const float4* dead = nullptr) {
   const int lane = tcx.tid & 31;
   CLB_PH(5);
   tc::issue_backward3(tcx, dp, ain, need_dx, build_from, img_base, next_img);
+  // `ain` has been consumed (it went into the dW operand image): its four scratch lines are dead
+  if (dead != nullptr && (tcx.row & 7) == 0) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) discard_line(dead + (size_t)c * tc::kThreads);
+  }
   CLB_PH(7);
   // everything that does not feed the tensor cores runs while they work: the sign mask of a_k (leaky' of the layer
   // below) and the bias gradient (column sums of dp)
@@ -984,7 +998,8 @@ __global__ void __launch_bounds__(tc::kThreads2, 2) k_obs_tc2(ObsArgs a) {
       if (k > 0) load_act(nxt, k - 1);
       // the pass after this layer's dX: the next layer's dX (k - 1 >= 1), else the next tile's first forward layer
       const float* next = (k > 1) ? gimg(k - 1, 1) : (more_tiles ? gimg(0, 0) : nullptr);
-      tc_layer_backward2(tcx, dp, ain, k > 0, is_il ? wsrc(k) : nullptr, tc_img, next, wk, bk2, il_w, mask);
+      const float4* dead = (a.discard_scratch && k > 0) ? &scr[((size_t)(k - 1) * NC + 4 * hf) * TR + rrow] : nullptr;
+      tc_layer_backward2(tcx, dp, ain, k > 0, is_il ? wsrc(k) : nullptr, tc_img, next, wk, bk2, il_w, mask, dead);
     }
   }
   // ---- flush: the log-likelihood sum ----
@@ -1172,9 +1187,12 @@ struct VarTable {
 };
 
 // grid = (chunks, n_vars).  sums[2*v] = raw sum of squares (NaN/inf propagate), sums[2*v+1] = filtered.
-__global__ void __launch_bounds__(256) k_var_sumsq(const float* grad, VarTable vt, double* sums) {
+// which: 0 = every variable, 1 = rank-local variables only, 2 = replicated variables only (in-library exchange: the local
+// sums travel with the all-reduce, the replicated ones are taken from the reduced gradient afterwards, identically on every rank).
+__global__ void __launch_bounds__(256) k_var_sumsq(const float* grad, VarTable vt, double* sums, int which) {
   const int v = blockIdx.y;
   if (!vt.trainable[v]) return;
+  if ((which == 1 && vt.replicated[v]) || (which == 2 && !vt.replicated[v])) return;
   const int64_t n = vt.size[v];
   const float* g = grad + vt.off[v];
   double raw = 0.0, filt = 0.0;
@@ -1210,14 +1228,15 @@ struct FinalizeArgs {
 };
 
 // Packs the local scalars into the reduce buffer (so one all-reduce covers them).
+// fused != 0 (in-library exchange): the replicated variables' slots are zeroed here and filled after the all-reduce.
 __global__ void k_pack_scalars(const double* acc, const double* var_sums, VarTable vt, double* red, int rank,
-                               double ll_const) {
+                               double ll_const, int fused) {
   const int i = threadIdx.x;
   if (i == 0) red[0] = acc[ACC_LOGQ_MINUS_LOGP];
   if (i == 1) red[1] = acc[ACC_LL] + ll_const;   // + constant log-density of this rank's empty Laue slots
   if (i < vt.n_vars) {
     // replicated variables hold the same (all-reduced) gradient on every rank: count them once
-    const bool mine = !vt.replicated[i] || rank == 0;
+    const bool mine = fused ? !vt.replicated[i] : (!vt.replicated[i] || rank == 0);
     red[2 + 2 * i] = mine ? var_sums[2 * i] : 0.0;
     red[3 + 2 * i] = mine ? var_sums[2 * i + 1] : 0.0;
   }

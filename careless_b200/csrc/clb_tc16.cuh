@@ -113,7 +113,7 @@ __device__ __forceinline__ void dw_store_row16(char* img, int k, const uint32_t 
 // All threads, after the pass's __syncthreads(): warp 0 waits for the layer's images and issues the MMAs: six products of
 // the three-way split in a forward pass (12 MMAs), three products of the two-way split in a dX pass (6 MMAs).
 // `next` / `next_n`: global images of the next pass and how many of them to prefetch.
-__device__ __forceinline__ void issue_chain16(Ctx16& c, bool fwd, const float* next, uint32_t next_n) {
+__device__ __forceinline__ void issue_chain16(Ctx16& c, bool fwd, const float* next, uint32_t next_n, bool tma = true) {
   const uint32_t b = c.pass & 1u;
   const uint32_t warp = uniform32((uint32_t)c.tid >> 5);
   if (warp == 0u) {
@@ -126,7 +126,7 @@ __device__ __forceinline__ void issue_chain16(Ctx16& c, bool fwd, const float* n
     const uint32_t wb = uniform32(b ? c.wbar1 : c.wbar0), wph = uniform32((c.wphase >> b) & 1u);
     const uint32_t nb = uniform32(b ? c.wbar0 : c.wbar1), ndst = uniform32(b ? c.wimg0 : c.wimg1);
     if (elect_one()) {
-      mbar_wait(wb, wph);
+      if (tma) mbar_wait(wb, wph);      // image layers: the threads built this pass's images themselves
 #define CLB_MMA16(acol, wdesc, first) \
       mma16_ts(d, base + (acol), (wdesc), (first) ? 0u : 1u); \
       mma16_ts(d, base + (acol) + 8u, (wdesc) + (uint64_t)((2u * kLBO16) >> 4), 1u)
@@ -142,11 +142,37 @@ __device__ __forceinline__ void issue_chain16(Ctx16& c, bool fwd, const float* n
     }
     __syncwarp();
   }
-  c.wphase ^= (1u << b);
+  if (tma) c.wphase ^= (1u << b);
   c.pass += 1u;
 }
 
-__device__ __forceinline__ void issue_fwd16(Ctx16& c, const float (&x)[16], const float* next, uint32_t next_n) {
+// Image layers (scaling/image.py:66-125): the tile's own 16 x 16 kernel (FP32 [in][out] in shared memory) is turned into
+// the operand images of this pass -- forward [hi, mid, lo] of B[n][k] = W[k][n], backward [hi, lo] of B[n][k] = W[n][k] --
+// in buffer (pass & 1) by threads 0..63 (one 16-byte group of four k each).  The caller's fences + __syncthreads() publish them.
+template <bool BWD>
+__device__ __forceinline__ void build_images16(Ctx16& c, const float* Wsm, char* w_img) {
+  if (c.tid < 64) {
+    const int n = c.tid & 15, kq = c.tid >> 4;
+    float w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) w[i] = BWD ? Wsm[n * 16 + 4 * kq + i] : Wsm[(4 * kq + i) * 16 + n];
+    float4 hi, mid, lo;
+    float* ph = &hi.x; float* pm = &mid.x; float* pl = &lo.x;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float h = tf32_rna(w[i]), r = w[i] - h, m = tf32_rna(r);
+      ph[i] = h;
+      if (BWD) { pm[i] = r; pl[i] = 0.f; } else { pm[i] = m; pl[i] = r - m; }
+    }
+    char* dst = w_img + (size_t)(c.pass & 1u) * 3 * kImg16 + kq * kLBO16 + (n >> 3) * kSBO + (n & 7) * 16;
+    *reinterpret_cast<float4*>(dst) = hi;
+    *reinterpret_cast<float4*>(dst + kImg16) = mid;
+    if (!BWD) *reinterpret_cast<float4*>(dst + 2 * kImg16) = lo;
+  }
+}
+
+__device__ __forceinline__ void issue_fwd16(Ctx16& c, const float (&x)[16], const float* next, uint32_t next_n,
+                                            const float* build_from = nullptr, char* w_img = nullptr) {
   {
     uint32_t hi[16], mid[16], lo[16];
     split16_3(x, hi, mid, lo);
@@ -154,10 +180,11 @@ __device__ __forceinline__ void issue_fwd16(Ctx16& c, const float (&x)[16], cons
     CLB_TMEM_ST16(c.row_addr + kA_mid, mid);
     CLB_TMEM_ST16(c.row_addr + kA_lo, lo);
   }
+  if (build_from != nullptr) { build_images16<false>(c, build_from, w_img); fence_async_smem(); }
   wait_st();
   fence_before();
   __syncthreads();
-  issue_chain16(c, true, next, next_n);
+  issue_chain16(c, true, next, next_n, build_from == nullptr);
 }
 
 __device__ __forceinline__ void collect16(Ctx16& c, float (&y)[16]) {
@@ -171,7 +198,8 @@ __device__ __forceinline__ void collect16(Ctx16& c, float (&y)[16]) {
   for (int k = 0; k < 16; ++k) y[k] = __uint_as_float(v[k]);
 }
 
-__device__ __forceinline__ void issue_bwd16(Ctx16& c, const float (&dp)[16], const float (&ain)[16], bool need_dx, const float* next, uint32_t next_n) {
+__device__ __forceinline__ void issue_bwd16(Ctx16& c, const float (&dp)[16], const float (&ain)[16], bool need_dx, const float* next, uint32_t next_n,
+                                            const float* build_from = nullptr, char* w_img = nullptr) {
   {
     uint32_t hi[16], lo[16];
     split16_rna(dp, hi, lo);
@@ -193,11 +221,12 @@ __device__ __forceinline__ void issue_bwd16(Ctx16& c, const float (&dp)[16], con
     }
     dw_store_row16(c.dw_a, c.tid, hi, lo, sw);
   }
+  if (need_dx && build_from != nullptr) build_images16<true>(c, build_from, w_img);
   wait_st();
   fence_async_smem();
   fence_before();
   __syncthreads();
-  if (need_dx) issue_chain16(c, false, next, next_n);
+  if (need_dx) issue_chain16(c, false, next, next_n, build_from == nullptr);
   const uint32_t warp = uniform32((uint32_t)c.tid >> 5);
   if (warp == 3u) {
     fence_after();
@@ -215,7 +244,8 @@ __device__ __forceinline__ void issue_bwd16(Ctx16& c, const float (&dp)[16], con
 }
 
 // D_dw rows 0..15 (a_hi) = lanes 0..15 of warp 0, rows 16..31 (a_lo) = lanes 0..15 of warp 1; 32 columns [.dp_hi | .dp_lo].
-__device__ __forceinline__ void collect_dw16(Ctx16& c, float* wk) {
+// il_w > 0: an image layer's kernel gradient, stored (out, in) with width il_w in that image's slot (scalar REDs).
+__device__ __forceinline__ void collect_dw16(Ctx16& c, float* wk, int il_w = 0) {
   mbar_wait(c.mbar_dw, c.parity_dw);
   c.parity_dw ^= 1u;
   fence_after();
@@ -225,13 +255,19 @@ __device__ __forceinline__ void collect_dw16(Ctx16& c, float* wk) {
     CLB_TMEM_LD32(c.row_addr + kDdw, v);
     wait_ld();
     if (lane < 16 && wk != nullptr) {
-      float4* dst = reinterpret_cast<float4*>(wk + lane * 16);
+      if (il_w == 0) {
+        float4* dst = reinterpret_cast<float4*>(wk + lane * 16);
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
-        atomicAdd(dst + q, make_float4(__uint_as_float(v[4 * q]) + __uint_as_float(v[16 + 4 * q]),
-                                       __uint_as_float(v[4 * q + 1]) + __uint_as_float(v[16 + 4 * q + 1]),
-                                       __uint_as_float(v[4 * q + 2]) + __uint_as_float(v[16 + 4 * q + 2]),
-                                       __uint_as_float(v[4 * q + 3]) + __uint_as_float(v[16 + 4 * q + 3])));
+        for (int q = 0; q < 4; ++q)
+          atomicAdd(dst + q, make_float4(__uint_as_float(v[4 * q]) + __uint_as_float(v[16 + 4 * q]),
+                                         __uint_as_float(v[4 * q + 1]) + __uint_as_float(v[16 + 4 * q + 1]),
+                                         __uint_as_float(v[4 * q + 2]) + __uint_as_float(v[16 + 4 * q + 2]),
+                                         __uint_as_float(v[4 * q + 3]) + __uint_as_float(v[16 + 4 * q + 3])));
+      } else if (lane < il_w) {          // row i = lane (a_hi rows in warp 0, a_lo rows in warp 1) of dK[i = in][j = out]
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (j < il_w) atomicAdd(&wk[j * il_w + lane], __uint_as_float(v[j]) + __uint_as_float(v[16 + j]));
+      }
     }
   }
 }
@@ -239,17 +275,19 @@ __device__ __forceinline__ void collect_dw16(Ctx16& c, float* wk) {
 }  // namespace tc16
 
 struct ObsSmem16 {
-  static size_t bytes(int n_layers) {
-    return 2 * (size_t)tc16::kDwImg16 + 6 * (size_t)tc16::kImg16 + 64 + sizeof(float) * (32 + (size_t)n_layers * 16) + 64 * sizeof(double) + 128;
+  static size_t bytes(int n_layers, int n_img_layers = 0) {
+    return 2 * (size_t)tc16::kDwImg16 + 6 * (size_t)tc16::kImg16 + 64 + sizeof(float) * (32 + (size_t)n_layers * 16 + (size_t)n_img_layers * (256 + 16))
+           + 64 * sizeof(double) + 128;
   }
 };
 
-template <int LIK>
+// IL = the model has image layers (their code is compiled out otherwise): rows are image-major, no image straddles a tile.
+template <int LIK, bool IL>
 __global__ void __launch_bounds__(tc16::kRows, 4) k_obs_tc16(ObsArgs a) {
   using namespace tc16;
   constexpr int WP = 16, TR = kRows, T = kRows, NC = 4;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  const int NL = a.lay.n_layers, L = NL - 1, LT = L;
+  const int NL = a.lay.n_layers, L = NL - 1, K = IL ? a.n_img_layers : 0, LT = L + K;
   char* dw_a = reinterpret_cast<char*>(smem_raw);
   char* dw_b = dw_a + kDwImg16;
   char* w_img = dw_b + kDwImg16;                                     // [2 buffers][hi, mid, lo][kImg16]
@@ -257,7 +295,9 @@ __global__ void __launch_bounds__(tc16::kRows, 4) k_obs_tc16(ObsArgs a) {
   uint32_t* slot = reinterpret_cast<uint32_t*>(bars + 4);
   float* Whead = reinterpret_cast<float*>(slot + 8);                 // [16][2]
   float* bsm = Whead + 32;                                           // [NL][16]
-  double* red = reinterpret_cast<double*>(bsm + (size_t)NL * WP + ((NL * WP) & 1));
+  float* Wimg = bsm + (size_t)NL * WP;                               // [K][16][16] this tile's image-layer kernels as [in][out]
+  float* bimg = Wimg + (size_t)K * WP * WP;                          // [K][16]
+  double* red = reinterpret_cast<double*>(bimg + (size_t)K * WP + (((NL + K) * WP) & 1));
 
   const int tid = threadIdx.x, lane = tid & 31;
   if (tid == 0) { for (int i = 0; i < 4; ++i) tc::mbar_init(tc::smem_u32(bars + i), 1); }
@@ -284,7 +324,9 @@ __global__ void __launch_bounds__(tc16::kRows, 4) k_obs_tc16(ObsArgs a) {
     c.tid = tid;
   }
   constexpr size_t IMGF = kImg16 / 4;
-  auto gimg = [&](int k, int dir) -> const float* { return a.wimg + ((size_t)(k * 2 + dir) * 3) * IMGF; };   // [hi, mid, lo] / [hi, lo, -]
+  // [hi, mid, lo] / [hi, lo, -] of hidden layer k; null for image layers, whose per-tile kernels the threads turn into images
+  auto gimg = [&](int k, int dir) -> const float* { return (!IL || k < L) ? a.wimg + ((size_t)(k * 2 + dir) * 3) * IMGF : nullptr; };
+  auto wsrc = [&](int k) -> const float* { return (IL && k >= L) ? Wimg + (size_t)(k - L) * WP * WP : nullptr; };
   float* part32 = a.partials32 + (size_t)blockIdx.x * NL * PSLOT16;
   float4* scr = a.scratch + (size_t)blockIdx.x * LT * NC * TR;
   double ll_sum = 0.0;
@@ -299,15 +341,30 @@ __global__ void __launch_bounds__(tc16::kRows, 4) k_obs_tc16(ObsArgs a) {
     const bool inb = row < a.n_rows;
     const int refl = inb ? a.refl[row] : -1;
     const bool active = refl >= 0;
+    const int timg = (IL && K > 0) ? a.image[tile * TR] : 0;
+    if (IL && K > 0) {
+      __syncthreads();                       // the previous tile is done with Wimg
+      const int w = a.il_width;
+      const size_t lstride = (size_t)a.il_n_images * w * (w + 1);
+      for (int idx = tid; idx < K * WP * WP; idx += T) {
+        const int l = idx / (WP * WP), i = (idx / WP) % WP, j = idx % WP;
+        Wimg[idx] = (i < w && j < w) ? a.theta_il[l * lstride + ((size_t)timg * w + j) * w + i] : 0.f;   // stored (out, in)
+      }
+      for (int idx = tid; idx < K * WP; idx += T) {
+        const int l = idx / WP, j = idx % WP;
+        bimg[idx] = (j < w) ? a.theta_il[l * lstride + (size_t)a.il_n_images * w * w + (size_t)timg * w + j] : 0.f;
+      }
+      __syncthreads();
+    }
     // ---------------- forward ----------------
     float h[WP];
 #pragma unroll
     for (int i = 0; i < WP; ++i) h[i] = (inb && i < a.d) ? a.meta[(size_t)i * a.n_rows + row] : 0.f;
     for (int k = 0; k < LT; ++k) {
-      const float* bk = bsm + (size_t)k * WP;
+      const float* bk = (IL && k >= L) ? bimg + (size_t)(k - L) * WP : bsm + (size_t)k * WP;
       const bool next_bwd = !(k + 1 < LT) && a.train_mlp && LT > 1;
       const float* next = (k + 1 < LT) ? gimg(k + 1, 0) : next_bwd ? gimg(LT - 1, 1) : (more_tiles ? gimg(0, 0) : nullptr);
-      issue_fwd16(c, h, next, next_bwd ? 2u : 3u);
+      issue_fwd16(c, h, next, next_bwd ? 2u : 3u, wsrc(k), w_img);
       float o[WP];
       collect16(c, o);
 #pragma unroll
@@ -340,22 +397,27 @@ __global__ void __launch_bounds__(tc16::kRows, 4) k_obs_tc16(ObsArgs a) {
         for (int i = 0; i < WP; ++i) dst[i] = (inb && i < a.d) ? a.meta[(size_t)i * a.n_rows + row] : 0.f;
       }
     };
-    auto layer_backward = [&](const float (&ain)[WP], bool need_dx, const float* next, uint32_t next_n, float* wk, unsigned& mask_out) {
-      issue_bwd16(c, dp, ain, need_dx, next, next_n);
+    auto layer_backward = [&](const float (&ain)[WP], bool need_dx, const float* next, uint32_t next_n, float* wk, float* bk2, int il_w,
+                              const float* build_from, unsigned& mask_out, const float4* dead) {
+      issue_bwd16(c, dp, ain, need_dx, next, next_n, build_from, w_img);
+      if (dead != nullptr && (tid & 7) == 0) {       // `ain` has been consumed: its scratch lines are dead (see discard_line)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) discard_line(dead + (size_t)q * TR);
+      }
       unsigned m = 0u;
 #pragma unroll
       for (int i = 0; i < WP; ++i) m |= (ain[i] > 0.f ? 1u : 0u) << i;
       mask_out = m;
-      bias_red16(dp, wk + WP * WP, lane, 16);
+      bias_red16(dp, bk2, lane, il_w > 0 ? il_w : 16);
       if (need_dx) collect16(c, dp);
-      collect_dw16(c, wk);
+      collect_dw16(c, wk, il_w);
     };
     if (LT > 0) load_act(nxt, LT - 1);
 #pragma unroll
     for (int j = 0; j < WP; ++j) dp[j] = 0.f;
     dp[0] = dmu; dp[1] = drho;
     unsigned mask = 0u;
-    layer_backward(h, false, nullptr, 0u, part32 + (size_t)L * PSLOT16, mask);     // head: dW_out = a_L^T [dmu, drho]
+    layer_backward(h, false, nullptr, 0u, part32 + (size_t)L * PSLOT16, part32 + (size_t)L * PSLOT16 + WP * WP, 0, nullptr, mask, nullptr);     // head: dW_out = a_L^T [dmu, drho]
 #pragma unroll
     for (int i = 0; i < WP; ++i) {
       const float2 w = *reinterpret_cast<const float2*>(&Whead[i * 2]);
@@ -369,7 +431,17 @@ __global__ void __launch_bounds__(tc16::kRows, 4) k_obs_tc16(ObsArgs a) {
       for (int i = 0; i < WP; ++i) ain[i] = nxt[i];
       if (k > 0) load_act(nxt, k - 1);
       const float* next = (k > 1) ? gimg(k - 1, 1) : (more_tiles ? gimg(0, 0) : nullptr);
-      layer_backward(ain, k > 0, next, (k > 1) ? 2u : 3u, part32 + (size_t)k * PSLOT16, mask);
+      const bool is_il = IL && k >= L;
+      float* wk = part32 + (size_t)k * PSLOT16; float* bk2 = wk + WP * WP; int il_w = 0;
+      if (is_il) {            // image layers send their gradient to the tile's image slot
+        const int w = a.il_width;
+        const size_t lstride = (size_t)a.il_n_images * w * (w + 1);
+        wk = a.g_il != nullptr ? a.g_il + (size_t)(k - L) * lstride + (size_t)timg * w * w : nullptr;
+        bk2 = a.g_il != nullptr ? a.g_il + (size_t)(k - L) * lstride + (size_t)a.il_n_images * w * w + (size_t)timg * w : nullptr;
+        il_w = w;
+      }
+      const float4* dead = (a.discard_scratch && k > 0) ? &scr[((size_t)(k - 1) * NC) * TR + tid] : nullptr;
+      layer_backward(ain, k > 0, next, (k > 1) ? 2u : 3u, wk, bk2, il_w, wsrc(k), mask, dead);
     }
   }
   __syncthreads();

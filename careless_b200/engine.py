@@ -95,6 +95,7 @@ class Engine:
         ccfg = cfg.to_c()
         L.check(self.lib.clb_create(C.byref(ccfg), C.byref(self._h)))
         self.n_rows_total = 0
+        self.has_comm = False
 
     # -- lifetime -------------------------------------------------------------------
     def close(self):
@@ -232,6 +233,14 @@ class Engine:
         nf, nd = C.c_int64(), C.c_int64()
         self._check(self.lib.clb_reduce_buffers(self._h, C.byref(pf), C.byref(nf), C.byref(pd), C.byref(nd)))
         return pf.value, int(nf.value), pd.value, int(nd.value)
+
+    def init_comm(self, unique_id: bytes):
+        """Library-side NCCL communicator (clb_comm_init): afterwards ``step(n)`` runs on world_size GPUs without Python in the loop."""
+        if len(unique_id) != 128:
+            raise ValueError("the communicator id is 128 bytes")
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        self._check(self.lib.clb_comm_init(self._h, buf))
+        self.has_comm = True
 
     # -- debug / measurement ---------------------------------------------------------
     def get_samples(self) -> np.ndarray:

@@ -14,6 +14,7 @@ from ..base import BaseModel
 from ..priors.wilson import DoubleWilsonPrior, WilsonPrior
 from ..scaling.image import HybridImageScaler, NeuralImageScaler
 from ..scaling.nn import MetadataScaler
+from ... import parallel
 from ...engine import Engine, EngineConfig
 from ...optimizers import Adam
 
@@ -34,6 +35,8 @@ class VariationalMergingModel(BaseModel):
         self.device = 0
         self._engine = None
         self._engine_key = None
+        self._engine_data = None
+        self._ranks = None
 
     def compile(self, optimizer=None, run_eagerly=None, **kwargs):
         if optimizer is not None and not isinstance(optimizer, str):
@@ -51,7 +54,10 @@ class VariationalMergingModel(BaseModel):
             return sm, None
         raise TypeError(f"unsupported scaling model {type(sm).__name__}")
 
-    def _build_engine(self, data):
+    def _build_engine(self, data, validation_data=None):
+        """The engine holding `data` (cached per input tuple).  In a multi-process job (``parallel.context()``: torchrun
+        sets WORLD_SIZE > 1) the reflections are partitioned over the ranks: this process's engine holds
+        its own surrogate entries and their observations, and the library's NCCL communicator is created for it."""
         mlp, img = self._parts()
         metadata = self.get_metadata(data)
         refl_id = np.asarray(self.get_refl_id(data)).reshape(-1)
@@ -64,6 +70,7 @@ class VariationalMergingModel(BaseModel):
         R = q.loc_raw.shape[0]
         dw = isinstance(prior, DoubleWilsonPrior)
         nis = self.scaling_model if isinstance(self.scaling_model, NeuralImageScaler) else None
+        ctx = parallel.context()
         cfg = EngineConfig(
             n_refl=R, n_meta=n_meta, mlp_width=mlp.width, mlp_layers=mlp.n_layers,
             n_images=(img.max_images if img is not None else (nis.max_images if nis is not None else 0)), image_scales=img is not None,
@@ -75,25 +82,80 @@ class VariationalMergingModel(BaseModel):
             scale_shift=mlp.scale_multiplier, epsilon=q.scale_shift, kl_weight=self.kl_weight,
             learning_rate=opt.learning_rate, beta_1=opt.beta_1, beta_2=opt.beta_2, adam_epsilon=opt.epsilon,
             clipnorm=opt.clipnorm, clipvalue=opt.clipvalue, global_clipnorm=opt.global_clipnorm,
-            seed=self.seed, device=self.device)
-        key = (tuple(sorted(cfg.__dict__.items())), id(data))
-        if self._engine is not None and self._engine_key == key:
+            seed=self.seed, device=(ctx.local_rank if ctx.active else self.device), rank=ctx.rank, world_size=ctx.world)
+        # the cache holds a strong reference to the tuple it was built from and compares identity (`is`): an id() alone
+        # could be reused by a new tuple after the old one was garbage-collected
+        key = tuple(sorted(cfg.__dict__.items()))
+        if self._engine is not None and self._engine_key == key and self._engine_data is data:
             return self._engine
         if self._engine is not None:
             self._engine.close()
-        eng = Engine(cfg)
-        eng.set_observations(refl_id, self.get_image_id(data), metadata, self.get_intensities(data),
-                             self.get_uncertainties(data), harmonic_id=self.get_harmonic_id(data) if laue else None)
-        eng.set_prior(prior.centric, prior.epsilon, prior.sigma, dw_parent=prior.dw_parent if dw else None,
-                      asu_id=prior.asu_ids if dw else None, r=prior.r if dw else None, init_scale=-1.0)
-        self._engine, self._engine_key = eng, key
+        self._ranks = None
+        if ctx.active:
+            extra = ()
+            if validation_data is not None:
+                extra = ((self.get_refl_id(validation_data), self.get_harmonic_id(validation_data) if laue else None),)
+            self._ranks = parallel.partition(R, refl_id, ctx.world, self.get_harmonic_id(data) if laue else None,
+                                             prior.dw_parent if dw else None, extra=extra)
+        eng = self._engine_for(data, cfg, self._ranks)
+        self._engine, self._engine_key, self._engine_data = eng, key, data
         return eng
+
+    def _engine_for(self, data, cfg, ranks):
+        """An engine with the rows of `data` (all of them, or this rank's share under the partition `ranks`)."""
+        import dataclasses
+        ctx = parallel.context()
+        laue, prior = bool(cfg.laue), self.prior
+        dw = isinstance(prior, DoubleWilsonPrior)
+        refl_id = np.asarray(self.get_refl_id(data)).reshape(-1)
+        R = self.surrogate_posterior.loc_raw.shape[0]
+        if ranks is None:
+            eng = Engine(cfg)
+            eng.mine = None
+            eng.set_observations(refl_id, self.get_image_id(data), self.get_metadata(data), self.get_intensities(data),
+                                 self.get_uncertainties(data), harmonic_id=self.get_harmonic_id(data) if laue else None)
+            eng.set_prior(prior.centric, prior.epsilon, prior.sigma, dw_parent=prior.dw_parent if dw else None,
+                          asu_id=prior.asu_ids if dw else None, r=prior.r if dw else None, init_scale=-1.0)
+            return eng
+        inputs = {"refl_id": refl_id, "image_id": self.get_image_id(data), "metadata": self.get_metadata(data),
+                  "intensities": self.get_intensities(data), "uncertainties": self.get_uncertainties(data),
+                  "harmonic_id": self.get_harmonic_id(data) if laue else None}
+        sigma = prior.sigma
+        tables = {"centric": prior.centric, "multiplicity": prior.epsilon,
+                  "sigma": None if sigma is None else np.broadcast_to(np.asarray(sigma, dtype=np.float32), (R,)),
+                  "dw_parent": prior.dw_parent if dw else None, "asu_id": prior.asu_ids if dw else None}
+        li, lt = parallel.shard(inputs, tables, ranks, ctx.rank, laue=laue)
+        mine = lt["refl_index"]
+        if len(mine) == 0 or len(li["refl_id"]) == 0:
+            raise ValueError(f"rank {ctx.rank} of {ctx.world} received no reflections / observations: use fewer processes for this data set")
+        eng = Engine(dataclasses.replace(cfg, n_refl=len(mine), n_refl_total=R))
+        eng.mine = mine
+        eng.set_observations(li["refl_id"], li.get("image_id"), li["metadata"], li["intensities"], li["uncertainties"],
+                             harmonic_id=li.get("harmonic_id"), obs_index=li["obs_index"], n_rows_total=len(refl_id))
+        eng.set_prior(lt["centric"], lt["multiplicity"], lt.get("sigma"), dw_parent=lt.get("dw_parent"), asu_id=lt.get("asu_id"),
+                      r=prior.r if dw else None, refl_index=mine, init_scale=-1.0)
+        parallel.init_engine_comm(eng, ctx)
+        return eng
+
+    # per-reflection vectors travel as this rank's slice; gathered back with a host-side sum over ranks
+    @staticmethod
+    def _local(eng, full):
+        full = np.asarray(full)
+        return full if eng.mine is None else full[eng.mine]
+
+    @staticmethod
+    def _gather(eng, local, n_total):
+        if eng.mine is None:
+            return local
+        full = np.zeros(n_total, dtype=local.dtype)
+        full[eng.mine] = local
+        return parallel.context().allsum(full)
 
     def _push(self, eng):
         mlp, img = self._parts()
         q = self.surrogate_posterior
-        eng.set_params("sf_loc_raw", q.loc_raw)
-        eng.set_params("sf_scale_raw", q.scale_raw)
+        eng.set_params("sf_loc_raw", self._local(eng, q.loc_raw))
+        eng.set_params("sf_scale_raw", self._local(eng, q.scale_raw))
         eng.set_params("mlp", mlp.flat())
         if img is not None:
             eng.set_params("image_scales", img._scales)
@@ -112,7 +174,9 @@ class VariationalMergingModel(BaseModel):
     def _pull(self, eng):
         mlp, img = self._parts()
         q = self.surrogate_posterior
-        q.loc_raw, q.scale_raw = eng.get_params("sf_loc_raw"), eng.get_params("sf_scale_raw")
+        R = q.loc_raw.shape[0]
+        q.loc_raw = self._gather(eng, eng.get_params("sf_loc_raw"), R)
+        q.scale_raw = self._gather(eng, eng.get_params("sf_scale_raw"), R)
         mlp.from_flat(eng.get_params("mlp"))
         if img is not None:
             img._scales = eng.get_params("image_scales")
@@ -131,8 +195,9 @@ class VariationalMergingModel(BaseModel):
         With ``validation_data`` the held-out NLL (keras test_on_batch, :257-260) is evaluated after every
         ``validation_frequency``-th step on a second engine and logged as ``NLL_val`` scaled by
         len(train)/len(validation) (:249)."""
-        eng = self._build_engine(data)
+        eng = self._build_engine(data, validation_data)
         self._push(eng)
+        progress = progress and parallel.context().rank == 0
         veng, val_scale, nll_val = None, None, None
         if validation_data is not None:
             val_scale = len(data[0]) / len(validation_data[0])
@@ -165,7 +230,9 @@ class VariationalMergingModel(BaseModel):
             if bar is not None:
                 bar.update(len(rows))
                 bar.set_postfix({k: format_string.format(v[-1]) for k, v in history.items()})
-            if len(rows) < n:
+            # variational.py:271-274: the loop ends AFTER the step whose gradient norm was non-finite.  clb_step returns
+            # fewer rows only when the bad step is not the last of its chunk, so the metric itself is checked too.
+            if len(rows) < n or (rows and not np.isfinite(rows[-1]["Grad Norm"])):
                 print("Encountered numerical issues, terminating optimization early!")
                 stopped = True
         if bar is not None:
@@ -176,29 +243,18 @@ class VariationalMergingModel(BaseModel):
         return history
 
     def _validation_engine(self, validation_data):
-        """A second engine holding the held-out rows (same model configuration, its own RNG stream)."""
+        """A second engine holding the held-out rows (same model configuration and partition, its own RNG stream)."""
         import dataclasses
         eng = self._engine
-        mlp, img = self._parts()
-        laue = bool(getattr(self.likelihood, "laue", False))
-        prior = self.prior
-        dw = isinstance(prior, DoubleWilsonPrior)
-        cfg = dataclasses.replace(eng.cfg, seed=eng.cfg.seed + 0x9E3779B9)
-        veng = Engine(cfg)
-        veng.set_observations(np.asarray(self.get_refl_id(validation_data)).reshape(-1), self.get_image_id(validation_data),
-                              self.get_metadata(validation_data), self.get_intensities(validation_data),
-                              self.get_uncertainties(validation_data),
-                              harmonic_id=self.get_harmonic_id(validation_data) if laue else None)
-        veng.set_prior(prior.centric, prior.epsilon, prior.sigma, dw_parent=prior.dw_parent if dw else None,
-                       asu_id=prior.asu_ids if dw else None, r=prior.r if dw else None, init_scale=-1.0)
-        return veng
+        cfg = dataclasses.replace(eng.cfg, seed=eng.cfg.seed + 0x9E3779B9, n_refl=self.surrogate_posterior.loc_raw.shape[0])
+        return self._engine_for(validation_data, cfg, self._ranks)
 
     # ------------------------------------------------------------------ post-hoc moments ("next" row 2)
     def scale_mean_stddev(self, inputs):
         """variational.py:47-78: moments of the posterior of the scale of every observation (Laue: convolved)."""
         eng = self._build_engine(inputs)
         self._push(eng)
-        mean, stddev = eng.get_scale_moments()
+        mean, stddev = self._scale_moments(eng)
         if getattr(self.likelihood, "laue", False):
             hid = self.get_harmonic_id(inputs)
             mean = self.likelihood.convolve(mean, hid)
@@ -209,8 +265,8 @@ class VariationalMergingModel(BaseModel):
         """variational.py:80-121: expected intensity <Sigma><F^2> and its standard deviation per observation."""
         eng = self._build_engine(inputs)
         self._push(eng)
-        smean, sstd = eng.get_scale_moments()
-        res = eng.get_results()
+        smean, sstd = self._scale_moments(eng)
+        res = self._results(eng)
         refl_id = np.asarray(self.get_refl_id(inputs)).reshape(-1)
         f2 = np.square(res["F"]) + np.square(res["SigF"])
         iexp = smean * f2[refl_id]
@@ -227,12 +283,25 @@ class VariationalMergingModel(BaseModel):
         """Numeric part of DataManager.get_results (io/manager.py:188-209): dict of F, SigF, I, SigI, N per reflection."""
         eng = self._build_engine(inputs)
         self._push(eng)
-        return eng.get_results()
+        return self._results(eng)
+
+    def _scale_moments(self, eng):
+        mean, std = eng.get_scale_moments()          # original row order; rows of other ranks are 0
+        if eng.mine is not None:
+            ctx = parallel.context()
+            mean, std = ctx.allsum(mean), ctx.allsum(std)
+        return mean, std
+
+    def _results(self, eng):
+        res = eng.get_results()
+        R = self.surrogate_posterior.loc_raw.shape[0]
+        return {k: self._gather(eng, v, R) for k, v in res.items()}
 
     def close(self):
         if self._engine is not None:
             self._engine.close()
             self._engine = None
+            self._engine_data = None
 
     def __del__(self):
         try:

@@ -24,6 +24,10 @@ class MetadataScaler(Scaler):
 
     def build(self, n_meta):
         if self.weights is not None:
+            if self.weights[0].shape[0] != n_meta:
+                raise ValueError(f"the scale model was loaded for {self.weights[0].shape[0]} metadata columns, the data have {n_meta}")
+            if self.width is None:
+                self.width = int(self.weights[0].shape[1]) if self.n_layers > 0 else int(n_meta)
             return
         width = self.width if self.width is not None else n_meta
         self.width = int(width)
@@ -38,9 +42,28 @@ class MetadataScaler(Scaler):
         return [w.copy() for w in self.weights]
 
     def set_weights(self, ws):
+        ws = [np.asarray(w, dtype=np.float32) for w in ws]
+        if self.weights is None:
+            # not built yet (--scale-file on a fresh model, careless.py:48-51): adopt the stored shapes after checking
+            # them against the constructor arguments; build(n_meta) later keeps these weights
+            ok = len(ws) == 2 * (self.n_layers + 1) and all(w.ndim == (2 if i % 2 == 0 else 1) for i, w in enumerate(ws))
+            if ok:
+                width = ws[0].shape[1] if self.n_layers > 0 else ws[0].shape[0]
+                ok = (self.width is None or int(self.width) == width or self.n_layers == 0) and ws[-2].shape[1] == 2
+                fan_in = ws[0].shape[0]
+                for k in range(self.n_layers):
+                    ok = ok and ws[2 * k].shape == (fan_in, width) and ws[2 * k + 1].shape == (width,)
+                    fan_in = width
+                ok = ok and ws[-2].shape == (fan_in, 2) and ws[-1].shape == (2,)
+            if not ok:
+                raise ValueError("weight shapes do not match the model")
+            if self.n_layers > 0:
+                self.width = int(ws[0].shape[1])
+            self.weights = [w.copy() for w in ws]
+            return
         if len(ws) != len(self.weights) or any(a.shape != np.shape(b) for a, b in zip(self.weights, ws)):
             raise ValueError("weight shapes do not match the model")
-        self.weights = [np.asarray(w, dtype=np.float32).copy() for w in ws]
+        self.weights = [w.copy() for w in ws]
 
     def flat(self):
         return np.concatenate([w.reshape(-1) for w in self.weights])

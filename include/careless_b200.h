@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define CLB_ABI_VERSION 2
+#define CLB_ABI_VERSION 3
 
 typedef struct clb_handle clb_handle;
 
@@ -190,6 +190,16 @@ int clb_step_begin(clb_handle* h, const float* inj_u_f, const float* inj_eps_s);
 int clb_step_norms(clb_handle* h);
 int clb_step_end(clb_handle* h, clb_metrics* metrics_out);
 int clb_reduce_buffers(clb_handle* h, void** grads_f32, int64_t* n_f32, void** scalars_f64, int64_t* n_f64);
+
+/* In-library exchange step (B200-native addition; the reference is single-device, careless/parser.py:25-40).  Rank 0
+ * obtains an id (128 bytes, an ncclUniqueId) and hands it to the other ranks by any side channel (the Python layer
+ * broadcasts it over torch.distributed / a TCP store); every rank then calls clb_comm_init on its handle (created with its
+ * rank / world_size).  From then on clb_step(n) runs n steps on world_size GPUs with no host code between the steps:
+ * clb_step_norms issues ONE grouped NCCL all-reduce {replicated gradients f32 | scalars + local norms f64} on the
+ * handle's stream, and the caller-driven form is just begin -> norms -> end.  NCCL is bound with dlopen at the first
+ * call; a process that never calls these needs no NCCL. */
+int clb_comm_unique_id(uint8_t* id128);
+int clb_comm_init(clb_handle* h, const uint8_t* id128);
 
 /* Debug / parity hooks (variational.py:154,167): sampled structure factors z_f (S,R) and
  * predicted intensities ipred (S,N) in the caller's original row order, from the last step. */

@@ -1,6 +1,8 @@
 """Multi-GPU parity (needs >= 2 B200s on the box; skipped on a single-GPU box): a reflection-partitioned
 2-rank run over NCCL must reproduce the single-GPU run (same Philox draws by construction: counters are
-global indices)."""
+global indices).  Three forms are covered: the in-library exchange (clb_comm_init: `Engine.step(n)` with no host code
+between the steps), the caller-driven exchange (torch.distributed all-reduces around clb_step_begin/_norms/_end), and
+the product API (VariationalMergingModel.train_model / run_careless under WORLD_SIZE=2)."""
 import os
 import socket
 
@@ -26,6 +28,10 @@ def _cfg(kind, R, n_images, **kw):
     base = dict(n_refl=R, n_meta=3, mlp_width=10, mlp_layers=4, mc_samples=2, seed=99, learning_rate=1e-2)
     if kind == "mono":
         base.update(likelihood="studentt", dof=8.0, image_scales=True, n_images=n_images)
+    elif kind == "stills":         # configs[4]'s model: narrow MLP + per-image layers (k_obs_tc16<IL>)
+        base.update(mlp_layers=6, image_layers=2, n_images=n_images)
+    elif kind == "stills32":       # the same on the width-32 kernel (k_obs_tc2<IL>)
+        base.update(mlp_width=32, mlp_layers=3, image_layers=2, n_images=n_images)
     elif kind == "laue":
         base.update(laue=True, image_scales=True, n_images=n_images)
     else:
@@ -35,6 +41,11 @@ def _cfg(kind, R, n_images, **kw):
 
 
 def _problem(kind):
+    if kind in ("stills", "stills32"):
+        p = synth.make_mono(20000, 1500, d=3, n_images=24, seed=34)
+        p["image_id"] = np.sort(p["image_id"])          # image-major like stills data; refl_id stays unsorted relative to it
+        p["refl_id"] = np.random.default_rng(5).permutation(p["refl_id"])
+        return p
     if kind == "mono":
         p = synth.make_mono(20000, 1500, d=3, n_images=16, seed=31)
     elif kind == "laue":
@@ -59,7 +70,7 @@ def _tables(p, kind):
     return t
 
 
-def _worker(rank, world, port, kind, ret):
+def _worker(rank, world, port, kind, ret, in_library=True):
     import torch
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
@@ -81,10 +92,15 @@ def _worker(rank, world, port, kind, ret):
                              harmonic_id=li.get("harmonic_id"), obs_index=li["obs_index"], n_rows_total=N)
         eng.set_prior(lt["centric"], lt["multiplicity"], None, dw_parent=lt.get("dw_parent"), asu_id=lt.get("asu_id"),
                       r=p.get("r") if kind == "dw" else None, refl_index=lt["refl_index"])
-        g, s = parallel.reduce_tensors(eng, f"cuda:{rank}")
-        hist = [parallel.allreduce_step(eng, dist, g, s) for _ in range(4)]
+        if in_library:
+            parallel.init_engine_comm(eng, parallel.DistContext(rank, world, rank, dist.new_group(backend="gloo")))
+            hist = eng.step(4)                  # four steps, one library call, one grouped NCCL all-reduce per step
+        else:
+            g, s = parallel.reduce_tensors(eng, f"cuda:{rank}")
+            hist = [parallel.allreduce_step(eng, dist, g, s) for _ in range(4)]
         ret[rank] = {"hist": hist, "mine": lt["refl_index"], "loc": eng.get_params("sf_loc_raw"), "mlp": eng.get_params("mlp"),
                      "img": eng.get_params("image_scales") if cfg.image_scales else None,
+                     "il": eng.get_params("image_layers") if cfg.image_layers else None,
                      "r": eng.get_params("dw_r_logit") if kind == "dw" else None}
         eng.close()
     finally:
@@ -92,14 +108,15 @@ def _worker(rank, world, port, kind, ret):
 
 
 @pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("kind", ["mono", "laue", "dw"])
-def test_two_gpus_match_one(kind):
+@pytest.mark.parametrize("kind,in_library", [("mono", True), ("laue", True), ("dw", True), ("stills", True), ("stills32", True),
+                                             ("mono", False)])
+def test_two_gpus_match_one(kind, in_library):
     import torch.multiprocessing as mp
     world, port = 2, _free_port()
     ctx = mp.get_context("spawn")
     with ctx.Manager() as mgr:
         ret = mgr.dict()
-        mp.spawn(_worker, args=(world, port, kind, ret), nprocs=world, join=True)
+        mp.spawn(_worker, args=(world, port, kind, ret, in_library), nprocs=world, join=True)
         ret = dict(ret)
     p = _problem(kind)
     R = len(p["centric"])
@@ -118,7 +135,87 @@ def test_two_gpus_match_one(kind):
         assert np.allclose(ret[r]["loc"], eng.get_params("sf_loc_raw")[ret[r]["mine"]], rtol=2e-4, atol=2e-5)
         if ret[r]["img"] is not None:
             assert np.allclose(ret[r]["img"], eng.get_params("image_scales"), rtol=2e-4, atol=2e-5)
+        if ret[r]["il"] is not None:
+            assert np.allclose(ret[r]["il"], eng.get_params("image_layers"), rtol=2e-4, atol=2e-5)
         if ret[r]["r"] is not None:
             assert np.allclose(ret[r]["r"], eng.get_params("dw_r_logit"), rtol=2e-4, atol=2e-5)
     assert np.array_equal(np.sort(np.concatenate([ret[0]["mine"], ret[1]["mine"]])), np.arange(R))
     eng.close()
+
+
+# ---- the product API under WORLD_SIZE = 2 ------------------------------------------------------------------------
+def _model(p, kind):
+    from careless_b200.models.likelihoods import laue as ll, mono as lm
+    from careless_b200.models.merging.surrogate_posteriors import TruncatedNormal
+    from careless_b200.models.merging.variational import VariationalMergingModel
+    from careless_b200.models.priors.wilson import WilsonPrior
+    from careless_b200.models.scaling.image import NeuralImageScaler
+    from careless_b200.models.scaling.nn import MLPScaler
+    prior = WilsonPrior(p["centric"], p["multiplicity"], 1.0)
+    low = np.where(p["centric"], 0.0, 1e-32).astype(np.float32)
+    q = TruncatedNormal.from_loc_and_scale(prior.mean(), prior.stddev(), low)
+    if kind == "laue":
+        lik, scaler = ll.NormalLikelihood(), MLPScaler(4, 10, scale_bijector="exp")
+    elif kind == "stills":
+        lik, scaler = lm.NormalLikelihood(), NeuralImageScaler(2, int(p["n_images"]), 5, 10, scale_bijector="exp")
+    else:
+        lik, scaler = lm.StudentTLikelihood(8.0), MLPScaler(4, 10, scale_bijector="exp")
+    return VariationalMergingModel(q, prior, lik, scaler, mc_sample_size=2)
+
+
+def _tuple(p, kind):
+    col = lambda a, t: np.asarray(a).reshape(-1, 1).astype(t)
+    base = (col(p["refl_id"], np.int64), col(p["image_id"], np.int64), col(np.zeros(len(p["refl_id"])), np.int64),
+            p["metadata"].astype(np.float32), col(p["intensities"], np.float32), col(p["uncertainties"], np.float32))
+    if kind == "laue":
+        base += (col(p["wavelength"], np.float32), col(p["harmonic_id"], np.int64))
+    return base
+
+
+def _api_worker(rank, world, port, kind, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import torch
+    torch.cuda.set_device(rank)
+    parallel.set_context(None)
+    p = _problem(kind)
+    model = _model(p, kind)
+    data = _tuple(p, kind)
+    hist = model.train_model(data, 6, progress=False)
+    res = model.get_results(data)
+    smean, sstd = model.scale_mean_stddev(data)
+    ret[rank] = {"hist": hist, "loc": model.surrogate_posterior.loc_raw, "F": res["F"], "N": res["N"], "smean": smean}
+    model.close()
+    import torch.distributed as dist
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("kind", ["mono", "laue", "stills"])
+def test_train_model_on_two_gpus_equals_one(kind):
+    """`VariationalMergingModel.train_model` in a 2-process job (what `torchrun -m careless_b200.careless` runs) returns the
+    single-GPU history, surrogate, merged F and per-observation scale moments."""
+    import torch.multiprocessing as mp
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    with ctx.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_api_worker, args=(world, port, kind, ret), nprocs=world, join=True)
+        ret = dict(ret)
+    parallel.set_context(parallel.DistContext())
+    try:
+        p = _problem(kind)
+        model = _model(p, kind)
+        data = _tuple(p, kind)
+        hist = model.train_model(data, 6, progress=False)
+        res = model.get_results(data)
+        smean, _ = model.scale_mean_stddev(data)
+        for r in range(world):
+            for k in ("loss", "NLL", "F KLDiv", "Grad Norm"):
+                assert np.allclose(ret[r]["hist"][k], hist[k], rtol=2e-5, atol=1e-7), (r, k)
+            assert np.allclose(ret[r]["loc"], model.surrogate_posterior.loc_raw, rtol=2e-4, atol=2e-5)
+            assert np.allclose(ret[r]["F"], res["F"], rtol=2e-4, atol=2e-5)
+            assert np.array_equal(ret[r]["N"], res["N"])
+            assert np.allclose(ret[r]["smean"], smean, rtol=2e-4, atol=2e-5)
+        model.close()
+    finally:
+        parallel.set_context(None)

@@ -61,7 +61,40 @@ __global__ void __launch_bounds__(128, 1) rate(int M, int N, int variant, int n_
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tb) : "memory");
 }
-int main() {
+#include <cstring>
+// --peak: dense TF32 tcgen05 throughput of the whole chip (one CTA per SM, one issuer, back-to-back accumulating MMAs),
+// timed with CUDA events; prints one JSON line (-> profiles/tf32_peak.json: the denominator of bench.py's tensor_tf32 fraction).
+static int peak_mode() {
+  long long* d; CK(cudaMalloc(&d, 16));
+  CK(cudaFuncSetAttribute(rate, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
+  const int sms = prop.multiProcessorCount;
+  cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  struct { int M, N, variant; const char* name; } cases[] = {{128, 256, 0, "M128 N256 A-in-TMEM"}, {128, 256, 2, "M128 N256 A,B in smem"},
+                                                              {128, 32, 0, "M128 N32 A-in-TMEM (the chain pass shape)"},
+                                                              {64, 64, 2, "M64 N64 A,B in smem (the dW shape)"}};
+  double best = 0.0;
+  printf("{\"device\": \"%s\", \"sms\": %d, \"cases\": [", prop.name, sms);
+  for (int c = 0; c < 4; ++c) {
+    const int n_mma = 200000;
+    rate<<<sms, 128, 64 * 1024>>>(cases[c].M, cases[c].N, cases[c].variant, 4096, d, 1); CK(cudaDeviceSynchronize());
+    float ms_best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+      CK(cudaEventRecord(e0));
+      rate<<<sms, 128, 64 * 1024>>>(cases[c].M, cases[c].N, cases[c].variant, n_mma, d, 1);
+      CK(cudaEventRecord(e1)); CK(cudaDeviceSynchronize());
+      float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+      if (ms < ms_best) ms_best = ms;
+    }
+    const double tflops = 2.0 * cases[c].M * cases[c].N * 8.0 * (double)n_mma * sms / (ms_best * 1e-3) / 1e12;
+    if (c < 2 && tflops > best) best = tflops;
+    printf("%s{\"shape\": \"%s\", \"ms\": %.4f, \"tflops\": %.1f}", c ? ", " : "", cases[c].name, ms_best, tflops);
+  }
+  printf("], \"tf32_tflops\": %.1f, \"source\": \"tools/tc_rate --peak on this B200: tcgen05.mma kind::tf32 M=128 N=256 K=8 back to back, one CTA per SM, CUDA events, best of 5\"}\n", best);
+  return 0;
+}
+int main(int argc, char** argv) {
+  if (argc > 1 && !strcmp(argv[1], "--peak")) return peak_mode();
   long long* d; CK(cudaMalloc(&d, 16));
   CK(cudaFuncSetAttribute(rate, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   const char* vn[3] = {"TS same-D", "TS 2 D regions", "SS same-D"};
