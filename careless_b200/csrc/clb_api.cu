@@ -103,7 +103,7 @@ struct clb_handle {
   // sizes
   int64_t R = 0; int S = 1;
   int64_t n_rows_raw = 0, n_rows = 0 /*padded*/, n_rows_total = 0;
-  int WP = 0, NL = 0, KS = 1, grid_obs = 0;
+  int WP = 0, NL = 0, KS = 1, grid_obs = 0, n_partials = 0;
   size_t smem_obs = 0;
   MlpLayout lay{};
   VarTable vt{};
@@ -117,6 +117,7 @@ struct clb_handle {
   bool eval_mode = false;    // clb_eval: forward only (no gradients, no Adam)
   bool use_tc = false;       // tensor-core (tcgen05) path of k_obs: padded width 32, unless CLB_NO_TC=1
   bool use_tc2 = false;      // ... with two threads per observation row (k_obs_tc2), unless CLB_TC_ONE_THREAD_PER_ROW=1
+  bool use_pp = false;       // width 32 without image layers: warp-specialised two-tile ping-pong kernel (k_obs_pp), unless CLB_PP=0
   bool use_tc16 = false;     // narrow MLPs (padded width <= 16, with or without image layers) on the tensor cores (k_obs_tc16), unless CLB_TC16=0
   bool discard_scratch = true;   // consumed activation-scratch lines are discarded from L2 (no DRAM write-back), unless CLB_DISCARD=0
   bool debug_sync = false;   // CLB_DEBUG_SYNC=1: synchronise + log after every kernel launch
@@ -214,6 +215,13 @@ cudaError_t dispatch_obs(clb_handle* h, const ObsArgs& a) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_obs);
     if (e != cudaSuccess) return e;
     kern<<<h->grid_obs, tc16::kRows, h->smem_obs, h->stream>>>(a);
+    return cudaGetLastError();
+  }
+  if (h->use_pp) {
+    auto kern = lik ? k_obs_pp<1> : k_obs_pp<0>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_obs);
+    if (e != cudaSuccess) return e;
+    kern<<<h->grid_obs, pp::kThreadsPP, h->smem_obs, h->stream>>>(a);
     return cudaGetLastError();
   }
   if (h->use_tc2) {
@@ -472,6 +480,9 @@ int clb_create(const clb_config* cfg, clb_handle** out) {
   { const char* t16 = getenv("CLB_TC16"); const char* no_tc = getenv("CLB_NO_TC");
     h->use_tc16 = (WP <= 16) && cfg->mlp_layers > 0 && cfg->n_meta <= 16 &&
                   !(t16 && t16[0] == '0') && !(no_tc && no_tc[0] == '1'); }
+  // k_obs_pp (one CTA per SM, two tiles ping-ponging through a dedicated issuer warp) is parity-green but measured slower than
+  // k_obs_tc2 on B200 (18.7 vs 16.8 ms: two warps per scheduler cannot cover the ALU / TMEM latencies); opt-in with CLB_PP=1
+  { const char* ppe = getenv("CLB_PP"); h->use_pp = h->use_tc2 && cfg->image_layers == 0 && cfg->mlp_layers > 0 && (ppe && ppe[0] == '1'); }
   h->obs_threads = (h->use_tc || h->use_tc16) ? tc::kThreads : kObsThreads;      // = observation rows per CTA tile
   switch (WP) {
     case 8: h->smem_obs = ObsSmem<8>::bytes(h->NL, false, cfg->image_layers); break;
@@ -480,6 +491,7 @@ int clb_create(const clb_config* cfg, clb_handle** out) {
   }
   if (h->use_tc2) h->smem_obs = ObsSmem2::bytes(h->NL, cfg->image_layers);
   if (h->use_tc16) h->smem_obs = ObsSmem16::bytes(h->NL, cfg->image_layers);
+  if (h->use_pp) h->smem_obs = pp::SmemPP::bytes(h->NL);
   if (h->smem_obs > (size_t)prop.sharedMemPerBlockOptin) {
     fail(h, CLB_ERR_INVALID, "scale MLP (%d layers x padded width %d) needs %zu B of shared memory; the device offers %zu",
          cfg->mlp_layers, WP, h->smem_obs, (size_t)prop.sharedMemPerBlockOptin);
@@ -599,16 +611,20 @@ int clb_set_observations(clb_handle* h, int64_t n, int64_t n_total, const int64_
   // ---- launch geometry + per-CTA buffers of the observation kernel ----
   const int64_t n_tiles = (npad + h->obs_threads - 1) / h->obs_threads;
   h->grid_obs = (int)std::min<int64_t>(n_tiles, (int64_t)h->n_sms * (h->use_tc16 ? 4 : h->use_tc ? 2 : 1));
+  if (h->use_pp) h->grid_obs = (int)std::min<int64_t>((n_tiles + 1) / 2, (int64_t)h->n_sms);     // one CTA per SM, two tiles in flight each
   {
     // One allocation [weight-gradient partials | activation scratch] so that a single L2 access-policy window can cover
     // both: the partials are read-modify-written once per tile and layer and must not be evicted by the scratch
     // streaming through the same cache; whatever persisting capacity is left keeps the most recently written
     // activations on chip until the backward pass reads them.  CLB_L2_WINDOW=0 no window, 1 partials only, 2 both.
-    const size_t pbytes = h->use_tc16 ? sizeof(float) * (size_t)h->grid_obs * h->NL * tc16::PSLOT16
-                          : h->use_tc2 ? sizeof(float) * (size_t)h->grid_obs * h->NL * (32 * 32 + 32)
+    // tensor-core kernels: the CTAs accumulate with REDs, so several of them can share one partial buffer -- a quarter as
+    // many buffers as CTAs keeps the L2 footprint (and the persisting carve-out) small without measurable contention
+    h->n_partials = h->use_pp ? std::max(1, h->grid_obs / 2) : (h->use_tc16 || h->use_tc2) ? std::max(1, h->grid_obs / 4) : h->grid_obs;
+    const size_t pbytes = h->use_tc16 ? sizeof(float) * (size_t)h->n_partials * h->NL * tc16::PSLOT16
+                          : h->use_tc2 ? sizeof(float) * (size_t)h->n_partials * h->NL * (32 * 32 + 32)
                                        : sizeof(double) * (size_t)h->grid_obs * h->KS * partial_row_size(h->NL, h->WP);
     const size_t pb = (pbytes + 255) & ~(size_t)255;
-    const size_t sbytes = sizeof(float4) * (size_t)h->grid_obs * std::max(1, c.mlp_layers + c.image_layers) * ((h->use_tc16 ? 16 : h->WP) / 4) * h->obs_threads;
+    const size_t sbytes = sizeof(float4) * (size_t)h->grid_obs * (h->use_pp ? 2 : 1) * std::max(1, c.mlp_layers + c.image_layers) * ((h->use_tc16 ? 16 : h->WP) / 4) * h->obs_threads;
     CLB_CUDA(h, h->partials.alloc(pb + sbytes));
     h->partial_bytes = pbytes;
     h->scratch_ptr = reinterpret_cast<float4*>(h->partials.as<char>() + pb);
@@ -956,6 +972,7 @@ static int step_begin_impl(clb_handle* h, const float* inj_u, const float* inj_e
     }
     a.seed = c.seed; a.step = h->step_counter; a.laue = c.laue; a.train_mlp = train_mlp ? 1 : 0;
     a.discard_scratch = h->discard_scratch ? 1 : 0;
+    a.n_partials = h->n_partials;
     if (h->timing) {
       while (h->ev.size() < h->ev_used + 2) { cudaEvent_t e; CLB_CUDA(h, cudaEventCreate(&e)); h->ev.push_back(e); }
       CLB_CUDA(h, cudaEventRecord(h->ev[h->ev_used], st));
@@ -966,8 +983,8 @@ static int step_begin_impl(clb_handle* h, const float* inj_u, const float* inj_e
   }
   if (train_mlp) {
     const int np = h->lay.n_params;
-    if (h->use_tc16) k_reduce_partials16<<<(np + 255) / 256, 256, 0, st>>>(h->partials.as<float>(), h->grid_obs, h->lay, grad + h->goff[CLB_GROUP_MLP]);
-    else if (h->use_tc2) k_reduce_partials32<<<(np + 255) / 256, 256, 0, st>>>(h->partials.as<float>(), h->grid_obs, h->lay, grad + h->goff[CLB_GROUP_MLP]);
+    if (h->use_tc16) k_reduce_partials16<<<(np + 255) / 256, 256, 0, st>>>(h->partials.as<float>(), h->n_partials, h->lay, grad + h->goff[CLB_GROUP_MLP]);
+    else if (h->use_tc2) k_reduce_partials32<<<(np + 255) / 256, 256, 0, st>>>(h->partials.as<float>(), h->n_partials, h->lay, grad + h->goff[CLB_GROUP_MLP]);
     else k_reduce_partials<<<(np + 255) / 256, 256, 0, st>>>(h->partials.as<double>(), h->grid_obs * h->KS, h->lay, h->WP, grad + h->goff[CLB_GROUP_MLP]);
     CLB_LAUNCHED(h);
   }

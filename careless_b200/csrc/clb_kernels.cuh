@@ -7,6 +7,14 @@
 #include "clb_math.cuh"
 #include "clb_tc.cuh"
 
+#ifndef CLB_BWD_ORDER
+// How the warps of k_obs_tc2 hand a pass over to the tensor pipe (all three are parity-green; B200 timings of the 10 M-observation
+// step in profiles/README.md):  2 = __syncthreads() between the operand stores and the issue, warps 0 / 7 issue (16.8 ms, default);
+// 0 = barrier-free: every warp arrives on a shared-memory counter, the LAST one issues chain + dW (17.8 ms);
+// 1 = barrier-free, chain handed over before the dW operand images, dW collected one layer later (17.5 ms).
+#define CLB_BWD_ORDER 2
+#endif
+
 namespace clb {
 
 constexpr int kMaxLayers = 48;       // MLP layers incl. the Dense(2) head
@@ -170,6 +178,7 @@ struct ObsArgs {
   int bijector; float shift; float eps;
   uint64_t seed; uint32_t step;
   int laue; int train_mlp;
+  int n_partials;                  // tensor-core kernels: number of FP32 partial buffers the CTAs share (blockIdx % n_partials)
   int discard_scratch;             // 1: drop the activation scratch lines from L2 once the backward pass has consumed them (discard.global.L2)
 };
 
@@ -780,21 +789,35 @@ __device__ __forceinline__ void bias_red16(const float (&dp)[16], float* dst, in
 }
 
 // One layer's backward on the tensor cores, two threads per row: dW_k = a_k^T dp_k and, when need_dx, dp <- dp_k W_k^T.
-// The tile's dW leaves tensor memory straight into the CTA's private FP32 partial in L2 (vector REDs, no staging, no
-// barrier); `wk` / `bk` = kernel [32][32] and bias [32] slots of this layer in that partial, or the image's gradient
-// slots (il_w > 0: kernel stored (out, in), width il_w).
+// Order (see clb_tc.cuh, "barrier-free hand-over"): chain operands -> collect the PREVIOUS layer's dW (tensor memory straight
+// into the CTA's FP32 partial in L2, vector REDs) -> this layer's dW operand images -> sign mask / bias gradient in the shadow
+// of the tensor pipe -> collect the chain.  `wk` / `bk` = kernel [32][32] and bias [32] slots of this layer in the partial, or
+// the image's gradient slots (il_w > 0: kernel stored (out, in), width il_w); `dead` = scratch slot of `ain` (or null).
 __device__ __forceinline__ void tc_layer_backward2(tc::Ctx& tcx, float (&dp)[16], const float (&ain)[16], bool need_dx,
                                                    const float* build_from, char* img_base, const float* next_img,
                                                    float* wk, float* bk, int il_w, unsigned& mask_out, const float4* dead = nullptr) {
   const int lane = tcx.tid & 31;
-  CLB_PH(5);
+#if CLB_BWD_ORDER == 2
+  // round-1 structure: __syncthreads() between the operand stores and the issue (warps 0 and 7 issue)
   tc::issue_backward3(tcx, dp, ain, need_dx, build_from, img_base, next_img);
-  // `ain` has been consumed (it went into the dW operand image): its four scratch lines are dead
-  if (dead != nullptr && (tcx.row & 7) == 0) {
+  if (dead != nullptr && (tcx.tid >> 5) == 5) {
 #pragma unroll
-    for (int c = 0; c < 4; ++c) discard_line(dead + (size_t)c * tc::kThreads);
+    for (int i = 0; i < 4; ++i) asm volatile("discard.global.L2 [%0], 128;" :: "l"(reinterpret_cast<const char*>(dead) + (size_t)(32 * i + lane) * 128) : "memory");
   }
-  CLB_PH(7);
+#else
+  uint32_t hi[16], lo[16];
+  tc::split16(dp, hi, lo);
+#endif
+#if CLB_BWD_ORDER == 1
+  // chain first, dW images while it runs, dW collected one layer later
+  if (need_dx) tc::chain_handover<true>(tcx, hi, lo, build_from, img_base, next_img, lane);
+  if (tcx.dw_pending) tc::collect_dw_red(tcx, tcx.pend_wk, tcx.pend_ilw);     // frees the operand images and the accumulator
+  tc::dw_handover(tcx, hi, lo, ain, dead, lane);
+  tcx.dw_pending = true; tcx.pend_wk = wk; tcx.pend_ilw = il_w;
+#elif CLB_BWD_ORDER == 0
+  // one hand-over per layer (chain operands + dW images); dW collected at the end of this layer
+  tc::bwd_handover(tcx, hi, lo, ain, need_dx, build_from, img_base, next_img, dead, lane);
+#endif
   // everything that does not feed the tensor cores runs while they work: the sign mask of a_k (leaky' of the layer
   // below) and the bias gradient (column sums of dp)
   unsigned mask = 0u;
@@ -802,11 +825,10 @@ __device__ __forceinline__ void tc_layer_backward2(tc::Ctx& tcx, float (&dp)[16]
   for (int i = 0; i < 16; ++i) mask |= (ain[i] > 0.f ? 1u : 0u) << i;
   mask_out = mask;
   bias_red16(dp, bk != nullptr ? bk + 16 * tcx.hf : nullptr, lane, il_w > 0 ? il_w - 16 * tcx.hf : 16);
-  CLB_PH(6);
   if (need_dx) tc::collect2(tcx, dp);
-  CLB_PH(8);
+#if CLB_BWD_ORDER != 1
   tc::collect_dw_red(tcx, wk, il_w);
-  CLB_PH(9);
+#endif
 }
 
 // IL = the model has image layers (their code is compiled out otherwise)
@@ -826,7 +848,7 @@ __global__ void __launch_bounds__(tc::kThreads2, 2) k_obs_tc2(ObsArgs a) {
   double* red = reinterpret_cast<double*>(bimg + (size_t)K * WP);
   char* tc_img = reinterpret_cast<char*>(red + 64);         // [2 buffers][hi, lo][kImgBytes] chain B operand images
   uint64_t* tc_bar = reinterpret_cast<uint64_t*>(tc_img + 4 * tc::kImgBytes);   // [0] chain, [1] dW, [2..3] image buffers
-  uint32_t* tc_slot = reinterpret_cast<uint32_t*>(tc_bar + 4);
+  uint32_t* tc_slot = reinterpret_cast<uint32_t*>(tc_bar + 4);   // [0] tensor-memory base, [2] / [3] arrival counters (chain, dW)
   float2* xch = reinterpret_cast<float2*>(tc_slot + 4);     // [2][128]: head partial sums of hf = 1, then (dmu, drho)
 
   const int tid = threadIdx.x, lane = tid & 31, rrow = tid & (TR - 1), hf = tid >> 7;
@@ -834,6 +856,7 @@ __global__ void __launch_bounds__(tc::kThreads2, 2) k_obs_tc2(ObsArgs a) {
   if (tid == 0) {
     tc::mbar_init(tc::smem_u32(tc_bar), 1); tc::mbar_init(tc::smem_u32(tc_bar + 1), 1);
     tc::mbar_init(tc::smem_u32(tc_bar + 2), 1); tc::mbar_init(tc::smem_u32(tc_bar + 3), 1);
+    tc_slot[2] = 0u; tc_slot[3] = 0u;
   }
   if (tid < 32) tc::tmem_alloc(tc::smem_u32(tc_slot));
   tc::fence_before();
@@ -866,13 +889,15 @@ __global__ void __launch_bounds__(tc::kThreads2, 2) k_obs_tc2(ObsArgs a) {
       tcx.wbar[b] = tc::smem_u32(tc_bar + 2 + b);
     }
     tcx.pass = 0; tcx.wphase = 0;
+    tcx.cnt_chain = tc::smem_u32(tc_slot + 2); tcx.cnt_dw = tc::smem_u32(tc_slot + 3); tcx.n_warps_m1 = T / 32 - 1;
+    tcx.dw_pending = false; tcx.pend_wk = nullptr; tcx.pend_ilw = 0;
   }
   // ready-made images of hidden layer k in global memory: dir 0 = forward (B[n][k] = W[k][n]), 1 = backward; null for
   // image layers, whose per-tile kernels are turned into images by the threads themselves
   constexpr size_t IMGF = tc::kImgBytes / 4;
   auto gimg = [&](int k, int dir) -> const float* { return (!IL || k < L) ? a.wimg + ((size_t)(k * 2 + dir) * 2) * IMGF : nullptr; };
   constexpr int PSLOT = WP * WP + WP;                        // one layer of the CTA's FP32 partial: kernel [32][32], bias [32]
-  float* part32 = a.partials32 + (size_t)blockIdx.x * NL * PSLOT;
+  float* part32 = a.partials32 + (size_t)(blockIdx.x % a.n_partials) * NL * PSLOT;     // shared by a few CTAs (REDs): small L2 footprint
   float4* scr = a.scratch + (size_t)blockIdx.x * LT * NC * TR;
   double ll_sum = 0.0;
   float ev_f = 1.f, ev_a = 0.f, ev_b = 0.f;
@@ -914,14 +939,18 @@ __global__ void __launch_bounds__(tc::kThreads2, 2) k_obs_tc2(ObsArgs a) {
       CLB_PH(0);
       // the pass after this one: next forward layer, else the first dX pass, else the next tile's first layer
       const float* next = (k + 1 < LT) ? gimg(k + 1, 0) : (a.train_mlp && LT > 1) ? gimg(LT - 1, 1) : (more_tiles ? gimg(0, 0) : nullptr);
+#if CLB_BWD_ORDER == 2
       tc::issue3(tcx, h, (IL && k >= L) ? wsrc(k) : nullptr, tc_img, next);
+#else
+      tc::issue4(tcx, h, (IL && k >= L) ? wsrc(k) : nullptr, tc_img, next, lane);
+#endif
       CLB_PH(1);
       tc::collect2(tcx, o);
       CLB_PH(2);
 #pragma unroll
       for (int j = 0; j < HW; ++j) { const float v = o[j] + bk[j]; h[j] = fmaxf(v, kLeak * v); }
 #ifndef CLB_ABL_SCR
-      if (a.train_mlp) {
+      if (a.train_mlp && k + 1 < LT) {          // the last layer's output stays in registers (h) for the head
 #pragma unroll
         for (int c = 0; c < 4; ++c) scr[((size_t)k * NC + 4 * hf + c) * TR + rrow] = make_float4(h[4 * c], h[4 * c + 1], h[4 * c + 2], h[4 * c + 3]);
       }
@@ -998,9 +1027,10 @@ __global__ void __launch_bounds__(tc::kThreads2, 2) k_obs_tc2(ObsArgs a) {
       if (k > 0) load_act(nxt, k - 1);
       // the pass after this layer's dX: the next layer's dX (k - 1 >= 1), else the next tile's first forward layer
       const float* next = (k > 1) ? gimg(k - 1, 1) : (more_tiles ? gimg(0, 0) : nullptr);
-      const float4* dead = (a.discard_scratch && k > 0) ? &scr[((size_t)(k - 1) * NC + 4 * hf) * TR + rrow] : nullptr;
+      const float4* dead = (a.discard_scratch && k > 0) ? scr + (size_t)(k - 1) * NC * TR : nullptr;      // the 16 KB slot of a_k
       tc_layer_backward2(tcx, dp, ain, k > 0, is_il ? wsrc(k) : nullptr, tc_img, next, wk, bk2, il_w, mask, dead);
     }
+    if (tcx.dw_pending) { tc::collect_dw_red(tcx, tcx.pend_wk, tcx.pend_ilw); tcx.dw_pending = false; }
   }
   // ---- flush: the log-likelihood sum ----
   __syncthreads();
@@ -1112,7 +1142,7 @@ __global__ void __launch_bounds__(256) k_reduce_partials32(const float* partials
     const int nk = lay.in_dim[k] * lay.out_dim[k];
     if (p >= lay.koff[k] && p < lay.koff[k] + nk) {
       const int i = (p - lay.koff[k]) / lay.out_dim[k], j = (p - lay.koff[k]) % lay.out_dim[k];
-      src = k * PSLOT + i * 32 + j;
+      src = k * PSLOT + tc::dw_slot32(i, j);
       break;
     }
     if (p >= lay.boff[k] && p < lay.boff[k] + lay.out_dim[k]) { src = k * PSLOT + 1024 + (p - lay.boff[k]); break; }
@@ -1296,3 +1326,4 @@ __global__ void __launch_bounds__(256) k_adam(float* theta, float* m, float* v, 
 }  // namespace clb
 
 #include "clb_tc16.cuh"
+#include "clb_pp.cuh"

@@ -137,6 +137,9 @@ struct Ctx {
   uint64_t wdesc_hi[2], wdesc_lo[2];
   uint32_t wimg[2], wbar[2];
   uint32_t pass, wphase;               // chain passes started so far (buffer = pass & 1); phase bit of each buffer's barrier
+  // barrier-free hand-over (k_obs_tc2): arrival counters in shared memory; the deferred dW collection of the previous layer
+  uint32_t cnt_chain, cnt_dw, n_warps_m1;
+  float* pend_wk; int pend_ilw; bool dw_pending;
 };
 
 __device__ __forceinline__ void split32(const float (&x)[32], uint32_t (&hi)[32], uint32_t (&lo)[32]) {
@@ -411,6 +414,14 @@ __device__ __forceinline__ void collect2(Ctx& c, float (&y)[16]) {
   for (int k = 0; k < 16; ++k) y[k] = __uint_as_float(v[k]);
 }
 
+// Offset (in floats) of element (i = in, j = out) of a 32 x 32 kernel gradient inside one layer's slot of the FP32 partial.
+// The slot is laid out so that every warp-level vector RED of collect_dw_red covers 256 contiguous bytes (16 lanes x 16 B):
+// [i / 16][j / 16][(j % 16) / 4][i % 16][j % 4].  (A row-major slot made each RED instruction touch 16 different 128-byte
+// lines: 13 L1 requests per instruction, a quarter of all LSU wavefronts of the kernel.)
+__host__ __device__ inline int dw_slot32(int i, int j) {
+  return (((((i >> 4) * 2 + (j >> 4)) * 4 + ((j & 15) >> 2)) * 16 + (i & 15)) << 2) + (j & 3);
+}
+
 // dW rows live at lanes (r % 16) + 32 (r / 16): in every warp the lanes < 16 hold row r = 16 (warp % 4) + lane, i.e.
 // feature i = r % 32 (rows 0..31 from a_hi, 32..63 from a_lo).  The thread folds the delta-hi and delta-lo column blocks of
 // ITS 16 columns and adds them to wk[i][16 hf ..] with four 16-byte REDs (il_w > 0: an image layer's kernel, stored
@@ -432,9 +443,9 @@ __device__ __forceinline__ void collect_dw_red(Ctx& c, float* wk, int il_w) {
 #pragma unroll
     for (int k = 0; k < 16; ++k) f[k] = __uint_as_float(v0[k]) + __uint_as_float(v1[k]);
     if (il_w == 0) {
-      float4* dst = reinterpret_cast<float4*>(wk + i * 32 + 16 * c.hf);
+      float4* dst = reinterpret_cast<float4*>(wk) + (((q & 1) * 2 + c.hf) * 4) * 16 + lane;      // dw_slot32(i, 16 hf + 4 qq) / 4
 #pragma unroll
-      for (int qq = 0; qq < 4; ++qq) atomicAdd(dst + qq, make_float4(f[4 * qq], f[4 * qq + 1], f[4 * qq + 2], f[4 * qq + 3]));
+      for (int qq = 0; qq < 4; ++qq) atomicAdd(dst + qq * 16, make_float4(f[4 * qq], f[4 * qq + 1], f[4 * qq + 2], f[4 * qq + 3]));
     } else if (i < il_w) {
 #pragma unroll
       for (int k = 0; k < 16; ++k) { const int j = 16 * c.hf + k; if (j < il_w) atomicAdd(&wk[j * il_w + i], f[k]); }
@@ -568,6 +579,165 @@ __device__ __forceinline__ void issue_backward3(Ctx& c, const float (&dp)[16], c
       commit(bar);
     }
     __syncwarp();
+  }
+}
+
+
+// ---- barrier-free hand-over (k_obs_tc2, round 2) -----------------------------------------------------------------
+// A pass used to be: all warps store operands -> __syncthreads() -> warp 0 issues -> everybody waits.  ncu (round 1): 13 % of
+// the stall samples sat at that barrier, and every warp paid for the slowest one twice (at the barrier and at the mbarrier).
+// Now each warp ARRIVES on a shared-memory counter (one acq_rel atomic per warp) and goes on; the warp that arrives LAST
+// finds all operands in place and issues the tcgen05.mma's itself.  No warp ever waits for another warp -- only for the
+// tensor pipe.  The backward step of a layer hands over the critical chain (delta-a = delta-p W^T) first, builds the dW operand
+// images while it runs, and collects the dW accumulator one layer later (after the next chain has been handed over).
+__device__ __forceinline__ bool arrive_last(uint32_t cnt_smem, int lane, uint32_t last) {
+  __syncwarp();
+  uint32_t old = 0;
+  if (lane == 0) asm volatile("atom.acq_rel.cta.shared.inc.u32 %0, [%1], %2;" : "=r"(old) : "r"(cnt_smem), "r"(last) : "memory");   // wraps to 0
+  old = __shfl_sync(0xffffffffu, old, 0);
+  return old == last;
+}
+
+// The 12 tcgen05.mma of one chain pass from weight buffer (pass & 1); all 32 lanes of the issuing warp call it.
+__device__ __forceinline__ void chain_issue(Ctx& c, bool tma, const float* next) {
+  const uint32_t b = c.pass & 1u;
+  fence_after();
+  const uint32_t base = uniform32(c.base);
+  const uint64_t bhi = uniform64(b ? c.wdesc_hi[1] : c.wdesc_hi[0]), blo = uniform64(b ? c.wdesc_lo[1] : c.wdesc_lo[0]);
+  const uint32_t d = base + kColD;
+  const uint32_t bar = uniform32(c.mbar);
+  const uint32_t wb = uniform32(b ? c.wbar[1] : c.wbar[0]), wph = uniform32((c.wphase >> b) & 1u);
+  const uint32_t nb = uniform32(b ? c.wbar[0] : c.wbar[1]), ndst = uniform32(b ? c.wimg[0] : c.wimg[1]);
+  if (elect_one()) {
+    if (tma) mbar_wait(wb, wph);
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks)
+      mma_tf32_ts(d, base + kColAhi + 8u * (uint32_t)ks, blo + (uint64_t)((2u * kLBO * (uint32_t)ks) >> 4), ks > 0 ? 1u : 0u);
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks)
+      mma_tf32_ts(d, base + kColAlo + 8u * (uint32_t)ks, bhi + (uint64_t)((2u * kLBO * (uint32_t)ks) >> 4), 1u);
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks)
+      mma_tf32_ts(d, base + kColAhi + 8u * (uint32_t)ks, bhi + (uint64_t)((2u * kLBO * (uint32_t)ks) >> 4), 1u);
+    commit(bar);
+    if (next != nullptr) tma_fetch_image(ndst, next, nb);
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ void pass_advance(Ctx& c, bool tma) {
+  if (tma) c.wphase ^= (1u << (c.pass & 1u));
+  c.pass += 1u;
+}
+
+// Hand one chain pass over: operands hi / lo of my half row go to tensor memory, (image layers: my piece of the weight image
+// to shared memory), then arrive; the last warp issues.
+template <bool BWD>
+__device__ __forceinline__ void chain_handover(Ctx& c, const uint32_t (&hi)[16], const uint32_t (&lo)[16], const float* build_from,
+                                               char* img_base, const float* next, int lane) {
+  CLB_TMEM_ST16(c.row_addr + kColAhi + c.col, hi);
+  CLB_TMEM_ST16(c.row_addr + kColAlo + c.col, lo);
+  if (build_from != nullptr) { build_weight_image3<BWD>(c, build_from, img_base); fence_async_smem(); }
+  wait_st();
+  fence_before();
+  if (arrive_last(c.cnt_chain, lane, c.n_warps_m1)) chain_issue(c, build_from == nullptr, next);
+  pass_advance(c, build_from == nullptr);
+}
+
+__device__ __forceinline__ void issue4(Ctx& c, const float (&x)[16], const float* build_from, char* img_base, const float* next, int lane) {
+  uint32_t hi[16], lo[16];
+  split16(x, hi, lo);
+  chain_handover<false>(c, hi, lo, build_from, img_base, next, lane);
+}
+
+__device__ __forceinline__ void dw_issue(Ctx& c, const float4* dead, int lane) {     // all 32 lanes of the issuing warp
+  fence_after();
+  const uint32_t d = uniform32(c.base) + kColDw;
+  const uint64_t a0 = uniform64(c.desc_dwa), b0 = uniform64(c.desc_dwb);
+  const uint32_t bar = uniform32(c.mbar_dw);
+  if (elect_one()) {
+#pragma unroll
+    for (int ks = 0; ks < kThreads / 8; ++ks)
+      mma_tf32_ss(d, a0 + (uint64_t)((2u * kDwSBO * (uint32_t)ks) >> 4), b0 + (uint64_t)((2u * kDwSBO * (uint32_t)ks) >> 4), kIdescDw, ks > 0 ? 1u : 0u);
+    commit(bar);
+  }
+  __syncwarp();
+  if (dead != nullptr) {      // every warp has consumed the layer's input activations: drop their 128 scratch lines from the L2
+#pragma unroll
+    for (int i = 0; i < 4; ++i) asm volatile("discard.global.L2 [%0], 128;" :: "l"(reinterpret_cast<const char*>(dead) + (size_t)(32 * i + lane) * 128) : "memory");
+  }
+}
+
+// One hand-over per backward layer: chain operands (if need_dx) AND the dW operand images, one arrival; the last warp issues
+// the chain first, then dW.
+__device__ __forceinline__ void bwd_handover(Ctx& c, uint32_t (&hi)[16], uint32_t (&lo)[16], const float (&ain)[16], bool need_dx,
+                                             const float* build_from, char* img_base, const float* next, const float4* dead, int lane) {
+  if (need_dx) {
+    CLB_TMEM_ST16(c.row_addr + kColAhi + c.col, hi);
+    CLB_TMEM_ST16(c.row_addr + kColAlo + c.col, lo);
+    if (build_from != nullptr) build_weight_image3<true>(c, build_from, img_base);
+  }
+  const int sw = (c.row >> 2) & 1;       // conflict-free image stores: see dw_store_half
+  swap_blocks(hi, sw); swap_blocks(lo, sw);
+  dw_store_half(c.dw_b, c.row, c.hf, hi, lo, sw);
+  {
+    uint32_t a2[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) a2[k] = __float_as_uint(ain[k]);
+    swap_blocks(a2, sw);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      hi[k] = a2[k];
+      lo[k] = __float_as_uint(__uint_as_float(a2[k]) - __uint_as_float(a2[k] & 0xFFFFE000u));
+    }
+  }
+  dw_store_half(c.dw_a, c.row, c.hf, hi, lo, sw);
+  wait_st();
+  fence_async_smem();
+  fence_before();
+  if (arrive_last(c.cnt_dw, lane, c.n_warps_m1)) {
+    if (need_dx) chain_issue(c, build_from == nullptr, next);
+    dw_issue(c, dead, lane);
+  }
+  if (need_dx) pass_advance(c, build_from == nullptr);
+}
+
+// dW operand images of this layer (delta-p split in hi / lo, the layer input `ain`), then arrive; the last warp issues the 16
+// tcgen05.mma of dW = a^T delta-p and, the layer's input activations now being consumed by every warp, drops their 128
+// scratch lines (`dead`: the 16 KB slot, or null) from the L2.
+__device__ __forceinline__ void dw_handover(Ctx& c, uint32_t (&hi)[16], uint32_t (&lo)[16], const float (&ain)[16], const float4* dead, int lane) {
+  const int sw = (c.row >> 2) & 1;       // conflict-free image stores: see dw_store_half
+  swap_blocks(hi, sw); swap_blocks(lo, sw);
+  dw_store_half(c.dw_b, c.row, c.hf, hi, lo, sw);
+  {
+    uint32_t a2[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) a2[k] = __float_as_uint(ain[k]);
+    swap_blocks(a2, sw);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      hi[k] = a2[k];
+      lo[k] = __float_as_uint(__uint_as_float(a2[k]) - __uint_as_float(a2[k] & 0xFFFFE000u));
+    }
+  }
+  dw_store_half(c.dw_a, c.row, c.hf, hi, lo, sw);
+  fence_async_smem();
+  fence_before();
+  if (arrive_last(c.cnt_dw, lane, c.n_warps_m1)) {
+    fence_after();
+    const uint32_t d = uniform32(c.base) + kColDw;
+    const uint64_t a0 = uniform64(c.desc_dwa), b0 = uniform64(c.desc_dwb);
+    const uint32_t bar = uniform32(c.mbar_dw);
+    if (elect_one()) {
+#pragma unroll
+      for (int ks = 0; ks < kThreads / 8; ++ks)
+        mma_tf32_ss(d, a0 + (uint64_t)((2u * kDwSBO * (uint32_t)ks) >> 4), b0 + (uint64_t)((2u * kDwSBO * (uint32_t)ks) >> 4), kIdescDw, ks > 0 ? 1u : 0u);
+      commit(bar);
+    }
+    __syncwarp();
+    if (dead != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) asm volatile("discard.global.L2 [%0], 128;" :: "l"(reinterpret_cast<const char*>(dead) + (size_t)(32 * i + lane) * 128) : "memory");
+    }
   }
 }
 

@@ -255,11 +255,11 @@ __device__ __forceinline__ void collect_dw16(Ctx16& c, float* wk, int il_w = 0) 
     CLB_TMEM_LD32(c.row_addr + kDdw, v);
     wait_ld();
     if (lane < 16 && wk != nullptr) {
-      if (il_w == 0) {
-        float4* dst = reinterpret_cast<float4*>(wk + lane * 16);
+      if (il_w == 0) {          // slot layout [j / 4][i][j % 4]: each RED instruction covers 256 contiguous bytes
+        float4* dst = reinterpret_cast<float4*>(wk) + lane;
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-          atomicAdd(dst + q, make_float4(__uint_as_float(v[4 * q]) + __uint_as_float(v[16 + 4 * q]),
+          atomicAdd(dst + q * 16, make_float4(__uint_as_float(v[4 * q]) + __uint_as_float(v[16 + 4 * q]),
                                          __uint_as_float(v[4 * q + 1]) + __uint_as_float(v[16 + 4 * q + 1]),
                                          __uint_as_float(v[4 * q + 2]) + __uint_as_float(v[16 + 4 * q + 2]),
                                          __uint_as_float(v[4 * q + 3]) + __uint_as_float(v[16 + 4 * q + 3])));
@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(tc16::kRows, 4) k_obs_tc16(ObsArgs a) {
   // [hi, mid, lo] / [hi, lo, -] of hidden layer k; null for image layers, whose per-tile kernels the threads turn into images
   auto gimg = [&](int k, int dir) -> const float* { return (!IL || k < L) ? a.wimg + ((size_t)(k * 2 + dir) * 3) * IMGF : nullptr; };
   auto wsrc = [&](int k) -> const float* { return (IL && k >= L) ? Wimg + (size_t)(k - L) * WP * WP : nullptr; };
-  float* part32 = a.partials32 + (size_t)blockIdx.x * NL * PSLOT16;
+  float* part32 = a.partials32 + (size_t)(blockIdx.x % a.n_partials) * NL * PSLOT16;
   float4* scr = a.scratch + (size_t)blockIdx.x * LT * NC * TR;
   double ll_sum = 0.0;
   float ev_f = 1.f, ev_a = 0.f, ev_b = 0.f;
@@ -369,7 +369,7 @@ __global__ void __launch_bounds__(tc16::kRows, 4) k_obs_tc16(ObsArgs a) {
       collect16(c, o);
 #pragma unroll
       for (int j = 0; j < WP; ++j) { const float v = o[j] + bk[j]; h[j] = fmaxf(v, kLeak * v); }
-      if (a.train_mlp) {
+      if (a.train_mlp && k + 1 < LT) {          // the last layer's output stays in registers for the head
 #pragma unroll
         for (int q = 0; q < 4; ++q) scr[((size_t)k * NC + q) * TR + tid] = make_float4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
       }
@@ -400,10 +400,9 @@ __global__ void __launch_bounds__(tc16::kRows, 4) k_obs_tc16(ObsArgs a) {
     auto layer_backward = [&](const float (&ain)[WP], bool need_dx, const float* next, uint32_t next_n, float* wk, float* bk2, int il_w,
                               const float* build_from, unsigned& mask_out, const float4* dead) {
       issue_bwd16(c, dp, ain, need_dx, next, next_n, build_from, w_img);
-      if (dead != nullptr && (tid & 7) == 0) {       // `ain` has been consumed: its scratch lines are dead (see discard_line)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) discard_line(dead + (size_t)q * TR);
-      }
+      // every warp has consumed `ain` (issue_bwd16 ends after a __syncthreads()): warp 2 drops the layer's 8 KB scratch slot from the L2
+      if (dead != nullptr && (tid >> 5) == 2) { discard_line(reinterpret_cast<const char*>(dead) + (size_t)lane * 128);
+                                                discard_line(reinterpret_cast<const char*>(dead) + (size_t)(32 + lane) * 128); }
       unsigned m = 0u;
 #pragma unroll
       for (int i = 0; i < WP; ++i) m |= (ain[i] > 0.f ? 1u : 0u) << i;
@@ -440,7 +439,7 @@ __global__ void __launch_bounds__(tc16::kRows, 4) k_obs_tc16(ObsArgs a) {
         bk2 = a.g_il != nullptr ? a.g_il + (size_t)(k - L) * lstride + (size_t)a.il_n_images * w * w + (size_t)timg * w : nullptr;
         il_w = w;
       }
-      const float4* dead = (a.discard_scratch && k > 0) ? &scr[((size_t)(k - 1) * NC) * TR + tid] : nullptr;
+      const float4* dead = (a.discard_scratch && k > 0) ? scr + (size_t)(k - 1) * NC * TR : nullptr;
       layer_backward(ain, k > 0, next, (k > 1) ? 2u : 3u, wk, bk2, il_w, wsrc(k), mask, dead);
     }
   }
@@ -485,7 +484,7 @@ __global__ void __launch_bounds__(256) k_reduce_partials16(const float* partials
     const int nk = lay.in_dim[k] * lay.out_dim[k];
     if (p >= lay.koff[k] && p < lay.koff[k] + nk) {
       const int i = (p - lay.koff[k]) / lay.out_dim[k], j = (p - lay.koff[k]) % lay.out_dim[k];
-      src = k * PSLOT + i * 16 + j;
+      src = k * PSLOT + (((j >> 2) * 16 + i) << 2) + (j & 3);
       break;
     }
     if (p >= lay.boff[k] && p < lay.boff[k] + lay.out_dim[k]) { src = k * PSLOT + 256 + (p - lay.boff[k]); break; }
