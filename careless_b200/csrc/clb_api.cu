@@ -115,6 +115,8 @@ struct clb_handle {
   uint32_t step_counter = 0;   // RNG step index
   bool have_obs = false, have_prior = false, in_step = false;
   bool eval_mode = false;    // clb_eval: forward only (no gradients, no Adam)
+  bool adam_fused = false;   // this step's surrogate Adam update ran inside k_refl_backward
+  bool no_fused_adam = false;   // CLB_FUSED_ADAM=0: keep the surrogate's update in k_adam (A/B and tests)
   bool use_tc = false;       // tensor-core (tcgen05) path of k_obs: padded width 32, unless CLB_NO_TC=1
   bool use_tc2 = false;      // ... with two threads per observation row (k_obs_tc2), unless CLB_TC_ONE_THREAD_PER_ROW=1
   bool use_pp = false;       // width 32 without image layers: warp-specialised two-tile ping-pong kernel (k_obs_pp), unless CLB_PP=0
@@ -299,6 +301,11 @@ void refresh_trainable(clb_handle* h) {
 
 double lgamma_d(double x) { return std::lgamma(x); }
 
+// [3P] tf_keras Adam: alpha_t = lr sqrt(1 - beta2^t) / (1 - beta1^t); computed once per step on the host and used by every kernel
+float adam_alpha_host(const clb_config& c, int64_t t) {
+  return (float)((double)c.learning_rate * std::sqrt(1.0 - std::pow((double)c.beta_2, (double)t)) / (1.0 - std::pow((double)c.beta_1, (double)t)));
+}
+
 // log-density of x=0 under the likelihood with (loc, scale): the empty Laue slots (laue.py:23-25)
 double lik_logpdf_zero(const clb_config& c, double loc, double scale) {
   const double t = (0.0 - loc) / scale;
@@ -465,6 +472,7 @@ int clb_create(const clb_config* cfg, clb_handle** out) {
   if (h->cfg.world_size <= 0) { h->cfg.world_size = 1; h->cfg.rank = 0; }
   { const char* dbg = getenv("CLB_DEBUG_SYNC"); h->debug_sync = dbg && dbg[0] == '1'; }
   { const char* dis = getenv("CLB_DISCARD"); h->discard_scratch = !(dis && dis[0] == '0'); }
+  { const char* fa = getenv("CLB_FUSED_ADAM"); h->no_fused_adam = fa && fa[0] == '0'; }
   h->R = cfg->n_refl; h->S = cfg->mc_samples; h->WP = WP; h->KS = 1;
   auto bail = [&](int code) { g_create_error = h->err; delete h; return code; };
 #define CREATE_CUDA(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { fail(h, CLB_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); return bail(CLB_ERR_CUDA); } } while (0)
@@ -905,8 +913,8 @@ static int step_begin_impl(clb_handle* h, const float* inj_u, const float* inj_e
     a.refl_index = h->refl_index.as<uint32_t>(); a.inj_u = d_inj_u;
     a.z = h->z.as<float>(); a.gz = h->gz.as<float>(); a.acc = h->acc.as<double>();
     a.R = R; a.S = S; a.eps = c.epsilon; a.cq = cq; a.seed = c.seed; a.step = h->step_counter;
-    const int64_t nthr = R * S;
-    k_refl_sample<<<(unsigned)((nthr + 255) / 256), 256, 0, st>>>(a);
+    const int64_t nthr = ((R + 3) / 4) * S;          // four reflections per thread
+    k_refl_sample<<<(unsigned)((nthr + 255) / 256), 256, 0, st>>>(a, (R % 4 == 0) ? 1 : 0);
     CLB_LAUNCHED(h);
   }
   if (dw) {
@@ -995,7 +1003,19 @@ static int step_begin_impl(clb_handle* h, const float* inj_u, const float* inj_e
     a.inj_u = d_inj_u; a.gz = h->gz.as<float>();
     a.g_loc = grad + h->goff[CLB_GROUP_SF_LOC]; a.g_scale = grad + h->goff[CLB_GROUP_SF_SCALE];
     a.R = R; a.S = S; a.eps = c.epsilon; a.cq = cq; a.seed = c.seed; a.step = h->step_counter;
-    k_refl_backward<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(a);
+    // fused tail of the per-reflection chain: sums of squares always; Adam on the surrogate slice whenever no norm-based
+    // clipping is configured (then an element's update needs nothing but its own gradient)
+    a.var_sums = h->var_sums.as<double>();
+    h->adam_fused = h->gtrain[CLB_GROUP_SF_LOC] && h->gtrain[CLB_GROUP_SF_SCALE] && !(c.clipnorm > 0.f) && !(c.global_clipnorm > 0.f)
+                    && !h->no_fused_adam;
+    if (h->adam_fused) {
+      a.theta_loc = theta + h->goff[CLB_GROUP_SF_LOC]; a.theta_scale = theta + h->goff[CLB_GROUP_SF_SCALE];
+      a.m_loc = h->m.as<float>() + h->goff[CLB_GROUP_SF_LOC]; a.m_scale = h->m.as<float>() + h->goff[CLB_GROUP_SF_SCALE];
+      a.v2_loc = h->v.as<float>() + h->goff[CLB_GROUP_SF_LOC]; a.v2_scale = h->v.as<float>() + h->goff[CLB_GROUP_SF_SCALE];
+    }
+    a.alpha = adam_alpha_host(c, h->adam_t + 1); a.beta1 = c.beta_1; a.beta2 = c.beta_2; a.adam_eps = c.adam_epsilon; a.clipvalue = c.clipvalue;
+    a.stop_step = h->stop_step.as<int>(); a.step_index = (int)h->step_counter;
+    k_refl_backward<<<(unsigned)(((R + 3) / 4 + 255) / 256), 256, 0, st>>>(a, (R % 4 == 0) ? 1 : 0);
     CLB_LAUNCHED(h);
   }
   h->in_step = true;
@@ -1012,7 +1032,7 @@ static int step_norms_impl(clb_handle* h) {
   const int chunks = (int)std::min<int64_t>((maxsz + 256 * 8 - 1) / (256 * 8), 4 * h->n_sms);
   const dim3 grid(std::max(chunks, 1), h->vt.n_vars);
   if (h->comm == nullptr) {
-    k_var_sumsq<<<grid, 256, 0, st>>>(h->grad.as<float>(), h->vt, h->var_sums.as<double>(), 0);
+    k_var_sumsq<<<grid, 256, 0, st>>>(h->grad.as<float>(), h->vt, h->var_sums.as<double>(), 0, 1);      // the surrogate's sums come from k_refl_backward
     CLB_LAUNCHED(h);
     k_pack_scalars<<<1, 128, 0, st>>>(h->acc.as<double>(), h->var_sums.as<double>(), h->vt, h->red.as<double>(), h->cfg.rank,
                                     (double)h->S * h->ll_const, 0);
@@ -1023,8 +1043,7 @@ static int step_norms_impl(clb_handle* h) {
   // the surrogate gradients -- is known BEFORE the replicated gradients are reduced, so the float32 gradient buffer and the
   // float64 scalar buffer travel in ONE grouped NCCL all-reduce on the step's stream; the replicated variables' norms are
   // then taken from the reduced gradient, identically on every rank.
-  k_var_sumsq<<<grid, 256, 0, st>>>(h->grad.as<float>(), h->vt, h->var_sums.as<double>(), 1);
-  CLB_LAUNCHED(h);
+  // (the only rank-local variables are the surrogate's, whose sums k_refl_backward has already accumulated)
   k_pack_scalars<<<1, 128, 0, st>>>(h->acc.as<double>(), h->var_sums.as<double>(), h->vt, h->red.as<double>(), h->cfg.rank,
                                   (double)h->S * h->ll_const, 1);
   CLB_LAUNCHED(h);
@@ -1039,7 +1058,7 @@ static int step_norms_impl(clb_handle* h) {
     if (rc != 0) return fail(h, CLB_ERR_CUDA, "NCCL all-reduce failed: %s", g_nccl.GetErrorString(rc));
     h->exchanges++;
   }
-  k_var_sumsq<<<grid, 256, 0, st>>>(h->grad.as<float>(), h->vt, h->red.as<double>() + 2, 2);
+  k_var_sumsq<<<grid, 256, 0, st>>>(h->grad.as<float>(), h->vt, h->red.as<double>() + 2, 2, 0);
   CLB_LAUNCHED(h);
   return CLB_OK;
 }
@@ -1058,6 +1077,7 @@ static int step_end_impl(clb_handle* h, double* d_metrics) {
   f.ll_div = c.use_kl_weight ? (double)S * (double)h->n_rows_total : (double)S;
   f.clipnorm = c.clipnorm; f.global_clipnorm = c.global_clipnorm;
   f.lr = c.learning_rate; f.beta1 = c.beta_1; f.beta2 = c.beta_2; f.t = h->adam_t + 1;
+  f.alpha = adam_alpha_host(c, h->adam_t + 1);
   k_finalize<<<1, 32, 0, st>>>(f);
   CLB_LAUNCHED(h);
   int64_t maxsz = 1;
@@ -1065,7 +1085,8 @@ static int step_end_impl(clb_handle* h, double* d_metrics) {
   const int chunks = (int)std::min<int64_t>((maxsz + 256 * 4 - 1) / (256 * 4), 8 * h->n_sms);
   k_adam<<<dim3(std::max(chunks, 1), h->vt.n_vars), 256, 0, st>>>(h->theta.as<float>(), h->m.as<float>(), h->v.as<float>(), h->grad.as<float>(),
                                                                    h->vt, h->var_scale.as<float>(), h->adam_alpha.as<float>(),
-                                                                   c.clipvalue, c.beta_1, c.beta_2, c.adam_epsilon, h->stop_step.as<int>(), (int)h->step_counter);
+                                                                   c.clipvalue, c.beta_1, c.beta_2, c.adam_epsilon, h->stop_step.as<int>(), (int)h->step_counter,
+                                                                   h->adam_fused ? 1 : 0);
   CLB_LAUNCHED(h);
   h->adam_t += 1;
   h->step_counter += 1;
@@ -1100,7 +1121,7 @@ int clb_eval(clb_handle* h, const float* inj_u_f, const float* inj_eps_s, clb_me
   f.kl_div = c.use_kl_weight ? (double)h->S * (double)c.n_refl_total : (double)h->S;
   f.kl_coef = c.use_kl_weight ? (double)c.kl_weight : 1.0;
   f.ll_div = c.use_kl_weight ? (double)h->S * (double)h->n_rows_total : (double)h->S;
-  f.lr = c.learning_rate; f.beta1 = c.beta_1; f.beta2 = c.beta_2; f.t = 1;
+  f.lr = c.learning_rate; f.beta1 = c.beta_1; f.beta2 = c.beta_2; f.t = 1; f.alpha = 0.f;
   k_finalize<<<1, 32, 0, st>>>(f);
   CLB_LAUNCHED(h);
   h->step_counter += 1;

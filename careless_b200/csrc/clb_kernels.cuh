@@ -53,28 +53,66 @@ struct ReflArgs {
   uint64_t seed; uint32_t step;
 };
 
-__global__ void __launch_bounds__(256) k_refl_sample(ReflArgs a) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// Four consecutive reflections per thread: v_loc / v_scale / eps_sigma / injected draws are read and z / gz written as one
+// 16-byte access each (4 bytes for the centric flags), so a warp moves 512 contiguous bytes per instruction.  `vec` = the
+// arrays are 16-byte aligned (R % 4 == 0 and aligned bases); otherwise the same code falls back to element accesses.
+struct Vec4 { float v[4]; };
+__device__ __forceinline__ Vec4 ld4(const float* p, int64_t i, int64_t n, bool vec, float fill = 0.f) {
+  Vec4 o;
+  if (vec) { const float4 t = *reinterpret_cast<const float4*>(p + i); o.v[0] = t.x; o.v[1] = t.y; o.v[2] = t.z; o.v[3] = t.w; }
+  else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o.v[j] = (i + j < n) ? p[i + j] : fill;
+  }
+  return o;
+}
+__device__ __forceinline__ void st4(float* p, int64_t i, int64_t n, bool vec, const Vec4& x) {
+  if (vec) *reinterpret_cast<float4*>(p + i) = make_float4(x.v[0], x.v[1], x.v[2], x.v[3]);
+  else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) if (i + j < n) p[i + j] = x.v[j];
+  }
+}
+
+__global__ void __launch_bounds__(256) k_refl_sample(ReflArgs a, int vec) {
+  const int64_t nq = (a.R + 3) >> 2;                    // groups of four reflections
+  const int64_t gidx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   double kl = 0.0;
-  if (idx < a.R * a.S) {
-    const int64_t r = idx % a.R;
-    const int s = (int)(idx / a.R);
-    const bool centric = a.centric[r] != 0;
-    const float low = centric ? 0.0f : 1e-32f;     // manager.py:434
-    const float u = a.inj_u ? a.inj_u[idx] : refl_uniform(a.seed, a.step, (uint32_t)s, a.refl_index[r]);
-    const TnSample t = tn_forward(a.v_loc[r], a.v_scale[r], low, a.eps, u);
-    a.z[idx] = t.z;
-    float g = t.dlogq_dz;
-    float term = t.logq;
-    const bool wilson = (a.dw_parent == nullptr) || (a.dw_parent[r] == -2);
-    if (wilson) {
-      float lp, dlp;
-      wilson_logp(t.z, centric, a.eps_sigma[r], lp, dlp);
-      term -= lp;
-      g -= dlp;
+  if (gidx < nq * a.S) {
+    const int64_t r0 = (gidx % nq) << 2;
+    const int s = (int)(gidx / nq);
+    const bool v = vec != 0;
+    const Vec4 vl = ld4(a.v_loc, r0, a.R, v), vs = ld4(a.v_scale, r0, a.R, v), es = ld4(a.eps_sigma, r0, a.R, v, 1.f);
+    uint8_t cen[4] = {0, 0, 0, 0};
+    if (v) { const uchar4 c4 = *reinterpret_cast<const uchar4*>(a.centric + r0); cen[0] = c4.x; cen[1] = c4.y; cen[2] = c4.z; cen[3] = c4.w; }
+    else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) if (r0 + j < a.R) cen[j] = a.centric[r0 + j];
     }
-    a.gz[idx] = a.cq * g;
-    kl = (double)term;
+    Vec4 u;
+    if (a.inj_u) u = ld4(a.inj_u + (size_t)s * a.R, r0, a.R, v, 0.5f);
+    else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) u.v[j] = (r0 + j < a.R) ? refl_uniform(a.seed, a.step, (uint32_t)s, a.refl_index[r0 + j]) : 0.5f;
+    }
+    Vec4 z, gz;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const bool live = r0 + j < a.R;
+      const bool centric = cen[j] != 0;
+      const TnSample t = tn_forward(vl.v[j], vs.v[j], centric ? 0.0f : 1e-32f /* manager.py:434 */, a.eps, u.v[j]);
+      float g = t.dlogq_dz, term = t.logq;
+      const bool wilson = (a.dw_parent == nullptr) || (live && a.dw_parent[r0 + j] == -2);
+      if (wilson) {
+        float lp, dlp;
+        wilson_logp(t.z, centric, es.v[j], lp, dlp);
+        term -= lp; g -= dlp;
+      }
+      z.v[j] = t.z; gz.v[j] = a.cq * g;
+      if (live) kl += (double)term;
+    }
+    st4(a.z + (size_t)s * a.R, r0, a.R, v, z);
+    st4(a.gz + (size_t)s * a.R, r0, a.R, v, gz);
   }
   kl = warp_sum(kl);
   __shared__ double sm[8];
@@ -1184,26 +1222,94 @@ struct ReflBwdArgs {
   const float* inj_u; const float* gz;
   float* g_loc; float* g_scale;
   int64_t R; int S; float eps; float cq; uint64_t seed; uint32_t step;
+  // fused tail of the per-reflection chain (rows A8 / A9 on the surrogate slice)
+  double* var_sums;             // [0..1] raw / filtered sum of squares of g_loc, [2..3] of g_scale (null: do not accumulate)
+  // Adam on (v_loc, v_scale) inside this kernel: legal whenever no NORM-based clipping is configured, because then the update
+  // of an element depends on nothing but its own gradient ([3P] tf_keras Adam.update_step; non-finite elements -> 0,
+  // variational.py:208).  alpha = lr sqrt(1 - b2^t) / (1 - b1^t) comes from the host; stop_step as in k_adam.
+  float* theta_loc; float* theta_scale; float* m_loc; float* m_scale; float* v2_loc; float* v2_scale;   // null: no fused update
+  float alpha, beta1, beta2, adam_eps, clipvalue;
+  const int* stop_step; int step_index;
 };
 
-__global__ void __launch_bounds__(256) k_refl_backward(ReflBwdArgs a) {
-  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= a.R) return;
-  const bool centric = a.centric[r] != 0;
-  const float low = centric ? 0.0f : 1e-32f;
-  const float vl = a.v_loc[r], vs = a.v_scale[r];
-  float gmu = 0.f, gsig = 0.f, mu = 0.f, sigma = 0.f;
-  for (int s = 0; s < a.S; ++s) {
-    const int64_t idx = (int64_t)s * a.R + r;
-    const float u = a.inj_u ? a.inj_u[idx] : refl_uniform(a.seed, a.step, (uint32_t)s, a.refl_index[r]);
-    const TnSample t = tn_forward(vl, vs, low, a.eps, u);
-    const float g = a.gz[idx];
-    gmu += g * t.dz_dmu + a.cq * t.dlogq_dmu;
-    gsig += g * t.dz_dsigma + a.cq * t.dlogq_dsigma;
-    mu = t.mu; sigma = t.sigma;
+// Chain dL/dz to (v_loc, v_scale), four reflections per thread with 16-byte accesses (see k_refl_sample); the truncated-normal
+// forward quantities are RECOMPUTED from the parameters this kernel reads anyway (17 B per reflection) -- storing them in the
+// forward kernel would cost 32 B per (sample, reflection) of extra HBM traffic in a kernel that is bandwidth-bound.
+__global__ void __launch_bounds__(256) k_refl_backward(ReflBwdArgs a, int vec) {
+  const int64_t nq = (a.R + 3) >> 2;
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double ss[4] = {0.0, 0.0, 0.0, 0.0};                   // raw / filtered sums of squares of g_loc, g_scale
+  if (q < nq) {
+    const int64_t r0 = q << 2;
+    const bool v = vec != 0;
+    const Vec4 vl = ld4(a.v_loc, r0, a.R, v), vs = ld4(a.v_scale, r0, a.R, v);
+    uint8_t cen[4] = {0, 0, 0, 0};
+    if (v) { const uchar4 c4 = *reinterpret_cast<const uchar4*>(a.centric + r0); cen[0] = c4.x; cen[1] = c4.y; cen[2] = c4.z; cen[3] = c4.w; }
+    else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) if (r0 + j < a.R) cen[j] = a.centric[r0 + j];
+    }
+    Vec4 gl, gs;
+    float mu[4], sg[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { gl.v[j] = 0.f; gs.v[j] = 0.f; mu[j] = 0.f; sg[j] = 0.f; }
+    for (int s = 0; s < a.S; ++s) {
+      const Vec4 g = ld4(a.gz + (size_t)s * a.R, r0, a.R, v);
+      Vec4 u;
+      if (a.inj_u) u = ld4(a.inj_u + (size_t)s * a.R, r0, a.R, v, 0.5f);
+      else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) u.v[j] = (r0 + j < a.R) ? refl_uniform(a.seed, a.step, (uint32_t)s, a.refl_index[r0 + j]) : 0.5f;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const TnSample t = tn_forward(vl.v[j], vs.v[j], cen[j] ? 0.0f : 1e-32f, a.eps, u.v[j]);
+        gl.v[j] += g.v[j] * t.dz_dmu + a.cq * t.dlogq_dmu;
+        gs.v[j] += g.v[j] * t.dz_dsigma + a.cq * t.dlogq_dsigma;
+        mu[j] = t.mu; sg[j] = t.sigma;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      gl.v[j] *= mu[j];                    // d mu / d v_loc = mu
+      gs.v[j] *= (sg[j] - a.eps);          // d sigma / d v_scale = exp(v_scale)
+      if (r0 + j < a.R) {
+        const double a2 = (double)gl.v[j] * (double)gl.v[j], b2 = (double)gs.v[j] * (double)gs.v[j];
+        ss[0] += a2; ss[2] += b2;
+        if (isfinite(gl.v[j])) ss[1] += a2;
+        if (isfinite(gs.v[j])) ss[3] += b2;
+      }
+    }
+    st4(a.g_loc, r0, a.R, v, gl);
+    st4(a.g_scale, r0, a.R, v, gs);
+    if (a.theta_loc != nullptr && a.step_index <= *a.stop_step) {
+      auto adam = [&](float* theta, float* m, float* v2, const Vec4& par, const Vec4& grad) {
+        Vec4 mm = ld4(m, r0, a.R, v), vv = ld4(v2, r0, a.R, v), th;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float g = isfinite(grad.v[j]) ? grad.v[j] : 0.f;
+          if (a.clipvalue > 0.f) g = fminf(fmaxf(g, -a.clipvalue), a.clipvalue);
+          mm.v[j] += (g - mm.v[j]) * (1.0f - a.beta1);
+          vv.v[j] += (g * g - vv.v[j]) * (1.0f - a.beta2);
+          th.v[j] = par.v[j] - a.alpha * mm.v[j] / (sqrtf(vv.v[j]) + a.adam_eps);
+        }
+        st4(m, r0, a.R, v, mm); st4(v2, r0, a.R, v, vv); st4(theta, r0, a.R, v, th);
+      };
+      adam(a.theta_loc, a.m_loc, a.v2_loc, vl, gl);
+      adam(a.theta_scale, a.m_scale, a.v2_scale, vs, gs);
+    }
   }
-  a.g_loc[r] = gmu * mu;                 // d mu / d v_loc = mu
-  a.g_scale[r] = gsig * (sigma - a.eps); // d sigma / d v_scale = exp(v_scale)
+  if (a.var_sums != nullptr) {
+    __shared__ double sm[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { ss[i] = warp_sum(ss[i]); if ((threadIdx.x & 31) == 0) sm[i][threadIdx.x >> 5] = ss[i]; }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+      double t = 0.0;
+      for (int i = 0; i < 8; ++i) t += sm[threadIdx.x][i];
+      if (t != 0.0) atomicAdd(&a.var_sums[threadIdx.x], t);      // NaN != 0 is true, so NaN propagates
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1219,18 +1325,25 @@ struct VarTable {
 // grid = (chunks, n_vars).  sums[2*v] = raw sum of squares (NaN/inf propagate), sums[2*v+1] = filtered.
 // which: 0 = every variable, 1 = rank-local variables only, 2 = replicated variables only (in-library exchange: the local
 // sums travel with the all-reduce, the replicated ones are taken from the reduced gradient afterwards, identically on every rank).
-__global__ void __launch_bounds__(256) k_var_sumsq(const float* grad, VarTable vt, double* sums, int which) {
+__global__ void __launch_bounds__(256) k_var_sumsq(const float* grad, VarTable vt, double* sums, int which, int skip_surrogate) {
   const int v = blockIdx.y;
   if (!vt.trainable[v]) return;
   if ((which == 1 && vt.replicated[v]) || (which == 2 && !vt.replicated[v])) return;
+  if (skip_surrogate && v < 2) return;          // the surrogate's sums were accumulated by k_refl_backward
   const int64_t n = vt.size[v];
   const float* g = grad + vt.off[v];
   double raw = 0.0, filt = 0.0;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const float x = g[i];
-    const double x2 = (double)x * (double)x;
-    raw += x2;
-    if (isfinite(x)) filt += x2;
+  auto add = [&](float x) { const double x2 = (double)x * (double)x; raw += x2; if (isfinite(x)) filt += x2; };
+  if ((reinterpret_cast<uintptr_t>(g) & 15) == 0) {       // 16-byte accesses; the (< 4) tail elements by the first threads
+    const int64_t n4 = n >> 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+      const float4 x = reinterpret_cast<const float4*>(g)[i];
+      add(x.x); add(x.y); add(x.z); add(x.w);
+    }
+    const int64_t t = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) add(g[t]);
+  } else {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) add(g[i]);
   }
   raw = warp_sum(raw); filt = warp_sum(filt);
   __shared__ double sm[2][8];
@@ -1255,6 +1368,7 @@ struct FinalizeArgs {
   double kl_div, kl_coef, ll_div;   // kl = sum/kl_div ; loss = kl_coef*kl - ll/ll_div
   float clipnorm, global_clipnorm;
   float lr, beta1, beta2; int64_t t;   // t = step index (1-based) for bias correction
+  float alpha;                  // lr sqrt(1 - beta2^t) / (1 - beta1^t), computed on the host (the same value k_refl_backward uses)
 };
 
 // Packs the local scalars into the reduce buffer (so one all-reduce covers them).
@@ -1293,33 +1407,48 @@ __global__ void k_finalize(FinalizeArgs a) {
     if (a.clipnorm > 0.f) sc = (float)(a.clipnorm / fmax(sqrt(a.red[3 + 2 * v]), (double)a.clipnorm));
     a.var_scale[v] = sc * gscale;
   }
-  const double t = (double)a.t;
-  a.adam_alpha[0] = (float)(a.lr * sqrt(1.0 - pow((double)a.beta2, t)) / (1.0 - pow((double)a.beta1, t)));
+  a.adam_alpha[0] = a.alpha;
   if (!isfinite(gn) && a.step < *a.stop_step) *a.stop_step = a.step;
 }
 
 // grid = (chunks, n_vars).  [3P] tf_keras Adam.update_step; non-finite gradient elements -> 0 (variational.py:208).
+// 16-byte accesses when the variable's slice is aligned (m, v, theta, grad share the offset).  skip_surrogate: variables 0 / 1
+// (v_loc, v_scale) were already updated inside k_refl_backward.
 __global__ void __launch_bounds__(256) k_adam(float* theta, float* m, float* v, const float* grad, VarTable vt,
                                               const float* var_scale, const float* adam_alpha,
                                               float clipvalue, float beta1, float beta2, float adam_eps,
-                                              const int* stop_step, int step) {
+                                              const int* stop_step, int step, int skip_surrogate) {
   const int var = blockIdx.y;
   if (!vt.trainable[var]) return;
+  if (skip_surrogate && var < 2) return;
   // variational.py:271-274: the loop breaks AFTER the step whose norm was non-finite has been
   // applied (with the filtered gradient); later enqueued steps must not touch the state.
   if (step > *stop_step) return;
   const float sc = var_scale[var];
   const float alpha = adam_alpha[0];
   const int64_t n = vt.size[var], off = vt.off[var];
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    float g = grad[off + i];
+  auto upd = [&](float g, float& mi, float& vi, float& th) {
     g = isfinite(g) ? g * sc : 0.f;
     if (clipvalue > 0.f) g = fminf(fmaxf(g, -clipvalue), clipvalue);
-    float mi = m[off + i], vi = v[off + i];
     mi += (g - mi) * (1.0f - beta1);
     vi += (g * g - vi) * (1.0f - beta2);
-    m[off + i] = mi; v[off + i] = vi;
-    theta[off + i] -= alpha * mi / (sqrtf(vi) + adam_eps);
+    th -= alpha * mi / (sqrtf(vi) + adam_eps);
+  };
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+  if ((off & 3) == 0) {
+    const int64_t n4 = n >> 2;
+    float4* t4 = reinterpret_cast<float4*>(theta + off); float4* m4 = reinterpret_cast<float4*>(m + off);
+    float4* v4 = reinterpret_cast<float4*>(v + off); const float4* g4 = reinterpret_cast<const float4*>(grad + off);
+    for (int64_t i = tid; i < n4; i += stride) {
+      const float4 g = g4[i];
+      float4 mi = m4[i], vi = v4[i], th = t4[i];
+      upd(g.x, mi.x, vi.x, th.x); upd(g.y, mi.y, vi.y, th.y); upd(g.z, mi.z, vi.z, th.z); upd(g.w, mi.w, vi.w, th.w);
+      m4[i] = mi; v4[i] = vi; t4[i] = th;
+    }
+    const int64_t t = (n4 << 2) + tid;
+    if (t < n) upd(grad[off + t], m[off + t], v[off + t], theta[off + t]);
+  } else {
+    for (int64_t i = tid; i < n; i += stride) upd(grad[off + i], m[off + i], v[off + i], theta[off + i]);
   }
 }
 
