@@ -131,7 +131,7 @@ struct clb_handle {
   // device state
   DevBuf theta, m, v, grad;
   DevBuf centric, eps_sigma, dw_parent, asu_id, r_const, refl_index;
-  DevBuf z, gz;
+  DevBuf z, gz, bwd_coef;
   DevBuf rows;             // one allocation holding all row arrays
   PinBuf rows_host;        // pinned mirror (for re-upload)
   size_t rows_bytes = 0;
@@ -913,6 +913,7 @@ static int step_begin_impl(clb_handle* h, const float* inj_u, const float* inj_e
     a.refl_index = h->refl_index.as<uint32_t>(); a.inj_u = d_inj_u;
     a.z = h->z.as<float>(); a.gz = h->gz.as<float>(); a.acc = h->acc.as<double>();
     a.R = R; a.S = S; a.eps = c.epsilon; a.cq = cq; a.seed = c.seed; a.step = h->step_counter;
+    if (!h->eval_mode) { CLB_CUDA(h, h->bwd_coef.alloc(sizeof(float4) * (size_t)R * S)); a.bwd_coef = h->bwd_coef.as<float4>(); }
     const int64_t nthr = ((R + 3) / 4) * S;          // four reflections per thread
     k_refl_sample<<<(unsigned)((nthr + 255) / 256), 256, 0, st>>>(a, (R % 4 == 0) ? 1 : 0);
     CLB_LAUNCHED(h);
@@ -999,10 +1000,9 @@ static int step_begin_impl(clb_handle* h, const float* inj_u, const float* inj_e
   if (!h->eval_mode) {
     ReflBwdArgs a{};
     a.v_loc = theta + h->goff[CLB_GROUP_SF_LOC]; a.v_scale = theta + h->goff[CLB_GROUP_SF_SCALE];
-    a.centric = h->centric.as<uint8_t>(); a.refl_index = h->refl_index.as<uint32_t>();
-    a.inj_u = d_inj_u; a.gz = h->gz.as<float>();
+    a.bwd_coef = h->bwd_coef.as<float4>(); a.gz = h->gz.as<float>();
     a.g_loc = grad + h->goff[CLB_GROUP_SF_LOC]; a.g_scale = grad + h->goff[CLB_GROUP_SF_SCALE];
-    a.R = R; a.S = S; a.eps = c.epsilon; a.cq = cq; a.seed = c.seed; a.step = h->step_counter;
+    a.R = R; a.S = S;
     // fused tail of the per-reflection chain: sums of squares always; Adam on the surrogate slice whenever no norm-based
     // clipping is configured (then an element's update needs nothing but its own gradient)
     a.var_sums = h->var_sums.as<double>();
@@ -1028,7 +1028,7 @@ static int step_norms_impl(clb_handle* h) {
   cudaStream_t st = h->stream;
   refresh_trainable(h);
   int64_t maxsz = 1;
-  for (int v = 0; v < h->vt.n_vars; ++v) maxsz = std::max(maxsz, h->vt.size[v]);
+  for (int v = 2; v < h->vt.n_vars; ++v) maxsz = std::max(maxsz, h->vt.size[v]);     // variables 0 / 1 (the surrogate) are summed in k_refl_backward
   const int chunks = (int)std::min<int64_t>((maxsz + 256 * 8 - 1) / (256 * 8), 4 * h->n_sms);
   const dim3 grid(std::max(chunks, 1), h->vt.n_vars);
   if (h->comm == nullptr) {
@@ -1081,8 +1081,8 @@ static int step_end_impl(clb_handle* h, double* d_metrics) {
   k_finalize<<<1, 32, 0, st>>>(f);
   CLB_LAUNCHED(h);
   int64_t maxsz = 1;
-  for (int v = 0; v < h->vt.n_vars; ++v) if (h->vt.trainable[v]) maxsz = std::max(maxsz, h->vt.size[v]);
-  const int chunks = (int)std::min<int64_t>((maxsz + 256 * 4 - 1) / (256 * 4), 8 * h->n_sms);
+  for (int v = h->adam_fused ? 2 : 0; v < h->vt.n_vars; ++v) if (h->vt.trainable[v]) maxsz = std::max(maxsz, h->vt.size[v]);
+  const int chunks = (int)std::min<int64_t>((maxsz + 256 * 16 - 1) / (256 * 16), 8 * h->n_sms);
   k_adam<<<dim3(std::max(chunks, 1), h->vt.n_vars), 256, 0, st>>>(h->theta.as<float>(), h->m.as<float>(), h->v.as<float>(), h->grad.as<float>(),
                                                                    h->vt, h->var_scale.as<float>(), h->adam_alpha.as<float>(),
                                                                    c.clipvalue, c.beta_1, c.beta_2, c.adam_epsilon, h->stop_step.as<int>(), (int)h->step_counter,

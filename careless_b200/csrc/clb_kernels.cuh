@@ -48,6 +48,9 @@ struct ReflArgs {
   const uint32_t* refl_index;                     // (R) global index for the RNG
   const float* inj_u;                             // (S,R) or null
   float* z; float* gz;                            // (S,R)
+  // (S,R) or null (forward-only calls): what the backward kernel needs of this draw, so that it does not have to repeat the
+  // truncated-normal arithmetic -- {mu dz/dmu, (sigma - eps) dz/dsigma, cq mu dlogq/dmu, cq (sigma - eps) dlogq/dsigma}
+  float4* bwd_coef;
   double* acc;
   int64_t R; int S; float eps; float cq;          // cq: KL coefficient per element
   uint64_t seed; uint32_t step;
@@ -110,6 +113,10 @@ __global__ void __launch_bounds__(256) k_refl_sample(ReflArgs a, int vec) {
       }
       z.v[j] = t.z; gz.v[j] = a.cq * g;
       if (live) kl += (double)term;
+      if (a.bwd_coef != nullptr && live) {        // chain rule to the raw variables: d mu / d v_loc = mu, d sigma / d v_scale = sigma - eps
+        const float dm = t.mu, ds = t.sigma - a.eps;
+        a.bwd_coef[(size_t)s * a.R + r0 + j] = make_float4(dm * t.dz_dmu, ds * t.dz_dsigma, a.cq * dm * t.dlogq_dmu, a.cq * ds * t.dlogq_dsigma);
+      }
     }
     st4(a.z + (size_t)s * a.R, r0, a.R, v, z);
     st4(a.gz + (size_t)s * a.R, r0, a.R, v, gz);
@@ -454,11 +461,12 @@ __device__ __forceinline__ void obs_epilogue(const ObsArgs& a, int64_t row, bool
   float sig_s, dsig;
   if (a.bijector == 0) { dsig = expf(out1); sig_s = dsig + a.eps; }
   else { sig_s = softplusf(out1) + a.eps; dsig = sigmoidf(out1); }
-  const int img = (a.image != nullptr && inb) ? a.image[row] : 0;
+  // (the observation rows are read once per step: streaming loads, so that they do not displace the activation scratch from the L2)
+  const int img = (a.image != nullptr && inb) ? __ldcs(&a.image[row]) : 0;
   const float aimg = (a.theta_img != nullptr && img > 0) ? a.theta_img[img - 1] : 1.0f;
-  const uint32_t oi = inb ? a.oidx[row] : 0u;
-  const float iobs = inb ? a.iobs[row] : 0.f;
-  const float sg = inb ? a.sig[row] : 1.f;
+  const uint32_t oi = inb ? __ldcs(&a.oidx[row]) : 0u;
+  const float iobs = inb ? __ldcs(&a.iobs[row]) : 0.f;
+  const float sg = inb ? __ldcs(&a.sig[row]) : 1.f;
   if (a.scale_mean_out != nullptr && active) {     // variational.py:67-69: scale_dist.mean() / .stddev()
     a.scale_mean_out[oi] = aimg * (out0 + a.shift);
     a.scale_std_out[oi] = fabsf(aimg) * sig_s;
@@ -466,7 +474,7 @@ __device__ __forceinline__ void obs_epilogue(const ObsArgs& a, int64_t row, bool
   // runs of equal keys inside the warp (same for every MC sample)
   const WarpRuns refl_runs = warp_runs(active ? refl : -1 - lane, lane);
   WarpRuns spot_runs = refl_runs, img_runs = refl_runs;
-  if (a.laue) spot_runs = warp_runs(inb ? a.spot[row] : -1, lane);   // padding rows carry spot -1
+  if (a.laue) spot_runs = warp_runs(inb ? __ldcs(&a.spot[row]) : -1, lane);   // padding rows carry spot -1
   const bool img_live = active && img > 0;
   if (a.g_img != nullptr) img_runs = warp_runs(img_live ? img : -1 - lane, lane);
   float d_aimg = 0.f;
@@ -950,7 +958,7 @@ __global__ void __launch_bounds__(tc::kThreads2, 2) k_obs_tc2(ObsArgs a) {
     const bool more_tiles = tile + gridDim.x < n_tiles;
     const int64_t row = tile * TR + rrow;
     const bool inb = row < a.n_rows;
-    const int refl = inb ? a.refl[row] : -1;
+    const int refl = inb ? __ldcs(&a.refl[row]) : -1;
     const bool active = refl >= 0;
     const int timg = (IL && K > 0) ? a.image[tile * TR] : 0;
     if (IL && K > 0) {
@@ -970,7 +978,7 @@ __global__ void __launch_bounds__(tc::kThreads2, 2) k_obs_tc2(ObsArgs a) {
     // ---------------- forward: my 16 features ----------------
     float h[HW];
 #pragma unroll
-    for (int i = 0; i < HW; ++i) { const int f = HW * hf + i; h[i] = (inb && f < a.d) ? a.meta[(size_t)f * a.n_rows + row] : 0.f; }
+    for (int i = 0; i < HW; ++i) { const int f = HW * hf + i; h[i] = (inb && f < a.d) ? __ldcs(&a.meta[(size_t)f * a.n_rows + row]) : 0.f; }
     for (int k = 0; k < LT; ++k) {
       const float* bk = ((IL && k >= L) ? bimg + (size_t)(k - L) * WP : bsm + (size_t)k * WP) + HW * hf;
       float o[HW];
@@ -1030,7 +1038,7 @@ __global__ void __launch_bounds__(tc::kThreads2, 2) k_obs_tc2(ObsArgs a) {
         }
       } else {
 #pragma unroll
-        for (int i = 0; i < HW; ++i) { const int f = HW * hf + i; dst[i] = (inb && f < a.d) ? a.meta[(size_t)f * a.n_rows + row] : 0.f; }
+        for (int i = 0; i < HW; ++i) { const int f = HW * hf + i; dst[i] = (inb && f < a.d) ? __ldcs(&a.meta[(size_t)f * a.n_rows + row]) : 0.f; }
       }
     };
     if (LT > 0) load_act(nxt, LT - 1);
@@ -1218,10 +1226,10 @@ __global__ void __launch_bounds__(256) k_reduce_partials(const double* partials,
 // Per-reflection backward: chain dL/dz to (v_loc, v_scale).  One thread per reflection.
 // ---------------------------------------------------------------------------------------
 struct ReflBwdArgs {
-  const float* v_loc; const float* v_scale; const uint8_t* centric; const uint32_t* refl_index;
-  const float* inj_u; const float* gz;
+  const float* v_loc; const float* v_scale;
+  const float4* bwd_coef; const float* gz;        // (S,R): written by k_refl_sample; dL/dz after the observation kernel
   float* g_loc; float* g_scale;
-  int64_t R; int S; float eps; float cq; uint64_t seed; uint32_t step;
+  int64_t R; int S;
   // fused tail of the per-reflection chain (rows A8 / A9 on the surrogate slice)
   double* var_sums;             // [0..1] raw / filtered sum of squares of g_loc, [2..3] of g_scale (null: do not accumulate)
   // Adam on (v_loc, v_scale) inside this kernel: legal whenever no NORM-based clipping is configured, because then the update
@@ -1232,9 +1240,9 @@ struct ReflBwdArgs {
   const int* stop_step; int step_index;
 };
 
-// Chain dL/dz to (v_loc, v_scale), four reflections per thread with 16-byte accesses (see k_refl_sample); the truncated-normal
-// forward quantities are RECOMPUTED from the parameters this kernel reads anyway (17 B per reflection) -- storing them in the
-// forward kernel would cost 32 B per (sample, reflection) of extra HBM traffic in a kernel that is bandwidth-bound.
+// Chain dL/dz to (v_loc, v_scale): g_loc = sum_s gz A + C, g_scale = sum_s gz B + D with the four coefficients the forward
+// kernel left behind -- no transcendental arithmetic here, the kernel streams {gz, coefficients, parameters, Adam moments} and
+// is bound by HBM bandwidth.  Four reflections per thread, 16-byte accesses (see k_refl_sample).
 __global__ void __launch_bounds__(256) k_refl_backward(ReflBwdArgs a, int vec) {
   const int64_t nq = (a.R + 3) >> 2;
   const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1242,37 +1250,22 @@ __global__ void __launch_bounds__(256) k_refl_backward(ReflBwdArgs a, int vec) {
   if (q < nq) {
     const int64_t r0 = q << 2;
     const bool v = vec != 0;
-    const Vec4 vl = ld4(a.v_loc, r0, a.R, v), vs = ld4(a.v_scale, r0, a.R, v);
-    uint8_t cen[4] = {0, 0, 0, 0};
-    if (v) { const uchar4 c4 = *reinterpret_cast<const uchar4*>(a.centric + r0); cen[0] = c4.x; cen[1] = c4.y; cen[2] = c4.z; cen[3] = c4.w; }
-    else {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) if (r0 + j < a.R) cen[j] = a.centric[r0 + j];
-    }
     Vec4 gl, gs;
-    float mu[4], sg[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { gl.v[j] = 0.f; gs.v[j] = 0.f; mu[j] = 0.f; sg[j] = 0.f; }
+    for (int j = 0; j < 4; ++j) { gl.v[j] = 0.f; gs.v[j] = 0.f; }
     for (int s = 0; s < a.S; ++s) {
       const Vec4 g = ld4(a.gz + (size_t)s * a.R, r0, a.R, v);
-      Vec4 u;
-      if (a.inj_u) u = ld4(a.inj_u + (size_t)s * a.R, r0, a.R, v, 0.5f);
-      else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) u.v[j] = (r0 + j < a.R) ? refl_uniform(a.seed, a.step, (uint32_t)s, a.refl_index[r0 + j]) : 0.5f;
-      }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const TnSample t = tn_forward(vl.v[j], vs.v[j], cen[j] ? 0.0f : 1e-32f, a.eps, u.v[j]);
-        gl.v[j] += g.v[j] * t.dz_dmu + a.cq * t.dlogq_dmu;
-        gs.v[j] += g.v[j] * t.dz_dsigma + a.cq * t.dlogq_dsigma;
-        mu[j] = t.mu; sg[j] = t.sigma;
+        if (r0 + j < a.R) {
+          const float4 c = __ldcs(&a.bwd_coef[(size_t)s * a.R + r0 + j]);
+          gl.v[j] += fmaf(g.v[j], c.x, c.z);
+          gs.v[j] += fmaf(g.v[j], c.y, c.w);
+        }
       }
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      gl.v[j] *= mu[j];                    // d mu / d v_loc = mu
-      gs.v[j] *= (sg[j] - a.eps);          // d sigma / d v_scale = exp(v_scale)
       if (r0 + j < a.R) {
         const double a2 = (double)gl.v[j] * (double)gl.v[j], b2 = (double)gs.v[j] * (double)gs.v[j];
         ss[0] += a2; ss[2] += b2;
@@ -1283,6 +1276,7 @@ __global__ void __launch_bounds__(256) k_refl_backward(ReflBwdArgs a, int vec) {
     st4(a.g_loc, r0, a.R, v, gl);
     st4(a.g_scale, r0, a.R, v, gs);
     if (a.theta_loc != nullptr && a.step_index <= *a.stop_step) {
+      const Vec4 vl = ld4(a.v_loc, r0, a.R, v), vs = ld4(a.v_scale, r0, a.R, v);
       auto adam = [&](float* theta, float* m, float* v2, const Vec4& par, const Vec4& grad) {
         Vec4 mm = ld4(m, r0, a.R, v), vv = ld4(v2, r0, a.R, v), th;
 #pragma unroll

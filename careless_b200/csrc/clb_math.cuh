@@ -77,7 +77,10 @@ CLB_DEV TnSample tn_forward(float v_loc, float v_scale, float low, float eps, fl
   const float alpha = (low - t.mu) * inv_s;
   const float beta = (kHigh - t.mu) * inv_s;
   const float Pa = normcdff(alpha);
-  const float Qb = normcdff(-beta);                 // upper tail mass beyond high
+  // high = 1e10 (surrogate_posteriors.py:105), so beta is ~1e9 or more and every beta term below is exactly 0 in FP32
+  // (Phi(-40) and exp(-800) underflow): skip their transcendental arithmetic -- the kernel is instruction-bound, not HBM-bound
+  const bool far = beta > 40.0f;
+  const float Qb = far ? 0.0f : normcdff(-beta);    // upper tail mass beyond high
   const float Z = normcdff(-alpha) - Qb;            // Phi(beta) - Phi(alpha)
   const float p = fmaf(u, Z, Pa);
   const float q = fmaf(1.0f - u, Z, Qb);            // 1 - p without cancellation
@@ -88,12 +91,12 @@ CLB_DEV TnSample tn_forward(float v_loc, float v_scale, float low, float eps, fl
   t.ez = free_ ? e : alpha;
   const float uc = fminf(fmaxf(u, FLT_MIN), 1.0f - FLT_EPSILON);
   const float dl = expf(0.5f * (e * e - alpha * alpha)) * (1.0f - uc);
-  const float du = expf(0.5f * (e * e - beta * beta)) * uc;
+  const float du = far ? 0.0f : expf(0.5f * (e * e - beta * beta)) * uc;
   t.dz_dmu = free_ ? (1.0f - dl - du) : 0.0f;
   const float bdu = (du == 0.0f) ? 0.0f : beta * du;
   t.dz_dsigma = free_ ? (e - alpha * dl - bdu) : 0.0f;
   const float phi_a = kInvSqrt2Pi * expf(-0.5f * alpha * alpha);
-  const float phi_b = kInvSqrt2Pi * expf(-0.5f * beta * beta);
+  const float phi_b = far ? 0.0f : kInvSqrt2Pi * expf(-0.5f * beta * beta);
   const float b_phi_b = (phi_b == 0.0f) ? 0.0f : beta * phi_b;
   const float invZ = 1.0f / Z;
   t.logq = -0.5f * t.ez * t.ez - 0.5f * kLog2Pi - logf(t.sigma) - logf(Z);

@@ -339,7 +339,7 @@ __global__ void __launch_bounds__(tc16::kRows, 4) k_obs_tc16(ObsArgs a) {
     const bool more_tiles = tile + gridDim.x < n_tiles;
     const int64_t row = tile * TR + tid;
     const bool inb = row < a.n_rows;
-    const int refl = inb ? a.refl[row] : -1;
+    const int refl = inb ? __ldcs(&a.refl[row]) : -1;
     const bool active = refl >= 0;
     const int timg = (IL && K > 0) ? a.image[tile * TR] : 0;
     if (IL && K > 0) {
@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(tc16::kRows, 4) k_obs_tc16(ObsArgs a) {
     // ---------------- forward ----------------
     float h[WP];
 #pragma unroll
-    for (int i = 0; i < WP; ++i) h[i] = (inb && i < a.d) ? a.meta[(size_t)i * a.n_rows + row] : 0.f;
+    for (int i = 0; i < WP; ++i) h[i] = (inb && i < a.d) ? __ldcs(&a.meta[(size_t)i * a.n_rows + row]) : 0.f;
     for (int k = 0; k < LT; ++k) {
       const float* bk = (IL && k >= L) ? bimg + (size_t)(k - L) * WP : bsm + (size_t)k * WP;
       const bool next_bwd = !(k + 1 < LT) && a.train_mlp && LT > 1;
@@ -394,7 +394,7 @@ __global__ void __launch_bounds__(tc16::kRows, 4) k_obs_tc16(ObsArgs a) {
         }
       } else {
 #pragma unroll
-        for (int i = 0; i < WP; ++i) dst[i] = (inb && i < a.d) ? a.meta[(size_t)i * a.n_rows + row] : 0.f;
+        for (int i = 0; i < WP; ++i) dst[i] = (inb && i < a.d) ? __ldcs(&a.meta[(size_t)i * a.n_rows + row]) : 0.f;
       }
     };
     auto layer_backward = [&](const float (&ain)[WP], bool need_dx, const float* next, uint32_t next_n, float* wk, float* bk2, int il_w,

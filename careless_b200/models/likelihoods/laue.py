@@ -5,8 +5,31 @@ import numpy as np
 from .mono import Ev11Likelihood, Likelihood
 
 
+class ConvolvedLikelihood:
+    """laue.py:9-34: log-density of the per-spot sums of the predicted harmonics (host-side protocol object)."""
+
+    def __init__(self, distribution, harmonic_id):
+        self.distribution = distribution
+        self.harmonic_id = np.asarray(harmonic_id).reshape(-1)
+
+    def convolve(self, value):
+        return LaueBase.convolve(value, self.harmonic_id)
+
+    def mean(self):
+        return self.distribution.mean()
+
+    def stddev(self):
+        return self.distribution.stddev()
+
+    def log_prob(self, value):
+        return self.distribution.log_prob(self.convolve(value))
+
+
 class LaueBase(Likelihood):
     laue = True
+
+    def call(self, inputs):                       # laue.py:42-47
+        return ConvolvedLikelihood(self.dist(inputs), self.get_harmonic_id(inputs))
 
     @staticmethod
     def convolve(value, harmonic_id):

@@ -54,6 +54,27 @@ class TruncatedNormal:
         a, b, loc, scale = self._ab(high)
         return truncnorm.moment(4, a, b, loc, scale)
 
+    # ---- the rest of the reference protocol (surrogate_posteriors.py:11-37, :50-53), host side, float64 scipy ----
+    def sample(self, n=1, seed=None):
+        """(n, R) draws: inverse-CDF transform of uniforms, then max(low, .) as surrogate_posteriors.py:50-53."""
+        from scipy.stats import truncnorm
+        a, b, loc, scale = self._ab()
+        rng = np.random.default_rng(seed)
+        u = rng.random((int(n),) + loc.shape)
+        s = truncnorm.ppf(u, a, b, loc, scale)
+        return np.maximum(self.low, s).astype(np.float32)
+
+    def log_prob(self, z):
+        from scipy.stats import truncnorm
+        a, b, loc, scale = self._ab()
+        return truncnorm.logpdf(np.asarray(z, dtype=np.float64), a, b, loc, scale)
+
+    def parameter_properties(self):
+        """Which unconstraining transform each parameter trains under (the role of tfd's ParameterProperties here)."""
+        return {"loc": {"trainable": True, "bijector": "Exp", "raw": "loc_raw"},
+                "scale": {"trainable": True, "bijector": f"Chain([Shift({self.scale_shift:g}), Exp])", "raw": "scale_raw"},
+                "low": {"trainable": False}, "high": {"trainable": False}}
+
     def save_weights(self, path):
         np.savez(path if str(path).endswith(".npz") else str(path) + ".npz", loc_raw=self.loc_raw, scale_raw=self.scale_raw)
 

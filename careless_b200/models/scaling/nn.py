@@ -5,8 +5,55 @@ import numpy as np
 from ..base import BaseModel
 
 
+class ScaleDistribution:
+    """What `scaling_model(inputs)` returns (nn.py:22-25, image.py:58-63): the per-observation Normal over the scale, with the
+    moments computed ON THE GPU by the observation kernel's forward pass (clb_get_scale_moments)."""
+
+    def __init__(self, mean, stddev):
+        self._mean, self._std = np.asarray(mean, dtype=np.float32), np.asarray(stddev, dtype=np.float32)
+
+    def mean(self):
+        return self._mean
+
+    def stddev(self):
+        return self._std
+
+    def sample(self, n=1, seed=None):
+        rng = np.random.default_rng(seed)
+        return (self._mean + self._std * rng.standard_normal((int(n),) + self._mean.shape)).astype(np.float32)
+
+    def log_prob(self, value):
+        from scipy.stats import norm
+        return norm.logpdf(np.asarray(value, dtype=np.float64), self._mean, self._std)
+
+
 class Scaler(BaseModel):
     trainable = True
+
+    def __call__(self, inputs):
+        """`scaling_model(inputs) -> dist` of the reference (variational.py:67-69, 156-157).  The network runs on the GPU: a
+        forward-only engine is built for `inputs` (any prior: the scale does not depend on the structure factors)."""
+        from ..likelihoods.mono import NormalLikelihood
+        from ..merging.surrogate_posteriors import TruncatedNormal
+        from ..merging.variational import VariationalMergingModel
+        from ..priors.wilson import WilsonPrior
+        refl_id = np.asarray(self.get_refl_id(inputs)).reshape(-1)
+        R = int(refl_id.max()) + 1
+        prior = WilsonPrior(np.zeros(R, dtype=bool), np.ones(R, dtype=np.float32), 1.0)
+        q = TruncatedNormal.from_loc_and_scale(prior.mean(), prior.stddev(), 1e-32)
+        if self.is_laue(inputs):
+            from ..likelihoods.laue import NormalLikelihood as LaueNormal
+            lik = LaueNormal()
+        else:
+            lik = NormalLikelihood()
+        model = VariationalMergingModel(q, prior, lik, self, 1)
+        try:
+            eng = model._build_engine(inputs)
+            model._push(eng)
+            mean, std = model._scale_moments(eng)          # per row, before any Laue convolution
+        finally:
+            model.close()
+        return ScaleDistribution(mean, std)
 
 
 class MetadataScaler(Scaler):

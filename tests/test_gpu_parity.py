@@ -37,6 +37,19 @@ def _draws(rng, S, R, N, n_steps=1):
     return u, e
 
 
+def _record_strict(label, strict, errs):
+    """Append the strict-criterion counts to gpurun_out/parity_strict_counts.jsonl (copied to profiles/ per round)."""
+    import json, os
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_strict_counts.jsonl"), "a") as f:
+            f.write(json.dumps({"case": label, "strict": strict, "rms": {k[4:]: v for k, v in errs.items() if k.startswith("rms:")},
+                                "scalars": {k: errs[k] for k in ("loss", "NLL", "F KLDiv", "Grad Norm")}}) + "\n")
+    except OSError:
+        pass
+
+
 def _compare_step(problem, label, frozen=(), floor_factor=3.0, **kw):
     rng = np.random.default_rng(7)
     ocfg, oprior, eng = U.build(problem, **kw)
@@ -73,6 +86,18 @@ def _compare_step(problem, label, frozen=(), floor_factor=3.0, **kw):
             errs["gmax:" + k] = U.rel_err(ge[k], go[k])
             tol["gmax:" + k] = 5.0 * t
             errs["rms:" + k] = U.rms_err(ge[k], go[k])
+        # north_star's flat criterion, reported (not asserted) next to the conditioned one: how many gradient elements differ
+        # from the float64 oracle by more than rtol 1e-4 STRICTLY (|a-b| > 1e-4 |b|, no floor), for the CUDA engine and for the
+        # float32 twin of the oracle (= any float32 implementation of the same graph, the TF reference included)
+        strict = {}
+        for k in go:
+            b = np.asarray(go[k], dtype=np.float64).reshape(-1)
+            strict[k] = {"n": int(b.size),
+                         "cuda_outside_1e-4": int(np.sum(np.abs(np.asarray(ge[k], dtype=np.float64).reshape(-1) - b) > RTOL * np.abs(b))),
+                         "f32_oracle_outside_1e-4": int(np.sum(np.abs(np.asarray(g32[k], dtype=np.float64).reshape(-1) - b) > RTOL * np.abs(b)))}
+        _record_strict(label, strict, errs)
+        print(f"[{label}] strict rtol 1e-4 (no floor): " + "  ".join(f"{k}: cuda {v['cuda_outside_1e-4']}/{v['n']}, f32 oracle {v['f32_oracle_outside_1e-4']}/{v['n']}"
+                                                                       for k, v in strict.items()))
         print(f"\n[{label}] " + "  ".join(f"{k}={v:.2e}" for k, v in errs.items()))
         print(f"[{label}] f32-oracle floor x3: " + "  ".join(f"{k}={v:.2e}" for k, v in tol.items()))
         print(f"[{label}] metrics gpu={hist[0]}  oracle={metrics}")
