@@ -624,7 +624,9 @@ int clb_set_observations(clb_handle* h, int64_t n, int64_t n_total, const int64_
     // One allocation [weight-gradient partials | activation scratch] so that a single L2 access-policy window can cover
     // both: the partials are read-modify-written once per tile and layer and must not be evicted by the scratch
     // streaming through the same cache; whatever persisting capacity is left keeps the most recently written
-    // activations on chip until the backward pass reads them.  CLB_L2_WINDOW=0 no window, 1 partials only, 2 both.
+    // activations on chip until the backward pass reads them (and discards them).  CLB_L2_WINDOW=0 no window, 1 partials
+    // only, 2 both (default).  Measured on B200 (10 M observations, ncu dram bytes per launch of k_obs_tc2, discard on):
+    // no window 7.96 GB, partials only 5.30 GB, partials + scratch 1.98 GB (5.6x the algorithmic 0.356 GB); time unchanged.
     // tensor-core kernels: the CTAs accumulate with REDs, so several of them can share one partial buffer -- a quarter as
     // many buffers as CTAs keeps the L2 footprint (and the persisting carve-out) small without measurable contention
     h->n_partials = h->use_pp ? std::max(1, h->grid_obs / 2) : (h->use_tc16 || h->use_tc2) ? std::max(1, h->grid_obs / 4) : h->grid_obs;
@@ -637,7 +639,7 @@ int clb_set_observations(clb_handle* h, int64_t n, int64_t n_total, const int64_
     h->partial_bytes = pbytes;
     h->scratch_ptr = reinterpret_cast<float4*>(h->partials.as<char>() + pb);
     const char* mode_s = getenv("CLB_L2_WINDOW");
-    const int mode = mode_s ? atoi(mode_s) : 1;
+    const int mode = mode_s ? atoi(mode_s) : 2;
     int max_persist = 0, max_window = 0;
     cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, c.device);
     cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, c.device);

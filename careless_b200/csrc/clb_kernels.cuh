@@ -807,7 +807,7 @@ __global__ void __launch_bounds__(TC ? tc::kThreads : kObsThreads, TC ? 2 : 1) k
 // ---------------------------------------------------------------------------------------
 struct ObsSmem2 {
   static size_t bytes(int n_layers, int n_img_layers) {
-    return 2 * (size_t)tc::kDwImgBytes + sizeof(float) * (64 + (size_t)n_layers * 32 + (size_t)n_img_layers * (1024 + 32))
+    return 2 * (size_t)tc::kDwImgBytes + (size_t)tc::kDwLBO + sizeof(float) * (64 + (size_t)n_layers * 32 + (size_t)n_img_layers * (1024 + 32))
            + 64 * sizeof(double) + 4 * (size_t)tc::kImgBytes + 64 + 4 * 128 * sizeof(float) + 128;
   }
 };
@@ -841,7 +841,7 @@ __device__ __forceinline__ void bias_red16(const float (&dp)[16], float* dst, in
 // the image's gradient slots (il_w > 0: kernel stored (out, in), width il_w); `dead` = scratch slot of `ain` (or null).
 __device__ __forceinline__ void tc_layer_backward2(tc::Ctx& tcx, float (&dp)[16], const float (&ain)[16], bool need_dx,
                                                    const float* build_from, char* img_base, const float* next_img,
-                                                   float* wk, float* bk, int il_w, unsigned& mask_out, const float4* dead = nullptr) {
+                                                   float* wk, float* bk, int il_w, const float4* dead = nullptr) {
   const int lane = tcx.tid & 31;
 #if CLB_BWD_ORDER == 2
   // round-1 structure: __syncthreads() between the operand stores and the issue (warps 0 and 7 issue)
@@ -857,23 +857,23 @@ __device__ __forceinline__ void tc_layer_backward2(tc::Ctx& tcx, float (&dp)[16]
 #if CLB_BWD_ORDER == 1
   // chain first, dW images while it runs, dW collected one layer later
   if (need_dx) tc::chain_handover<true>(tcx, hi, lo, build_from, img_base, next_img, lane);
-  if (tcx.dw_pending) tc::collect_dw_red(tcx, tcx.pend_wk, tcx.pend_ilw);     // frees the operand images and the accumulator
+  if (tcx.dw_pending) tc::collect_dw_red(tcx, tcx.pend_wk, tcx.pend_ilw, tcx.pend_bk);     // frees the operand images and the accumulator
   tc::dw_handover(tcx, hi, lo, ain, dead, lane);
-  tcx.dw_pending = true; tcx.pend_wk = wk; tcx.pend_ilw = il_w;
+  tcx.dw_pending = true; tcx.pend_wk = wk; tcx.pend_ilw = il_w; tcx.pend_bk = bk;
 #elif CLB_BWD_ORDER == 0
   // one hand-over per layer (chain operands + dW images); dW collected at the end of this layer
   tc::bwd_handover(tcx, hi, lo, ain, need_dx, build_from, img_base, next_img, dead, lane);
 #endif
-  // everything that does not feed the tensor cores runs while they work: the sign mask of a_k (leaky' of the layer
-  // below) and the bias gradient (column sums of dp)
-  unsigned mask = 0u;
+  // (the bias gradient, the column sums of dp, is row 64 of the dW product: see collect_dw_red)
+  if (need_dx) {
+    tc::collect2(tcx, dp);               // delta a_k
+    // delta p_{k-1} = delta a_k * leaky'(pre-activation of layer k-1); sign(a_k) == sign(pre-activation), and a_k is still in
+    // registers (compare + predicated multiply per value; the round-1 kernel built and re-read a 16-bit mask instead)
 #pragma unroll
-  for (int i = 0; i < 16; ++i) mask |= (ain[i] > 0.f ? 1u : 0u) << i;
-  mask_out = mask;
-  bias_red16(dp, bk != nullptr ? bk + 16 * tcx.hf : nullptr, lane, il_w > 0 ? il_w - 16 * tcx.hf : 16);
-  if (need_dx) tc::collect2(tcx, dp);
+    for (int j = 0; j < 16; ++j) dp[j] = ain[j] > 0.f ? dp[j] : kLeak * dp[j];
+  }
 #if CLB_BWD_ORDER != 1
-  tc::collect_dw_red(tcx, wk, il_w);
+  tc::collect_dw_red(tcx, wk, il_w, bk);
 #endif
 }
 
@@ -884,9 +884,10 @@ __global__ void __launch_bounds__(tc::kThreads2, 2) k_obs_tc2(ObsArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const int NL = a.lay.n_layers, L = NL - 1, K = IL ? a.n_img_layers : 0, LT = L + K;
   unsigned char* sp = smem_raw;
-  char* tc_dwa = reinterpret_cast<char*>(sp);
-  char* tc_dwb = tc_dwa + tc::kDwImgBytes;
-  sp += 2 * tc::kDwImgBytes;
+  char* tc_dwa = reinterpret_cast<char*>(sp);               // dW A operand: MN groups [a_hi | a_lo | ONES | (delta-p_hi: unused rows)]
+  float* ones = reinterpret_cast<float*>(tc_dwa + tc::kDwImgBytes);   // 16 KB of 1.0f: rows 64..95 of the product = column sums of delta-p
+  char* tc_dwb = tc_dwa + tc::kDwImgBytes + tc::kDwLBO;     // dW B operand: [delta-p_hi | delta-p_lo]
+  sp += 2 * tc::kDwImgBytes + tc::kDwLBO;
   float* Whead = reinterpret_cast<float*>(sp);              // [32][2]
   float* bsm = Whead + 64;                                  // [NL][32]
   float* Wimg = bsm + (size_t)NL * WP;                      // [K][32][32] this tile's image-layer kernels as [in][out]
@@ -914,6 +915,8 @@ __global__ void __launch_bounds__(tc::kThreads2, 2) k_obs_tc2(ObsArgs a) {
     const int k = idx / WP, j = idx % WP;
     bsm[idx] = (j < a.lay.out_dim[k]) ? a.theta_mlp[a.lay.boff[k] + j] : 0.f;
   }
+  for (int idx = tid; idx < (int)(tc::kDwLBO / 16); idx += T) reinterpret_cast<float4*>(ones)[idx] = make_float4(1.f, 1.f, 1.f, 1.f);
+  tc::fence_async_smem();
   __syncthreads();
   {
     tc::fence_after();
@@ -936,7 +939,7 @@ __global__ void __launch_bounds__(tc::kThreads2, 2) k_obs_tc2(ObsArgs a) {
     }
     tcx.pass = 0; tcx.wphase = 0;
     tcx.cnt_chain = tc::smem_u32(tc_slot + 2); tcx.cnt_dw = tc::smem_u32(tc_slot + 3); tcx.n_warps_m1 = T / 32 - 1;
-    tcx.dw_pending = false; tcx.pend_wk = nullptr; tcx.pend_ilw = 0;
+    tcx.dw_pending = false; tcx.pend_wk = nullptr; tcx.pend_ilw = 0; tcx.pend_bk = nullptr;
   }
   // ready-made images of hidden layer k in global memory: dir 0 = forward (B[n][k] = W[k][n]), 1 = backward; null for
   // image layers, whose per-tile kernels are turned into images by the threads themselves
@@ -1046,12 +1049,12 @@ __global__ void __launch_bounds__(tc::kThreads2, 2) k_obs_tc2(ObsArgs a) {
     for (int j = 0; j < HW; ++j) dp[j] = 0.f;
     if (hf == 0) { dp[0] = dmu; dp[1] = drho; }
     // head: dW_out = a_L^T [dmu, drho]
-    unsigned mask = 0u;                  // sign bits of the layer input just processed: leaky'(pre-activation) of the layer below
-    tc_layer_backward2(tcx, dp, h, false, nullptr, tc_img, nullptr, part32 + (size_t)L * PSLOT, part32 + (size_t)L * PSLOT + WP * WP, 0, mask);
+    tc_layer_backward2(tcx, dp, h, false, nullptr, tc_img, nullptr, part32 + (size_t)L * PSLOT, part32 + (size_t)L * PSLOT + WP * WP, 0);
 #pragma unroll
-    for (int i = 0; i < HW; ++i) {
+    for (int i = 0; i < HW; ++i) {       // delta a_LT from the head, times leaky' of the last hidden layer (sign of its output h)
       const float2 w = *reinterpret_cast<const float2*>(&Whead[(HW * hf + i) * 2]);
-      dp[i] = w.x * dmu + w.y * drho;
+      const float da = w.x * dmu + w.y * drho;
+      dp[i] = h[i] > 0.f ? da : kLeak * da;
     }
     for (int k = LT - 1; k >= 0; --k) {
       const bool is_il = IL && k >= L;
@@ -1065,8 +1068,6 @@ __global__ void __launch_bounds__(tc::kThreads2, 2) k_obs_tc2(ObsArgs a) {
       const int il_w = is_il ? a.il_width : 0;
       float* wk = is_il ? il_gk : part32 + (size_t)k * PSLOT;
       float* bk2 = is_il ? il_gb : part32 + (size_t)k * PSLOT + WP * WP;
-#pragma unroll
-      for (int j = 0; j < HW; ++j) dp[j] = ((mask >> j) & 1u) ? dp[j] : kLeak * dp[j];
       float ain[HW];
 #pragma unroll
       for (int i = 0; i < HW; ++i) ain[i] = nxt[i];
@@ -1074,9 +1075,9 @@ __global__ void __launch_bounds__(tc::kThreads2, 2) k_obs_tc2(ObsArgs a) {
       // the pass after this layer's dX: the next layer's dX (k - 1 >= 1), else the next tile's first forward layer
       const float* next = (k > 1) ? gimg(k - 1, 1) : (more_tiles ? gimg(0, 0) : nullptr);
       const float4* dead = (a.discard_scratch && k > 0) ? scr + (size_t)(k - 1) * NC * TR : nullptr;      // the 16 KB slot of a_k
-      tc_layer_backward2(tcx, dp, ain, k > 0, is_il ? wsrc(k) : nullptr, tc_img, next, wk, bk2, il_w, mask, dead);
+      tc_layer_backward2(tcx, dp, ain, k > 0, is_il ? wsrc(k) : nullptr, tc_img, next, wk, bk2, il_w, dead);
     }
-    if (tcx.dw_pending) { tc::collect_dw_red(tcx, tcx.pend_wk, tcx.pend_ilw); tcx.dw_pending = false; }
+    if (tcx.dw_pending) { tc::collect_dw_red(tcx, tcx.pend_wk, tcx.pend_ilw, tcx.pend_bk); tcx.dw_pending = false; }
   }
   // ---- flush: the log-likelihood sum ----
   __syncthreads();

@@ -252,10 +252,11 @@ __global__ void __launch_bounds__(pp::kThreadsPP, 1) k_obs_pp(ObsArgs a) {
       CLB_TMEM_LD16(tm + cDw + 32 + col, v1);
       wait_ld();
       if (lane < 16) {
-        float4* dst = reinterpret_cast<float4*>(part32 + (size_t)layer * PSLOT) + (((warp & 1) * 2 + hf) * 4) * 16 + lane;
+        // M = 64 product: lanes < 16 of quarter q hold rows 16 q + lane, i.e. dW row i = (16 q + lane) % 32; tc::dw_slot32 layout
+        float4* dst = reinterpret_cast<float4*>(part32 + (size_t)layer * PSLOT) + (4 * hf) * 32 + ((16 * (warp & 3) + lane) & 31);
 #pragma unroll
         for (int qq = 0; qq < 4; ++qq)
-          atomicAdd(dst + qq * 16, make_float4(__uint_as_float(v0[4 * qq]) + __uint_as_float(v1[4 * qq]),
+          atomicAdd(dst + qq * 32, make_float4(__uint_as_float(v0[4 * qq]) + __uint_as_float(v1[4 * qq]),
                                                __uint_as_float(v0[4 * qq + 1]) + __uint_as_float(v1[4 * qq + 1]),
                                                __uint_as_float(v0[4 * qq + 2]) + __uint_as_float(v1[4 * qq + 2]),
                                                __uint_as_float(v0[4 * qq + 3]) + __uint_as_float(v1[4 * qq + 3])));

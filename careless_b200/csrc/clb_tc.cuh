@@ -139,7 +139,7 @@ struct Ctx {
   uint32_t pass, wphase;               // chain passes started so far (buffer = pass & 1); phase bit of each buffer's barrier
   // barrier-free hand-over (k_obs_tc2): arrival counters in shared memory; the deferred dW collection of the previous layer
   uint32_t cnt_chain, cnt_dw, n_warps_m1;
-  float* pend_wk; int pend_ilw; bool dw_pending;
+  float* pend_wk; float* pend_bk; int pend_ilw; bool dw_pending;
 };
 
 __device__ __forceinline__ void split32(const float (&x)[32], uint32_t (&hi)[32], uint32_t (&lo)[32]) {
@@ -416,39 +416,53 @@ __device__ __forceinline__ void collect2(Ctx& c, float (&y)[16]) {
 
 // Offset (in floats) of element (i = in, j = out) of a 32 x 32 kernel gradient inside one layer's slot of the FP32 partial.
 // The slot is laid out so that every warp-level vector RED of collect_dw_red covers 256 contiguous bytes (16 lanes x 16 B):
-// [i / 16][j / 16][(j % 16) / 4][i % 16][j % 4].  (A row-major slot made each RED instruction touch 16 different 128-byte
-// lines: 13 L1 requests per instruction, a quarter of all LSU wavefronts of the kernel.)
+// [j / 4][i][j % 4]: the 32 lanes of a warp (rows i = 0..31) write 512 contiguous bytes per RED.128.  (A row-major slot made
+// each RED instruction touch 16 different 128-byte lines: 13 L1 requests per instruction, a quarter of all LSU wavefronts.)
 __host__ __device__ inline int dw_slot32(int i, int j) {
-  return (((((i >> 4) * 2 + (j >> 4)) * 4 + ((j & 15) >> 2)) * 16 + (i & 15)) << 2) + (j & 3);
+  return ((((j >> 2) << 5) + i) << 2) + (j & 3);
 }
+// k_obs_tc2's dW product has M = 128 rows: [a_hi (32) | a_lo (32) | ONES (32) | unused (32)] -- an M = 64 instruction
+// costs the tensor pipe exactly as much, and the row of ones turns the bias gradient (column sums of delta-p) into one more
+// row of the same product instead of ~55 shuffle / select / add instructions per thread and layer.
+constexpr uint32_t kIdescDw128 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
 
 // dW rows live at lanes (r % 16) + 32 (r / 16): in every warp the lanes < 16 hold row r = 16 (warp % 4) + lane, i.e.
 // feature i = r % 32 (rows 0..31 from a_hi, 32..63 from a_lo).  The thread folds the delta-hi and delta-lo column blocks of
 // ITS 16 columns and adds them to wk[i][16 hf ..] with four 16-byte REDs (il_w > 0: an image layer's kernel, stored
 // (out, in) with width il_w, scalar REDs).  When this returns the dW MMAs are complete: the operand images and the
 // accumulator may be reused after the next __syncthreads().
-__device__ __forceinline__ void collect_dw_red(Ctx& c, float* wk, int il_w) {
+__device__ __forceinline__ void collect_dw_red(Ctx& c, float* wk, int il_w, float* bk = nullptr) {
   mbar_wait(c.mbar_dw, c.parity_dw);
   c.parity_dw ^= 1u;
   fence_after();
   const int q = (c.tid >> 5) & 3, lane = c.tid & 31;
+  if (q == 3) return;                      // rows 96..127 of the product are not used
   const uint32_t addr = c.row_addr + kColDw + c.col;
   uint32_t v0[16], v1[16];
   CLB_TMEM_LD16(addr, v0);
   CLB_TMEM_LD16(addr + 32, v1);
   wait_ld();
-  if (lane < 16 && wk != nullptr) {
-    const int i = (16 * q + lane) & 31;
-    float f[16];
+  float f[16];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) f[k] = __uint_as_float(v0[k]) + __uint_as_float(v1[k]);
+  for (int k = 0; k < 16; ++k) f[k] = __uint_as_float(v0[k]) + __uint_as_float(v1[k]);     // . delta-p_hi  +  . delta-p_lo
+  if (q < 2) {                             // lane = row i of a_hi^T dp (q = 0) / a_lo^T dp (q = 1): both add into dW[i][16 hf ..]
+    if (wk == nullptr) return;
     if (il_w == 0) {
-      float4* dst = reinterpret_cast<float4*>(wk) + (((q & 1) * 2 + c.hf) * 4) * 16 + lane;      // dw_slot32(i, 16 hf + 4 qq) / 4
+      float4* dst = reinterpret_cast<float4*>(wk) + (4 * c.hf) * 32 + lane;           // dw_slot32(lane, 16 hf + 4 qq) / 4
 #pragma unroll
-      for (int qq = 0; qq < 4; ++qq) atomicAdd(dst + qq * 16, make_float4(f[4 * qq], f[4 * qq + 1], f[4 * qq + 2], f[4 * qq + 3]));
-    } else if (i < il_w) {
+      for (int qq = 0; qq < 4; ++qq) atomicAdd(dst + qq * 32, make_float4(f[4 * qq], f[4 * qq + 1], f[4 * qq + 2], f[4 * qq + 3]));
+    } else if (lane < il_w) {              // an image layer's kernel, stored (out, in) with width il_w
 #pragma unroll
-      for (int k = 0; k < 16; ++k) { const int j = 16 * c.hf + k; if (j < il_w) atomicAdd(&wk[j * il_w + i], f[k]); }
+      for (int k = 0; k < 16; ++k) { const int j = 16 * c.hf + k; if (j < il_w) atomicAdd(&wk[j * il_w + lane], f[k]); }
+    }
+  } else if (lane == 0 && bk != nullptr) { // row 64 = ones^T dp: the bias gradient of my 16 columns
+    if (il_w == 0) {
+      float4* dst = reinterpret_cast<float4*>(bk + 16 * c.hf);
+#pragma unroll
+      for (int qq = 0; qq < 4; ++qq) atomicAdd(dst + qq, make_float4(f[4 * qq], f[4 * qq + 1], f[4 * qq + 2], f[4 * qq + 3]));
+    } else {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) { const int j = 16 * c.hf + k; if (j < il_w) atomicAdd(&bk[j], f[k]); }
     }
   }
 }
@@ -574,7 +588,7 @@ __device__ __forceinline__ void issue_backward3(Ctx& c, const float (&dp)[16], c
 #ifndef CLB_ABL_DW
 #pragma unroll
       for (int ks = 0; ks < kThreads / 8; ++ks)
-        mma_tf32_ss(d, a0 + (uint64_t)((2u * kDwSBO * (uint32_t)ks) >> 4), b0 + (uint64_t)((2u * kDwSBO * (uint32_t)ks) >> 4), kIdescDw, ks > 0 ? 1u : 0u);
+        mma_tf32_ss(d, a0 + (uint64_t)((2u * kDwSBO * (uint32_t)ks) >> 4), b0 + (uint64_t)((2u * kDwSBO * (uint32_t)ks) >> 4), kIdescDw128, ks > 0 ? 1u : 0u);
 #endif
       commit(bar);
     }
@@ -657,7 +671,7 @@ __device__ __forceinline__ void dw_issue(Ctx& c, const float4* dead, int lane) {
   if (elect_one()) {
 #pragma unroll
     for (int ks = 0; ks < kThreads / 8; ++ks)
-      mma_tf32_ss(d, a0 + (uint64_t)((2u * kDwSBO * (uint32_t)ks) >> 4), b0 + (uint64_t)((2u * kDwSBO * (uint32_t)ks) >> 4), kIdescDw, ks > 0 ? 1u : 0u);
+      mma_tf32_ss(d, a0 + (uint64_t)((2u * kDwSBO * (uint32_t)ks) >> 4), b0 + (uint64_t)((2u * kDwSBO * (uint32_t)ks) >> 4), kIdescDw128, ks > 0 ? 1u : 0u);
     commit(bar);
   }
   __syncwarp();
@@ -730,7 +744,7 @@ __device__ __forceinline__ void dw_handover(Ctx& c, uint32_t (&hi)[16], uint32_t
     if (elect_one()) {
 #pragma unroll
       for (int ks = 0; ks < kThreads / 8; ++ks)
-        mma_tf32_ss(d, a0 + (uint64_t)((2u * kDwSBO * (uint32_t)ks) >> 4), b0 + (uint64_t)((2u * kDwSBO * (uint32_t)ks) >> 4), kIdescDw, ks > 0 ? 1u : 0u);
+        mma_tf32_ss(d, a0 + (uint64_t)((2u * kDwSBO * (uint32_t)ks) >> 4), b0 + (uint64_t)((2u * kDwSBO * (uint32_t)ks) >> 4), kIdescDw128, ks > 0 ? 1u : 0u);
       commit(bar);
     }
     __syncwarp();
