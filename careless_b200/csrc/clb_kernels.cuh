@@ -807,7 +807,7 @@ __global__ void __launch_bounds__(TC ? tc::kThreads : kObsThreads, TC ? 2 : 1) k
 // ---------------------------------------------------------------------------------------
 struct ObsSmem2 {
   static size_t bytes(int n_layers, int n_img_layers) {
-    return 2 * (size_t)tc::kDwImgBytes + (size_t)tc::kDwLBO + sizeof(float) * (64 + (size_t)n_layers * 32 + (size_t)n_img_layers * (1024 + 32))
+    return 2 * (size_t)tc::kDwImgBytes + (CLB_BIAS_ONES ? (size_t)tc::kDwLBO : 0) + sizeof(float) * (64 + (size_t)n_layers * 32 + (size_t)n_img_layers * (1024 + 32))
            + 64 * sizeof(double) + 4 * (size_t)tc::kImgBytes + 64 + 4 * 128 * sizeof(float) + 128;
   }
 };
@@ -864,7 +864,10 @@ __device__ __forceinline__ void tc_layer_backward2(tc::Ctx& tcx, float (&dp)[16]
   // one hand-over per layer (chain operands + dW images); dW collected at the end of this layer
   tc::bwd_handover(tcx, hi, lo, ain, need_dx, build_from, img_base, next_img, dead, lane);
 #endif
-  // (the bias gradient, the column sums of dp, is row 64 of the dW product: see collect_dw_red)
+#if !CLB_BIAS_ONES
+  // what does not feed the tensor cores runs while they work: the bias gradient (column sums of dp)
+  bias_red16(dp, bk != nullptr ? bk + 16 * tcx.hf : nullptr, lane, il_w > 0 ? il_w - 16 * tcx.hf : 16);
+#endif
   if (need_dx) {
     tc::collect2(tcx, dp);               // delta a_k
     // delta p_{k-1} = delta a_k * leaky'(pre-activation of layer k-1); sign(a_k) == sign(pre-activation), and a_k is still in
@@ -885,9 +888,10 @@ __global__ void __launch_bounds__(tc::kThreads2, 2) k_obs_tc2(ObsArgs a) {
   const int NL = a.lay.n_layers, L = NL - 1, K = IL ? a.n_img_layers : 0, LT = L + K;
   unsigned char* sp = smem_raw;
   char* tc_dwa = reinterpret_cast<char*>(sp);               // dW A operand: MN groups [a_hi | a_lo | ONES | (delta-p_hi: unused rows)]
-  float* ones = reinterpret_cast<float*>(tc_dwa + tc::kDwImgBytes);   // 16 KB of 1.0f: rows 64..95 of the product = column sums of delta-p
-  char* tc_dwb = tc_dwa + tc::kDwImgBytes + tc::kDwLBO;     // dW B operand: [delta-p_hi | delta-p_lo]
-  sp += 2 * tc::kDwImgBytes + tc::kDwLBO;
+  constexpr size_t kOnes = CLB_BIAS_ONES ? tc::kDwLBO : 0;  // CLB_BIAS_ONES: 16 KB of 1.0f, rows 64..95 of the product = column sums of delta-p
+  float* ones = reinterpret_cast<float*>(tc_dwa + tc::kDwImgBytes);
+  char* tc_dwb = tc_dwa + tc::kDwImgBytes + kOnes;          // dW B operand: [delta-p_hi | delta-p_lo]
+  sp += 2 * tc::kDwImgBytes + kOnes;
   float* Whead = reinterpret_cast<float*>(sp);              // [32][2]
   float* bsm = Whead + 64;                                  // [NL][32]
   float* Wimg = bsm + (size_t)NL * WP;                      // [K][32][32] this tile's image-layer kernels as [in][out]
@@ -915,7 +919,7 @@ __global__ void __launch_bounds__(tc::kThreads2, 2) k_obs_tc2(ObsArgs a) {
     const int k = idx / WP, j = idx % WP;
     bsm[idx] = (j < a.lay.out_dim[k]) ? a.theta_mlp[a.lay.boff[k] + j] : 0.f;
   }
-  for (int idx = tid; idx < (int)(tc::kDwLBO / 16); idx += T) reinterpret_cast<float4*>(ones)[idx] = make_float4(1.f, 1.f, 1.f, 1.f);
+  for (int idx = tid; idx < (int)(kOnes / 16); idx += T) reinterpret_cast<float4*>(ones)[idx] = make_float4(1.f, 1.f, 1.f, 1.f);
   tc::fence_async_smem();
   __syncthreads();
   {

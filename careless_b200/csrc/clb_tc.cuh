@@ -431,6 +431,12 @@ constexpr uint32_t kIdescDw128 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15)
 // ITS 16 columns and adds them to wk[i][16 hf ..] with four 16-byte REDs (il_w > 0: an image layer's kernel, stored
 // (out, in) with width il_w, scalar REDs).  When this returns the dW MMAs are complete: the operand images and the
 // accumulator may be reused after the next __syncthreads().
+#ifndef CLB_BIAS_ONES
+#define CLB_BIAS_ONES 0     // 1: bias gradient as a ones row of an M = 128 dW product (parity-green; measured SLOWER on B200, 17.2 vs
+                            // 16.8 ms: the M = 128 product reads twice the A operand from shared memory and the dW MMAs get longer)
+#endif
+#if CLB_BIAS_ONES
+constexpr uint32_t kIdescDwTc2 = kIdescDw128;
 __device__ __forceinline__ void collect_dw_red(Ctx& c, float* wk, int il_w, float* bk = nullptr) {
   mbar_wait(c.mbar_dw, c.parity_dw);
   c.parity_dw ^= 1u;
@@ -466,6 +472,36 @@ __device__ __forceinline__ void collect_dw_red(Ctx& c, float* wk, int il_w, floa
     }
   }
 }
+#else
+constexpr uint32_t kIdescDwTc2 = kIdescDw;
+// M = 64 product: D rows live at lanes (r % 16) + 32 (r / 16): in every warp the lanes < 16 hold row r = 16 (warp % 4) + lane,
+// i.e. feature i = r % 32 (rows 0..31 from a_hi, 32..63 from a_lo, both added into dW[i][16 hf ..]).
+__device__ __forceinline__ void collect_dw_red(Ctx& c, float* wk, int il_w, float* bk = nullptr) {
+  mbar_wait(c.mbar_dw, c.parity_dw);
+  c.parity_dw ^= 1u;
+  fence_after();
+  const int q = (c.tid >> 5) & 3, lane = c.tid & 31;
+  const uint32_t addr = c.row_addr + kColDw + c.col;
+  uint32_t v0[16], v1[16];
+  CLB_TMEM_LD16(addr, v0);
+  CLB_TMEM_LD16(addr + 32, v1);
+  wait_ld();
+  if (lane < 16 && wk != nullptr) {
+    const int i = (16 * q + lane) & 31;
+    float f[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) f[k] = __uint_as_float(v0[k]) + __uint_as_float(v1[k]);
+    if (il_w == 0) {
+      float4* dst = reinterpret_cast<float4*>(wk) + (4 * c.hf) * 32 + i;               // dw_slot32(i, 16 hf + 4 qq) / 4
+#pragma unroll
+      for (int qq = 0; qq < 4; ++qq) atomicAdd(dst + qq * 32, make_float4(f[4 * qq], f[4 * qq + 1], f[4 * qq + 2], f[4 * qq + 3]));
+    } else if (i < il_w) {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) { const int j = 16 * c.hf + k; if (j < il_w) atomicAdd(&wk[j * il_w + i], f[k]); }
+    }
+  }
+}
+#endif
 
 // ---- weight images by TMA --------------------------------------------------------------------------------------
 // The hi / lo B-operand images of every hidden layer (both orientations) are prepared once per step in global memory
@@ -588,7 +624,7 @@ __device__ __forceinline__ void issue_backward3(Ctx& c, const float (&dp)[16], c
 #ifndef CLB_ABL_DW
 #pragma unroll
       for (int ks = 0; ks < kThreads / 8; ++ks)
-        mma_tf32_ss(d, a0 + (uint64_t)((2u * kDwSBO * (uint32_t)ks) >> 4), b0 + (uint64_t)((2u * kDwSBO * (uint32_t)ks) >> 4), kIdescDw128, ks > 0 ? 1u : 0u);
+        mma_tf32_ss(d, a0 + (uint64_t)((2u * kDwSBO * (uint32_t)ks) >> 4), b0 + (uint64_t)((2u * kDwSBO * (uint32_t)ks) >> 4), kIdescDwTc2, ks > 0 ? 1u : 0u);
 #endif
       commit(bar);
     }
@@ -671,7 +707,7 @@ __device__ __forceinline__ void dw_issue(Ctx& c, const float4* dead, int lane) {
   if (elect_one()) {
 #pragma unroll
     for (int ks = 0; ks < kThreads / 8; ++ks)
-      mma_tf32_ss(d, a0 + (uint64_t)((2u * kDwSBO * (uint32_t)ks) >> 4), b0 + (uint64_t)((2u * kDwSBO * (uint32_t)ks) >> 4), kIdescDw128, ks > 0 ? 1u : 0u);
+      mma_tf32_ss(d, a0 + (uint64_t)((2u * kDwSBO * (uint32_t)ks) >> 4), b0 + (uint64_t)((2u * kDwSBO * (uint32_t)ks) >> 4), kIdescDwTc2, ks > 0 ? 1u : 0u);
     commit(bar);
   }
   __syncwarp();
@@ -744,7 +780,7 @@ __device__ __forceinline__ void dw_handover(Ctx& c, uint32_t (&hi)[16], uint32_t
     if (elect_one()) {
 #pragma unroll
       for (int ks = 0; ks < kThreads / 8; ++ks)
-        mma_tf32_ss(d, a0 + (uint64_t)((2u * kDwSBO * (uint32_t)ks) >> 4), b0 + (uint64_t)((2u * kDwSBO * (uint32_t)ks) >> 4), kIdescDw128, ks > 0 ? 1u : 0u);
+        mma_tf32_ss(d, a0 + (uint64_t)((2u * kDwSBO * (uint32_t)ks) >> 4), b0 + (uint64_t)((2u * kDwSBO * (uint32_t)ks) >> 4), kIdescDwTc2, ks > 0 ? 1u : 0u);
       commit(bar);
     }
     __syncwarp();

@@ -398,33 +398,32 @@ __global__ void __launch_bounds__(tc16::kRows, 4) k_obs_tc16(ObsArgs a) {
       }
     };
     auto layer_backward = [&](const float (&ain)[WP], bool need_dx, const float* next, uint32_t next_n, float* wk, float* bk2, int il_w,
-                              const float* build_from, unsigned& mask_out, const float4* dead) {
+                              const float* build_from, const float4* dead) {
       issue_bwd16(c, dp, ain, need_dx, next, next_n, build_from, w_img);
       // every warp has consumed `ain` (issue_bwd16 ends after a __syncthreads()): warp 2 drops the layer's 8 KB scratch slot from the L2
       if (dead != nullptr && (tid >> 5) == 2) { discard_line(reinterpret_cast<const char*>(dead) + (size_t)lane * 128);
                                                 discard_line(reinterpret_cast<const char*>(dead) + (size_t)(32 + lane) * 128); }
-      unsigned m = 0u;
-#pragma unroll
-      for (int i = 0; i < WP; ++i) m |= (ain[i] > 0.f ? 1u : 0u) << i;
-      mask_out = m;
       bias_red16(dp, bk2, lane, il_w > 0 ? il_w : 16);
-      if (need_dx) collect16(c, dp);
+      if (need_dx) {
+        collect16(c, dp);                  // delta a_k
+        // delta p_{k-1} = delta a_k * leaky'(pre-activation of layer k-1); sign(a_k) == sign(pre-activation), a_k is still in registers
+#pragma unroll
+        for (int j = 0; j < WP; ++j) dp[j] = ain[j] > 0.f ? dp[j] : kLeak * dp[j];
+      }
       collect_dw16(c, wk, il_w);
     };
     if (LT > 0) load_act(nxt, LT - 1);
 #pragma unroll
     for (int j = 0; j < WP; ++j) dp[j] = 0.f;
     dp[0] = dmu; dp[1] = drho;
-    unsigned mask = 0u;
-    layer_backward(h, false, nullptr, 0u, part32 + (size_t)L * PSLOT16, part32 + (size_t)L * PSLOT16 + WP * WP, 0, nullptr, mask, nullptr);     // head: dW_out = a_L^T [dmu, drho]
+    layer_backward(h, false, nullptr, 0u, part32 + (size_t)L * PSLOT16, part32 + (size_t)L * PSLOT16 + WP * WP, 0, nullptr, nullptr);     // head: dW_out = a_L^T [dmu, drho]
 #pragma unroll
-    for (int i = 0; i < WP; ++i) {
+    for (int i = 0; i < WP; ++i) {         // delta a_LT from the head, times leaky' of the last hidden layer (sign of its output h)
       const float2 w = *reinterpret_cast<const float2*>(&Whead[i * 2]);
-      dp[i] = w.x * dmu + w.y * drho;
+      const float da = w.x * dmu + w.y * drho;
+      dp[i] = h[i] > 0.f ? da : kLeak * da;
     }
     for (int k = LT - 1; k >= 0; --k) {
-#pragma unroll
-      for (int j = 0; j < WP; ++j) dp[j] = ((mask >> j) & 1u) ? dp[j] : kLeak * dp[j];
       float ain[WP];
 #pragma unroll
       for (int i = 0; i < WP; ++i) ain[i] = nxt[i];
@@ -440,7 +439,7 @@ __global__ void __launch_bounds__(tc16::kRows, 4) k_obs_tc16(ObsArgs a) {
         il_w = w;
       }
       const float4* dead = (a.discard_scratch && k > 0) ? scr + (size_t)(k - 1) * NC * TR : nullptr;
-      layer_backward(ain, k > 0, next, (k > 1) ? 2u : 3u, wk, bk2, il_w, wsrc(k), mask, dead);
+      layer_backward(ain, k > 0, next, (k > 1) ? 2u : 3u, wk, bk2, il_w, wsrc(k), dead);
     }
   }
   __syncthreads();
