@@ -335,7 +335,7 @@ def run_ours(args, c):
                        likelihood=c["likelihood"], dof=c["dof"], laue=(name == "laue"),
                        n_images=c["n_images"] if use_img else 0, image_layers=c["image_layers"],
                        prior="double_wilson" if name == "dw" else "wilson", n_asu=4 if name == "dw" else 0,
-                       seed=1234, device=local, stream=stream.cuda_stream, rank=rank, world_size=world)
+                       seed=1234, device=local, stream=stream.cuda_stream, rank=rank, world_size=world, deterministic=args.deterministic)
     eng = Engine(cfg)
     t_prep = time.perf_counter()
     eng.set_observations(li["refl_id"], li.get("image_id") if use_img else None, li["metadata"], li["intensities"], li["uncertainties"],
@@ -447,6 +447,7 @@ def run_ours(args, c):
             cpu = cpu_reference(c, 12.0, 250_000, max(500, int(250_000 * c["refl"] / c["obs"])))
             cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
         cfgd = workload_config(args, c, world, N_glob, R_glob)
+        cfgd["deterministic"] = bool(args.deterministic)
         cfgd["partition"] = {"obs_per_rank": ex["obs_per_rank"], "refl_per_rank": ex["refl_per_rank"],
                              "imbalance": max(ex["obs_per_rank"]) / (sum(ex["obs_per_rank"]) / world),
                              "ids_s": ex["t_ids_s"], "partition_and_shard_s": ex["t_partition_s"]}
@@ -486,6 +487,7 @@ def main():
     ap.add_argument("--refl", type=int, default=None)
     ap.add_argument("--scaling", default=None, choices=["weak", "strong"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--deterministic", action="store_true", help="clb_config.deterministic: bitwise reproducible steps (costs time; not the default)")
     args = ap.parse_args()
     c = dict(CONFIGS[args.config])
     if args.scaling:

@@ -11,7 +11,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CLB_LIB_PATH") or os.path.join(HERE, "libcareless_b200.so")   # CLB_LIB_PATH: instrumented debug builds (tools/)
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # enums of include/careless_b200.h
 LIK_NORMAL, LIK_STUDENTT = 0, 1
@@ -35,7 +35,7 @@ class clb_config(C.Structure):
         ("use_kl_weight", C.c_int32), ("kl_weight", C.c_float),
         ("learning_rate", C.c_float), ("beta_1", C.c_float), ("beta_2", C.c_float), ("adam_epsilon", C.c_float),
         ("clipnorm", C.c_float), ("clipvalue", C.c_float), ("global_clipnorm", C.c_float),
-        ("seed", C.c_uint64), ("rank", C.c_int32), ("world_size", C.c_int32), ("image_layers", C.c_int32), ("refine_uncertainties", C.c_int32),
+        ("seed", C.c_uint64), ("rank", C.c_int32), ("world_size", C.c_int32), ("image_layers", C.c_int32), ("deterministic", C.c_int32), ("refine_uncertainties", C.c_int32),
     ]
 
 

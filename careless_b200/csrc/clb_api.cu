@@ -132,6 +132,10 @@ struct clb_handle {
   DevBuf theta, m, v, grad;
   DevBuf centric, eps_sigma, dw_parent, asu_id, r_const, refl_index;
   DevBuf z, gz, bwd_coef;
+  // deterministic mode
+  bool det = false;
+  DevBuf dzf_rows, refl_ptr, refl_rows, ll_part, kl_part, ss_part;
+  int kl_blocks = 0, ss_blocks = 0;
   DevBuf rows;             // one allocation holding all row arrays
   PinBuf rows_host;        // pinned mirror (for re-upload)
   size_t rows_bytes = 0;
@@ -462,6 +466,9 @@ int clb_create(const clb_config* cfg, clb_handle** out) {
     return fail(nullptr, CLB_ERR_INVALID, "image layers without MLP layers need n_meta == mlp_width");
   if (cfg->mlp_layers + cfg->image_layers + 1 > kMaxLayers) return fail(nullptr, CLB_ERR_INVALID, "too many layers");
   if (cfg->prior == CLB_PRIOR_DOUBLE_WILSON && cfg->n_asu <= 0) return fail(nullptr, CLB_ERR_INVALID, "DoubleWilson needs n_asu > 0");
+  if (cfg->deterministic && (cfg->image_scales || cfg->image_layers > 0 || cfg->refine_uncertainties || cfg->prior != CLB_PRIOR_WILSON))
+    return fail(nullptr, CLB_ERR_INVALID, "deterministic mode supports MLPScaler models with the Wilson prior (no image scales / image layers / "
+                                          "refined uncertainties / DoubleWilson: their gradients are accumulated with atomics)");
   const int wmax = std::max(std::max(cfg->n_meta, cfg->mlp_width), 2);
   const int WP = round_width(wmax);
   if (WP < 0) return fail(nullptr, CLB_ERR_INVALID, "max(n_meta, mlp_width) = %d exceeds the supported width 32", wmax);
@@ -473,6 +480,7 @@ int clb_create(const clb_config* cfg, clb_handle** out) {
   { const char* dbg = getenv("CLB_DEBUG_SYNC"); h->debug_sync = dbg && dbg[0] == '1'; }
   { const char* dis = getenv("CLB_DISCARD"); h->discard_scratch = !(dis && dis[0] == '0'); }
   { const char* fa = getenv("CLB_FUSED_ADAM"); h->no_fused_adam = fa && fa[0] == '0'; }
+  h->det = cfg->deterministic != 0;
   h->R = cfg->n_refl; h->S = cfg->mc_samples; h->WP = WP; h->KS = 1;
   auto bail = [&](int code) { g_create_error = h->err; delete h; return code; };
 #define CREATE_CUDA(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { fail(h, CLB_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); return bail(CLB_ERR_CUDA); } } while (0)
@@ -490,7 +498,7 @@ int clb_create(const clb_config* cfg, clb_handle** out) {
                   !(t16 && t16[0] == '0') && !(no_tc && no_tc[0] == '1'); }
   // k_obs_pp (one CTA per SM, two tiles ping-ponging through a dedicated issuer warp) is parity-green but measured slower than
   // k_obs_tc2 on B200 (18.7 vs 16.8 ms: two warps per scheduler cannot cover the ALU / TMEM latencies); opt-in with CLB_PP=1
-  { const char* ppe = getenv("CLB_PP"); h->use_pp = h->use_tc2 && cfg->image_layers == 0 && cfg->mlp_layers > 0 && (ppe && ppe[0] == '1'); }
+  { const char* ppe = getenv("CLB_PP"); h->use_pp = h->use_tc2 && cfg->image_layers == 0 && cfg->mlp_layers > 0 && (ppe && ppe[0] == '1') && !cfg->deterministic; }
   h->obs_threads = (h->use_tc || h->use_tc16) ? tc::kThreads : kObsThreads;      // = observation rows per CTA tile
   switch (WP) {
     case 8: h->smem_obs = ObsSmem<8>::bytes(h->NL, false, cfg->image_layers); break;
@@ -630,8 +638,9 @@ int clb_set_observations(clb_handle* h, int64_t n, int64_t n_total, const int64_
     // tensor-core kernels: the CTAs accumulate with REDs, so several of them can share one partial buffer -- a quarter as
     // many buffers as CTAs keeps the L2 footprint (and the persisting carve-out) small without measurable contention
     h->n_partials = h->use_pp ? std::max(1, h->grid_obs / 2) : (h->use_tc16 || h->use_tc2) ? std::max(1, h->grid_obs / 4) : h->grid_obs;
-    const size_t pbytes = h->use_tc16 ? sizeof(float) * (size_t)h->n_partials * h->NL * tc16::PSLOT16
-                          : h->use_tc2 ? sizeof(float) * (size_t)h->n_partials * h->NL * (32 * 32 + 32)
+    if (h->det) h->n_partials = h->grid_obs;          // exclusive buffers: one writer per address
+    const size_t pbytes = h->use_tc16 ? sizeof(float) * (size_t)h->n_partials * h->NL * (h->det ? tc16::PSLOT16_DET : tc16::PSLOT16)
+                          : h->use_tc2 ? sizeof(float) * (size_t)h->n_partials * h->NL * (h->det ? tc::kPslotDet : 32 * 32 + 32)
                                        : sizeof(double) * (size_t)h->grid_obs * h->KS * partial_row_size(h->NL, h->WP);
     const size_t pb = (pbytes + 255) & ~(size_t)255;
     const size_t sbytes = sizeof(float4) * (size_t)h->grid_obs * (h->use_pp ? 2 : 1) * std::max(1, c.mlp_layers + c.image_layers) * ((h->use_tc16 ? 16 : h->WP) / 4) * h->obs_threads;
@@ -661,6 +670,25 @@ int clb_set_observations(clb_handle* h, int64_t n, int64_t n_total, const int64_
     const size_t nb = (size_t)std::max(1, c.mlp_layers) * (h->use_tc16 ? 6 * (size_t)tc16::kImg16 : 4 * (size_t)tc::kImgBytes);
     CLB_CUDA(h, h->wimg.alloc(nb));
     CLB_CUDA(h, cudaMemsetAsync(h->wimg.p, 0, nb, h->stream));
+  }
+  if (h->det) {
+    // CSR of the padded row positions of every reflection, in row order: the fixed summation order of k_gz_reduce
+    std::vector<int32_t> ptr((size_t)h->R + 1, 0), rows((size_t)n);
+    for (int64_t sidx = 0; sidx < n; ++sidx) ptr[(size_t)refl_id[plan.perm[sidx]] + 1]++;
+    for (int64_t r = 0; r < h->R; ++r) ptr[r + 1] += ptr[r];
+    {
+      std::vector<int32_t> cur(ptr.begin(), ptr.end() - 1);
+      std::vector<std::pair<int64_t, int64_t>> order((size_t)n);      // (padded position, reflection): ascending position within a reflection
+      for (int64_t sidx = 0; sidx < n; ++sidx) order[sidx] = {plan.pos[sidx], refl_id[plan.perm[sidx]]};
+      std::sort(order.begin(), order.end());
+      for (const auto& pr : order) rows[cur[pr.second]++] = (int32_t)pr.first;
+    }
+    CLB_CUDA(h, h->refl_ptr.alloc(sizeof(int32_t) * ptr.size())); CLB_CUDA(h, h->refl_rows.alloc(sizeof(int32_t) * rows.size()));
+    CLB_CUDA(h, cudaMemcpyAsync(h->refl_ptr.p, ptr.data(), sizeof(int32_t) * ptr.size(), cudaMemcpyHostToDevice, h->stream));
+    CLB_CUDA(h, cudaMemcpyAsync(h->refl_rows.p, rows.data(), sizeof(int32_t) * rows.size(), cudaMemcpyHostToDevice, h->stream));
+    CLB_CUDA(h, h->dzf_rows.alloc(sizeof(float) * (size_t)npad * h->S));
+    CLB_CUDA(h, h->ll_part.alloc(sizeof(double) * h->grid_obs));
+    CLB_CUDA(h, cudaStreamSynchronize(h->stream));
   }
   h->have_obs = true;
   return clb_upload_observations(h);
@@ -917,8 +945,11 @@ static int step_begin_impl(clb_handle* h, const float* inj_u, const float* inj_e
     a.R = R; a.S = S; a.eps = c.epsilon; a.cq = cq; a.seed = c.seed; a.step = h->step_counter;
     if (!h->eval_mode) { CLB_CUDA(h, h->bwd_coef.alloc(sizeof(float4) * (size_t)R * S)); a.bwd_coef = h->bwd_coef.as<float4>(); }
     const int64_t nthr = ((R + 3) / 4) * S;          // four reflections per thread
-    k_refl_sample<<<(unsigned)((nthr + 255) / 256), 256, 0, st>>>(a, (R % 4 == 0) ? 1 : 0);
+    const unsigned nblk = (unsigned)((nthr + 255) / 256);
+    if (h->det) { CLB_CUDA(h, h->kl_part.alloc(sizeof(double) * nblk)); a.kl_part = h->kl_part.as<double>(); h->kl_blocks = (int)nblk; }
+    k_refl_sample<<<nblk, 256, 0, st>>>(a, (R % 4 == 0) ? 1 : 0);
     CLB_LAUNCHED(h);
+    if (h->det) { k_sum_partials<<<1, 32, 0, st>>>(h->kl_part.as<double>(), (int)nblk, (int)nblk, 1, h->acc.as<double>() + ACC_LOGQ_MINUS_LOGP); CLB_LAUNCHED(h); }
   }
   if (dw) {
     DwArgs a{};
@@ -984,18 +1015,31 @@ static int step_begin_impl(clb_handle* h, const float* inj_u, const float* inj_e
     a.seed = c.seed; a.step = h->step_counter; a.laue = c.laue; a.train_mlp = train_mlp ? 1 : 0;
     a.discard_scratch = h->discard_scratch ? 1 : 0;
     a.n_partials = h->n_partials;
+    a.det = h->det ? 1 : 0;
+    if (h->det) {
+      a.dzf_rows = h->dzf_rows.as<float>(); a.ll_part = h->ll_part.as<double>();
+      CLB_CUDA(h, cudaMemsetAsync(h->ll_part.p, 0, sizeof(double) * h->grid_obs, st));
+    }
     if (h->timing) {
       while (h->ev.size() < h->ev_used + 2) { cudaEvent_t e; CLB_CUDA(h, cudaEventCreate(&e)); h->ev.push_back(e); }
       CLB_CUDA(h, cudaEventRecord(h->ev[h->ev_used], st));
     }
     CLB_CUDA(h, dispatch_obs(h, a)); h->obs_launches++; CLB_LAUNCHED(h);
+    if (h->det) {
+      k_sum_partials<<<1, 32, 0, st>>>(h->ll_part.as<double>(), h->grid_obs, h->grid_obs, 1, h->acc.as<double>() + ACC_LL); CLB_LAUNCHED(h);
+      if (!h->eval_mode) {
+        k_gz_reduce<<<(unsigned)((R * S + 255) / 256), 256, 0, st>>>(h->dzf_rows.as<float>(), h->refl_ptr.as<int32_t>(), h->refl_rows.as<int32_t>(),
+                                                                    h->gz.as<float>(), R, S, h->n_rows);
+        CLB_LAUNCHED(h);
+      }
+    }
     if (h->copy_stream) CLB_CUDA(h, cudaEventRecord(h->ev_rows_free[h->cur_rows], st));   // the row buffer of this step may be refilled after this point
     if (h->timing) { CLB_CUDA(h, cudaEventRecord(h->ev[h->ev_used + 1], st)); h->ev_used += 2; }
   }
   if (train_mlp) {
     const int np = h->lay.n_params;
-    if (h->use_tc16) k_reduce_partials16<<<(np + 255) / 256, 256, 0, st>>>(h->partials.as<float>(), h->n_partials, h->lay, grad + h->goff[CLB_GROUP_MLP]);
-    else if (h->use_tc2) k_reduce_partials32<<<(np + 255) / 256, 256, 0, st>>>(h->partials.as<float>(), h->n_partials, h->lay, grad + h->goff[CLB_GROUP_MLP]);
+    if (h->use_tc16) k_reduce_partials16<<<(np + 255) / 256, 256, 0, st>>>(h->partials.as<float>(), h->n_partials, h->lay, grad + h->goff[CLB_GROUP_MLP], h->det ? 1 : 0);
+    else if (h->use_tc2) k_reduce_partials32<<<(np + 255) / 256, 256, 0, st>>>(h->partials.as<float>(), h->n_partials, h->lay, grad + h->goff[CLB_GROUP_MLP], h->det ? 1 : 0);
     else k_reduce_partials<<<(np + 255) / 256, 256, 0, st>>>(h->partials.as<double>(), h->grid_obs * h->KS, h->lay, h->WP, grad + h->goff[CLB_GROUP_MLP]);
     CLB_LAUNCHED(h);
   }
@@ -1017,8 +1061,11 @@ static int step_begin_impl(clb_handle* h, const float* inj_u, const float* inj_e
     }
     a.alpha = adam_alpha_host(c, h->adam_t + 1); a.beta1 = c.beta_1; a.beta2 = c.beta_2; a.adam_eps = c.adam_epsilon; a.clipvalue = c.clipvalue;
     a.stop_step = h->stop_step.as<int>(); a.step_index = (int)h->step_counter;
-    k_refl_backward<<<(unsigned)(((R + 3) / 4 + 255) / 256), 256, 0, st>>>(a, (R % 4 == 0) ? 1 : 0);
+    const unsigned nblk = (unsigned)(((R + 3) / 4 + 255) / 256);
+    if (h->det) { CLB_CUDA(h, h->ss_part.alloc(sizeof(double) * 4 * nblk)); a.ss_part = h->ss_part.as<double>(); }
+    k_refl_backward<<<nblk, 256, 0, st>>>(a, (R % 4 == 0) ? 1 : 0);
     CLB_LAUNCHED(h);
+    if (h->det) { k_sum_partials<<<1, 32, 0, st>>>(h->ss_part.as<double>(), (int)nblk, (int)nblk, 4, h->var_sums.as<double>()); CLB_LAUNCHED(h); }
   }
   h->in_step = true;
   return CLB_OK;
@@ -1032,7 +1079,7 @@ static int step_norms_impl(clb_handle* h) {
   int64_t maxsz = 1;
   for (int v = 2; v < h->vt.n_vars; ++v) maxsz = std::max(maxsz, h->vt.size[v]);     // variables 0 / 1 (the surrogate) are summed in k_refl_backward
   const int chunks = (int)std::min<int64_t>((maxsz + 256 * 8 - 1) / (256 * 8), 4 * h->n_sms);
-  const dim3 grid(std::max(chunks, 1), h->vt.n_vars);
+  const dim3 grid(h->det ? 1 : std::max(chunks, 1), h->vt.n_vars);      // deterministic: one block per variable, no cross-block atomics
   if (h->comm == nullptr) {
     k_var_sumsq<<<grid, 256, 0, st>>>(h->grad.as<float>(), h->vt, h->var_sums.as<double>(), 0, 1);      // the surrogate's sums come from k_refl_backward
     CLB_LAUNCHED(h);

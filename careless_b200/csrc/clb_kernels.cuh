@@ -52,6 +52,7 @@ struct ReflArgs {
   // truncated-normal arithmetic -- {mu dz/dmu, (sigma - eps) dz/dsigma, cq mu dlogq/dmu, cq (sigma - eps) dlogq/dsigma}
   float4* bwd_coef;
   double* acc;
+  double* kl_part;                                // deterministic mode: one partial per block (summed in a fixed order), else null
   int64_t R; int S; float eps; float cq;          // cq: KL coefficient per element
   uint64_t seed; uint32_t step;
 };
@@ -128,7 +129,7 @@ __global__ void __launch_bounds__(256) k_refl_sample(ReflArgs a, int vec) {
   if (threadIdx.x == 0) {
     double t = 0.0;
     for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += sm[i];
-    atomicAdd(&a.acc[ACC_LOGQ_MINUS_LOGP], t);
+    if (a.kl_part != nullptr) a.kl_part[blockIdx.x] = t; else atomicAdd(&a.acc[ACC_LOGQ_MINUS_LOGP], t);
   }
 }
 
@@ -224,6 +225,12 @@ struct ObsArgs {
   uint64_t seed; uint32_t step;
   int laue; int train_mlp;
   int n_partials;                  // tensor-core kernels: number of FP32 partial buffers the CTAs share (blockIdx % n_partials)
+  // Deterministic mode (clb_config.deterministic): no floating-point atomics whose order could differ between runs.
+  //  * dzf_rows (S, n_rows): every row's dL/dz_f is written out and k_gz_reduce sums each reflection's rows in a fixed order;
+  //  * ll_part [grid]: per-CTA log-likelihood sums, added up in a fixed order by k_pack_scalars;
+  //  * det: the CTA's partial buffer is exclusive (n_partials == grid) and every address receives REDs from ONE thread only
+  //    (separate slots for the a_hi / a_lo rows of a kernel gradient and for every warp's bias sums), in program order.
+  float* dzf_rows; double* ll_part; int det;
   int discard_scratch;             // 1: drop the activation scratch lines from L2 once the backward pass has consumed them (discard.global.L2)
 };
 
@@ -507,8 +514,12 @@ __device__ __forceinline__ void obs_epilogue(const ObsArgs& a, int64_t row, bool
     const float d_zs = G * zf * zf;
     const float d_zf = G * zs * 2.0f * zf;
     // segmented reduction of dL/dz_f over runs of equal refl_id, one atomic per run
-    const float tot = warp_segsum(d_zf, refl_runs, lane);
-    if (active && refl_runs.tail) atomicAdd(&a.gz[(size_t)s * a.R + refl], tot);
+    if (a.dzf_rows != nullptr) {       // deterministic mode: k_gz_reduce adds the rows of a reflection in a fixed order
+      if (active) a.dzf_rows[(size_t)s * a.n_rows + row] = d_zf;
+    } else {
+      const float tot = warp_segsum(d_zf, refl_runs, lane);
+      if (active && refl_runs.tail) atomicAdd(&a.gz[(size_t)s * a.R + refl], tot);
+    }
     const float d_base = aimg * d_zs;
     d_aimg += base * d_zs;
     dmu += d_base;
@@ -526,6 +537,30 @@ __device__ __forceinline__ void obs_epilogue(const ObsArgs& a, int64_t row, bool
       atomicAdd(&a.g_lik[2], a.cl * ev_gb * sigmoidf(a.theta_lik[2]));
     }
   }
+}
+
+__device__ __forceinline__ void flush_ll(double* ll_part, double* acc, double t) {     // (pointers by value: a reference to the kernel's parameter struct would force a local copy)
+  if (ll_part != nullptr) ll_part[blockIdx.x] = t; else atomicAdd(&acc[ACC_LL], t);
+}
+
+// dL/dz_f of every reflection from the per-row values, in the fixed order of the host-built CSR (deterministic mode).
+__global__ void __launch_bounds__(256) k_gz_reduce(const float* dzf_rows, const int32_t* refl_ptr, const int32_t* refl_rows,
+                                                   float* gz, int64_t R, int S, int64_t n_rows) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= R * S) return;
+  const int64_t r = idx % R, s = idx / R;
+  float sum = 0.f;
+  for (int32_t i = refl_ptr[r]; i < refl_ptr[r + 1]; ++i) sum += dzf_rows[(size_t)s * n_rows + refl_rows[i]];
+  gz[idx] += sum;
+}
+
+// Fixed-order sum of per-block partials (deterministic mode): out[q] += sum_b part[q * stride + b].
+__global__ void k_sum_partials(const double* part, int n_blocks, int stride, int n_quantities, double* out) {
+  const int q = threadIdx.x;
+  if (q >= n_quantities) return;
+  double t = 0.0;
+  for (int b = 0; b < n_blocks; ++b) t += part[(size_t)q * stride + b];
+  out[q] += t;
 }
 
 // TC = true (WP == 32 only): the forward and dX products of the hidden layers run on the tensor cores
@@ -789,7 +824,7 @@ __global__ void __launch_bounds__(TC ? tc::kThreads : kObsThreads, TC ? 2 : 1) k
   if (tid == 0) {
     double t = 0.0;
     for (int i = 0; i < T / 32; ++i) t += red[i];
-    atomicAdd(&a.acc[ACC_LL], t);
+    flush_ll(a.ll_part, a.acc, t);
   }
   if constexpr (TC) {
     if (tid < 32) tc::tmem_dealloc(*tc_slot);
@@ -944,12 +979,16 @@ __global__ void __launch_bounds__(tc::kThreads2, 2) k_obs_tc2(ObsArgs a) {
     tcx.pass = 0; tcx.wphase = 0;
     tcx.cnt_chain = tc::smem_u32(tc_slot + 2); tcx.cnt_dw = tc::smem_u32(tc_slot + 3); tcx.n_warps_m1 = T / 32 - 1;
     tcx.dw_pending = false; tcx.pend_wk = nullptr; tcx.pend_ilw = 0; tcx.pend_bk = nullptr;
+    tcx.lo_off = a.det ? WP * WP : 0;
   }
   // ready-made images of hidden layer k in global memory: dir 0 = forward (B[n][k] = W[k][n]), 1 = backward; null for
   // image layers, whose per-tile kernels are turned into images by the threads themselves
   constexpr size_t IMGF = tc::kImgBytes / 4;
   auto gimg = [&](int k, int dir) -> const float* { return (!IL || k < L) ? a.wimg + ((size_t)(k * 2 + dir) * 2) * IMGF : nullptr; };
-  constexpr int PSLOT = WP * WP + WP;                        // one layer of the CTA's FP32 partial: kernel [32][32], bias [32]
+  // one layer of the CTA's FP32 partial: kernel [32][32], bias [32]; deterministic mode: kernel from a_hi rows, kernel from a_lo
+  // rows, bias per row quarter [4][32] (see ObsArgs::det)
+  const int PSLOT = a.det ? tc::kPslotDet : WP * WP + WP;
+  const int BOFF = a.det ? 2 * WP * WP + 32 * ((tid >> 5) & 3) : WP * WP;      // this warp's bias slot inside a layer's slot
   float* part32 = a.partials32 + (size_t)(blockIdx.x % a.n_partials) * NL * PSLOT;     // shared by a few CTAs (REDs): small L2 footprint
   float4* scr = a.scratch + (size_t)blockIdx.x * LT * NC * TR;
   double ll_sum = 0.0;
@@ -1053,7 +1092,7 @@ __global__ void __launch_bounds__(tc::kThreads2, 2) k_obs_tc2(ObsArgs a) {
     for (int j = 0; j < HW; ++j) dp[j] = 0.f;
     if (hf == 0) { dp[0] = dmu; dp[1] = drho; }
     // head: dW_out = a_L^T [dmu, drho]
-    tc_layer_backward2(tcx, dp, h, false, nullptr, tc_img, nullptr, part32 + (size_t)L * PSLOT, part32 + (size_t)L * PSLOT + WP * WP, 0);
+    tc_layer_backward2(tcx, dp, h, false, nullptr, tc_img, nullptr, part32 + (size_t)L * PSLOT, part32 + (size_t)L * PSLOT + BOFF, 0);
 #pragma unroll
     for (int i = 0; i < HW; ++i) {       // delta a_LT from the head, times leaky' of the last hidden layer (sign of its output h)
       const float2 w = *reinterpret_cast<const float2*>(&Whead[(HW * hf + i) * 2]);
@@ -1071,7 +1110,7 @@ __global__ void __launch_bounds__(tc::kThreads2, 2) k_obs_tc2(ObsArgs a) {
       }
       const int il_w = is_il ? a.il_width : 0;
       float* wk = is_il ? il_gk : part32 + (size_t)k * PSLOT;
-      float* bk2 = is_il ? il_gb : part32 + (size_t)k * PSLOT + WP * WP;
+      float* bk2 = is_il ? il_gb : part32 + (size_t)k * PSLOT + BOFF;
       float ain[HW];
 #pragma unroll
       for (int i = 0; i < HW; ++i) ain[i] = nxt[i];
@@ -1092,7 +1131,7 @@ __global__ void __launch_bounds__(tc::kThreads2, 2) k_obs_tc2(ObsArgs a) {
   if (tid == 0) {
     double t = 0.0;
     for (int i = 0; i < T / 32; ++i) t += red[i];
-    atomicAdd(&a.acc[ACC_LL], t);
+    flush_ll(a.ll_part, a.acc, t);
   }
   if (tid < 32) tc::tmem_dealloc(*tc_slot);
 }
@@ -1184,22 +1223,26 @@ __global__ void __launch_bounds__(256) k_pack_images(const float* theta_mlp, Mlp
 
 // k_obs_tc2's partials: [rows][n_layers][32*32 + 32] FP32 (kernel [in][out] padded to 32 x 32, then the bias), summed over
 // the CTAs in FP64 in a fixed order.
-__global__ void __launch_bounds__(256) k_reduce_partials32(const float* partials, int rows, MlpLayout lay, float* grad) {
+__global__ void __launch_bounds__(256) k_reduce_partials32(const float* partials, int rows, MlpLayout lay, float* grad, int det) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= lay.n_params) return;
-  const int PSLOT = 32 * 32 + 32, PP = lay.n_layers * PSLOT;
+  const int PSLOT = det ? tc::kPslotDet : 32 * 32 + 32, PP = lay.n_layers * PSLOT;
+  const int BIAS = det ? 2048 : 1024;
+  int extra = 0, n_extra = 0;            // deterministic layout: further slots to add (a_lo rows; the other row quarters' bias sums)
   int src = -1;
   for (int k = 0; k < lay.n_layers; ++k) {
     const int nk = lay.in_dim[k] * lay.out_dim[k];
     if (p >= lay.koff[k] && p < lay.koff[k] + nk) {
       const int i = (p - lay.koff[k]) / lay.out_dim[k], j = (p - lay.koff[k]) % lay.out_dim[k];
       src = k * PSLOT + tc::dw_slot32(i, j);
+      if (det) { extra = 1024; n_extra = 1; }
       break;
     }
-    if (p >= lay.boff[k] && p < lay.boff[k] + lay.out_dim[k]) { src = k * PSLOT + 1024 + (p - lay.boff[k]); break; }
+    if (p >= lay.boff[k] && p < lay.boff[k] + lay.out_dim[k]) { src = k * PSLOT + BIAS + (p - lay.boff[k]); if (det) { extra = 32; n_extra = 3; } break; }
   }
   double acc = 0.0;
-  if (src >= 0) for (int r = 0; r < rows; ++r) acc += (double)partials[(size_t)r * PP + src];
+  if (src >= 0) for (int r = 0; r < rows; ++r)
+    for (int e = 0; e <= n_extra; ++e) acc += (double)partials[(size_t)r * PP + src + e * extra];
   grad[p] = (float)acc;
 }
 
@@ -1237,6 +1280,7 @@ struct ReflBwdArgs {
   int64_t R; int S;
   // fused tail of the per-reflection chain (rows A8 / A9 on the surrogate slice)
   double* var_sums;             // [0..1] raw / filtered sum of squares of g_loc, [2..3] of g_scale (null: do not accumulate)
+  double* ss_part;              // deterministic mode: [4][gridDim.x] per-block partials instead of atomics on var_sums
   // Adam on (v_loc, v_scale) inside this kernel: legal whenever no NORM-based clipping is configured, because then the update
   // of an element depends on nothing but its own gradient ([3P] tf_keras Adam.update_step; non-finite elements -> 0,
   // variational.py:208).  alpha = lr sqrt(1 - b2^t) / (1 - b1^t) comes from the host; stop_step as in k_adam.
@@ -1306,7 +1350,8 @@ __global__ void __launch_bounds__(256) k_refl_backward(ReflBwdArgs a, int vec) {
     if (threadIdx.x < 4) {
       double t = 0.0;
       for (int i = 0; i < 8; ++i) t += sm[threadIdx.x][i];
-      if (t != 0.0) atomicAdd(&a.var_sums[threadIdx.x], t);      // NaN != 0 is true, so NaN propagates
+      if (a.ss_part != nullptr) a.ss_part[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = t;
+      else if (t != 0.0) atomicAdd(&a.var_sums[threadIdx.x], t);      // NaN != 0 is true, so NaN propagates
     }
   }
 }

@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(pp::kThreadsPP, 1) k_obs_pp(ObsArgs a) {
   if (tid == 0) {
     double t = 0.0;
     for (int i = 0; i < kWorkers / 32; ++i) t += red[i];
-    atomicAdd(&a.acc[ACC_LL], t);
+    flush_ll(a.ll_part, a.acc, t);
   }
   if (is_issuer) { fence_after(); tmem_dealloc512(tbase); }
 }

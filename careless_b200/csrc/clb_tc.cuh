@@ -140,6 +140,7 @@ struct Ctx {
   // barrier-free hand-over (k_obs_tc2): arrival counters in shared memory; the deferred dW collection of the previous layer
   uint32_t cnt_chain, cnt_dw, n_warps_m1;
   float* pend_wk; float* pend_bk; int pend_ilw; bool dw_pending;
+  int lo_off;                          // deterministic mode: float offset of the slot that takes the a_lo rows of a kernel gradient (else 0)
 };
 
 __device__ __forceinline__ void split32(const float (&x)[32], uint32_t (&hi)[32], uint32_t (&lo)[32]) {
@@ -424,6 +425,7 @@ __host__ __device__ inline int dw_slot32(int i, int j) {
 // k_obs_tc2's dW product has M = 128 rows: [a_hi (32) | a_lo (32) | ONES (32) | unused (32)] -- an M = 64 instruction
 // costs the tensor pipe exactly as much, and the row of ones turns the bias gradient (column sums of delta-p) into one more
 // row of the same product instead of ~55 shuffle / select / add instructions per thread and layer.
+constexpr int kPslotDet = 2 * 1024 + 4 * 32;   // deterministic layout of one layer's slot: [kernel from a_hi rows | from a_lo rows | bias [4 quarters][32]]
 constexpr uint32_t kIdescDw128 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
 
 // dW rows live at lanes (r % 16) + 32 (r / 16): in every warp the lanes < 16 hold row r = 16 (warp % 4) + lane, i.e.
@@ -492,7 +494,7 @@ __device__ __forceinline__ void collect_dw_red(Ctx& c, float* wk, int il_w, floa
 #pragma unroll
     for (int k = 0; k < 16; ++k) f[k] = __uint_as_float(v0[k]) + __uint_as_float(v1[k]);
     if (il_w == 0) {
-      float4* dst = reinterpret_cast<float4*>(wk) + (4 * c.hf) * 32 + i;               // dw_slot32(i, 16 hf + 4 qq) / 4
+      float4* dst = reinterpret_cast<float4*>(wk + (q >= 2 ? c.lo_off : 0)) + (4 * c.hf) * 32 + i;      // dw_slot32(i, 16 hf + 4 qq) / 4
 #pragma unroll
       for (int qq = 0; qq < 4; ++qq) atomicAdd(dst + qq * 32, make_float4(f[4 * qq], f[4 * qq + 1], f[4 * qq + 2], f[4 * qq + 3]));
     } else if (i < il_w) {

@@ -26,6 +26,7 @@ constexpr uint32_t kDwImg16 = kRows * 128;         // one MN-major operand image
 constexpr uint32_t kIdesc16 = (1u << 4) | (2u << 7) | (2u << 10) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
 constexpr uint32_t kIdescDw16 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((32u >> 3) << 17) | ((64u >> 4) << 24);
 constexpr int PSLOT16 = 16 * 16 + 16;              // one layer of the CTA's FP32 partial
+constexpr int PSLOT16_DET = 2 * 256 + 4 * 16;      // deterministic mode: [kernel from a_hi rows | from a_lo rows | bias per warp [4][16]]
 
 __device__ __forceinline__ uint64_t make_desc16(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((kLBO16 >> 4) & 0x3FFF) << 16) |
@@ -245,7 +246,7 @@ __device__ __forceinline__ void issue_bwd16(Ctx16& c, const float (&dp)[16], con
 
 // D_dw rows 0..15 (a_hi) = lanes 0..15 of warp 0, rows 16..31 (a_lo) = lanes 0..15 of warp 1; 32 columns [.dp_hi | .dp_lo].
 // il_w > 0: an image layer's kernel gradient, stored (out, in) with width il_w in that image's slot (scalar REDs).
-__device__ __forceinline__ void collect_dw16(Ctx16& c, float* wk, int il_w = 0) {
+__device__ __forceinline__ void collect_dw16(Ctx16& c, float* wk, int il_w = 0, int lo_off = 0) {
   mbar_wait(c.mbar_dw, c.parity_dw);
   c.parity_dw ^= 1u;
   fence_after();
@@ -256,7 +257,7 @@ __device__ __forceinline__ void collect_dw16(Ctx16& c, float* wk, int il_w = 0) 
     wait_ld();
     if (lane < 16 && wk != nullptr) {
       if (il_w == 0) {          // slot layout [j / 4][i][j % 4]: each RED instruction covers 256 contiguous bytes
-        float4* dst = reinterpret_cast<float4*>(wk) + lane;
+        float4* dst = reinterpret_cast<float4*>(wk + (warp == 1 ? lo_off : 0)) + lane;      // warp 1 holds the a_lo rows
 #pragma unroll
         for (int q = 0; q < 4; ++q)
           atomicAdd(dst + q * 16, make_float4(__uint_as_float(v[4 * q]) + __uint_as_float(v[16 + 4 * q]),
@@ -327,7 +328,10 @@ __global__ void __launch_bounds__(tc16::kRows, 4) k_obs_tc16(ObsArgs a) {
   // [hi, mid, lo] / [hi, lo, -] of hidden layer k; null for image layers, whose per-tile kernels the threads turn into images
   auto gimg = [&](int k, int dir) -> const float* { return (!IL || k < L) ? a.wimg + ((size_t)(k * 2 + dir) * 3) * IMGF : nullptr; };
   auto wsrc = [&](int k) -> const float* { return (IL && k >= L) ? Wimg + (size_t)(k - L) * WP * WP : nullptr; };
-  float* part32 = a.partials32 + (size_t)(blockIdx.x % a.n_partials) * NL * PSLOT16;
+  const int PSLOT = a.det ? PSLOT16_DET : PSLOT16;
+  const int BOFF = a.det ? 2 * WP * WP + 16 * (tid >> 5) : WP * WP;       // this warp's bias slot inside a layer's slot
+  const int lo_off = a.det ? WP * WP : 0;
+  float* part32 = a.partials32 + (size_t)(blockIdx.x % a.n_partials) * NL * PSLOT;
   float4* scr = a.scratch + (size_t)blockIdx.x * LT * NC * TR;
   double ll_sum = 0.0;
   float ev_f = 1.f, ev_a = 0.f, ev_b = 0.f;
@@ -410,13 +414,13 @@ __global__ void __launch_bounds__(tc16::kRows, 4) k_obs_tc16(ObsArgs a) {
 #pragma unroll
         for (int j = 0; j < WP; ++j) dp[j] = ain[j] > 0.f ? dp[j] : kLeak * dp[j];
       }
-      collect_dw16(c, wk, il_w);
+      collect_dw16(c, wk, il_w, lo_off);
     };
     if (LT > 0) load_act(nxt, LT - 1);
 #pragma unroll
     for (int j = 0; j < WP; ++j) dp[j] = 0.f;
     dp[0] = dmu; dp[1] = drho;
-    layer_backward(h, false, nullptr, 0u, part32 + (size_t)L * PSLOT16, part32 + (size_t)L * PSLOT16 + WP * WP, 0, nullptr, nullptr);     // head: dW_out = a_L^T [dmu, drho]
+    layer_backward(h, false, nullptr, 0u, part32 + (size_t)L * PSLOT, part32 + (size_t)L * PSLOT + BOFF, 0, nullptr, nullptr);     // head: dW_out = a_L^T [dmu, drho]
 #pragma unroll
     for (int i = 0; i < WP; ++i) {         // delta a_LT from the head, times leaky' of the last hidden layer (sign of its output h)
       const float2 w = *reinterpret_cast<const float2*>(&Whead[i * 2]);
@@ -430,7 +434,7 @@ __global__ void __launch_bounds__(tc16::kRows, 4) k_obs_tc16(ObsArgs a) {
       if (k > 0) load_act(nxt, k - 1);
       const float* next = (k > 1) ? gimg(k - 1, 1) : (more_tiles ? gimg(0, 0) : nullptr);
       const bool is_il = IL && k >= L;
-      float* wk = part32 + (size_t)k * PSLOT16; float* bk2 = wk + WP * WP; int il_w = 0;
+      float* wk = part32 + (size_t)k * PSLOT; float* bk2 = wk + BOFF; int il_w = 0;
       if (is_il) {            // image layers send their gradient to the tile's image slot
         const int w = a.il_width;
         const size_t lstride = (size_t)a.il_n_images * w * (w + 1);
@@ -450,7 +454,7 @@ __global__ void __launch_bounds__(tc16::kRows, 4) k_obs_tc16(ObsArgs a) {
   if (tid == 0) {
     double t = 0.0;
     for (int i = 0; i < T / 32; ++i) t += red[i];
-    atomicAdd(&a.acc[ACC_LL], t);
+    flush_ll(a.ll_part, a.acc, t);
   }
   if (tid < 32) tmem_dealloc16(*slot);
 }
@@ -474,22 +478,26 @@ __global__ void __launch_bounds__(256) k_pack_images16(const float* theta_mlp, M
   else base[IMGF + off] = r;                                                     // backward: [hi, lo]
 }
 
-__global__ void __launch_bounds__(256) k_reduce_partials16(const float* partials, int rows, MlpLayout lay, float* grad) {
+__global__ void __launch_bounds__(256) k_reduce_partials16(const float* partials, int rows, MlpLayout lay, float* grad, int det) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= lay.n_params) return;
-  const int PSLOT = tc16::PSLOT16, PP = lay.n_layers * PSLOT;
+  const int PSLOT = det ? tc16::PSLOT16_DET : tc16::PSLOT16, PP = lay.n_layers * PSLOT;
+  const int BIAS = det ? 512 : 256;
+  int extra = 0, n_extra = 0;
   int src = -1;
   for (int k = 0; k < lay.n_layers; ++k) {
     const int nk = lay.in_dim[k] * lay.out_dim[k];
     if (p >= lay.koff[k] && p < lay.koff[k] + nk) {
       const int i = (p - lay.koff[k]) / lay.out_dim[k], j = (p - lay.koff[k]) % lay.out_dim[k];
       src = k * PSLOT + (((j >> 2) * 16 + i) << 2) + (j & 3);
+      if (det) { extra = 256; n_extra = 1; }
       break;
     }
-    if (p >= lay.boff[k] && p < lay.boff[k] + lay.out_dim[k]) { src = k * PSLOT + 256 + (p - lay.boff[k]); break; }
+    if (p >= lay.boff[k] && p < lay.boff[k] + lay.out_dim[k]) { src = k * PSLOT + BIAS + (p - lay.boff[k]); if (det) { extra = 16; n_extra = 3; } break; }
   }
   double acc = 0.0;
-  if (src >= 0) for (int r = 0; r < rows; ++r) acc += (double)partials[(size_t)r * PP + src];
+  if (src >= 0) for (int r = 0; r < rows; ++r)
+    for (int e = 0; e <= n_extra; ++e) acc += (double)partials[(size_t)r * PP + src + e * extra];
   grad[p] = (float)acc;
 }
 

@@ -49,6 +49,7 @@ class EngineConfig:
     stream: int = 0
     rank: int = 0
     world_size: int = 1
+    deterministic: bool = False
 
     def to_c(self) -> L.clb_config:
         c = L.clb_config()
@@ -80,6 +81,7 @@ class EngineConfig:
         c.global_clipnorm = self.global_clipnorm or 0.0
         c.seed = self.seed & 0xFFFFFFFFFFFFFFFF
         c.rank, c.world_size = self.rank, self.world_size
+        c.deterministic = int(self.deterministic)
         return c
 
 

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define CLB_ABI_VERSION 3
+#define CLB_ABI_VERSION 4
 
 typedef struct clb_handle clb_handle;
 
@@ -89,6 +89,10 @@ typedef struct {
   uint64_t seed;              /* Philox key for in-kernel draws (--seed, args/tf_options.py:50-54) */
   int32_t rank, world_size;   /* reflection-partitioned data parallelism; 0,1 on one GPU */
   int32_t image_layers;       /* NeuralImageScaler per-image dense layers (--image-layers, args/scaling.py:33-37); needs n_images */
+  int32_t deterministic;      /* 1: bitwise run-to-run reproducible steps -- no floating-point atomics whose order could vary: dL/dz_f is
+                                 reduced per reflection in a fixed row order, weight-gradient partials are exclusive per CTA with
+                                 one writer per address, scalar sums are added in block order.  Supported for MLPScaler models with
+                                 the Wilson prior (no image scales / image layers / Ev11 / DoubleWilson); costs time, see DESIGN.md */
   int32_t refine_uncertainties; /* Ev11 error model (--refine-uncertainties, likelihoods/mono.py:39-73, laue.py:49-65): group
                                  CLB_GROUP_LIKELIHOOD holds the raw (pre-softplus) Sdfac, Sdadd, SdB, each initialised to 1 */
 } clb_config;

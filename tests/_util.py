@@ -34,7 +34,7 @@ def il_flat(params, cfg):
 
 def build(problem, *, mlp_width, mlp_layers, likelihood="normal", dof=None, laue=False, prior="wilson", image_layers=0, refine_uncertainties=False,
           mc_samples=1, kl_weight=None, scale_bijector="exp", scale_shift=None, image_scales=False,
-          optimize_dw_r=False, sigma=1.0, opt=None, seed=1234, eps=1e-7):
+          optimize_dw_r=False, sigma=1.0, opt=None, seed=1234, eps=1e-7, deterministic=False):
     """(oracle cfg, oracle prior, engine) for a synthetic problem dict from careless_b200.synth."""
     R = len(problem["centric"])
     d = problem["metadata"].shape[1]
@@ -53,7 +53,8 @@ def build(problem, *, mlp_width, mlp_layers, likelihood="normal", dof=None, laue
                         prior=prior, n_asu=int(problem.get("n_asu", 0)), optimize_dw_r=optimize_dw_r,
                         scale_bijector=scale_bijector, scale_shift=scale_shift, epsilon=eps, kl_weight=kl_weight,
                         learning_rate=opt.lr, beta_1=opt.beta1, beta_2=opt.beta2, adam_epsilon=opt.eps,
-                        clipnorm=opt.clipnorm, clipvalue=opt.clipvalue, global_clipnorm=opt.global_clipnorm, seed=seed)
+                        clipnorm=opt.clipnorm, clipvalue=opt.clipvalue, global_clipnorm=opt.global_clipnorm, seed=seed,
+                        deterministic=deterministic)
     eng = Engine(ecfg)
     eng.set_observations(problem["refl_id"], problem["image_id"], problem["metadata"], problem["intensities"],
                          problem["uncertainties"], harmonic_id=problem.get("harmonic_id") if laue else None)

@@ -414,3 +414,48 @@ def test_narrow_tensor_core_kernel(case, monkeypatch):
     else:
         _cmp(synth.make_laue(5000, 600, d=3, n_images=15, seed=64), "tc16-ev11", mlp_width=8, mlp_layers=3, laue=True,
                       likelihood="studentt", dof=6.0, refine_uncertainties=True, mc_samples=2)
+
+
+# ---- deterministic mode (clb_config.deterministic) -------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["w32", "w10", "laue-w12", "w8-fp32"])
+def test_deterministic_mode_is_bitwise_reproducible(case, monkeypatch):
+    """Two runs of the same three steps give bit-identical metrics, gradients, parameters and Adam moments (no float atomics whose
+    order could differ), and the deterministic step still passes the oracle parity criterion."""
+    laue = case.startswith("laue")
+    if laue:
+        p = synth.make_laue(6000, 500, d=3, n_images=12, seed=41)
+        kw = dict(mlp_width=12, mlp_layers=5, laue=True)
+    else:
+        p = synth.make_mono(9000, 700, d=4, n_images=10, seed=42)
+        kw = {"w32": dict(mlp_width=32, mlp_layers=20, likelihood="studentt", dof=12.0),
+              "w10": dict(mlp_width=10, mlp_layers=20, likelihood="studentt", dof=12.0, mc_samples=2),
+              "w8-fp32": dict(mlp_width=8, mlp_layers=4)}[case]
+    if case == "w8-fp32":
+        monkeypatch.setenv("CLB_TC16", "0")
+    runs = []
+    for _ in range(2):
+        ocfg, oprior, eng = U.build(p, deterministic=True, **kw)
+        try:
+            params = U.perturbed_params(ocfg, oprior, np.random.default_rng(7))
+            U.push_params(eng, params, ocfg)
+            hist = eng.step(3)
+            runs.append({"hist": [tuple(h[k] for k in ("loss", "NLL", "F KLDiv", "Grad Norm")) for h in hist],
+                         "g": {g: eng.get_grads(g) for g in ("sf_loc_raw", "sf_scale_raw", "mlp")},
+                         "p": {g: eng.get_params(g) for g in ("sf_loc_raw", "sf_scale_raw", "mlp")},
+                         "m": eng.get_adam_state("mlp")[0]})
+        finally:
+            eng.close()
+    a, b = runs
+    assert a["hist"] == b["hist"]
+    for g in a["g"]:
+        assert np.array_equal(a["g"][g], b["g"][g]), g
+        assert np.array_equal(a["p"][g], b["p"][g]), g
+    assert np.array_equal(a["m"], b["m"])
+    _compare_step(p, f"deterministic-{case}", deterministic=True, **kw)
+
+
+def test_deterministic_mode_rejects_models_with_atomic_gradients():
+    from careless_b200._lib import ClbError
+    from careless_b200.engine import Engine, EngineConfig
+    with pytest.raises(ClbError, match="deterministic"):
+        Engine(EngineConfig(n_refl=10, n_meta=2, mlp_width=4, mlp_layers=2, n_images=3, image_scales=True, deterministic=True))
