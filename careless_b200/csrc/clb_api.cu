@@ -197,7 +197,7 @@ int fail(clb_handle* h, int code, const char* fmt, ...) {
        if ((h)->debug_sync) { fprintf(stderr, "[clb] launch %lld at %s:%d ...", (long long)(h)->total_launches, __FILE__, __LINE__); \
                               fflush(stderr); CLB_CUDA(h, cudaStreamSynchronize((h)->stream)); fprintf(stderr, " done\n"); } } while (0)
 
-int round_width(int w) { return w <= 8 ? 8 : w <= 16 ? 16 : w <= 32 ? 32 : -1; }
+int round_width(int w) { return w <= 8 ? 8 : w <= 16 ? 16 : w <= 32 ? 32 : w <= 64 ? 64 : -1; }
 
 template <int WP, int LIK, bool TC> cudaError_t launch_obs(clb_handle* h, const ObsArgs& a) {
   cudaError_t e = cudaFuncSetAttribute(k_obs<WP, LIK, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_obs);
@@ -240,6 +240,7 @@ cudaError_t dispatch_obs(clb_handle* h, const ObsArgs& a) {
     case 32:
       if (h->use_tc) return lik ? launch_obs<32, 1, true>(h, a) : launch_obs<32, 0, true>(h, a);
       return lik ? launch_obs<32, 1, false>(h, a) : launch_obs<32, 0, false>(h, a);
+    case 64: return lik ? launch_obs<64, 1, false>(h, a) : launch_obs<64, 0, false>(h, a);     // FP32-FMA only (no tensor-core tiling at this width yet)
   }
   return cudaErrorInvalidValue;
 }
@@ -471,7 +472,7 @@ int clb_create(const clb_config* cfg, clb_handle** out) {
                                           "refined uncertainties / DoubleWilson: their gradients are accumulated with atomics)");
   const int wmax = std::max(std::max(cfg->n_meta, cfg->mlp_width), 2);
   const int WP = round_width(wmax);
-  if (WP < 0) return fail(nullptr, CLB_ERR_INVALID, "max(n_meta, mlp_width) = %d exceeds the supported width 32", wmax);
+  if (WP < 0) return fail(nullptr, CLB_ERR_INVALID, "max(n_meta, mlp_width) = %d exceeds the supported width 64", wmax);
 
   clb_handle* h = new clb_handle();
   h->cfg = *cfg;
@@ -503,6 +504,7 @@ int clb_create(const clb_config* cfg, clb_handle** out) {
   switch (WP) {
     case 8: h->smem_obs = ObsSmem<8>::bytes(h->NL, false, cfg->image_layers); break;
     case 16: h->smem_obs = ObsSmem<16>::bytes(h->NL, false, cfg->image_layers); break;
+    case 64: h->smem_obs = ObsSmem<64>::bytes(h->NL, false, cfg->image_layers); break;
     default: h->smem_obs = ObsSmem<32>::bytes(h->NL, h->use_tc, cfg->image_layers); break;
   }
   if (h->use_tc2) h->smem_obs = ObsSmem2::bytes(h->NL, cfg->image_layers);
@@ -665,7 +667,7 @@ int clb_set_observations(clb_handle* h, int64_t n, int64_t n_total, const int64_
       if (cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
     }
   }
-  if (h->use_tc) CLB_CUDA(h, h->wpack.alloc(sizeof(float) * (size_t)std::max(1, c.mlp_layers) * 1024));
+  if (h->use_tc || h->WP == 64) CLB_CUDA(h, h->wpack.alloc(sizeof(float) * (size_t)std::max(1, c.mlp_layers) * h->WP * h->WP));
   if (h->use_tc2 || h->use_tc16) {     // [L][fwd, bwd][hi, lo][image bytes]; the padding bytes of the images stay zero
     const size_t nb = (size_t)std::max(1, c.mlp_layers) * (h->use_tc16 ? 6 * (size_t)tc16::kImg16 : 4 * (size_t)tc::kImgBytes);
     CLB_CUDA(h, h->wimg.alloc(nb));
@@ -971,7 +973,11 @@ static int step_begin_impl(clb_handle* h, const float* inj_u, const float* inj_e
     a.n_rows = h->n_rows; a.n_rows_total = h->n_rows_total; a.d = c.n_meta;
     a.theta_mlp = theta + h->goff[CLB_GROUP_MLP];
     a.theta_img = c.image_scales ? theta + h->goff[CLB_GROUP_IMAGE_SCALES] : nullptr;
-    a.wpack = h->use_tc ? h->wpack.as<float>() : nullptr;
+    a.wpack = (h->use_tc || h->WP == 64) ? h->wpack.as<float>() : nullptr;
+    if (h->WP == 64 && c.mlp_layers > 0) {
+      k_pack_weights<<<(c.mlp_layers * 4096 + 255) / 256, 256, 0, st>>>(a.theta_mlp, h->lay, h->wpack.as<float>(), 64);
+      CLB_LAUNCHED(h);
+    }
     a.wimg = (h->use_tc2 || h->use_tc16) ? h->wimg.as<float>() : nullptr;
     if (h->use_tc16 && c.mlp_layers > 0) {
       k_pack_images16<<<(c.mlp_layers * 512 + 255) / 256, 256, 0, st>>>(a.theta_mlp, h->lay, h->wimg.as<float>());
@@ -983,7 +989,7 @@ static int step_begin_impl(clb_handle* h, const float* inj_u, const float* inj_e
     if (h->use_tc) {
       if (c.mlp_layers > 0) {
         if (h->use_tc2) k_pack_images<<<(c.mlp_layers * 2048 + 255) / 256, 256, 0, st>>>(a.theta_mlp, h->lay, h->wimg.as<float>());
-        else k_pack_weights<<<(c.mlp_layers * 1024 + 255) / 256, 256, 0, st>>>(a.theta_mlp, h->lay, h->wpack.as<float>());
+        else k_pack_weights<<<(c.mlp_layers * 1024 + 255) / 256, 256, 0, st>>>(a.theta_mlp, h->lay, h->wpack.as<float>(), 32);
         CLB_LAUNCHED(h);
       }
     }

@@ -252,7 +252,7 @@ template <int WP> struct ObsSmem {
     if (tensor_cores)     // dW operand images, compact head weights, biases, bias sums, reductions, chain images (128-thread CTA)
       return 2 * (size_t)tc::kDwImgBytes + sizeof(float) * (2 * WP + 2 * (size_t)n_layers * WP + (size_t)(tc::kThreads / 32) * WP)
              + 64 * sizeof(double) + 2 * (size_t)tc::kImgBytes + 128;
-    return sizeof(float) * ((size_t)n_layers * WP * WP + (size_t)n_layers * WP   // W, b
+    return sizeof(float) * ((size_t)(WP == 64 ? 1 : n_layers) * WP * WP + (size_t)n_layers * WP   // W (width 64: only the head; the rest is streamed), b
                             + (size_t)n_layers * WP                                // bias-grad accumulators
                             + (size_t)WP * HS + (size_t)T * WP      // staged activation / delta tiles
                             + (size_t)T * 16                          // K-split reduction buffer
@@ -266,7 +266,7 @@ template <int WP> struct ObsSmem {
 // leaves one lane per column with the warp's sum (WP-1 shuffles), stored to bias_part[warp][column].
 template <int WP>
 __device__ __forceinline__ void bias_partial(const float (&dp)[WP], float* bias_part, int tid) {
-  constexpr int NH = (WP == 32) ? 5 : (WP == 16) ? 4 : 3;      // log2(WP) halving steps
+  constexpr int NH = (WP >= 32) ? 5 : (WP == 16) ? 4 : 3;      // halving steps (at most 5: 32 lanes)
   float v[WP];
 #pragma unroll
   for (int j = 0; j < WP; ++j) v[j] = dp[j];
@@ -284,8 +284,13 @@ __device__ __forceinline__ void bias_partial(const float (&dp)[WP], float* bias_
   }
 #pragma unroll
   for (int st = NH; st < 5; ++st) v[0] += __shfl_xor_sync(0xffffffffu, v[0], 16 >> st);
-  constexpr int SH = 5 - NH;                                     // lanes sharing a column
-  if ((lane & ((1 << SH) - 1)) == 0) bias_part[(tid >> 5) * WP + (lane >> SH)] = v[0];
+  if constexpr (WP == 64) {                                      // five halvings leave two columns per lane: 2 lane, 2 lane + 1
+    bias_part[(tid >> 5) * WP + 2 * lane] = v[0];
+    bias_part[(tid >> 5) * WP + 2 * lane + 1] = v[1];
+  } else {
+    constexpr int SH = 5 - NH;                                   // lanes sharing a column
+    if ((lane & ((1 << SH) - 1)) == 0) bias_part[(tid >> 5) * WP + (lane >> SH)] = v[0];
+  }
 }
 
 // One layer's weight gradient over the CTA tile: dW[i][j] = sum_obs a[obs][i] * dp[obs][j].
@@ -307,13 +312,18 @@ __device__ __forceinline__ void stage_and_accumulate(const float (&ain)[WP], con
   constexpr int KS4 = T / TPL4;           // K (observation) split
   constexpr int OBS = T / KS4;            // observations per K-split group
   constexpr int NOUT4 = WP * WP / 4;      // float4 outputs of one layer
+  constexpr int NOWN = (NOUT4 + T - 1) / T;   // float4 outputs owned by one thread (1 up to width 32, 4 at width 64): tid, tid + T, ...
   static_assert(OBS % 4 == 0 && OBS >= 4, "tile too small for the K split");
   const bool owner = tid < NOUT4;
   const bool to_image = il_w > 0;         // image layer: the tile's gradient goes to that image's slot (atomics)
-  double2 p01 = make_double2(0.0, 0.0), p23 = make_double2(0.0, 0.0);
-  if (owner && !to_image) {
-    p01 = __ldcg(reinterpret_cast<const double2*>(part));
-    p23 = __ldcg(reinterpret_cast<const double2*>(part) + 1);
+  double2 p01[NOWN], p23[NOWN];
+#pragma unroll
+  for (int m = 0; m < NOWN; ++m) {
+    p01[m] = p23[m] = make_double2(0.0, 0.0);
+    if (owner && !to_image) {
+      p01[m] = __ldcg(reinterpret_cast<const double2*>(part + (size_t)m * T * 4));
+      p23[m] = __ldcg(reinterpret_cast<const double2*>(part + (size_t)m * T * 4) + 1);
+    }
   }
   __syncthreads();                        // previous consumers of the staging / reduction buffers are done
 #pragma unroll
@@ -367,23 +377,27 @@ __device__ __forceinline__ void stage_and_accumulate(const float (&ain)[WP], con
     else if (il_gb != nullptr && tid < il_w) atomicAdd(&il_gb[tid], sum);
   }
   if (owner) {
-    float4 t = Rbuf[tid];
 #pragma unroll
-    for (int k2 = 1; k2 < KS4; ++k2) {
-      const float4 v = Rbuf[k2 * NOUT4 + tid];
-      t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
-    }
-    if (!to_image) {
-      __stcg(reinterpret_cast<double2*>(part), make_double2(p01.x + (double)t.x, p01.y + (double)t.y));
-      __stcg(reinterpret_cast<double2*>(part) + 1, make_double2(p23.x + (double)t.z, p23.y + (double)t.w));
-    } else if (il_gk != nullptr) {
-      // float4 output tid = r*Q*Q + pj*Q + pi holds dK[i = pi + Q r][j = 4 pj ..]; image kernels are stored (out, in)
-      const int r4 = tid / TPL4, pj4 = (tid % TPL4) / Q, pi4 = tid % Q;
-      const int i = pi4 + Q * r4;
-      const float tv[4] = {t.x, t.y, t.z, t.w};
-      if (i < il_w) {
+    for (int m = 0; m < NOWN; ++m) {
+      const int o4 = tid + m * T;           // this output: dK[i = pi + Q r][j = 4 pj ..] with o4 = r*Q*Q + pj*Q + pi
+      float4 t = Rbuf[o4];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) { const int j = 4 * pj4 + c; if (j < il_w) atomicAdd(&il_gk[j * il_w + i], tv[c]); }
+      for (int k2 = 1; k2 < KS4; ++k2) {
+        const float4 v = Rbuf[k2 * NOUT4 + o4];
+        t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+      }
+      if (!to_image) {
+        double* pm = part + (size_t)m * T * 4;
+        __stcg(reinterpret_cast<double2*>(pm), make_double2(p01[m].x + (double)t.x, p01[m].y + (double)t.y));
+        __stcg(reinterpret_cast<double2*>(pm) + 1, make_double2(p23[m].x + (double)t.z, p23[m].y + (double)t.w));
+      } else if (il_gk != nullptr) {        // image kernels are stored (out, in)
+        const int r4 = o4 / TPL4, pj4 = (o4 % TPL4) / Q, pi4 = o4 % Q;
+        const int i = pi4 + Q * r4;
+        const float tv[4] = {t.x, t.y, t.z, t.w};
+        if (i < il_w) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) { const int j = 4 * pj4 + c; if (j < il_w) atomicAdd(&il_gk[j * il_w + i], tv[c]); }
+        }
       }
     }
   }
@@ -577,8 +591,11 @@ __global__ void __launch_bounds__(TC ? tc::kThreads : kObsThreads, TC ? 2 : 1) k
   unsigned char* sp = smem_raw;
   char* tc_dwa = nullptr; char* tc_dwb = nullptr;
   if constexpr (TC) { tc_dwa = reinterpret_cast<char*>(sp); tc_dwb = tc_dwa + tc::kDwImgBytes; sp += 2 * tc::kDwImgBytes; }
+  // width 64 (FP32 path): the hidden-layer kernels do not fit in shared memory (L x 16 KB); they are read from the zero-padded
+  // packed copy in global memory instead (k_pack_weights; every lane of a warp reads the same address: L1 broadcast)
+  constexpr bool STREAM_W = !TC && WP == 64;
   float* Wsm = reinterpret_cast<float*>(sp);                // [L][WP][WP] hidden layers (FP32 path only), then the head [WP][HSTR]
-  float* Whead = Wsm + (TC ? 0 : (size_t)L * WP * WP);
+  float* Whead = Wsm + ((TC || STREAM_W) ? 0 : (size_t)L * WP * WP);
   float* bsm = Whead + (size_t)WP * HSTR;                   // [NL][WP]
   float* dbacc = bsm + (size_t)NL * WP;                     // [NL][WP]
   const int K = a.n_img_layers;           // image layers sit between the hidden layers and the head
@@ -607,7 +624,7 @@ __global__ void __launch_bounds__(TC ? tc::kThreads : kObsThreads, TC ? 2 : 1) k
     tc::fence_before();
   }
   // ---- stage the weights (zero padded to WP x WP) ----
-  if constexpr (!TC) {
+  if constexpr (!TC && !STREAM_W) {
     for (int idx = tid; idx < L * WP * WP; idx += T) {
       const int k = idx / (WP * WP), i = (idx / WP) % WP, j = idx % WP;
       float w = 0.f;
@@ -678,7 +695,7 @@ __global__ void __launch_bounds__(TC ? tc::kThreads : kObsThreads, TC ? 2 : 1) k
     float wreg[8];                       // TC: this thread's share of the next pass's weights
     auto wsrc = [&](int k) -> const float* {      // FP32 weights of chain layer k as [in][out] (TC: 32x32 padded)
       if (k >= L) return Wimg + (size_t)(k - L) * WP * WP;
-      if constexpr (TC) return a.wpack + (size_t)k * 1024; else return Wsm + (size_t)k * WP * WP;
+      if constexpr (TC || STREAM_W) return a.wpack + (size_t)k * WP * WP; else return Wsm + (size_t)k * WP * WP;
     };
     if constexpr (TC) { if (LT > 0) tc::load_w<false>(wsrc(0), tid, wreg); }
     for (int k = 0; k < LT; ++k) {
@@ -753,9 +770,10 @@ __global__ void __launch_bounds__(TC ? tc::kThreads : kObsThreads, TC ? 2 : 1) k
     // head: dW_out = a_L^T [dmu, drho]
     if constexpr (TC) tc_layer_backward(tcx, dp, h, wreg, false, bias_part, dbacc + L * WP, part_rows + (size_t)L * WP * WP, tid);
     else stage_and_accumulate<WP>(h, dp, S_h, S_d, Rbuf, bias_part, dbacc + L * WP, part_rows + (size_t)L * WP * WP, tid);
-    unsigned mask = 0u;                        // sign bits of a_{k+1}: leaky'(pre-activation)
+    using mask_t = typename std::conditional<(WP > 32), unsigned long long, unsigned>::type;
+    mask_t mask = 0;                           // sign bits of a_{k+1}: leaky'(pre-activation)
 #pragma unroll
-    for (int j = 0; j < WP; ++j) mask |= (h[j] > 0.f ? 1u : 0u) << j;
+    for (int j = 0; j < WP; ++j) mask |= (mask_t)(h[j] > 0.f ? 1u : 0u) << j;
 #pragma unroll
     for (int i = 0; i < WP; ++i) {
       const float2 w = *reinterpret_cast<const float2*>(&Whead[i * HSTR]);
@@ -778,9 +796,9 @@ __global__ void __launch_bounds__(TC ? tc::kThreads : kObsThreads, TC ? 2 : 1) k
 #pragma unroll
       for (int j = 0; j < WP; ++j) dp[j] = ((mask >> j) & 1u) ? dp[j] : kLeak * dp[j];
       float ain[WP];
-      mask = 0u;
+      mask = 0;
 #pragma unroll
-      for (int i = 0; i < WP; ++i) { ain[i] = nxt[i]; mask |= (ain[i] > 0.f ? 1u : 0u) << i; }
+      for (int i = 0; i < WP; ++i) { ain[i] = nxt[i]; mask |= (mask_t)(ain[i] > 0.f ? 1u : 0u) << i; }
       if (k > 0) load_act(nxt, k - 1);           // in flight during this layer's dW loop
       if constexpr (TC) {
         // delta a_k = delta p_k W_k^T and dW_k = a_k^T delta p_k, both on the tensor cores
@@ -1195,11 +1213,11 @@ __global__ void __launch_bounds__(256) k_count_obs(const int32_t* refl, int64_t 
 
 // Zero-padded [L][32][32] FP32 copy of the hidden-layer kernels for the tensor-core kernels (they read 4 KB per
 // pass through L1/L2 instead of keeping 80 KB of weights in shared memory, which makes room for two CTAs per SM).
-__global__ void __launch_bounds__(256) k_pack_weights(const float* theta_mlp, MlpLayout lay, float* wpack) {
+__global__ void __launch_bounds__(256) k_pack_weights(const float* theta_mlp, MlpLayout lay, float* wpack, int WP) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int L = lay.n_layers - 1;
-  if (idx >= L * 1024) return;
-  const int k = idx >> 10, i = (idx >> 5) & 31, j = idx & 31;
+  if (idx >= L * WP * WP) return;
+  const int k = idx / (WP * WP), i = (idx / WP) % WP, j = idx % WP;
   wpack[idx] = (i < lay.in_dim[k] && j < lay.out_dim[k]) ? theta_mlp[lay.koff[k] + i * lay.out_dim[k] + j] : 0.f;
 }
 

@@ -617,7 +617,10 @@ __device__ __forceinline__ void issue_backward3(Ctx& c, const float (&dp)[16], c
   __syncthreads();
   if (need_dx) issue_chain_mmas2(c, build_from == nullptr, next);
   const uint32_t warp = uniform32((uint32_t)c.tid >> 5);
-  if (warp == 7u) {
+#ifndef CLB_DW_ISSUER
+#define CLB_DW_ISSUER 7     // which warp issues the dW product: 7 = concurrently with warp 0's chain (default), 0 = warp 0, after its chain
+#endif
+  if (warp == (uint32_t)CLB_DW_ISSUER) {
     fence_after();
     const uint32_t d = uniform32(c.base) + kColDw;
     const uint64_t a0 = uniform64(c.desc_dwa), b0 = uniform64(c.desc_dwb);

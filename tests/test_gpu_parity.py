@@ -279,7 +279,7 @@ def test_nonfinite_gradient_stops_training():
 def test_errors_are_reported():
     from careless_b200 import ClbError, EngineConfig, Engine
     with pytest.raises(ClbError):
-        Engine(EngineConfig(n_refl=10, n_meta=3, mlp_width=64, mlp_layers=2))       # unsupported width
+        Engine(EngineConfig(n_refl=10, n_meta=3, mlp_width=65, mlp_layers=2))       # unsupported width (> 64)
     eng = Engine(EngineConfig(n_refl=10, n_meta=2, mlp_width=4, mlp_layers=1))
     try:
         with pytest.raises(ClbError):
@@ -459,3 +459,25 @@ def test_deterministic_mode_rejects_models_with_atomic_gradients():
     from careless_b200.engine import Engine, EngineConfig
     with pytest.raises(ClbError, match="deterministic"):
         Engine(EngineConfig(n_refl=10, n_meta=2, mlp_width=4, mlp_layers=2, n_images=3, image_scales=True, deterministic=True))
+
+
+# ---- models wider than 32 (scaling/nn.py:55-68 takes any width; positional encodings multiply the metadata columns) ----
+@pytest.mark.parametrize("width,d,layers,extra", [(64, 5, 4, {}), (32, 40, 3, {}), (48, 40, 5, dict(likelihood="studentt", dof=9.0, image_scales=True)),
+                                                   (40, 6, 3, dict(image_layers=1)), (64, 4, 3, dict(laue=True))])
+def test_wide_models(width, d, layers, extra):
+    """max(metadata columns, mlp width) in (32, 64]: the FP32-FMA observation kernel at padded width 64 (weights streamed from
+    the packed global copy)."""
+    if extra.get("laue"):
+        p = synth.make_laue(3000, 300, d=d, n_images=8, seed=51)
+    else:
+        p = synth.make_mono(4000, 400, d=d, n_images=8, seed=52)
+        if extra.get("image_layers"):
+            p["image_id"] = np.sort(p["image_id"])
+    _compare_step(p, f"wide-W{width}-d{d}", mlp_width=width, mlp_layers=layers, **extra)
+
+
+def test_width_above_64_is_rejected():
+    from careless_b200._lib import ClbError
+    from careless_b200.engine import Engine, EngineConfig
+    with pytest.raises(ClbError, match="64"):
+        Engine(EngineConfig(n_refl=10, n_meta=3, mlp_width=65, mlp_layers=2))
