@@ -629,7 +629,7 @@ int clb_set_observations(clb_handle* h, int64_t n, int64_t n_total, const int64_
   // ---- launch geometry + per-CTA buffers of the observation kernel ----
   const int64_t n_tiles = (npad + h->obs_threads - 1) / h->obs_threads;
   h->grid_obs = (int)std::min<int64_t>(n_tiles, (int64_t)h->n_sms * (h->use_tc16 ? 4 : h->use_tc ? 2 : 1));
-  if (h->use_pp) h->grid_obs = (int)std::min<int64_t>((n_tiles + 1) / 2, (int64_t)h->n_sms);     // one CTA per SM, two tiles in flight each
+  if (h->use_pp) h->grid_obs = (int)std::min<int64_t>((n_tiles + 1) / 2, (int64_t)h->n_sms * pp::kCtasPerSM);     // two CTAs per SM, two tiles in flight each
   {
     // One allocation [weight-gradient partials | activation scratch] so that a single L2 access-policy window can cover
     // both: the partials are read-modify-written once per tile and layer and must not be evicted by the scratch
@@ -639,7 +639,7 @@ int clb_set_observations(clb_handle* h, int64_t n, int64_t n_total, const int64_
     // no window 7.96 GB, partials only 5.30 GB, partials + scratch 1.98 GB (5.6x the algorithmic 0.356 GB); time unchanged.
     // tensor-core kernels: the CTAs accumulate with REDs, so several of them can share one partial buffer -- a quarter as
     // many buffers as CTAs keeps the L2 footprint (and the persisting carve-out) small without measurable contention
-    h->n_partials = h->use_pp ? std::max(1, h->grid_obs / 2) : (h->use_tc16 || h->use_tc2) ? std::max(1, h->grid_obs / 4) : h->grid_obs;
+    h->n_partials = (h->use_tc16 || h->use_tc2) ? std::max(1, h->grid_obs / 4) : h->grid_obs;
     if (h->det) h->n_partials = h->grid_obs;          // exclusive buffers: one writer per address
     const size_t pbytes = h->use_tc16 ? sizeof(float) * (size_t)h->n_partials * h->NL * (h->det ? tc16::PSLOT16_DET : tc16::PSLOT16)
                           : h->use_tc2 ? sizeof(float) * (size_t)h->n_partials * h->NL * (h->det ? tc::kPslotDet : 32 * 32 + 32)
