@@ -380,6 +380,10 @@ def run_ours(args, c):
         raise SystemExit(f"bench.py: the step produced non-finite metrics {last}: timing such a run would be meaningless")
 
     # ---- timed region 2: end to end through the C-ABI with host buffers ----
+    # (the rows were prepared on the device; their pinned host mirror -- the buffer every step's H2D copy starts from -- is
+    # created by the first upload, outside the timed region like any other allocation)
+    eng.upload_observations()
+    eng.synchronize()
     barrier()
     t0 = time.perf_counter()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -5,12 +5,14 @@
 // SoA device layout, kernel launches, and the parameter / optimiser state.
 #include "../../include/careless_b200.h"
 #include "clb_kernels.cuh"
+#include "clb_prep.cuh"
 
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <dlfcn.h>
 #include <string>
@@ -138,6 +140,9 @@ struct clb_handle {
   int kl_blocks = 0, ss_blocks = 0;
   DevBuf rows;             // one allocation holding all row arrays
   PinBuf rows_host;        // pinned mirror (for re-upload)
+  bool rows_host_valid = false;   // device-side prep: the mirror is filled (device -> host) only when a re-upload is asked for
+  bool device_prep = true;        // rows are sorted / padded / gathered on the GPU (clb_prep.cuh), unless CLB_DEVICE_PREP=0
+  double prep_ms = 0.0;           // wall time of the last clb_set_observations row preparation
   size_t rows_bytes = 0;
   // double-buffered input pipeline (clb_prefetch_observations): the next step's rows travel on a copy stream into the
   // other buffer while the current step computes; step_begin switches buffers once the copy has landed
@@ -334,28 +339,85 @@ struct RowPlan {
   std::vector<int64_t> pos;           // sorted position -> padded row
 };
 
-int plan_rows(std::string& err, RowPlan& plan, int64_t n, int64_t n_total, int64_t R, int n_images, int laue,
-              int likelihood, float dof, const int64_t* refl_id, const int64_t* image_id, const float* metadata,
-              const float* iobs, const float* sig, const int64_t* harmonic_id, const int64_t* obs_index, int order,
-              int image_tile = 0) {
-  // image_tile > 0 (image layers): rows are image-major and no image may straddle a tile of image_tile rows
+// Argument checks and the resolution of CLB_ORDER_AUTO shared by the host and the device preparation.
+int resolve_order(std::string& err, int64_t n, int laue, const int64_t* refl_id, const int64_t* image_id, const float* metadata,
+                  const float* iobs, const float* sig, const int64_t* harmonic_id, int& order, int image_tile) {
   char buf[256];
-  auto bad = [&](const char* fmt, long long a, long long b, long long c2) { snprintf(buf, sizeof buf, fmt, a, b, c2); err = buf; return 1; };
   if (n <= 0 || !refl_id || !metadata || !iobs || !sig) { err = "clb_set_observations: null/empty input"; return 1; }
   if (laue && !harmonic_id) { err = "Laue model needs harmonic_id"; return 1; }
-  if (n >= ((int64_t)1 << 31) - 64) return bad("n_rows %lld exceeds 2^31 per handle", n, 0, 0);
+  if (n >= ((int64_t)1 << 31) - 64) { snprintf(buf, sizeof buf, "n_rows %lld exceeds 2^31 per handle", (long long)n); err = buf; return 1; }
   if (order == CLB_ORDER_AUTO) order = laue ? CLB_ORDER_SPOT : (image_tile > 0 ? CLB_ORDER_IMAGE : CLB_ORDER_REFL);
   if (image_tile > 0 && !image_id) { err = "image layers need image_id"; return 1; }
   if (image_tile > 0 && order != CLB_ORDER_SPOT && order != CLB_ORDER_IMAGE) { err = "image layers need image-major rows (CLB_ORDER_IMAGE or CLB_ORDER_SPOT)"; return 1; }
   if (laue && order != CLB_ORDER_SPOT) { err = "Laue rows must use CLB_ORDER_SPOT"; return 1; }
   if (!laue && order == CLB_ORDER_SPOT) { err = "CLB_ORDER_SPOT needs a Laue model"; return 1; }
   if (order == CLB_ORDER_IMAGE && !image_id) { err = "CLB_ORDER_IMAGE needs image_id"; return 1; }
+  return 0;
+}
+
+// The first problem of input row i, in the order the checks are made (empty string: the row is fine).
+std::string check_row(int64_t i, int64_t n, int64_t n_total, int64_t R, int n_images, int laue, const int64_t* refl_id,
+                      const int64_t* image_id, const int64_t* harmonic_id, const int64_t* obs_index) {
+  char buf[256]; buf[0] = 0;
+  if (refl_id[i] < 0 || refl_id[i] >= R) snprintf(buf, sizeof buf, "refl_id[%lld]=%lld outside [0,%lld)", (long long)i, (long long)refl_id[i], (long long)R);
+  else if (n_images > 0 && image_id && (image_id[i] < 0 || image_id[i] >= n_images)) snprintf(buf, sizeof buf, "image_id[%lld]=%lld outside [0,%lld)", (long long)i, (long long)image_id[i], (long long)n_images);
+  else if (obs_index && (obs_index[i] < 0 || obs_index[i] >= n_total)) snprintf(buf, sizeof buf, "obs_index[%lld]=%lld outside [0,%lld)", (long long)i, (long long)obs_index[i], (long long)n_total);
+  else if (laue && (harmonic_id[i] < 0 || harmonic_id[i] >= n)) snprintf(buf, sizeof buf, "harmonic_id[%lld]=%lld outside [0,%lld)", (long long)i, (long long)harmonic_id[i], (long long)n);
+  return buf;
+}
+
+// Start position of every key's run of rows in the padded layout (kpos), from the run lengths.  The padding rules are a
+// sequential recurrence over KEYS: a Laue spot must not straddle a 32-row warp chunk, an image (image layers) starts a new tile.
+// `len(k)` = rows of key k, `first_image(k)` = image of the key's first row (Laue + image layers).  Returns the padded row count
+// in npad (before the final rounding to 32); SPOT order also collects the empty slots and their constant log-likelihood.
+template <class Len, class FirstImage>
+int plan_key_positions(std::string& err, RowPlan& plan, int order, int64_t n_keys, int image_tile, int likelihood, float dof,
+                       const float* iobs, const float* sig, Len len_of, FirstImage first_image, uint32_t* kpos, int64_t& npad) {
+  char buf[256];
+  int64_t p = 0, prev_img = -1;
+  if (order == CLB_ORDER_SPOT) {
+    clb_config lc{}; lc.likelihood = likelihood; lc.dof = dof;
+    std::vector<float> empty_i, empty_s;
+    for (int64_t k = 0; k < n_keys; ++k) {
+      const int64_t len = len_of(k);
+      kpos[k] = (uint32_t)p;
+      if (len == 0) { plan.ll_const += lik_logpdf_zero(lc, iobs[k], sig[k]); empty_i.push_back(iobs[k]); empty_s.push_back(sig[k]); continue; }
+      if (len > 32) { snprintf(buf, sizeof buf, "spot %lld has %lld harmonics; at most 32 are supported", (long long)k, (long long)len); err = buf; return 1; }
+      if (image_tile > 0) {                          // harmonic ids are image-major (formatter.py:617)
+        const int64_t img = first_image(k);
+        if (img < prev_img) { snprintf(buf, sizeof buf, "image layers need harmonic_id to be image-major (spot %lld)", (long long)k); err = buf; return 1; }
+        if (img != prev_img) p = (p + image_tile - 1) / image_tile * image_tile;
+        prev_img = img;
+      }
+      if ((p & 31) + len > 32) p = (p + 31) & ~(int64_t)31;
+      kpos[k] = (uint32_t)p;
+      p += len;
+    }
+    plan.empty = empty_i;
+    plan.empty.insert(plan.empty.end(), empty_s.begin(), empty_s.end());
+  } else {                                           // CLB_ORDER_IMAGE with image layers: every image starts a new tile
+    for (int64_t k = 0; k < n_keys; ++k) {
+      const int64_t len = len_of(k);
+      if (len > 0) p = (p + image_tile - 1) / image_tile * image_tile;
+      kpos[k] = (uint32_t)p;
+      p += len;
+    }
+  }
+  npad = p;
+  return 0;
+}
+
+int plan_rows(std::string& err, RowPlan& plan, int64_t n, int64_t n_total, int64_t R, int n_images, int laue,
+              int likelihood, float dof, const int64_t* refl_id, const int64_t* image_id, const float* metadata,
+              const float* iobs, const float* sig, const int64_t* harmonic_id, const int64_t* obs_index, int order,
+              int image_tile = 0) {
+  // image_tile > 0 (image layers): rows are image-major and no image may straddle a tile of image_tile rows
+  if (resolve_order(err, n, laue, refl_id, image_id, metadata, iobs, sig, harmonic_id, order, image_tile)) return 1;
   plan.order = order;
   for (int64_t i = 0; i < n; ++i) {
-    if (refl_id[i] < 0 || refl_id[i] >= R) return bad("refl_id[%lld]=%lld outside [0,%lld)", i, refl_id[i], R);
-    if (n_images > 0 && image_id && (image_id[i] < 0 || image_id[i] >= n_images)) return bad("image_id[%lld]=%lld outside [0,%lld)", i, image_id[i], n_images);
-    if (obs_index && (obs_index[i] < 0 || obs_index[i] >= n_total)) return bad("obs_index[%lld]=%lld outside [0,%lld)", i, obs_index[i], n_total);
-    if (laue && (harmonic_id[i] < 0 || harmonic_id[i] >= n)) return bad("harmonic_id[%lld]=%lld outside [0,%lld)", i, harmonic_id[i], n);
+    const bool ok = !(refl_id[i] < 0 || refl_id[i] >= R) && !(n_images > 0 && image_id && (image_id[i] < 0 || image_id[i] >= n_images)) &&
+                    !(obs_index && (obs_index[i] < 0 || obs_index[i] >= n_total)) && !(laue && (harmonic_id[i] < 0 || harmonic_id[i] >= n));
+    if (!ok) { err = check_row(i, n, n_total, R, n_images, laue, refl_id, image_id, harmonic_id, obs_index); return 1; }
   }
   std::vector<int32_t> key;
   int64_t n_keys = 0;
@@ -379,36 +441,13 @@ int plan_rows(std::string& err, RowPlan& plan, int64_t n, int64_t n_total, int64
   plan.pos.resize(n);
   plan.ll_const = 0.0;
   int64_t npad = n;
-  if (order == CLB_ORDER_SPOT) {
-    clb_config lc{}; lc.likelihood = likelihood; lc.dof = dof;
-    std::vector<float> empty_i, empty_s;
-    int64_t p = 0, prev_img = -1;
-    for (int64_t k = 0; k < n_keys; ++k) {
-      const int64_t len = count[k + 1] - count[k];
-      if (len == 0) { plan.ll_const += lik_logpdf_zero(lc, iobs[k], sig[k]); empty_i.push_back(iobs[k]); empty_s.push_back(sig[k]); continue; }
-      if (len > 32) return bad("spot %lld has %lld harmonics; at most 32 are supported", k, len, 0);
-      if (image_tile > 0) {                          // harmonic ids are image-major (formatter.py:617)
-        const int64_t img = image_id[plan.perm[count[k]]];
-        if (img < prev_img) return bad("image layers need harmonic_id to be image-major (spot %lld)", k, 0, 0);
-        if (img != prev_img) p = (p + image_tile - 1) / image_tile * image_tile;
-        prev_img = img;
-      }
-      if ((p & 31) + len > 32) p = (p + 31) & ~(int64_t)31;
-      for (int64_t j = 0; j < len; ++j) plan.pos[count[k] + j] = p + j;
-      p += len;
-    }
-    npad = p;
-    plan.empty = empty_i;
-    plan.empty.insert(plan.empty.end(), empty_s.begin(), empty_s.end());
-  } else if (order == CLB_ORDER_IMAGE && image_tile > 0) {
-    int64_t p = 0, prev_img = -1;
-    for (int64_t sidx = 0; sidx < n; ++sidx) {
-      const int64_t img = image_id[plan.perm[sidx]];
-      if (img != prev_img) p = (p + image_tile - 1) / image_tile * image_tile;
-      prev_img = img;
-      plan.pos[sidx] = p++;
-    }
-    npad = p;
+  if (order == CLB_ORDER_SPOT || (order == CLB_ORDER_IMAGE && image_tile > 0)) {
+    std::vector<uint32_t> kpos((size_t)n_keys);
+    if (plan_key_positions(err, plan, order, n_keys, image_tile, likelihood, dof, iobs, sig,
+                           [&](int64_t k) { return count[k + 1] - count[k]; },
+                           [&](int64_t k) { return image_id[plan.perm[count[k]]]; }, kpos.data(), npad)) return 1;
+    for (int64_t k = 0; k < n_keys; ++k)
+      for (int64_t j = count[k]; j < count[k + 1]; ++j) plan.pos[j] = (int64_t)kpos[k] + (j - count[k]);
   } else {
     for (int64_t i = 0; i < n; ++i) plan.pos[i] = i;
   }
@@ -436,6 +475,154 @@ void fill_rows(const RowPlan& plan, int64_t n, int d, const int64_t* refl_id, co
       p_spot[p] = (int32_t)k; p_iobs[p] = iobs[k]; p_sig[p] = sig[k];     // formatter.py:637-640: spot k's value sits at index k
     } else { p_iobs[p] = iobs[i]; p_sig[p] = sig[i]; }
   }
+}
+
+// Exclusive prefix sum of m uint32 on the device, in place (recursive over 2 048-element tiles; tmp: m / 2047 + 16 elements).
+cudaError_t device_exclusive_scan(uint32_t* data, int64_t m, uint32_t* tmp, cudaStream_t st) {
+  if (m <= 0) return cudaSuccess;
+  const int64_t nt = (m + prep::kScanTile - 1) / prep::kScanTile;
+  prep::k_scan_tile<<<(unsigned)nt, prep::kScanThreads, 0, st>>>(data, m, tmp);
+  if (nt > 1) {
+    cudaError_t e = device_exclusive_scan(tmp, nt, tmp + nt, st);
+    if (e != cudaSuccess) return e;
+    prep::k_scan_add<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(data, m, tmp);
+  }
+  return cudaGetLastError();
+}
+
+struct RowLayout { size_t bytes = 0, o_refl = 0, o_img = 0, o_spot = 0, o_oidx = 0, o_meta = 0, o_iobs = 0, o_sig = 0; };
+RowLayout carve_rows(int64_t npad, int d, bool has_img, bool has_spot) {
+  RowLayout L;
+  auto carve = [&](size_t nbytes) { size_t o = L.bytes; L.bytes += (nbytes + 255) & ~(size_t)255; return o; };
+  L.o_refl = carve(sizeof(int32_t) * npad);
+  L.o_img = has_img ? carve(sizeof(int32_t) * npad) : 0;
+  L.o_spot = has_spot ? carve(sizeof(int32_t) * npad) : 0;
+  L.o_oidx = carve(sizeof(uint32_t) * npad);
+  L.o_meta = carve(sizeof(float) * npad * d);
+  L.o_iobs = carve(sizeof(float) * npad);
+  L.o_sig = carve(sizeof(float) * npad);
+  return L;
+}
+
+// Device-side version of plan_rows + fill_rows (clb_prep.cuh): the raw tuple is copied to the GPU, checked, sorted (stable LSD
+// radix sort), padded and gathered there; only the O(n_keys) padding recurrence of Laue spots / image tiles runs on the host.
+// On success h->rows holds the rows (layout L) and plan carries order, npad, ll_const and the empty Laue slots.
+int prep_rows_device(clb_handle* h, RowPlan& plan, RowLayout& L, int64_t n, int64_t n_total, int n_images, int image_tile,
+                     const int64_t* refl_id, const int64_t* image_id, const float* metadata, const float* iobs, const float* sig,
+                     const int64_t* harmonic_id, const int64_t* obs_index, int order) {
+  const clb_config& c = h->cfg;
+  std::string err;
+  if (resolve_order(err, n, c.laue, refl_id, image_id, metadata, iobs, sig, harmonic_id, order, image_tile)) return fail(h, CLB_ERR_INVALID, "%s", err.c_str());
+  plan.order = order; plan.ll_const = 0.0;
+  cudaStream_t st = h->stream;
+  const int d = c.n_meta;
+  const bool has_img = image_id != nullptr, has_spot = c.laue != 0;
+  const int64_t n_keys = order == CLB_ORDER_REFL ? h->R : order == CLB_ORDER_SPOT ? n : (int64_t)n_images;
+  const bool need_runs = order == CLB_ORDER_SPOT || (order == CLB_ORDER_IMAGE && image_tile > 0);
+  // ---- raw tuple -> device ----
+  DevBuf r_refl, r_img, r_harm, r_oidx, r_meta, r_iobs, r_sig, key[2], idx[2], G, tmp, count, off, kposb, posb, bad, kimgb;
+  auto up = [&](DevBuf& b, const void* src, size_t bytes) -> cudaError_t {
+    cudaError_t e = b.alloc(bytes);
+    return e != cudaSuccess ? e : cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, st);
+  };
+  CLB_CUDA(h, up(r_refl, refl_id, sizeof(int64_t) * n));
+  if (has_img) CLB_CUDA(h, up(r_img, image_id, sizeof(int64_t) * n));
+  if (has_spot) CLB_CUDA(h, up(r_harm, harmonic_id, sizeof(int64_t) * n));
+  if (obs_index) CLB_CUDA(h, up(r_oidx, obs_index, sizeof(int64_t) * n));
+  CLB_CUDA(h, up(r_meta, metadata, sizeof(float) * (size_t)n * d));
+  CLB_CUDA(h, up(r_iobs, iobs, sizeof(float) * n));
+  CLB_CUDA(h, up(r_sig, sig, sizeof(float) * n));
+  // ---- checks, keys, run lengths ----
+  CLB_CUDA(h, key[0].alloc(sizeof(uint32_t) * n)); CLB_CUDA(h, key[1].alloc(sizeof(uint32_t) * n));
+  CLB_CUDA(h, idx[0].alloc(sizeof(uint32_t) * n)); CLB_CUDA(h, idx[1].alloc(sizeof(uint32_t) * n));
+  CLB_CUDA(h, bad.alloc(sizeof(unsigned long long)));
+  CLB_CUDA(h, cudaMemsetAsync(bad.p, 0xff, sizeof(unsigned long long), st));
+  if (need_runs) { CLB_CUDA(h, count.alloc(sizeof(uint32_t) * n_keys)); CLB_CUDA(h, cudaMemsetAsync(count.p, 0, sizeof(uint32_t) * n_keys, st)); }
+  const unsigned gkeys = (unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)h->n_sms * 16);
+  prep::k_prep_keys<<<gkeys, 256, 0, st>>>(n, r_refl.as<int64_t>(), has_img ? r_img.as<int64_t>() : nullptr, has_spot ? r_harm.as<int64_t>() : nullptr,
+                                           obs_index ? r_oidx.as<int64_t>() : nullptr, h->R, (int64_t)n_images, n_total, c.laue, order,
+                                           key[0].as<uint32_t>(), bad.as<unsigned long long>(), need_runs ? count.as<uint32_t>() : nullptr);
+  CLB_LAUNCHED(h);
+  unsigned long long first_bad = prep::kNoBadRow;
+  CLB_CUDA(h, cudaMemcpyAsync(&first_bad, bad.p, sizeof first_bad, cudaMemcpyDeviceToHost, st));
+  CLB_CUDA(h, cudaStreamSynchronize(st));
+  if (first_bad != prep::kNoBadRow)
+    return fail(h, CLB_ERR_INVALID, "%s", check_row((int64_t)first_bad, n, n_total, h->R, n_images, c.laue, refl_id, image_id, harmonic_id, obs_index).c_str());
+  // ---- stable LSD radix sort of (key, row) ----
+  int bits = 1; while (bits < 32 && ((int64_t)1 << bits) < n_keys) ++bits;
+  const int passes = (bits + 7) / 8;
+  const int nblocks = (int)((n + prep::kRsTile - 1) / prep::kRsTile);
+  const int64_t gsize = 256 * (int64_t)nblocks;
+  CLB_CUDA(h, G.alloc(sizeof(uint32_t) * gsize));
+  CLB_CUDA(h, tmp.alloc(sizeof(uint32_t) * (std::max<int64_t>(gsize, n_keys) / (prep::kScanTile - 1) + 64)));
+  int cur = 0;
+  for (int pass = 0; pass < passes; ++pass) {
+    prep::k_rs_hist<<<nblocks, prep::kRsThreads, 0, st>>>(key[cur].as<uint32_t>(), n, 8 * pass, G.as<uint32_t>(), nblocks);
+    CLB_LAUNCHED(h);
+    CLB_CUDA(h, device_exclusive_scan(G.as<uint32_t>(), gsize, tmp.as<uint32_t>(), st));
+    prep::k_rs_scatter<<<nblocks, prep::kRsThreads, 0, st>>>(key[cur].as<uint32_t>(), pass == 0 ? nullptr : idx[cur].as<uint32_t>(), n, 8 * pass,
+                                                             G.as<uint32_t>(), nblocks, key[cur ^ 1].as<uint32_t>(), idx[cur ^ 1].as<uint32_t>());
+    CLB_LAUNCHED(h);
+    cur ^= 1;
+  }
+  const uint32_t* skey = key[cur].as<uint32_t>();
+  const uint32_t* perm = idx[cur].as<uint32_t>();
+  // ---- padded positions ----
+  int64_t npad = n;
+  const uint32_t* pos = nullptr;
+  if (need_runs) {
+    CLB_CUDA(h, off.alloc(sizeof(uint32_t) * n_keys));
+    CLB_CUDA(h, cudaMemcpyAsync(off.p, count.p, sizeof(uint32_t) * n_keys, cudaMemcpyDeviceToDevice, st));
+    CLB_CUDA(h, device_exclusive_scan(off.as<uint32_t>(), n_keys, tmp.as<uint32_t>(), st));
+    std::vector<uint32_t> cnt_h((size_t)n_keys), kpos_h((size_t)n_keys);
+    std::vector<int32_t> kimg_h;
+    CLB_CUDA(h, cudaMemcpyAsync(cnt_h.data(), count.p, sizeof(uint32_t) * n_keys, cudaMemcpyDeviceToHost, st));
+    if (order == CLB_ORDER_SPOT && image_tile > 0) {
+      kimg_h.resize((size_t)n_keys);
+      CLB_CUDA(h, kimgb.alloc(sizeof(int32_t) * n_keys));
+      prep::k_prep_first_image<<<(unsigned)((n_keys + 255) / 256), 256, 0, st>>>(n_keys, count.as<uint32_t>(), off.as<uint32_t>(), perm, r_img.as<int64_t>(), kimgb.as<int32_t>());
+      CLB_LAUNCHED(h);
+      CLB_CUDA(h, cudaMemcpyAsync(kimg_h.data(), kimgb.p, sizeof(int32_t) * n_keys, cudaMemcpyDeviceToHost, st));
+    }
+    CLB_CUDA(h, cudaStreamSynchronize(st));
+    if (plan_key_positions(err, plan, order, n_keys, image_tile, c.likelihood, c.dof, iobs, sig,
+                           [&](int64_t k) { return (int64_t)cnt_h[k]; }, [&](int64_t k) { return (int64_t)kimg_h[k]; }, kpos_h.data(), npad))
+      return fail(h, CLB_ERR_INVALID, "%s", err.c_str());
+    CLB_CUDA(h, kposb.alloc(sizeof(uint32_t) * n_keys)); CLB_CUDA(h, posb.alloc(sizeof(uint32_t) * n));
+    CLB_CUDA(h, cudaMemcpyAsync(kposb.p, kpos_h.data(), sizeof(uint32_t) * n_keys, cudaMemcpyHostToDevice, st));
+    prep::k_prep_pos<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, skey, off.as<uint32_t>(), kposb.as<uint32_t>(), posb.as<uint32_t>());
+    CLB_LAUNCHED(h);
+    CLB_CUDA(h, cudaStreamSynchronize(st));          // kpos_h goes out of scope
+    pos = posb.as<uint32_t>();
+  }
+  npad = (npad + 31) & ~(int64_t)31;
+  plan.npad = npad;
+  // ---- the rows ----
+  L = carve_rows(npad, d, has_img, has_spot);
+  CLB_CUDA(h, h->rows.alloc(L.bytes));
+  char* db = h->rows.as<char>();
+  int32_t* o_img = has_img ? reinterpret_cast<int32_t*>(db + L.o_img) : nullptr;
+  int32_t* o_spot = has_spot ? reinterpret_cast<int32_t*>(db + L.o_spot) : nullptr;
+  prep::k_fill_defaults<<<(unsigned)((npad + 255) / 256), 256, 0, st>>>(npad, d, reinterpret_cast<int32_t*>(db + L.o_refl), o_img, o_spot,
+      reinterpret_cast<uint32_t*>(db + L.o_oidx), reinterpret_cast<float*>(db + L.o_meta), reinterpret_cast<float*>(db + L.o_iobs), reinterpret_cast<float*>(db + L.o_sig));
+  CLB_LAUNCHED(h);
+  prep::k_fill_gather<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, npad, d, perm, pos, r_refl.as<int64_t>(), has_img ? r_img.as<int64_t>() : nullptr,
+      has_spot ? r_harm.as<int64_t>() : nullptr, obs_index ? r_oidx.as<int64_t>() : nullptr, r_meta.as<float>(), r_iobs.as<float>(), r_sig.as<float>(),
+      reinterpret_cast<int32_t*>(db + L.o_refl), o_img, o_spot, reinterpret_cast<uint32_t*>(db + L.o_oidx), reinterpret_cast<float*>(db + L.o_meta),
+      reinterpret_cast<float*>(db + L.o_iobs), reinterpret_cast<float*>(db + L.o_sig));
+  CLB_LAUNCHED(h);
+  CLB_CUDA(h, cudaStreamSynchronize(st));            // the temporaries are freed on return
+  return CLB_OK;
+}
+
+// The pinned host mirror of the prepared rows (re-upload / prefetch pipeline): after a device-side preparation it is filled on demand.
+int ensure_rows_host(clb_handle* h) {
+  if (h->rows_host_valid) return CLB_OK;
+  CLB_CUDA(h, h->rows_host.alloc(h->rows_bytes));
+  CLB_CUDA(h, cudaMemcpyAsync(h->rows_host.p, h->rows.p, h->rows_bytes, cudaMemcpyDeviceToHost, h->stream));
+  CLB_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->rows_host_valid = true;
+  return CLB_OK;
 }
 
 }  // namespace
@@ -480,6 +667,7 @@ int clb_create(const clb_config* cfg, clb_handle** out) {
   if (h->cfg.world_size <= 0) { h->cfg.world_size = 1; h->cfg.rank = 0; }
   { const char* dbg = getenv("CLB_DEBUG_SYNC"); h->debug_sync = dbg && dbg[0] == '1'; }
   { const char* dis = getenv("CLB_DISCARD"); h->discard_scratch = !(dis && dis[0] == '0'); }
+  { const char* dp = getenv("CLB_DEVICE_PREP"); h->device_prep = !(dp && dp[0] == '0'); }
   { const char* fa = getenv("CLB_FUSED_ADAM"); h->no_fused_adam = fa && fa[0] == '0'; }
   h->det = cfg->deterministic != 0;
   h->R = cfg->n_refl; h->S = cfg->mc_samples; h->WP = WP; h->KS = 1;
@@ -582,30 +770,41 @@ int clb_set_observations(clb_handle* h, int64_t n, int64_t n_total, const int64_
   if (n_total <= 0) n_total = n;
   RowPlan plan;
   std::string err;
-  if (plan_rows(err, plan, n, n_total, h->R, (c.image_scales || c.image_layers > 0) ? c.n_images : 0, c.laue, c.likelihood, c.dof,
-                refl_id, image_id, metadata, iobs, sig, harmonic_id, obs_index, order, c.image_layers > 0 ? h->obs_threads : 0))
-    return fail(h, CLB_ERR_INVALID, "%s", err.c_str());
   CLB_CUDA(h, cudaSetDevice(c.device));
   const int d = c.n_meta;
-  const int64_t npad = plan.npad;
   const bool has_img = image_id != nullptr;
   const bool has_spot = c.laue != 0;
-  size_t bytes = 0;
-  auto carve = [&](size_t nbytes) { size_t o = bytes; bytes += (nbytes + 255) & ~(size_t)255; return o; };
-  const size_t o_refl = carve(sizeof(int32_t) * npad);
-  const size_t o_img = has_img ? carve(sizeof(int32_t) * npad) : 0;
-  const size_t o_spot = has_spot ? carve(sizeof(int32_t) * npad) : 0;
-  const size_t o_oidx = carve(sizeof(uint32_t) * npad);
-  const size_t o_meta = carve(sizeof(float) * npad * d);
-  const size_t o_iobs = carve(sizeof(float) * npad);
-  const size_t o_sig = carve(sizeof(float) * npad);
-  CLB_CUDA(h, h->rows_host.alloc(bytes));
-  CLB_CUDA(h, h->rows.alloc(bytes));
-  char* hb = h->rows_host.as<char>();
-  fill_rows(plan, n, d, refl_id, image_id, metadata, iobs, sig, harmonic_id, obs_index,
-            reinterpret_cast<int32_t*>(hb + o_refl), has_img ? reinterpret_cast<int32_t*>(hb + o_img) : nullptr,
-            has_spot ? reinterpret_cast<int32_t*>(hb + o_spot) : nullptr, reinterpret_cast<uint32_t*>(hb + o_oidx),
-            reinterpret_cast<float*>(hb + o_meta), reinterpret_cast<float*>(hb + o_iobs), reinterpret_cast<float*>(hb + o_sig));
+  const int n_images_chk = (c.image_scales || c.image_layers > 0) ? c.n_images : 0;
+  const int image_tile = c.image_layers > 0 ? h->obs_threads : 0;
+  RowLayout L;
+  if (h->pending_swap || h->alt_used) { CLB_CUDA(h, cudaStreamSynchronize(h->copy_stream)); h->pending_swap = false; h->alt_used = false; }
+  h->rows_alt.free();
+  // device-side preparation (default): everything but the deterministic mode (which also wants the CSR of row positions per
+  // reflection, built from the host permutation) and a caller-forced image order without a known image count
+  const bool on_device = h->device_prep && !h->det && n > 0 && !(order == CLB_ORDER_IMAGE && n_images_chk == 0);
+  const auto t_prep0 = std::chrono::steady_clock::now();
+  if (on_device) {
+    const int rc = prep_rows_device(h, plan, L, n, n_total, n_images_chk, image_tile, refl_id, image_id, metadata, iobs, sig, harmonic_id, obs_index, order);
+    if (rc != CLB_OK) return rc;
+    h->rows_host_valid = false;
+  } else {
+    if (plan_rows(err, plan, n, n_total, h->R, n_images_chk, c.laue, c.likelihood, c.dof,
+                  refl_id, image_id, metadata, iobs, sig, harmonic_id, obs_index, order, image_tile))
+      return fail(h, CLB_ERR_INVALID, "%s", err.c_str());
+    L = carve_rows(plan.npad, d, has_img, has_spot);
+    CLB_CUDA(h, h->rows_host.alloc(L.bytes));
+    CLB_CUDA(h, h->rows.alloc(L.bytes));
+    char* hb = h->rows_host.as<char>();
+    fill_rows(plan, n, d, refl_id, image_id, metadata, iobs, sig, harmonic_id, obs_index,
+              reinterpret_cast<int32_t*>(hb + L.o_refl), has_img ? reinterpret_cast<int32_t*>(hb + L.o_img) : nullptr,
+              has_spot ? reinterpret_cast<int32_t*>(hb + L.o_spot) : nullptr, reinterpret_cast<uint32_t*>(hb + L.o_oidx),
+              reinterpret_cast<float*>(hb + L.o_meta), reinterpret_cast<float*>(hb + L.o_iobs), reinterpret_cast<float*>(hb + L.o_sig));
+    h->rows_host_valid = true;
+  }
+  h->prep_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_prep0).count();
+  const int64_t npad = plan.npad;
+  const size_t bytes = L.bytes;
+  const size_t o_refl = L.o_refl, o_img = L.o_img, o_spot = L.o_spot, o_oidx = L.o_oidx, o_meta = L.o_meta, o_iobs = L.o_iobs, o_sig = L.o_sig;
   h->ll_const = plan.ll_const;
   h->n_empty = 0;
   if (c.refine_uncertainties) {      // the empty slots' log-density depends on the error-model parameters: evaluated on the device
@@ -621,8 +820,6 @@ int clb_set_observations(clb_handle* h, int64_t n, int64_t n_total, const int64_
   h->row_off[0] = o_refl; h->row_off[1] = o_img; h->row_off[2] = o_spot; h->row_off[3] = o_oidx;
   h->row_off[4] = o_meta; h->row_off[5] = o_iobs; h->row_off[6] = o_sig;
   h->has_img_rows = has_img; h->has_spot_rows = has_spot;
-  if (h->pending_swap || h->alt_used) { CLB_CUDA(h, cudaStreamSynchronize(h->copy_stream)); h->pending_swap = false; h->alt_used = false; }
-  h->rows_alt.free();
   point_rows(h, h->rows.as<char>());
   h->n_rows_raw = n; h->n_rows = npad; h->n_rows_total = n_total; h->order = plan.order;
 
@@ -693,7 +890,7 @@ int clb_set_observations(clb_handle* h, int64_t n, int64_t n_total, const int64_
     CLB_CUDA(h, cudaStreamSynchronize(h->stream));
   }
   h->have_obs = true;
-  return clb_upload_observations(h);
+  return on_device ? CLB_OK : clb_upload_observations(h);
 }
 
 // Host prep only (no CUDA): the sorted / padded SoA device layout of clb_set_observations, written to
@@ -731,6 +928,7 @@ int clb_prefetch_observations(clb_handle* h) {
     CLB_CUDA(h, cudaEventCreateWithFlags(&h->ev_rows_free[0], cudaEventDisableTiming));
     CLB_CUDA(h, cudaEventCreateWithFlags(&h->ev_rows_free[1], cudaEventDisableTiming));
   }
+  { const int rc = ensure_rows_host(h); if (rc != CLB_OK) return rc; }
   if (!h->rows_alt.p) CLB_CUDA(h, h->rows_alt.alloc(h->rows_bytes));
   // the target buffer was last read by the step before the current one; wait until that step's kernels are done
   if (h->alt_used) CLB_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->ev_rows_free[h->cur_rows ^ 1], 0));
@@ -743,7 +941,30 @@ int clb_prefetch_observations(clb_handle* h) {
 int clb_upload_observations(clb_handle* h) {
   if (!h || !h->have_obs) return fail(h, CLB_ERR_STATE, "clb_upload_observations before clb_set_observations");
   CLB_CUDA(h, cudaSetDevice(h->cfg.device));
+  { const int rc = ensure_rows_host(h); if (rc != CLB_OK) return rc; }
   CLB_CUDA(h, cudaMemcpyAsync(h->rows.p, h->rows_host.p, h->rows_bytes, cudaMemcpyHostToDevice, h->stream));
+  return CLB_OK;
+}
+
+int clb_download_rows(clb_handle* h, int64_t capacity, int64_t* n_padded, int32_t* refl_out, int32_t* image_out, int32_t* spot_out,
+                      uint32_t* oidx_out, float* meta_out, float* iobs_out, float* sig_out, double* ll_const, double* prep_ms) {
+  if (!h || !h->have_obs) return fail(h, CLB_ERR_STATE, "clb_download_rows before clb_set_observations");
+  if (n_padded) *n_padded = h->n_rows;
+  if (ll_const) *ll_const = h->ll_const;
+  if (prep_ms) *prep_ms = h->prep_ms;
+  if (capacity < h->n_rows) return CLB_OK;
+  if (!refl_out || !oidx_out || !meta_out || !iobs_out || !sig_out) return fail(h, CLB_ERR_INVALID, "clb_download_rows: null output");
+  CLB_CUDA(h, cudaSetDevice(h->cfg.device));
+  const size_t np = (size_t)h->n_rows;
+  auto down = [&](void* dst, const void* src, size_t bytes) { return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream); };
+  CLB_CUDA(h, down(refl_out, h->d_refl, sizeof(int32_t) * np));
+  if (image_out && h->d_image) CLB_CUDA(h, down(image_out, h->d_image, sizeof(int32_t) * np));
+  if (spot_out && h->d_spot) CLB_CUDA(h, down(spot_out, h->d_spot, sizeof(int32_t) * np));
+  CLB_CUDA(h, down(oidx_out, h->d_oidx, sizeof(uint32_t) * np));
+  CLB_CUDA(h, down(meta_out, h->d_meta, sizeof(float) * np * h->cfg.n_meta));
+  CLB_CUDA(h, down(iobs_out, h->d_iobs, sizeof(float) * np));
+  CLB_CUDA(h, down(sig_out, h->d_sig, sizeof(float) * np));
+  CLB_CUDA(h, cudaStreamSynchronize(h->stream));
   return CLB_OK;
 }
 

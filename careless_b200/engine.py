@@ -135,6 +135,26 @@ class Engine:
                                                   _ptr(metadata), _ptr(intensities), _ptr(uncertainties),
                                                   _ptr(harmonic_id), _ptr(obs_index), order))
 
+    def download_rows(self):
+        """The prepared (sorted / padded SoA) rows as they sit on the device, plus ``ll_const`` and ``prep_ms`` (wall time of
+        the row preparation inside the last ``set_observations``): the same dictionary ``clb_prepare_rows`` fills on the host."""
+        npad = C.c_int64(); llc = C.c_double(); ms = C.c_double()
+        self._check(self.lib.clb_download_rows(self._h, 0, C.byref(npad), None, None, None, None, None, None, None, C.byref(llc), C.byref(ms)))
+        m, d = npad.value, self.cfg.n_meta
+        out = dict(refl=np.empty(m, np.int32), image=np.zeros(m, np.int32), spot=np.full(m, -1, np.int32), oidx=np.empty(m, np.uint32),
+                   meta=np.empty((d, m), np.float32), iobs=np.empty(m, np.float32), sig=np.empty(m, np.float32))
+        self._check(self.lib.clb_download_rows(self._h, m, C.byref(npad), _ptr(out["refl"]), _ptr(out["image"]), _ptr(out["spot"]),
+                                               _ptr(out["oidx"]), _ptr(out["meta"]), _ptr(out["iobs"]), _ptr(out["sig"]),
+                                               C.byref(llc), C.byref(ms)))
+        out["ll_const"] = llc.value; out["prep_ms"] = ms.value
+        return out
+
+    def download_rows_info(self):
+        """``n_padded``, ``ll_const`` and ``prep_ms`` of the prepared rows without copying them."""
+        npad = C.c_int64(); llc = C.c_double(); ms = C.c_double()
+        self._check(self.lib.clb_download_rows(self._h, 0, C.byref(npad), None, None, None, None, None, None, None, C.byref(llc), C.byref(ms)))
+        return {"n_padded": npad.value, "ll_const": llc.value, "prep_ms": ms.value}
+
     def upload_observations(self):
         self._check(self.lib.clb_upload_observations(self._h))
 

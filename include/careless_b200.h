@@ -122,7 +122,11 @@ void clb_destroy(clb_handle* h);
  * 1.0 padding).  harmonic_id == NULL for mono.  obs_index (optional, NULL = 0..N-1) is the
  * GLOBAL row index of each observation (used as RNG counter and to look up injected draws);
  * refl_id indexes this handle's n_refl surrogate entries.
- * The call sorts/pads the rows into the device layout and uploads them. */
+ * The call sorts/pads the rows into the device layout.  By default that happens ON THE GPU
+ * (csrc/clb_prep.cuh: range checks, stable radix sort by refl_id / harmonic_id / image_id, padding, gather) --
+ * the counterpart of the grouping the reference's formatter does with pandas on the host
+ * (io/formatter.py:145, :617); CLB_DEVICE_PREP=0 or the deterministic mode use the host version
+ * (clb_prepare_rows), which produces bit-identical rows. */
 int clb_set_observations(clb_handle* h, int64_t n_rows, int64_t n_rows_total,
                          const int64_t* refl_id, const int64_t* image_id,
                          const float* metadata, const float* intensities, const float* uncertainties,
@@ -138,6 +142,12 @@ int clb_prepare_rows(int64_t n_rows, int64_t n_refl, int32_t n_meta, int32_t n_i
                      const int64_t* obs_index, int32_t order, int32_t image_tile /* > 0: image layers, rows per tile */,
                      int64_t capacity, int64_t* n_padded, int32_t* refl_out, int32_t* image_out, int32_t* spot_out,
                      uint32_t* oidx_out, float* meta_out, float* iobs_out, float* sig_out, double* ll_const);
+/* Copy of the device-resident prepared rows back to the caller (same arrays and conventions as clb_prepare_rows'
+ * outputs): lets tests compare the device-side preparation with the host one bit by bit.  prep_ms (may be NULL)
+ * receives the wall time of the row preparation inside the last clb_set_observations. */
+int clb_download_rows(clb_handle* h, int64_t capacity, int64_t* n_padded, int32_t* refl_out, int32_t* image_out,
+                      int32_t* spot_out, uint32_t* oidx_out, float* meta_out, float* iobs_out, float* sig_out,
+                      double* ll_const, double* prep_ms);
 /* Re-upload of the already prepared (pinned) device-layout rows: the host->device copy of
  * one step's inputs, used by the end-to-end measurement. */
 int clb_upload_observations(clb_handle* h);
