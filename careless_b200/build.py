@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libcareless_b200.so")
 SOURCES = ["clb_api.cu"]
-HEADERS = ["clb_kernels.cuh", "clb_math.cuh", "clb_tc.cuh", "clb_tc16.cuh", "clb_pp.cuh", "clb_prep.cuh", os.path.join("..", "..", "include", "careless_b200.h")]
+HEADERS = ["clb_kernels.cuh", "clb_math.cuh", "clb_tc.cuh", "clb_tc16.cuh", "clb_pp.cuh", "clb_prep.cuh", "clb_tc3.cuh", os.path.join("..", "..", "include", "careless_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
 

@@ -122,6 +122,7 @@ struct clb_handle {
   bool use_tc = false;       // tensor-core (tcgen05) path of k_obs: padded width 32, unless CLB_NO_TC=1
   bool use_tc2 = false;      // ... with two threads per observation row (k_obs_tc2), unless CLB_TC_ONE_THREAD_PER_ROW=1
   bool use_pp = false;       // width 32 without image layers: warp-specialised two-tile ping-pong kernel (k_obs_pp), unless CLB_PP=0
+  bool use_tc3 = false;      // width 32 without image layers: k_obs_tc2 software-pipelined across tiles (k_obs_tc3), CLB_TC3=1
   bool use_tc16 = false;     // narrow MLPs (padded width <= 16, with or without image layers) on the tensor cores (k_obs_tc16), unless CLB_TC16=0
   bool discard_scratch = true;   // consumed activation-scratch lines are discarded from L2 (no DRAM write-back), unless CLB_DISCARD=0
   bool debug_sync = false;   // CLB_DEBUG_SYNC=1: synchronise + log after every kernel launch
@@ -233,6 +234,13 @@ cudaError_t dispatch_obs(clb_handle* h, const ObsArgs& a) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_obs);
     if (e != cudaSuccess) return e;
     kern<<<h->grid_obs, pp::kThreadsPP, h->smem_obs, h->stream>>>(a);
+    return cudaGetLastError();
+  }
+  if (h->use_tc3) {
+    auto kern = lik ? k_obs_tc3<1> : k_obs_tc3<0>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_obs);
+    if (e != cudaSuccess) return e;
+    kern<<<h->grid_obs, tc3::kThreads3, h->smem_obs, h->stream>>>(a);
     return cudaGetLastError();
   }
   if (h->use_tc2) {
@@ -688,6 +696,7 @@ int clb_create(const clb_config* cfg, clb_handle** out) {
   // k_obs_pp (one CTA per SM, two tiles ping-ponging through a dedicated issuer warp) is parity-green but measured slower than
   // k_obs_tc2 on B200 (18.7 vs 16.8 ms: two warps per scheduler cannot cover the ALU / TMEM latencies); opt-in with CLB_PP=1
   { const char* ppe = getenv("CLB_PP"); h->use_pp = h->use_tc2 && cfg->image_layers == 0 && cfg->mlp_layers > 0 && (ppe && ppe[0] == '1') && !cfg->deterministic; }
+  { const char* t3 = getenv("CLB_TC3"); h->use_tc3 = h->use_tc2 && !h->use_pp && cfg->image_layers == 0 && cfg->mlp_layers > 0 && (t3 && t3[0] == '1') && !cfg->deterministic; }
   h->obs_threads = (h->use_tc || h->use_tc16) ? tc::kThreads : kObsThreads;      // = observation rows per CTA tile
   switch (WP) {
     case 8: h->smem_obs = ObsSmem<8>::bytes(h->NL, false, cfg->image_layers); break;
@@ -698,6 +707,7 @@ int clb_create(const clb_config* cfg, clb_handle** out) {
   if (h->use_tc2) h->smem_obs = ObsSmem2::bytes(h->NL, cfg->image_layers);
   if (h->use_tc16) h->smem_obs = ObsSmem16::bytes(h->NL, cfg->image_layers);
   if (h->use_pp) h->smem_obs = pp::SmemPP::bytes(h->NL);
+  if (h->use_tc3) h->smem_obs = tc3::Smem3::bytes(h->NL);
   if (h->smem_obs > (size_t)prop.sharedMemPerBlockOptin) {
     fail(h, CLB_ERR_INVALID, "scale MLP (%d layers x padded width %d) needs %zu B of shared memory; the device offers %zu",
          cfg->mlp_layers, WP, h->smem_obs, (size_t)prop.sharedMemPerBlockOptin);
@@ -842,7 +852,7 @@ int clb_set_observations(clb_handle* h, int64_t n, int64_t n_total, const int64_
                           : h->use_tc2 ? sizeof(float) * (size_t)h->n_partials * h->NL * (h->det ? tc::kPslotDet : 32 * 32 + 32)
                                        : sizeof(double) * (size_t)h->grid_obs * h->KS * partial_row_size(h->NL, h->WP);
     const size_t pb = (pbytes + 255) & ~(size_t)255;
-    const size_t sbytes = sizeof(float4) * (size_t)h->grid_obs * (h->use_pp ? 2 : 1) * std::max(1, c.mlp_layers + c.image_layers) * ((h->use_tc16 ? 16 : h->WP) / 4) * h->obs_threads;
+    const size_t sbytes = sizeof(float4) * (size_t)h->grid_obs * ((h->use_pp || h->use_tc3) ? 2 : 1) * std::max(1, c.mlp_layers + c.image_layers) * ((h->use_tc16 ? 16 : h->WP) / 4) * h->obs_threads;
     CLB_CUDA(h, h->partials.alloc(pb + sbytes));
     h->partial_bytes = pbytes;
     h->scratch_ptr = reinterpret_cast<float4*>(h->partials.as<char>() + pb);

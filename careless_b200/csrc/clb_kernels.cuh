@@ -1518,3 +1518,4 @@ __global__ void __launch_bounds__(256) k_adam(float* theta, float* m, float* v, 
 
 #include "clb_tc16.cuh"
 #include "clb_pp.cuh"
+#include "clb_tc3.cuh"

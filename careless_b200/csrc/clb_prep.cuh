@@ -75,12 +75,18 @@ __global__ void __launch_bounds__(kRsThreads) k_rs_scatter(const uint32_t* key_i
   __syncthreads();
   const int64_t wbase = (int64_t)blockIdx.x * kRsTile + (int64_t)warp * kRsWarpItems;
   const unsigned lt = (1u << lane) - 1u;
-  uint32_t k[kRsItems]; uint32_t lr[kRsItems];
+  uint32_t k[kRsItems]; uint32_t lr[kRsItems]; uint32_t v[kRsItems];
+#pragma unroll
+  for (int c = 0; c < kRsItems; ++c) {               // all of the warp's loads are in flight before the (serial) ranking starts
+    const int64_t i = wbase + c * 32 + lane;
+    k[c] = i < n ? __ldcs(&key_in[i]) : 0u;
+    v[c] = (i < n && idx_in != nullptr) ? __ldcs(&idx_in[i]) : (uint32_t)i;
+  }
 #pragma unroll
   for (int c = 0; c < kRsItems; ++c) {
     const int64_t i = wbase + c * 32 + lane;
     const bool valid = i < n;
-    const uint32_t kk = valid ? key_in[i] : 0u;
+    const uint32_t kk = k[c];
     const uint32_t d = valid ? ((kk >> shift) & 255u) : 256u;
     const unsigned same = __match_any_sync(0xffffffffu, d);
     const uint32_t r = __popc(same & lt);
@@ -88,7 +94,7 @@ __global__ void __launch_bounds__(kRsThreads) k_rs_scatter(const uint32_t* key_i
     __syncwarp();
     if (r == 0u) wcnt[warp][d] = b + __popc(same);
     __syncwarp();
-    k[c] = kk; lr[c] = b + r;
+    lr[c] = b + r;
   }
   __syncthreads();
   {                                                  // digit tid: first output position of every warp's rows of that digit
@@ -103,7 +109,7 @@ __global__ void __launch_bounds__(kRsThreads) k_rs_scatter(const uint32_t* key_i
     if (i < n) {
       const uint32_t p = wcnt[warp][(k[c] >> shift) & 255u] + lr[c];
       key_out[p] = k[c];
-      idx_out[p] = idx_in != nullptr ? idx_in[i] : (uint32_t)i;
+      idx_out[p] = v[c];
     }
   }
 }
