@@ -1050,7 +1050,7 @@ __global__ void __launch_bounds__(tc::kThreads2, 2) k_obs_tc2(ObsArgs a) {
       // the pass after this one: next forward layer, else the first dX pass, else the next tile's first layer
       const float* next = (k + 1 < LT) ? gimg(k + 1, 0) : (a.train_mlp && LT > 1) ? gimg(LT - 1, 1) : (more_tiles ? gimg(0, 0) : nullptr);
 #if CLB_BWD_ORDER == 2
-      tc::issue3(tcx, h, (IL && k >= L) ? wsrc(k) : nullptr, tc_img, next);
+      tc::issue3(tcx, h, (IL && k >= L) ? wsrc(k) : nullptr, tc_img, next, CLB_BIAS_IN_MMA ? bk : nullptr);
 #else
       tc::issue4(tcx, h, (IL && k >= L) ? wsrc(k) : nullptr, tc_img, next, lane);
 #endif
@@ -1058,7 +1058,7 @@ __global__ void __launch_bounds__(tc::kThreads2, 2) k_obs_tc2(ObsArgs a) {
       tc::collect2(tcx, o);
       CLB_PH(2);
 #pragma unroll
-      for (int j = 0; j < HW; ++j) { const float v = o[j] + bk[j]; h[j] = fmaxf(v, kLeak * v); }
+      for (int j = 0; j < HW; ++j) { const float v = (CLB_BIAS_IN_MMA && CLB_BWD_ORDER == 2) ? o[j] : o[j] + bk[j]; h[j] = fmaxf(v, kLeak * v); }
 #ifndef CLB_ABL_SCR
       if (a.train_mlp && k + 1 < LT) {          // the last layer's output stays in registers (h) for the head
 #pragma unroll

@@ -476,6 +476,13 @@ __device__ __forceinline__ void collect_dw_red(Ctx& c, float* wk, int il_w, floa
 }
 #else
 constexpr uint32_t kIdescDwTc2 = kIdescDw;
+#ifndef CLB_DW_FOLD
+#define CLB_DW_FOLD 0       // 1: the delta-p_hi and delta-p_lo column blocks of the dW product accumulate into the SAME 32 tensor-memory
+                            // columns (two N = 32 instruction groups instead of one N = 64 group), so the collection reads 16 columns
+                            // per thread and adds nothing (-17 instructions per thread and layer).  Parity-green; measured SLOWER on B200
+                            // (16.94 vs 16.41 ms per 10 M observations): 32 MMAs to issue instead of 16 and no tensor time saved
+#endif
+constexpr uint32_t kIdescDwN32 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((32u >> 3) << 17) | ((64u >> 4) << 24);
 // M = 64 product: D rows live at lanes (r % 16) + 32 (r / 16): in every warp the lanes < 16 hold row r = 16 (warp % 4) + lane,
 // i.e. feature i = r % 32 (rows 0..31 from a_hi, 32..63 from a_lo, both added into dW[i][16 hf ..]).
 __device__ __forceinline__ void collect_dw_red(Ctx& c, float* wk, int il_w, float* bk = nullptr) {
@@ -484,15 +491,25 @@ __device__ __forceinline__ void collect_dw_red(Ctx& c, float* wk, int il_w, floa
   fence_after();
   const int q = (c.tid >> 5) & 3, lane = c.tid & 31;
   const uint32_t addr = c.row_addr + kColDw + c.col;
+#if CLB_DW_FOLD
+  uint32_t v0[16];
+  CLB_TMEM_LD16(addr, v0);
+  wait_ld();
+#else
   uint32_t v0[16], v1[16];
   CLB_TMEM_LD16(addr, v0);
   CLB_TMEM_LD16(addr + 32, v1);
   wait_ld();
+#endif
   if (lane < 16 && wk != nullptr) {
     const int i = (16 * q + lane) & 31;
     float f[16];
 #pragma unroll
+#if CLB_DW_FOLD
+    for (int k = 0; k < 16; ++k) f[k] = __uint_as_float(v0[k]);
+#else
     for (int k = 0; k < 16; ++k) f[k] = __uint_as_float(v0[k]) + __uint_as_float(v1[k]);
+#endif
     if (il_w == 0) {
       float4* dst = reinterpret_cast<float4*>(wk + (q >= 2 ? c.lo_off : 0)) + (4 * c.hf) * 32 + i;      // dw_slot32(i, 16 hf + 4 qq) / 4
 #pragma unroll
@@ -504,6 +521,24 @@ __device__ __forceinline__ void collect_dw_red(Ctx& c, float* wk, int il_w, floa
   }
 }
 #endif
+
+// The tcgen05.mma's of one tile's dW = [a_hi; a_lo]^T [delta-p_hi | delta-p_lo] (one elected lane; operands warp-uniform).
+__device__ __forceinline__ void issue_dw_mmas(uint32_t d, uint64_t a0, uint64_t b0) {
+#if CLB_DW_FOLD && !CLB_BIAS_ONES
+  // x delta-p_hi, then x delta-p_lo (MN group 1: + kDwLBO bytes) into the same 32 accumulator columns
+#pragma unroll
+  for (int ks = 0; ks < kThreads / 8; ++ks)
+    mma_tf32_ss(d, a0 + (uint64_t)((2u * kDwSBO * (uint32_t)ks) >> 4), b0 + (uint64_t)((2u * kDwSBO * (uint32_t)ks) >> 4), kIdescDwN32, ks > 0 ? 1u : 0u);
+  const uint64_t b1 = b0 + (uint64_t)(kDwLBO >> 4);
+#pragma unroll
+  for (int ks = 0; ks < kThreads / 8; ++ks)
+    mma_tf32_ss(d, a0 + (uint64_t)((2u * kDwSBO * (uint32_t)ks) >> 4), b1 + (uint64_t)((2u * kDwSBO * (uint32_t)ks) >> 4), kIdescDwN32, 1u);
+#else
+#pragma unroll
+  for (int ks = 0; ks < kThreads / 8; ++ks)
+    mma_tf32_ss(d, a0 + (uint64_t)((2u * kDwSBO * (uint32_t)ks) >> 4), b0 + (uint64_t)((2u * kDwSBO * (uint32_t)ks) >> 4), kIdescDwTc2, ks > 0 ? 1u : 0u);
+#endif
+}
 
 // ---- weight images by TMA --------------------------------------------------------------------------------------
 // The hi / lo B-operand images of every hidden layer (both orientations) are prepared once per step in global memory
@@ -518,7 +553,12 @@ __device__ __forceinline__ void tma_fetch_image(uint32_t dst_smem, const float* 
 
 // Issue one chain pass from buffer b; `tma` = the image came by TMA (wait for it), `next` = global image of the next
 // pass to prefetch into the other buffer (or null).  Called by all threads after the pass's __syncthreads().
-__device__ __forceinline__ void issue_chain_mmas2(Ctx& c, bool tma, const float* next) {
+#ifndef CLB_BIAS_IN_MMA
+#define CLB_BIAS_IN_MMA 0   // 1: a forward pass starts from an accumulator PRELOADED with the layer's bias (one tcgen05.st per thread
+                            // and every MMA accumulating) instead of 16 FADDs per thread after the collection.  Parity-green; measured
+                            // SLOWER on B200 (16.89 vs 16.41 ms): the third tcgen05.st per pass costs more than the 16 FADDs it saves
+#endif
+__device__ __forceinline__ void issue_chain_mmas2(Ctx& c, bool tma, const float* next, bool preloaded = false) {
   const uint32_t b = c.pass & 1u;
   const uint32_t warp = uniform32((uint32_t)c.tid >> 5);
   if (warp == 0u) {
@@ -534,7 +574,7 @@ __device__ __forceinline__ void issue_chain_mmas2(Ctx& c, bool tma, const float*
 #ifndef CLB_ABL_CHAIN
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks)
-        mma_tf32_ts(d, base + kColAhi + 8u * (uint32_t)ks, blo + (uint64_t)((2u * kLBO * (uint32_t)ks) >> 4), ks > 0 ? 1u : 0u);
+        mma_tf32_ts(d, base + kColAhi + 8u * (uint32_t)ks, blo + (uint64_t)((2u * kLBO * (uint32_t)ks) >> 4), (ks > 0 || preloaded) ? 1u : 0u);
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks)
         mma_tf32_ts(d, base + kColAlo + 8u * (uint32_t)ks, bhi + (uint64_t)((2u * kLBO * (uint32_t)ks) >> 4), 1u);
@@ -570,18 +610,30 @@ __device__ __forceinline__ void build_weight_image3(Ctx& c, const float* Wg, cha
 }
 
 // Forward pass of one layer.  build_from == nullptr: the layer's images were prefetched by TMA.
-__device__ __forceinline__ void issue3(Ctx& c, const float (&x)[16], const float* build_from, char* img_base, const float* next) {
+// bias16 (CLB_BIAS_IN_MMA): this thread's 16 biases of the layer (shared memory, 16-byte aligned); they are stored into the thread's
+// accumulator columns and every MMA of the pass accumulates on top.
+__device__ __forceinline__ void issue3(Ctx& c, const float (&x)[16], const float* build_from, char* img_base, const float* next,
+                                       const float* bias16 = nullptr) {
   {
     uint32_t hi[16], lo[16];
     split16(x, hi, lo);
     CLB_TMEM_ST16(c.row_addr + kColAhi + c.col, hi);
     CLB_TMEM_ST16(c.row_addr + kColAlo + c.col, lo);
   }
+  if (bias16 != nullptr) {
+    uint32_t b[16];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint4 v = *reinterpret_cast<const uint4*>(bias16 + 4 * q);
+      b[4 * q] = v.x; b[4 * q + 1] = v.y; b[4 * q + 2] = v.z; b[4 * q + 3] = v.w;
+    }
+    CLB_TMEM_ST16(c.row_addr + kColD + c.col, b);
+  }
   if (build_from != nullptr) { build_weight_image3<false>(c, build_from, img_base); fence_async_smem(); }
   wait_st();
   fence_before();
   __syncthreads();
-  issue_chain_mmas2(c, build_from == nullptr, next);
+  issue_chain_mmas2(c, build_from == nullptr, next, bias16 != nullptr);
 }
 
 // Backward of one layer: dX chain (if need_dx) and dW.
@@ -627,9 +679,7 @@ __device__ __forceinline__ void issue_backward3(Ctx& c, const float (&dp)[16], c
     const uint32_t bar = uniform32(c.mbar_dw);
     if (elect_one()) {
 #ifndef CLB_ABL_DW
-#pragma unroll
-      for (int ks = 0; ks < kThreads / 8; ++ks)
-        mma_tf32_ss(d, a0 + (uint64_t)((2u * kDwSBO * (uint32_t)ks) >> 4), b0 + (uint64_t)((2u * kDwSBO * (uint32_t)ks) >> 4), kIdescDwTc2, ks > 0 ? 1u : 0u);
+      issue_dw_mmas(d, a0, b0);
 #endif
       commit(bar);
     }
@@ -710,9 +760,7 @@ __device__ __forceinline__ void dw_issue(Ctx& c, const float4* dead, int lane) {
   const uint64_t a0 = uniform64(c.desc_dwa), b0 = uniform64(c.desc_dwb);
   const uint32_t bar = uniform32(c.mbar_dw);
   if (elect_one()) {
-#pragma unroll
-    for (int ks = 0; ks < kThreads / 8; ++ks)
-      mma_tf32_ss(d, a0 + (uint64_t)((2u * kDwSBO * (uint32_t)ks) >> 4), b0 + (uint64_t)((2u * kDwSBO * (uint32_t)ks) >> 4), kIdescDwTc2, ks > 0 ? 1u : 0u);
+    issue_dw_mmas(d, a0, b0);
     commit(bar);
   }
   __syncwarp();
@@ -783,9 +831,7 @@ __device__ __forceinline__ void dw_handover(Ctx& c, uint32_t (&hi)[16], uint32_t
     const uint64_t a0 = uniform64(c.desc_dwa), b0 = uniform64(c.desc_dwb);
     const uint32_t bar = uniform32(c.mbar_dw);
     if (elect_one()) {
-#pragma unroll
-      for (int ks = 0; ks < kThreads / 8; ++ks)
-        mma_tf32_ss(d, a0 + (uint64_t)((2u * kDwSBO * (uint32_t)ks) >> 4), b0 + (uint64_t)((2u * kDwSBO * (uint32_t)ks) >> 4), kIdescDwTc2, ks > 0 ? 1u : 0u);
+      issue_dw_mmas(d, a0, b0);
       commit(bar);
     }
     __syncwarp();
