@@ -367,6 +367,9 @@ __device__ __forceinline__ void swap_blocks(uint32_t (&v)[16], int sw) {
 }
 
 // This thread's 16 features (32-byte chunks 2 hf and 2 hf + 1) of row k of an MN-major operand image.
+// PACKED (the delta-p image of k_obs_tc2, CLB_DWB_PACK): MN group hf holds [hi of features 16 hf .. | lo of the same features], so that
+// a thread's 32 accumulator columns of the dW product are adjacent (one tcgen05.ld.x32 instead of two .x16).
+template <bool PACKED = false>
 __device__ __forceinline__ void dw_store_half(char* img, int k, int hf, const uint32_t (&hi)[16], const uint32_t (&lo)[16], int sw) {
 #ifdef CLB_ABL_STS
   if (hi[0] == 0x7fc01234u && lo[3] == 0x7fc04321u) *reinterpret_cast<uint32_t*>(img) = hi[1] ^ lo[2] ^ hi[15] ^ lo[15] ^ hi[8] ^ lo[8];
@@ -378,6 +381,19 @@ __device__ __forceinline__ void dw_store_half(char* img, int k, int hf, const ui
   // chunks: 4 wavefronts per STS.128 instead of 8.
   char* row = img + (size_t)(k >> 2) * kDwSBO + r * 128 + 16 * sw;
   const int odd = 16 - 32 * sw;
+  if (PACKED) {
+    row += (size_t)hf * kDwLBO;
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+      char* p = row + ((cc ^ r) * 32);
+      char* q = row + (((2 + cc) ^ r) * 32);
+      *reinterpret_cast<uint4*>(p) = make_uint4(hi[8 * cc], hi[8 * cc + 1], hi[8 * cc + 2], hi[8 * cc + 3]);
+      *reinterpret_cast<uint4*>(p + odd) = make_uint4(hi[8 * cc + 4], hi[8 * cc + 5], hi[8 * cc + 6], hi[8 * cc + 7]);
+      *reinterpret_cast<uint4*>(q) = make_uint4(lo[8 * cc], lo[8 * cc + 1], lo[8 * cc + 2], lo[8 * cc + 3]);
+      *reinterpret_cast<uint4*>(q + odd) = make_uint4(lo[8 * cc + 4], lo[8 * cc + 5], lo[8 * cc + 6], lo[8 * cc + 7]);
+    }
+    return;
+  }
 #pragma unroll
   for (int cc = 0; cc < 2; ++cc) {
     char* p = row + (((2 * hf + cc) ^ r) * 32);
@@ -387,6 +403,9 @@ __device__ __forceinline__ void dw_store_half(char* img, int k, int hf, const ui
     *reinterpret_cast<uint4*>(p + kDwLBO + odd) = make_uint4(lo[8 * cc + 4], lo[8 * cc + 5], lo[8 * cc + 6], lo[8 * cc + 7]);
   }
 }
+#ifndef CLB_DWB_PACK
+#define CLB_DWB_PACK 0
+#endif
 
 // The 4 weights this thread contributes to the B operand image of one layer (256 threads x 4 = 32 x 32):
 //   forward  (B[n][k] = W[k][n]): thread (n = tid % 32, kq = tid / 32) gathers k = 4 kq .. 4 kq + 3;
@@ -495,6 +514,15 @@ __device__ __forceinline__ void collect_dw_red(Ctx& c, float* wk, int il_w, floa
   uint32_t v0[16];
   CLB_TMEM_LD16(addr, v0);
   wait_ld();
+#elif CLB_DWB_PACK
+  uint32_t v0[16], v1[16];
+  {
+    uint32_t v[32];
+    CLB_TMEM_LD32(c.row_addr + kColDw + 32u * (uint32_t)c.hf, v);
+    wait_ld();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { v0[k] = v[k]; v1[k] = v[16 + k]; }
+  }
 #else
   uint32_t v0[16], v1[16];
   CLB_TMEM_LD16(addr, v0);
@@ -553,6 +581,25 @@ __device__ __forceinline__ void tma_fetch_image(uint32_t dst_smem, const float* 
 
 // Issue one chain pass from buffer b; `tma` = the image came by TMA (wait for it), `next` = global image of the next
 // pass to prefetch into the other buffer (or null).  Called by all threads after the pass's __syncthreads().
+#ifndef CLB_ST32
+#define CLB_ST32 1          // 1: the chain's A operand (hi and lo parts of a thread's 16 features) is written with ONE tcgen05.st.x32 into 32
+                            // adjacent columns [hi 16 | lo 16] per feature half instead of two .x16 stores into separate hi / lo regions
+#endif
+// first tensor-memory column (relative to the CTA base) of K-slice ks (features 8 ks .. 8 ks + 7) of the hi / lo operand
+__device__ __forceinline__ constexpr uint32_t acol_hi(int ks) { return CLB_ST32 ? (uint32_t)(32 * (ks >> 1) + 8 * (ks & 1)) : kColAhi + 8u * (uint32_t)ks; }
+__device__ __forceinline__ constexpr uint32_t acol_lo(int ks) { return CLB_ST32 ? (uint32_t)(32 * (ks >> 1) + 16 + 8 * (ks & 1)) : kColAlo + 8u * (uint32_t)ks; }
+// store this thread's hi / lo operand halves (two threads per row)
+__device__ __forceinline__ void store_operand16(uint32_t row_addr, int hf, const uint32_t (&hi)[16], const uint32_t (&lo)[16]) {
+#if CLB_ST32
+  uint32_t v[32];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) { v[k] = hi[k]; v[16 + k] = lo[k]; }
+  CLB_TMEM_ST32(row_addr + 32u * (uint32_t)hf, v);
+#else
+  CLB_TMEM_ST16(row_addr + kColAhi + 16u * (uint32_t)hf, hi);
+  CLB_TMEM_ST16(row_addr + kColAlo + 16u * (uint32_t)hf, lo);
+#endif
+}
 #ifndef CLB_BIAS_IN_MMA
 #define CLB_BIAS_IN_MMA 0   // 1: a forward pass starts from an accumulator PRELOADED with the layer's bias (one tcgen05.st per thread
                             // and every MMA accumulating) instead of 16 FADDs per thread after the collection.  Parity-green; measured
@@ -574,13 +621,13 @@ __device__ __forceinline__ void issue_chain_mmas2(Ctx& c, bool tma, const float*
 #ifndef CLB_ABL_CHAIN
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks)
-        mma_tf32_ts(d, base + kColAhi + 8u * (uint32_t)ks, blo + (uint64_t)((2u * kLBO * (uint32_t)ks) >> 4), (ks > 0 || preloaded) ? 1u : 0u);
+        mma_tf32_ts(d, base + acol_hi(ks), blo + (uint64_t)((2u * kLBO * (uint32_t)ks) >> 4), (ks > 0 || preloaded) ? 1u : 0u);
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks)
-        mma_tf32_ts(d, base + kColAlo + 8u * (uint32_t)ks, bhi + (uint64_t)((2u * kLBO * (uint32_t)ks) >> 4), 1u);
+        mma_tf32_ts(d, base + acol_lo(ks), bhi + (uint64_t)((2u * kLBO * (uint32_t)ks) >> 4), 1u);
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks)
-        mma_tf32_ts(d, base + kColAhi + 8u * (uint32_t)ks, bhi + (uint64_t)((2u * kLBO * (uint32_t)ks) >> 4), 1u);
+        mma_tf32_ts(d, base + acol_hi(ks), bhi + (uint64_t)((2u * kLBO * (uint32_t)ks) >> 4), 1u);
 #endif
       commit(bar);
       if (next != nullptr) tma_fetch_image(ndst, next, nb);
@@ -617,8 +664,7 @@ __device__ __forceinline__ void issue3(Ctx& c, const float (&x)[16], const float
   {
     uint32_t hi[16], lo[16];
     split16(x, hi, lo);
-    CLB_TMEM_ST16(c.row_addr + kColAhi + c.col, hi);
-    CLB_TMEM_ST16(c.row_addr + kColAlo + c.col, lo);
+    store_operand16(c.row_addr, c.hf, hi, lo);
   }
   if (bias16 != nullptr) {
     uint32_t b[16];
@@ -642,13 +688,10 @@ __device__ __forceinline__ void issue_backward3(Ctx& c, const float (&dp)[16], c
   {
     uint32_t hi[16], lo[16];
     split16(dp, hi, lo);
-    if (need_dx) {
-      CLB_TMEM_ST16(c.row_addr + kColAhi + c.col, hi);
-      CLB_TMEM_ST16(c.row_addr + kColAlo + c.col, lo);
-    }
+    if (need_dx) store_operand16(c.row_addr, c.hf, hi, lo);
     const int sw = (c.row >> 2) & 1;       // conflict-free image stores: see dw_store_half
     swap_blocks(hi, sw); swap_blocks(lo, sw);
-    dw_store_half(c.dw_b, c.row, c.hf, hi, lo, sw);
+    dw_store_half<CLB_DWB_PACK != 0>(c.dw_b, c.row, c.hf, hi, lo, sw);
     {
       uint32_t a2[16];
 #pragma unroll
@@ -781,7 +824,7 @@ __device__ __forceinline__ void bwd_handover(Ctx& c, uint32_t (&hi)[16], uint32_
   }
   const int sw = (c.row >> 2) & 1;       // conflict-free image stores: see dw_store_half
   swap_blocks(hi, sw); swap_blocks(lo, sw);
-  dw_store_half(c.dw_b, c.row, c.hf, hi, lo, sw);
+  dw_store_half<CLB_DWB_PACK != 0>(c.dw_b, c.row, c.hf, hi, lo, sw);
   {
     uint32_t a2[16];
 #pragma unroll
@@ -810,7 +853,7 @@ __device__ __forceinline__ void bwd_handover(Ctx& c, uint32_t (&hi)[16], uint32_
 __device__ __forceinline__ void dw_handover(Ctx& c, uint32_t (&hi)[16], uint32_t (&lo)[16], const float (&ain)[16], const float4* dead, int lane) {
   const int sw = (c.row >> 2) & 1;       // conflict-free image stores: see dw_store_half
   swap_blocks(hi, sw); swap_blocks(lo, sw);
-  dw_store_half(c.dw_b, c.row, c.hf, hi, lo, sw);
+  dw_store_half<CLB_DWB_PACK != 0>(c.dw_b, c.row, c.hf, hi, lo, sw);
   {
     uint32_t a2[16];
 #pragma unroll
