@@ -20,6 +20,21 @@ def _ngpu():
     return torch.cuda.device_count()
 
 
+def _spawn(fn, args_of_port, nprocs):
+    """mp.spawn with a fresh rendezvous port; ONE retry when the rendezvous itself failed (the port found free was taken between the
+    probe and the store's bind, or the store timed out while a fresh box was still paging torch in) -- never on a worker's own error."""
+    import torch.multiprocessing as mp
+    for attempt in range(2):
+        try:
+            return mp.spawn(fn, args=args_of_port(_free_port()), nprocs=nprocs, join=True)
+        except Exception as e:      # noqa: BLE001
+            msg = str(e)
+            rendezvous = any(k in msg for k in ("DistNetworkError", "DistStoreError", "address already in use", "EADDRINUSE", "TCPStore"))
+            if attempt == 1 or not rendezvous:
+                raise
+            print(f"[test_gpu_multi] rendezvous failed ({msg.splitlines()[-1][:200]}); retrying on another port")
+
+
 def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
@@ -112,11 +127,11 @@ def _worker(rank, world, port, kind, ret, in_library=True):
                                              ("mono", False)])
 def test_two_gpus_match_one(kind, in_library):
     import torch.multiprocessing as mp
-    world, port = 2, _free_port()
+    world = 2
     ctx = mp.get_context("spawn")
     with ctx.Manager() as mgr:
         ret = mgr.dict()
-        mp.spawn(_worker, args=(world, port, kind, ret, in_library), nprocs=world, join=True)
+        _spawn(_worker, lambda port: (world, port, kind, ret, in_library), world)
         ret = dict(ret)
     p = _problem(kind)
     R = len(p["centric"])
@@ -195,11 +210,11 @@ def test_train_model_on_two_gpus_equals_one(kind):
     """`VariationalMergingModel.train_model` in a 2-process job (what `torchrun -m careless_b200.careless` runs) returns the
     single-GPU history, surrogate, merged F and per-observation scale moments."""
     import torch.multiprocessing as mp
-    world, port = 2, _free_port()
+    world = 2
     ctx = mp.get_context("spawn")
     with ctx.Manager() as mgr:
         ret = mgr.dict()
-        mp.spawn(_api_worker, args=(world, port, kind, ret), nprocs=world, join=True)
+        _spawn(_api_worker, lambda port: (world, port, kind, ret), world)
         ret = dict(ret)
     parallel.set_context(parallel.DistContext())
     try:
