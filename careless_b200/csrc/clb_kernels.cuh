@@ -860,7 +860,7 @@ __global__ void __launch_bounds__(TC ? tc::kThreads : kObsThreads, TC ? 2 : 1) k
 // ---------------------------------------------------------------------------------------
 struct ObsSmem2 {
   static size_t bytes(int n_layers, int n_img_layers) {
-    return 2 * (size_t)tc::kDwImgBytes + (CLB_BIAS_ONES ? (size_t)tc::kDwLBO : 0) + sizeof(float) * (64 + (size_t)n_layers * 32 + (size_t)n_img_layers * (1024 + 32))
+    return 2 * (size_t)tc::kDwImgBytes + ((CLB_BIAS_ONES || CLB_BIAS_COL) ? (size_t)tc::kDwLBO : 0) + sizeof(float) * (64 + (size_t)n_layers * 32 + (size_t)n_img_layers * (1024 + 32))
            + 64 * sizeof(double) + 4 * (size_t)tc::kImgBytes + 64 + 4 * 128 * sizeof(float) + 128;
   }
 };
@@ -917,7 +917,7 @@ __device__ __forceinline__ void tc_layer_backward2(tc::Ctx& tcx, float (&dp)[16]
   // one hand-over per layer (chain operands + dW images); dW collected at the end of this layer
   tc::bwd_handover(tcx, hi, lo, ain, need_dx, build_from, img_base, next_img, dead, lane);
 #endif
-#if !CLB_BIAS_ONES
+#if !CLB_BIAS_ONES && !CLB_BIAS_COL
   // what does not feed the tensor cores runs while they work: the bias gradient (column sums of dp)
   bias_red16(dp, bk != nullptr ? bk + 16 * tcx.hf : nullptr, lane, il_w > 0 ? il_w - 16 * tcx.hf : 16);
 #endif
@@ -941,7 +941,7 @@ __global__ void __launch_bounds__(tc::kThreads2, 2) k_obs_tc2(ObsArgs a) {
   const int NL = a.lay.n_layers, L = NL - 1, K = IL ? a.n_img_layers : 0, LT = L + K;
   unsigned char* sp = smem_raw;
   char* tc_dwa = reinterpret_cast<char*>(sp);               // dW A operand: MN groups [a_hi | a_lo | ONES | (delta-p_hi: unused rows)]
-  constexpr size_t kOnes = CLB_BIAS_ONES ? tc::kDwLBO : 0;  // CLB_BIAS_ONES: 16 KB of 1.0f, rows 64..95 of the product = column sums of delta-p
+  constexpr size_t kOnes = (CLB_BIAS_ONES || CLB_BIAS_COL) ? tc::kDwLBO : 0;  // 16 KB of 1.0f after the a images: rows 64..95 (CLB_BIAS_ONES) / columns 64..71 (CLB_BIAS_COL) of the dW product = column sums of delta-p
   float* ones = reinterpret_cast<float*>(tc_dwa + tc::kDwImgBytes);
   char* tc_dwb = tc_dwa + tc::kDwImgBytes + kOnes;          // dW B operand: [delta-p_hi | delta-p_lo]
   sp += 2 * tc::kDwImgBytes + kOnes;
@@ -1241,7 +1241,7 @@ __global__ void __launch_bounds__(256) k_pack_images(const float* theta_mlp, Mlp
 
 // k_obs_tc2's partials: [rows][n_layers][32*32 + 32] FP32 (kernel [in][out] padded to 32 x 32, then the bias), summed over
 // the CTAs in FP64 in a fixed order.
-__global__ void __launch_bounds__(256) k_reduce_partials32(const float* partials, int rows, MlpLayout lay, float* grad, int det) {
+__global__ void __launch_bounds__(256) k_reduce_partials32(const float* partials, int rows, MlpLayout lay, float* grad, int det, int transposed = 0) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= lay.n_params) return;
   const int PSLOT = det ? tc::kPslotDet : 32 * 32 + 32, PP = lay.n_layers * PSLOT;
@@ -1252,7 +1252,7 @@ __global__ void __launch_bounds__(256) k_reduce_partials32(const float* partials
     const int nk = lay.in_dim[k] * lay.out_dim[k];
     if (p >= lay.koff[k] && p < lay.koff[k] + nk) {
       const int i = (p - lay.koff[k]) / lay.out_dim[k], j = (p - lay.koff[k]) % lay.out_dim[k];
-      src = k * PSLOT + tc::dw_slot32(i, j);
+      src = k * PSLOT + (transposed ? tc::dw_slot32(j, i) : tc::dw_slot32(i, j));     // CLB_BIAS_COL: k_obs_tc2 stores the slot transposed
       if (det) { extra = 1024; n_extra = 1; }
       break;
     }

@@ -406,6 +406,39 @@ __device__ __forceinline__ void dw_store_half(char* img, int k, int hf, const ui
 #ifndef CLB_DWB_PACK
 #define CLB_DWB_PACK 0
 #endif
+#ifndef CLB_STS_DIVERGE
+#define CLB_STS_DIVERGE 0   // 1: the conflict-free store order of the dW operand images (odd lane groups store the second 16-byte block of a chunk
+                            // first) by a two-way predicated store sequence instead of swapping the register blocks with selects (-68 SEL, +32
+                            // half-populated STS.128 per thread and layer).  Parity-green; measured MUCH slower on B200: 19.77 vs 16.23 ms --
+                            // a shared-memory store instruction costs its full wavefronts whatever the number of active lanes
+#endif
+// Same bytes and the same conflict-free instruction pairing as swap_blocks + dw_store_half, without the 48 selects per thread and layer:
+// lanes with sw = 0 store (block 0, block 1), lanes with sw = 1 store (block 1, block 0), each under its own predicate.
+__device__ __forceinline__ void dw_store_half_div(char* img, int k, int hf, const uint32_t (&hi)[16], const uint32_t (&lo)[16]) {
+  const int r = k & 3;
+  char* row = img + (size_t)(k >> 2) * kDwSBO + r * 128;
+  char* p0 = row + (((2 * hf) ^ r) * 32);
+  char* p1 = row + (((2 * hf + 1) ^ r) * 32);
+  if (((k >> 2) & 1) == 0) {
+    *reinterpret_cast<uint4*>(p0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(p0 + 16) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+    *reinterpret_cast<uint4*>(p0 + kDwLBO) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    *reinterpret_cast<uint4*>(p0 + kDwLBO + 16) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+    *reinterpret_cast<uint4*>(p1) = make_uint4(hi[8], hi[9], hi[10], hi[11]);
+    *reinterpret_cast<uint4*>(p1 + 16) = make_uint4(hi[12], hi[13], hi[14], hi[15]);
+    *reinterpret_cast<uint4*>(p1 + kDwLBO) = make_uint4(lo[8], lo[9], lo[10], lo[11]);
+    *reinterpret_cast<uint4*>(p1 + kDwLBO + 16) = make_uint4(lo[12], lo[13], lo[14], lo[15]);
+  } else {
+    *reinterpret_cast<uint4*>(p0 + 16) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+    *reinterpret_cast<uint4*>(p0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(p0 + kDwLBO + 16) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+    *reinterpret_cast<uint4*>(p0 + kDwLBO) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    *reinterpret_cast<uint4*>(p1 + 16) = make_uint4(hi[12], hi[13], hi[14], hi[15]);
+    *reinterpret_cast<uint4*>(p1) = make_uint4(hi[8], hi[9], hi[10], hi[11]);
+    *reinterpret_cast<uint4*>(p1 + kDwLBO + 16) = make_uint4(lo[12], lo[13], lo[14], lo[15]);
+    *reinterpret_cast<uint4*>(p1 + kDwLBO) = make_uint4(lo[8], lo[9], lo[10], lo[11]);
+  }
+}
 
 // The 4 weights this thread contributes to the B operand image of one layer (256 threads x 4 = 32 x 32):
 //   forward  (B[n][k] = W[k][n]): thread (n = tid % 32, kq = tid / 32) gathers k = 4 kq .. 4 kq + 3;
@@ -452,6 +485,15 @@ constexpr uint32_t kIdescDw128 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15)
 // ITS 16 columns and adds them to wk[i][16 hf ..] with four 16-byte REDs (il_w > 0: an image layer's kernel, stored
 // (out, in) with width il_w, scalar REDs).  When this returns the dW MMAs are complete: the operand images and the
 // accumulator may be reused after the next __syncthreads().
+#ifndef CLB_BIAS_COL
+#define CLB_BIAS_COL 0      // 1: the dW product is taken TRANSPOSED, D = [dp_hi; dp_lo]^T [a_hi | a_lo | ONES (8 columns)] (M = 64, N = 72): column 64
+                            // of the accumulator is the bias gradient (column sums of delta-p), so the 16 shuffles + ~45 ALU instructions per
+                            // thread and layer of bias_red16 go away for 12.5 % more dW tensor time.  The ones sit on the N side (one extra
+                            // 32-byte chunk per K row), not on the M side like CLB_BIAS_ONES (which doubled the A operand reads).
+                            // Parity-green (all of tests/test_gpu_parity.py); measured SLOWER on B200: 17.28 vs 16.23 ms per 10 M observations.
+#endif
+#define CLB_TMEM_LD1(taddr, v) asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory")
+constexpr uint32_t kIdescDwT72 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((72u >> 3) << 17) | ((64u >> 4) << 24);
 #ifndef CLB_BIAS_ONES
 #define CLB_BIAS_ONES 0     // 1: bias gradient as a ones row of an M = 128 dW product (parity-green; measured SLOWER on B200, 17.2 vs
                             // 16.8 ms: the M = 128 product reads twice the A operand from shared memory and the dW MMAs get longer)
@@ -491,6 +533,41 @@ __device__ __forceinline__ void collect_dw_red(Ctx& c, float* wk, int il_w, floa
 #pragma unroll
       for (int k = 0; k < 16; ++k) { const int j = 16 * c.hf + k; if (j < il_w) atomicAdd(&bk[j], f[k]); }
     }
+  }
+}
+#elif CLB_BIAS_COL
+constexpr uint32_t kIdescDwTc2 = kIdescDwT72;
+// Transposed product: D rows (lanes (r % 16) + 32 (r / 16)) are delta-p features j = r % 32 (rows 0..31 from dp_hi, 32..63 from dp_lo), columns
+// 0..31 / 32..63 the a_hi / a_lo features i, column 64 the sum over the tile's observations.  Lane j of a warp's lower half adds its 16 values
+// i = 16 hf .. to dW[i][j]: the partial's slot is stored TRANSPOSED ([i / 4][j][i % 4], dw_slot32(j, i)) so that these are again four 16-byte
+// REDs per thread covering 256 contiguous bytes per warp.  bk = bias slot (or an image layer's bias gradient).
+__device__ __forceinline__ void collect_dw_red(Ctx& c, float* wk, int il_w, float* bk = nullptr) {
+  mbar_wait(c.mbar_dw, c.parity_dw);
+  c.parity_dw ^= 1u;
+  fence_after();
+  const int q = (c.tid >> 5) & 3, lane = c.tid & 31;
+  const uint32_t addr = c.row_addr + kColDw + c.col;
+  uint32_t v0[16], v1[16], vb = 0u;
+  CLB_TMEM_LD16(addr, v0);
+  CLB_TMEM_LD16(addr + 32, v1);
+  if (c.hf == 0) CLB_TMEM_LD1(c.row_addr + kColDw + 64u, vb);
+  wait_ld();
+  if (lane < 16) {
+    const int j = (16 * q + lane) & 31;
+    if (wk != nullptr) {
+      float f[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) f[k] = __uint_as_float(v0[k]) + __uint_as_float(v1[k]);
+      if (il_w == 0) {
+        float4* dst = reinterpret_cast<float4*>(wk + (q >= 2 ? c.lo_off : 0)) + (4 * c.hf) * 32 + j;      // dw_slot32(j, 16 hf + 4 qq) / 4
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) atomicAdd(dst + qq * 32, make_float4(f[4 * qq], f[4 * qq + 1], f[4 * qq + 2], f[4 * qq + 3]));
+      } else if (j < il_w) {               // an image layer's kernel, stored (out, in) with width il_w
+#pragma unroll
+        for (int k = 0; k < 16; ++k) { const int i = 16 * c.hf + k; if (i < il_w) atomicAdd(&wk[j * il_w + i], f[k]); }
+      }
+    }
+    if (c.hf == 0 && bk != nullptr && (il_w == 0 || j < il_w)) atomicAdd(&bk[j], __uint_as_float(vb));
   }
 }
 #else
@@ -552,7 +629,12 @@ __device__ __forceinline__ void collect_dw_red(Ctx& c, float* wk, int il_w, floa
 
 // The tcgen05.mma's of one tile's dW = [a_hi; a_lo]^T [delta-p_hi | delta-p_lo] (one elected lane; operands warp-uniform).
 __device__ __forceinline__ void issue_dw_mmas(uint32_t d, uint64_t a0, uint64_t b0) {
-#if CLB_DW_FOLD && !CLB_BIAS_ONES
+#if CLB_BIAS_COL && !CLB_BIAS_ONES
+  // transposed: A operand = the delta-p images, B operand = [a_hi | a_lo | ones] (the ones block follows the a images)
+#pragma unroll
+  for (int ks = 0; ks < kThreads / 8; ++ks)
+    mma_tf32_ss(d, b0 + (uint64_t)((2u * kDwSBO * (uint32_t)ks) >> 4), a0 + (uint64_t)((2u * kDwSBO * (uint32_t)ks) >> 4), kIdescDwT72, ks > 0 ? 1u : 0u);
+#elif CLB_DW_FOLD && !CLB_BIAS_ONES
   // x delta-p_hi, then x delta-p_lo (MN group 1: + kDwLBO bytes) into the same 32 accumulator columns
 #pragma unroll
   for (int ks = 0; ks < kThreads / 8; ++ks)
@@ -689,6 +771,15 @@ __device__ __forceinline__ void issue_backward3(Ctx& c, const float (&dp)[16], c
     uint32_t hi[16], lo[16];
     split16(dp, hi, lo);
     if (need_dx) store_operand16(c.row_addr, c.hf, hi, lo);
+#if CLB_STS_DIVERGE
+    dw_store_half_div(c.dw_b, c.row, c.hf, hi, lo);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      hi[k] = __float_as_uint(ain[k]);
+      lo[k] = __float_as_uint(ain[k] - __uint_as_float(hi[k] & 0xFFFFE000u));
+    }
+    dw_store_half_div(c.dw_a, c.row, c.hf, hi, lo);
+#else
     const int sw = (c.row >> 2) & 1;       // conflict-free image stores: see dw_store_half
     swap_blocks(hi, sw); swap_blocks(lo, sw);
     dw_store_half<CLB_DWB_PACK != 0>(c.dw_b, c.row, c.hf, hi, lo, sw);
@@ -704,6 +795,7 @@ __device__ __forceinline__ void issue_backward3(Ctx& c, const float (&dp)[16], c
       }
     }
     dw_store_half(c.dw_a, c.row, c.hf, hi, lo, sw);
+#endif
   }
   if (need_dx && build_from != nullptr) build_weight_image3<true>(c, build_from, img_base);
   wait_st();
