@@ -344,6 +344,7 @@ def run_ours(args, c):
                   refl_index=lt["refl_index"])
     eng.synchronize()
     t_prep = time.perf_counter() - t_prep
+    row_prep_ms = eng.download_rows_info()["prep_ms"]      # the row preparation alone (GPU radix sort + gather incl. the copy of the raw tuple)
     if world > 1:        # library-side communicator: rank 0's id travels over the (already initialised) process group
         idt = torch.zeros(128, dtype=torch.uint8, device=f"cuda:{local}")
         if rank == 0:
@@ -462,7 +463,7 @@ def run_ours(args, c):
                         "d2h_bytes_per_step": 32 * world, "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": int(round(launches_per_step * args.steps)), "launches_per_step": launches_per_step,
                 "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-                "last_metrics": last, "host_prep_s": t_prep}
+                "last_metrics": last, "host_prep_s": t_prep, "row_prep_ms": row_prep_ms}
         print(json.dumps(line), flush=True)
     eng.close()
     if world > 1:
