@@ -134,8 +134,8 @@ __device__ __forceinline__ void issue_chain16(Ctx16& c, bool fwd, const float* n
       if (fwd) {          // images [hi, mid, lo]
         CLB_MMA16(kA_hi, w2, true);  CLB_MMA16(kA_lo, w0, false); CLB_MMA16(kA_mid, w1, false);
         CLB_MMA16(kA_hi, w1, false); CLB_MMA16(kA_mid, w0, false); CLB_MMA16(kA_hi, w0, false);
-      } else {            // images [hi, lo]; delta-p as (hi at kA_hi, lo at kA_lo)
-        CLB_MMA16(kA_hi, w1, true);  CLB_MMA16(kA_lo, w0, false); CLB_MMA16(kA_hi, w0, false);
+      } else {            // images [hi, lo]; delta-p as (hi at kA_hi, lo at kA_lo -- CLB_ST32: at kA_mid, next to hi)
+        CLB_MMA16(kA_hi, w1, true);  CLB_MMA16(CLB_ST32 ? kA_mid : kA_lo, w0, false); CLB_MMA16(kA_hi, w0, false);
       }
 #undef CLB_MMA16
       commit(bar);
@@ -177,8 +177,17 @@ __device__ __forceinline__ void issue_fwd16(Ctx16& c, const float (&x)[16], cons
   {
     uint32_t hi[16], mid[16], lo[16];
     split16_3(x, hi, mid, lo);
+#if CLB_ST32
+    {                                               // hi | mid sit in adjacent columns: one tcgen05.st.x32 + one .x16 instead of three .x16
+      uint32_t v[32];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) { v[k] = hi[k]; v[16 + k] = mid[k]; }
+      CLB_TMEM_ST32(c.row_addr + kA_hi, v);
+    }
+#else
     CLB_TMEM_ST16(c.row_addr + kA_hi, hi);
     CLB_TMEM_ST16(c.row_addr + kA_mid, mid);
+#endif
     CLB_TMEM_ST16(c.row_addr + kA_lo, lo);
   }
   if (build_from != nullptr) { build_images16<false>(c, build_from, w_img); fence_async_smem(); }
@@ -205,8 +214,15 @@ __device__ __forceinline__ void issue_bwd16(Ctx16& c, const float (&dp)[16], con
     uint32_t hi[16], lo[16];
     split16_rna(dp, hi, lo);
     if (need_dx) {
+#if CLB_ST32
+      uint32_t v[32];                               // backward: the lo part goes to the (unused) mid columns next to hi: one .x32 store
+#pragma unroll
+      for (int k = 0; k < 16; ++k) { v[k] = hi[k]; v[16 + k] = lo[k]; }
+      CLB_TMEM_ST32(c.row_addr + kA_hi, v);
+#else
       CLB_TMEM_ST16(c.row_addr + kA_hi, hi);
       CLB_TMEM_ST16(c.row_addr + kA_lo, lo);
+#endif
     }
     const int sw = (c.tid >> 2) & 1;
     swap_blocks(hi, sw); swap_blocks(lo, sw);
