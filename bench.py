@@ -449,7 +449,9 @@ def run_ours(args, c):
                     "kernel_ms": obs_avg_ms, "kernel_share_of_step": obs_avg_ms / ms_step, "flops_per_obs": fpo}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            cpu = cpu_reference(c, 12.0, 250_000, max(500, int(250_000 * c["refl"] / c["obs"])))
+            # the same 1 M-observation sample as the reference arm (run_reference): the CPU path's obs/s falls with the sample size
+            # (cache residency), so the two CPU legs are only comparable on equal samples
+            cpu = cpu_reference(c, 12.0, 1_000_000, max(1000, int(1_000_000 * c["refl"] / c["obs"])))
             cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
         cfgd = workload_config(args, c, world, N_glob, R_glob)
         cfgd["deterministic"] = bool(args.deterministic)

@@ -791,7 +791,8 @@ int clb_set_observations(clb_handle* h, int64_t n, int64_t n_total, const int64_
   h->rows_alt.free();
   // device-side preparation (default): everything but the deterministic mode (which also wants the CSR of row positions per
   // reflection, built from the host permutation) and a caller-forced image order without a known image count
-  const bool on_device = h->device_prep && !h->det && n > 0 && !(order == CLB_ORDER_IMAGE && n_images_chk == 0);
+  const bool on_device = h->device_prep && !h->det && n > 0 && !(order == CLB_ORDER_IMAGE && n_images_chk == 0) &&
+                         order >= CLB_ORDER_AUTO && order <= CLB_ORDER_IMAGE;        // CLB_ORDER_NONE (rows kept as given): nothing to sort
   const auto t_prep0 = std::chrono::steady_clock::now();
   if (on_device) {
     const int rc = prep_rows_device(h, plan, L, n, n_total, n_images_chk, image_tile, refl_id, image_id, metadata, iobs, sig, harmonic_id, obs_index, order);

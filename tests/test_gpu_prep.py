@@ -97,6 +97,19 @@ def test_images_without_rows_and_single_row_images():
     _compare(_shuffled(p, seed=10), image_layers=2, width=10)
 
 
+def test_rows_kept_as_given_with_order_none():
+    """CLB_ORDER_NONE: the caller's row order is kept (no sort on either path)."""
+    p = _shuffled(synth.make_mono(2000, 100, d=2, n_images=5, seed=21), seed=22)
+    eng = _engine(p)
+    try:
+        eng.set_observations(p["refl_id"], p["image_id"], p["metadata"], p["intensities"], p["uncertainties"], order=L.ORDER_NONE)
+        dev = eng.download_rows()
+    finally:
+        eng.close()
+    assert np.array_equal(dev["refl"][:2000], p["refl_id"]) and np.array_equal(dev["oidx"][:2000], np.arange(2000))
+    assert np.array_equal(dev["iobs"][:2000], p["intensities"])
+
+
 def test_device_prep_reports_the_same_first_bad_row():
     p = synth.make_mono(10_000, 100, d=2, n_images=3, seed=1)
     rid = p["refl_id"].copy(); rid[7777] = 100; rid[4321] = -1
