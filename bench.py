@@ -384,23 +384,31 @@ def run_ours(args, c):
     # (the rows were prepared on the device; their pinned host mirror -- the buffer every step's H2D copy starts from -- is
     # created by the first upload, outside the timed region like any other allocation)
     eng.upload_observations()
+    eng.prefetch_observations()            # also creates the copy stream, its events and the second device buffer (a 360 MB cudaMalloc
+    eng.step_begin(); eng.step_norms(); eng.step_end(True)      # that would otherwise land, with its implicit synchronisation, in step 0)
     eng.synchronize()
     barrier()
     t0 = time.perf_counter()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record(stream)
     eng.upload_observations()              # pinned host -> device copy of the first step's inputs (exposed)
+    step_wall = []
     for i in range(args.steps):
         # the step's kernels (and its exchange) are queued first, then the NEXT step's inputs start travelling on the copy
         # stream (second device buffer, clb_prefetch_observations), then this step's metrics are read back (4 doubles)
+        ts = time.perf_counter()
         eng.step_begin()
         eng.step_norms()
         if i + 1 < args.steps:
             eng.prefetch_observations()
         eng.step_end(True)
+        step_wall.append(1e3 * (time.perf_counter() - ts))
     e3.record(stream)
     barrier()
-    ms_e2e = max(e2.elapsed_time(e3), 1e3 * (time.perf_counter() - t0))
+    ms_e2e_dev, ms_e2e_wall = e2.elapsed_time(e3), 1e3 * (time.perf_counter() - t0)
+    ms_e2e = max(ms_e2e_dev, ms_e2e_wall)
+    if os.environ.get("CLB_BENCH_DEBUG"):
+        print(f"[bench] e2e device {ms_e2e_dev:.2f} ms, wall {ms_e2e_wall:.2f} ms; per-step wall: " + " ".join(f"{x:.1f}" for x in step_wall), file=sys.stderr)
     row_bytes = 4 + 4 + 4 * D_META + 4 + 4 + (4 if use_img else 0) + (4 if name == "laue" else 0)
     h2d = n_loc * row_bytes
     obs_ms = kt["obs_kernel_ms"]

@@ -1,0 +1,2 @@
+for i in 1 2 3 4; do timeout 300 python bench.py --steps 20 --no-cpu-baseline 2>/dev/null | python -c "
+import json,sys; d=json.loads([l for l in sys.stdin if l.startswith('{')][-1]); print('run $i', round(d['ms_per_step'],3), round(d['e2e']['ms_per_step'],3))"; done
