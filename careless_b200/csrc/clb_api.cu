@@ -1276,8 +1276,8 @@ static int step_begin_impl(clb_handle* h, const float* inj_u, const float* inj_e
   }
   if (train_mlp) {
     const int np = h->lay.n_params;
-    if (h->use_tc16) k_reduce_partials16<<<(np + 255) / 256, 256, 0, st>>>(h->partials.as<float>(), h->n_partials, h->lay, grad + h->goff[CLB_GROUP_MLP], h->det ? 1 : 0);
-    else if (h->use_tc2) k_reduce_partials32<<<(np + 255) / 256, 256, 0, st>>>(h->partials.as<float>(), h->n_partials, h->lay, grad + h->goff[CLB_GROUP_MLP], h->det ? 1 : 0,
+    if (h->use_tc16) k_reduce_partials16<<<(np + 31) / 32, 256, 0, st>>>(h->partials.as<float>(), h->n_partials, h->lay, grad + h->goff[CLB_GROUP_MLP], h->det ? 1 : 0);
+    else if (h->use_tc2) k_reduce_partials32<<<(np + 31) / 32, 256, 0, st>>>(h->partials.as<float>(), h->n_partials, h->lay, grad + h->goff[CLB_GROUP_MLP], h->det ? 1 : 0,
                                                                                (CLB_BIAS_COL && !h->use_pp && !h->use_tc3) ? 1 : 0);
     else k_reduce_partials<<<(np + 255) / 256, 256, 0, st>>>(h->partials.as<double>(), h->grid_obs * h->KS, h->lay, h->WP, grad + h->goff[CLB_GROUP_MLP]);
     CLB_LAUNCHED(h);
