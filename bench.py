@@ -501,6 +501,8 @@ def main():
     ap.add_argument("--obs", type=int, default=None, help="observations (per GPU for weak scaling, total for strong)")
     ap.add_argument("--refl", type=int, default=None)
     ap.add_argument("--scaling", default=None, choices=["weak", "strong"])
+    ap.add_argument("--images", type=int, default=None, help="override the number of images (e.g. one rank's share of configs[4] at N = 8: "
+                    "--config stills --obs 25000000 --refl 250000 --images 100000, 250 rows per image)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--deterministic", action="store_true", help="clb_config.deterministic: bitwise reproducible steps (costs time; not the default)")
     args = ap.parse_args()
@@ -514,6 +516,8 @@ def main():
     if args.obs != c["obs"] or args.refl != c["refl"]:
         c["n_images"] = max(2, int(c["n_images"] * args.obs / c["obs"]))
         c["obs"], c["refl"] = args.obs, args.refl
+    if args.images:
+        c["n_images"] = args.images
     if args.impl == "reference":
         run_reference(args, c)
     else:
