@@ -258,7 +258,6 @@ cudaError_t dispatch_obs(clb_handle* h, const ObsArgs& a) {
   return cudaErrorInvalidValue;
 }
 
-int ks_for(int WP) { return std::max(1, kObsThreads / (WP * (WP / 4))); }
 
 void build_layout(clb_handle* h) {
   const clb_config& c = h->cfg;
