@@ -143,6 +143,7 @@ struct clb_handle {
   PinBuf rows_host;        // pinned mirror (for re-upload)
   bool rows_host_valid = false;   // device-side prep: the mirror is filled (device -> host) only when a re-upload is asked for
   bool device_prep = true;        // rows are sorted / padded / gathered on the GPU (clb_prep.cuh), unless CLB_DEVICE_PREP=0
+  bool bias_feat15 = false;       // k_obs_tc16, max(n_meta, mlp_width) <= 15: bias gradients as row 15 of the dW products (unless CLB_BIAS_FEAT=0)
   double prep_ms = 0.0;           // wall time of the last clb_set_observations row preparation
   size_t rows_bytes = 0;
   // double-buffered input pipeline (clb_prefetch_observations): the next step's rows travel on a copy stream into the
@@ -695,6 +696,7 @@ int clb_create(const clb_config* cfg, clb_handle** out) {
   // k_obs_pp (one CTA per SM, two tiles ping-ponging through a dedicated issuer warp) is parity-green but measured slower than
   // k_obs_tc2 on B200 (18.7 vs 16.8 ms: two warps per scheduler cannot cover the ALU / TMEM latencies); opt-in with CLB_PP=1
   { const char* ppe = getenv("CLB_PP"); h->use_pp = h->use_tc2 && cfg->image_layers == 0 && cfg->mlp_layers > 0 && (ppe && ppe[0] == '1') && !cfg->deterministic; }
+  { const char* bf = getenv("CLB_BIAS_FEAT"); h->bias_feat15 = h->use_tc16 && std::max(cfg->n_meta, cfg->mlp_width) <= 15 && !(bf && bf[0] == '0'); }
   { const char* t3 = getenv("CLB_TC3"); h->use_tc3 = h->use_tc2 && !h->use_pp && cfg->image_layers == 0 && cfg->mlp_layers > 0 && (t3 && t3[0] == '1') && !cfg->deterministic; }
   h->obs_threads = (h->use_tc || h->use_tc16) ? tc::kThreads : kObsThreads;      // = observation rows per CTA tile
   switch (WP) {
@@ -1251,6 +1253,7 @@ static int step_begin_impl(clb_handle* h, const float* inj_u, const float* inj_e
     }
     a.seed = c.seed; a.step = h->step_counter; a.laue = c.laue; a.train_mlp = train_mlp ? 1 : 0;
     a.discard_scratch = h->discard_scratch ? 1 : 0;
+    a.bias_feat15 = (h->use_tc16 && h->bias_feat15) ? 1 : 0;
     a.n_partials = h->n_partials;
     a.det = h->det ? 1 : 0;
     if (h->det) {

@@ -232,6 +232,8 @@ struct ObsArgs {
   //    (separate slots for the a_hi / a_lo rows of a kernel gradient and for every warp's bias sums), in program order.
   float* dzf_rows; double* ll_part; int det;
   int discard_scratch;             // 1: drop the activation scratch lines from L2 once the backward pass has consumed them (discard.global.L2)
+  int bias_feat15;                 // k_obs_tc16 with max(metadata columns, width) <= 15: feature 15 of every layer input is padding, so the dW
+                                   // operand image carries a constant 1 there and row 15 of the dW product IS the bias gradient (no shuffles)
 };
 
 // The activation scratch is written in the forward pass and read exactly once in the backward pass.  Without help every

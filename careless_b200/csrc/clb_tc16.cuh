@@ -209,7 +209,7 @@ __device__ __forceinline__ void collect16(Ctx16& c, float (&y)[16]) {
 }
 
 __device__ __forceinline__ void issue_bwd16(Ctx16& c, const float (&dp)[16], const float (&ain)[16], bool need_dx, const float* next, uint32_t next_n,
-                                            const float* build_from = nullptr, char* w_img = nullptr) {
+                                            const float* build_from = nullptr, char* w_img = nullptr, bool ones15 = false) {
   {
     uint32_t hi[16], lo[16];
     split16_rna(dp, hi, lo);
@@ -230,6 +230,7 @@ __device__ __forceinline__ void issue_bwd16(Ctx16& c, const float (&dp)[16], con
     uint32_t a2[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) a2[k] = __float_as_uint(ain[k]);
+    if (ones15) a2[15] = 0x3f800000u;      // the padding feature carries 1.0: row 15 of dW = sum over the tile's rows of delta-p = the bias gradient
     swap_blocks(a2, sw);
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
@@ -262,7 +263,8 @@ __device__ __forceinline__ void issue_bwd16(Ctx16& c, const float (&dp)[16], con
 
 // D_dw rows 0..15 (a_hi) = lanes 0..15 of warp 0, rows 16..31 (a_lo) = lanes 0..15 of warp 1; 32 columns [.dp_hi | .dp_lo].
 // il_w > 0: an image layer's kernel gradient, stored (out, in) with width il_w in that image's slot (scalar REDs).
-__device__ __forceinline__ void collect_dw16(Ctx16& c, float* wk, int il_w = 0, int lo_off = 0) {
+// ones15: row 15 (lane 15 of warp 0) is the bias gradient (see issue_bwd16) and goes to bk instead of the kernel's slot.
+__device__ __forceinline__ void collect_dw16(Ctx16& c, float* wk, int il_w = 0, int lo_off = 0, float* bk = nullptr, bool ones15 = false) {
   mbar_wait(c.mbar_dw, c.parity_dw);
   c.parity_dw ^= 1u;
   fence_after();
@@ -271,7 +273,13 @@ __device__ __forceinline__ void collect_dw16(Ctx16& c, float* wk, int il_w = 0, 
     uint32_t v[32];
     CLB_TMEM_LD32(c.row_addr + kDdw, v);
     wait_ld();
-    if (lane < 16 && wk != nullptr) {
+    if (ones15 && warp == 0 && lane == 15) {
+      if (bk != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (il_w == 0 || j < il_w) atomicAdd(&bk[j], __uint_as_float(v[j]) + __uint_as_float(v[16 + j]));
+      }
+    } else if (lane < 16 && wk != nullptr) {
       if (il_w == 0) {          // slot layout [j / 4][i][j % 4]: each RED instruction covers 256 contiguous bytes
         float4* dst = reinterpret_cast<float4*>(wk + (warp == 1 ? lo_off : 0)) + lane;      // warp 1 holds the a_lo rows
 #pragma unroll
@@ -347,6 +355,7 @@ __global__ void __launch_bounds__(tc16::kRows, 4) k_obs_tc16(ObsArgs a) {
   const int PSLOT = a.det ? PSLOT16_DET : PSLOT16;
   const int BOFF = a.det ? 2 * WP * WP + 16 * (tid >> 5) : WP * WP;       // this warp's bias slot inside a layer's slot
   const int lo_off = a.det ? WP * WP : 0;
+  const bool ones15 = a.bias_feat15 != 0;
   float* part32 = a.partials32 + (size_t)(blockIdx.x % a.n_partials) * NL * PSLOT;
   float4* scr = a.scratch + (size_t)blockIdx.x * LT * NC * TR;
   double ll_sum = 0.0;
@@ -419,18 +428,19 @@ __global__ void __launch_bounds__(tc16::kRows, 4) k_obs_tc16(ObsArgs a) {
     };
     auto layer_backward = [&](const float (&ain)[WP], bool need_dx, const float* next, uint32_t next_n, float* wk, float* bk2, int il_w,
                               const float* build_from, const float4* dead) {
-      issue_bwd16(c, dp, ain, need_dx, next, next_n, build_from, w_img);
+      const bool o15 = ones15 && il_w == 0;      // (hidden layers and the head; image layers keep the shuffle reduction: measured faster)
+      issue_bwd16(c, dp, ain, need_dx, next, next_n, build_from, w_img, o15);
       // every warp has consumed `ain` (issue_bwd16 ends after a __syncthreads()): warp 2 drops the layer's 8 KB scratch slot from the L2
       if (dead != nullptr && (tid >> 5) == 2) { discard_line(reinterpret_cast<const char*>(dead) + (size_t)lane * 128);
                                                 discard_line(reinterpret_cast<const char*>(dead) + (size_t)(32 + lane) * 128); }
-      bias_red16(dp, bk2, lane, il_w > 0 ? il_w : 16);
+      if (!o15) bias_red16(dp, bk2, lane, il_w > 0 ? il_w : 16);
       if (need_dx) {
         collect16(c, dp);                  // delta a_k
         // delta p_{k-1} = delta a_k * leaky'(pre-activation of layer k-1); sign(a_k) == sign(pre-activation), a_k is still in registers
 #pragma unroll
         for (int j = 0; j < WP; ++j) dp[j] = ain[j] > 0.f ? dp[j] : kLeak * dp[j];
       }
-      collect_dw16(c, wk, il_w, lo_off);
+      collect_dw16(c, wk, il_w, lo_off, bk2, o15);
     };
     if (LT > 0) load_act(nxt, LT - 1);
 #pragma unroll
