@@ -1213,7 +1213,7 @@ static int step_begin_impl(clb_handle* h, const float* inj_u, const float* inj_e
     }
     a.wimg = (h->use_tc2 || h->use_tc16) ? h->wimg.as<float>() : nullptr;
     if (h->use_tc16 && c.mlp_layers > 0) {
-      k_pack_images16<<<(c.mlp_layers * 512 + 255) / 256, 256, 0, st>>>(a.theta_mlp, h->lay, h->wimg.as<float>());
+      k_pack_images16<<<(c.mlp_layers * 512 + 255) / 256, 256, 0, st>>>(a.theta_mlp, h->lay, h->wimg.as<float>(), h->bias_feat15 ? 1 : 0);
       CLB_LAUNCHED(h);
     }
     a.n_img_layers = c.image_layers; a.il_width = c.mlp_width; a.il_n_images = c.n_images;

@@ -393,11 +393,13 @@ __global__ void __launch_bounds__(tc16::kRows, 4) k_obs_tc16(ObsArgs a) {
       const float* bk = (IL && k >= L) ? bimg + (size_t)(k - L) * WP : bsm + (size_t)k * WP;
       const bool next_bwd = !(k + 1 < LT) && a.train_mlp && LT > 1;
       const float* next = (k + 1 < LT) ? gimg(k + 1, 0) : next_bwd ? gimg(LT - 1, 1) : (more_tiles ? gimg(0, 0) : nullptr);
+      if (ones15) h[15] = 1.f;               // the padding feature: multiplies the bias row of a hidden layer's forward image
       issue_fwd16(c, h, next, next_bwd ? 2u : 3u, wsrc(k), w_img);
       float o[WP];
       collect16(c, o);
+      const bool bias_in_product = ones15 && !(IL && k >= L);      // (image layers: per-tile images without a bias row)
 #pragma unroll
-      for (int j = 0; j < WP; ++j) { const float v = o[j] + bk[j]; h[j] = fmaxf(v, kLeak * v); }
+      for (int j = 0; j < WP; ++j) { const float v = bias_in_product ? o[j] : o[j] + bk[j]; h[j] = fmaxf(v, kLeak * v); }
       if (a.train_mlp && k + 1 < LT) {          // the last layer's output stays in registers for the head
 #pragma unroll
         for (int q = 0; q < 4; ++q) scr[((size_t)k * NC + q) * TR + tid] = make_float4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
@@ -486,13 +488,16 @@ __global__ void __launch_bounds__(tc16::kRows, 4) k_obs_tc16(ObsArgs a) {
 }
 
 // Ready-made 16 x 16 B operand images of every hidden layer for k_obs_tc16: per layer [fwd, bwd][hi, lo][kImg16].
-__global__ void __launch_bounds__(256) k_pack_images16(const float* theta_mlp, MlpLayout lay, float* wimg) {
+// bias15: the forward image's input row 15 (a padding feature that the kernel feeds with 1.0) holds the layer's BIAS, so the chain
+// product already includes it (three-way split like the weights: exact to 2^-24).
+__global__ void __launch_bounds__(256) k_pack_images16(const float* theta_mlp, MlpLayout lay, float* wimg, int bias15) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int L = lay.n_layers - 1;
   if (idx >= L * 2 * 256) return;
   const int layer = idx >> 9, dir = (idx >> 8) & 1, n = (idx >> 4) & 15, k = idx & 15;
   const int i = dir ? n : k, j = dir ? k : n;          // W[i = in][j = out]
-  const float w = (i < lay.in_dim[layer] && j < lay.out_dim[layer]) ? theta_mlp[lay.koff[layer] + i * lay.out_dim[layer] + j] : 0.f;
+  float w = (i < lay.in_dim[layer] && j < lay.out_dim[layer]) ? theta_mlp[lay.koff[layer] + i * lay.out_dim[layer] + j] : 0.f;
+  if (bias15 && dir == 0 && i == 15 && j < lay.out_dim[layer]) w = theta_mlp[lay.boff[layer] + j];
   const float hi = tc::tf32_rna(w);
   const float r = w - hi;
   const float mid = tc::tf32_rna(r);
