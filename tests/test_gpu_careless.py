@@ -138,3 +138,37 @@ def test_crystfel_stream_entry_point(tmp_path):
     assert len(merged) > 100 and np.all(np.isfinite(merged["F"])) and merged.spacegroup.name == "P 1"
     with pytest.raises(ValueError):
         main(["poly", "--iterations", "2", "--disable-progress-bar", "--spacegroups=1", "dHKL,image_id", path, out + "_p"])
+
+
+def _scaler_arrays(sm):
+    """Every trainable array of a scaling model mirror (MLPScaler / HybridImageScaler / NeuralImageScaler)."""
+    if hasattr(sm, "mlp_scaler"):
+        return [w.copy() for w in sm.mlp_scaler.get_weights()] + [np.array(sm.image_scaler._scales, copy=True)]
+    if hasattr(sm, "metadata_scaler"):
+        return [w.copy() for w in sm.metadata_scaler.get_weights()] + [np.array(sm.flat(), copy=True)]
+    return [w.copy() for w in sm.get_weights()]
+
+
+@pytest.mark.parametrize("flags", [dict(), dict(use_image_scales=False), dict(image_layers=1, mlp_width=8)])
+def test_scale_file_and_structure_factor_file_on_a_fresh_model(tmp_path, flags):
+    """careless.py:48-56, 79-80, 104: `--scale-file` / `--structure-factor-file` load the weights of an earlier run into a model that has
+    not been built yet; with `--freeze-scales --freeze-structure-factors` and no training noise the second run reproduces the first
+    run's merged structure factors exactly and leaves both weight sets untouched."""
+    common = dict(metadata_keys="dHKL,Hobs,Kobs,Lobs", iterations=10, mlp_layers=3, disable_progress_bar=True, **flags)
+    first = default_parser("mono", output_base=os.path.join(tmp_path, "a"), **common)
+    run1 = run_careless(first, datasets=[U.load_fixture("pyp_off")])
+    w1 = _scaler_arrays(run1["model"].scaling_model)
+    loc1 = run1["model"].surrogate_posterior.loc_raw.copy()
+    f1 = read_mtz(first.output_base + "_0.mtz")
+    run1["model"].close()
+    second = default_parser("mono", output_base=os.path.join(tmp_path, "b"), scale_file=first.output_base + "_scale",
+                            structure_factor_file=first.output_base + "_structure_factor", freeze_scales=True,
+                            freeze_structure_factors=True, **common)
+    run2 = run_careless(second, datasets=[U.load_fixture("pyp_off")])
+    w2 = _scaler_arrays(run2["model"].scaling_model)
+    assert len(w1) == len(w2) and all(np.array_equal(a, b) for a, b in zip(w1, w2))
+    assert np.array_equal(loc1, run2["model"].surrogate_posterior.loc_raw)
+    f2 = read_mtz(second.output_base + "_0.mtz")
+    assert np.array_equal(np.asarray(f1["F"]), np.asarray(f2["F"])) and np.array_equal(np.asarray(f1["SigF"]), np.asarray(f2["SigF"]))
+    assert len(run2["history"]["loss"]) == 10 and np.all(np.isfinite(run2["history"]["loss"]))
+    run2["model"].close()

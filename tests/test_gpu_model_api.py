@@ -217,3 +217,41 @@ def test_results_and_predictions(laue):
     ip, sip = model.prediction_mean_stddev(data)
     assert np.allclose(ip, iexp, rtol=5e-4, atol=1e-4) and np.allclose(sip, np.sqrt(ivar), rtol=2e-3, atol=1e-4)
     model.close()
+
+
+@pytest.mark.parametrize("with_validation", [False, True])
+@pytest.mark.parametrize("bad_step", [3, 4, 7])
+def test_nonfinite_gradient_norm_ends_training_at_any_chunk_position(monkeypatch, with_validation, bad_step):
+    """variational.py:271-274: the loop ends AFTER the first step whose gradient norm is not finite -- also when that step is the last
+    one of a chunk of steps handed to the library (clb_step then returns every row of the chunk) or a one-step chunk in front of a
+    validation step.  The non-finite norm is injected into the metrics the engine returns."""
+    from careless_b200.engine import Engine
+    p = synth.make_mono(1500, 120, d=3, n_images=5, seed=3)
+    model = _model(p, False, "normal", "wilson", "mlp", 1)
+    real_step = Engine.step
+    seen = {"n": 0}
+
+    def step(self, n, *a, **kw):
+        rows = real_step(self, n, *a, **kw)
+        for r in rows:
+            if seen["n"] == bad_step:
+                r["Grad Norm"] = float("nan")
+                del rows[rows.index(r) + 1:]           # the library stops after the bad step: later rows of the chunk do not exist
+                seen["n"] += 1
+                break
+            seen["n"] += 1
+        return rows
+
+    monkeypatch.setattr(Engine, "step", step)
+    kw = {}
+    if with_validation:
+        test = np.random.default_rng(0).random(1500) < 0.25
+        split = lambda m: {k: (v[m] if isinstance(v, np.ndarray) and v.shape[:1] == (1500,) else v) for k, v in p.items()}
+        kw = dict(validation_data=_inputs(split(test), False), validation_frequency=4)
+        data = _inputs(split(~test), False)
+    else:
+        data = _inputs(p, False)
+    hist = model.train_model(data, 20, progress=False, chunk=4, **kw)
+    assert len(hist["loss"]) == bad_step + 1, (len(hist["loss"]), bad_step)
+    assert not np.isfinite(hist["Grad Norm"][-1]) and np.all(np.isfinite(hist["Grad Norm"][:-1]))
+    model.close()
